@@ -1,0 +1,443 @@
+// bedmap.cu -- the bedmap overlap-mapping sweep as data-parallel kernels.
+//
+// Replaces WindowSweep::sweep + BedBaseVisitor::fixWindow + the visitor zoo
+// (interfaces/src/algorithm/sweep/WindowSweepImpl.cpp:174-256, visitors/bed/BedBaseVisitor.hpp:118-225).
+// The streaming window is replaced by a per-reference-row candidate range over the sorted map columns:
+//     hi = lower_bound(map.start, ref.end + pad)            first map row that starts at/after the reference end
+//     lo = lower_bound(map.pmax_end, ref.start - pad + 1)   first map row whose running max end reaches the reference
+// Every row in [lo,hi) is tested with the exact overlap predicate (Bed::Overlapping / RangedDist / PercentOverlap* /
+// Exact, BedDistances.hpp:41-317) and reduced; the prefix-max index makes the range tight under nesting.
+#include "common.cuh"
+#include "emit.cuh"
+#include "fmt.cuh"
+#include "parse.cuh"
+
+namespace bk {
+
+struct OverlapSpec {
+  int      kind;
+  uint32_t bp;    // BK_OVR_BP: required overlap; BK_OVR_RANGE: padding
+  double   frac;  // perc_ exactly as PercentOverlapMapping's constructor leaves it (BedDistances.hpp:120-131)
+};
+
+// PercentOverlapMapping::Ref2Map(ref=a, map=b) == 0 given that a and b overlap by ov > 0 bases
+__device__ __forceinline__ bool frac_of(uint32_t ov, uint32_t blen, double perc) {
+  return (double)ov / (double)blen >= perc;
+}
+
+// dist_.Map2Ref(m, r) == 0
+__device__ __forceinline__ bool qualifies(const OverlapSpec& o, uint32_t rs, uint32_t re, uint32_t ms, uint32_t me,
+                                          uint32_t& ov) {
+  const uint32_t mn = rs > ms ? rs : ms, mx = re < me ? re : me;
+  ov = mx > mn ? mx - mn : 0;
+  switch (o.kind) {
+    case BK_OVR_BP: return ov >= o.bp && ov > 0;
+    case BK_OVR_RANGE:
+      if (ms < re) return (uint64_t)me + o.bp > rs;
+      return (uint64_t)re + o.bp > ms;
+    case BK_OVR_FRAC_MAP: return ov > 0 && frac_of(ov, me - ms, o.frac);
+    case BK_OVR_FRAC_REF: return ov > 0 && frac_of(ov, re - rs, o.frac);
+    case BK_OVR_FRAC_EITHER: return ov > 0 && (frac_of(ov, me - ms, o.frac) || frac_of(ov, re - rs, o.frac));
+    case BK_OVR_FRAC_BOTH: return ov > 0 && frac_of(ov, me - ms, o.frac) && frac_of(ov, re - rs, o.frac);
+    case BK_OVR_EXACT: return rs == ms && re == me;
+  }
+  return false;
+}
+
+enum { NEED_BASES = 1, NEED_SUM = 2, NEED_MAX = 4, NEED_MIN = 8, NEED_IDS = 16 };
+
+struct MapStatsParams {
+  const uint32_t* rs;
+  const uint32_t* re;
+  uint64_t        row0, n;
+  const uint64_t* run_ref_begin;  // [nruns+1] ascending reference row numbers
+  const uint64_t* run_map_begin;  // [nruns] map rows of the same chromosome (empty range if absent)
+  const uint64_t* run_map_end;
+  int             nruns;
+  const uint32_t* ms;
+  const uint32_t* me;
+  const uint32_t* pm;
+  const double*   score;
+  const uint32_t* idspan;
+  OverlapSpec     ov;
+  unsigned        need;
+  uint32_t        mdelim_len;
+  uint32_t*       count;
+  uint64_t*       bases;
+  double*         sum;
+  double*         vmax;
+  double*         vmin;
+  uint64_t*       win_lo;
+  uint32_t*       win_n;
+  uint32_t*       idbytes;
+  uint64_t*       scratch;
+};
+
+constexpr int MS_THREADS = 256;
+
+__global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * MS_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x; i < p.n; i += stride) {
+    const uint64_t row = p.row0 + i;
+    const uint32_t rs = p.rs[row], re = p.re[row];
+    // chromosome run of this reference row: last run_ref_begin <= row
+    int lo_r = 0, hi_r = p.nruns;
+    while (hi_r - lo_r > 1) {
+      int mid = (lo_r + hi_r) >> 1;
+      if (p.run_ref_begin[mid] <= row) lo_r = mid; else hi_r = mid;
+    }
+    const uint64_t mb = p.run_map_begin[lo_r], mend = p.run_map_end[lo_r];
+    const uint32_t pad = p.ov.kind == BK_OVR_RANGE ? p.ov.bp : 0;
+    const uint64_t hi = lower_bound_u32(p.ms, mb, mend, (uint64_t)re + pad);
+    const uint64_t lo = rs >= pad ? lower_bound_u32(p.pm, mb, hi, (uint64_t)rs - pad + 1) : mb;
+    uint32_t cnt = 0, idb = 0;
+    uint64_t bases = 0;
+    double   sum = 0.0, vmax = 0.0, vmin = 0.0;
+    for (uint64_t k = lo; k < hi; k++) {
+      const uint32_t ms = __ldg(&p.ms[k]), me = __ldg(&p.me[k]);
+      uint32_t       ov;
+      if (!qualifies(p.ov, rs, re, ms, me, ov)) continue;
+      if (p.need & NEED_BASES) bases += ov;
+      if (p.need & (NEED_SUM | NEED_MAX | NEED_MIN)) {
+        const double v = __ldg(&p.score[k]);
+        sum += v;
+        if (cnt == 0) {
+          vmax = vmin = v;
+        } else {
+          vmax = v > vmax ? v : vmax;
+          vmin = v < vmin ? v : vmin;
+        }
+      }
+      if (p.need & NEED_IDS) idb += (__ldg(&p.idspan[k]) & 0xFFFFu) + (cnt ? p.mdelim_len : 0);
+      cnt++;
+    }
+    p.count[i] = cnt;
+    if (p.bases) p.bases[i] = bases;
+    if (p.sum) p.sum[i] = sum;
+    if (p.vmax) p.vmax[i] = vmax;
+    if (p.vmin) p.vmin[i] = vmin;
+    if (p.win_lo) {
+      p.win_lo[i] = lo;
+      p.win_n[i] = (uint32_t)(hi - lo);
+      p.idbytes[i] = idb;
+    }
+  }
+}
+
+// echo a B3Rest row: chrom \t start \t end <rest>   (Bed.hpp:316-320, :376-378): numbers are re-printed from the
+// parsed values, the rest of the line (including its leading tab) is copied verbatim.
+template <class Sink>
+__device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
+  const char* p = text + off;
+  int         n = 0;
+  while (is_tok((unsigned char)p[n])) n++;
+  s.copy(p, n);
+  s.put('\t');
+  s.put_u32(st);
+  s.put('\t');
+  s.put_u32(en);
+  const char* q = p + n;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  int m = 0;
+  while (q[m] != '\n') m++;
+  s.copy(q, m);
+}
+
+struct BedmapRow {
+  // reference rows
+  const char*     rtext;
+  const uint64_t* rline;
+  const uint32_t* rs;
+  const uint32_t* re;
+  uint64_t        row0;
+  // map side (echo-map-id)
+  const char*     mtext;
+  const uint64_t* mline;
+  const uint32_t* midspan;
+  const uint32_t* ms;
+  const uint32_t* me;
+  // per-row results (indexed by i = row - row0)
+  const uint32_t* count;
+  const uint64_t* bases;
+  const double*   sum;
+  const double*   vmax;
+  const double*   vmin;
+  const uint64_t* win_lo;
+  const uint32_t* win_n;
+  const uint32_t* idbytes;
+  OverlapSpec     ov;
+  int             n_ops;
+  unsigned char   ops[BK_MAX_OPS];
+  int             prec;
+  int             skip_unmapped;
+  char            delim[24];
+  int             delim_len;
+  char            mdelim[24];
+  int             mdelim_len;
+  uint64_t*       scratch;
+
+  template <class Sink>
+  __device__ __forceinline__ void put_score(Sink& s, double v, uint32_t cnt, uint64_t i) const {
+    if (cnt == 0) {
+      s.puts_("NAN", 3);  // Signal::NaN::nan_ (interfaces/src/data/measurement/NaN.cpp:27)
+      return;
+    }
+    Fixed f;
+    if (!to_fixed(v, prec, f)) {
+      dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);
+      s.put('?');
+      return;
+    }
+    put_fixed(s, f, prec);
+  }
+
+  template <class Sink>
+  __device__ void operator()(uint64_t i, Sink& s) const {
+    const uint32_t cnt = count[i];
+    if (skip_unmapped && cnt == 0) return;  // MultiVisitor.hpp:84-85
+    const uint64_t row = row0 + i;
+    for (int c = 0; c < n_ops; c++) {
+      if (c) s.puts_(delim, delim_len);
+      switch (ops[c]) {
+        case BK_OP_ECHO: echo_b3rest(s, rtext, rline[row], rs[row], re[row]); break;
+        case BK_OP_COUNT: s.put_u32(cnt); break;
+        case BK_OP_INDICATOR: s.put(cnt ? '1' : '0'); break;
+        case BK_OP_BASES: s.put_u64(bases[i]); break;
+        case BK_OP_SUM: put_score(s, sum[i], cnt, i); break;
+        case BK_OP_MEAN: put_score(s, cnt ? sum[i] / (double)(int)cnt : 0.0, cnt, i); break;
+        case BK_OP_MAX: put_score(s, vmax[i], cnt, i); break;
+        case BK_OP_MIN: put_score(s, vmin[i], cnt, i); break;
+        case BK_OP_ECHO_MAP_ID: {
+          if (Sink::counting) {
+            s.copy(nullptr, idbytes[i]);
+            break;
+          }
+          const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+          const uint32_t a = rs[row], b = re[row];
+          bool           first = true;
+          for (uint64_t k = lo; k < hi; k++) {
+            uint32_t ovl;
+            if (!qualifies(ov, a, b, ms[k], me[k], ovl)) continue;
+            if (!first) s.puts_(mdelim, mdelim_len);
+            first = false;
+            const uint32_t sp = midspan[k];
+            s.copy(mtext + mline[k] + (sp >> 16), sp & 0xFFFFu);
+          }
+          break;
+        }
+        case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
+        case BK_OP_ECHO_REF_NAME: {
+          const char* p = rtext + rline[row];
+          int         n = 0;
+          while (is_tok((unsigned char)p[n])) n++;
+          s.copy(p, n);
+          s.put(':');
+          s.put_u32(rs[row]);
+          s.put('-');
+          s.put_u32(re[row]);
+          break;
+        }
+        case BK_OP_ECHO_REF_ROW_ID:
+          s.puts_("id-", 3);
+          s.put_u64(row + 1);
+          break;
+      }
+    }
+    s.put('\n');
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+int finish_text(bk_ctx* ctx, char* d_out, uint64_t bytes, uint64_t rows, int on_device, bk_text* out);
+
+static int find_run(const bk_bed* b, const std::string& name) {
+  // runs are in strcmp order: binary search
+  int lo = 0, hi = (int)b->runs.size();
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    int c = strcmp(b->runs[mid].name.c_str(), name.c_str());
+    if (c == 0) return mid;
+    if (c < 0) lo = mid + 1; else hi = mid;
+  }
+  return -1;
+}
+
+}  // namespace bk
+
+using namespace bk;
+
+extern "C" void bk_mapspec_default(bk_mapspec* spec) {
+  memset(spec, 0, sizeof(*spec));
+  spec->overlap_kind = BK_OVR_BP;
+  spec->overlap_bp = 1;
+  spec->precision = 6;
+  spec->delim = "|";
+  spec->multidelim = ";";
+}
+
+extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, const bk_mapspec* spec, bk_text* out) {
+  if (!ctx || !ref || !spec || !out) return BK_ERR_ARG;
+  ctx->last_error.clear();
+  memset(out, 0, sizeof(*out));
+  if (!map) map = ref;
+  if (spec->n_ops <= 0 || spec->n_ops > BK_MAX_OPS) return fail(ctx, BK_ERR_ARG, "No processing option specified (ie; --max).");
+  if (spec->sci) return fail(ctx, BK_ERR_UNSUPPORTED, "--sci output is not implemented on the device formatter yet");
+  if (spec->precision < 0 || spec->precision > 18)
+    return fail(ctx, BK_ERR_UNSUPPORTED, "--prec %d: the exact device formatter supports 0..18", spec->precision);
+  const char* delim = spec->delim ? spec->delim : "|";
+  const char* mdelim = spec->multidelim ? spec->multidelim : ";";
+  if (strlen(delim) > 23 || strlen(mdelim) > 23) return fail(ctx, BK_ERR_UNSUPPORTED, "delimiter longer than 23 bytes");
+
+  unsigned need = 0;
+  bool     need_echo = false, need_refline = false;
+  for (int c = 0; c < spec->n_ops; c++) {
+    switch (spec->ops[c]) {
+      case BK_OP_ECHO: need_echo = true; need_refline = true; break;
+      case BK_OP_ECHO_REF_NAME: need_refline = true; break;
+      case BK_OP_COUNT: case BK_OP_INDICATOR: case BK_OP_ECHO_REF_SIZE: case BK_OP_ECHO_REF_ROW_ID: break;
+      case BK_OP_BASES: need |= NEED_BASES; break;
+      case BK_OP_SUM: case BK_OP_MEAN: need |= NEED_SUM; break;
+      case BK_OP_MAX: need |= NEED_MAX; break;
+      case BK_OP_MIN: need |= NEED_MIN; break;
+      case BK_OP_ECHO_MAP_ID: need |= NEED_IDS; break;
+      default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
+    }
+  }
+  (void)need_echo;
+  if (need_refline && !ref->line_off && ref->nrows)
+    return fail(ctx, BK_ERR_ARG, "reference file was loaded without BK_COL_LINE but --echo needs it");
+  if ((need & (NEED_SUM | NEED_MAX | NEED_MIN)) && !map->score && map->nrows)
+    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_SCORE but a score operation needs it");
+  if ((need & NEED_IDS) && (!map->idspan || !map->line_off) && map->nrows)
+    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_ID|BK_COL_LINE but --echo-map-id needs it");
+
+  OverlapSpec ov{};
+  ov.kind = spec->overlap_kind;
+  switch (spec->overlap_kind) {
+    case BK_OVR_BP:
+    case BK_OVR_RANGE:
+      if (spec->overlap_bp > 0xFFFFFFFEull) return fail(ctx, BK_ERR_UNSUPPORTED, "overlap/range value beyond 32 bits");
+      ov.bp = (uint32_t)spec->overlap_bp;
+      break;
+    case BK_OVR_FRAC_REF: case BK_OVR_FRAC_MAP: case BK_OVR_FRAC_EITHER: case BK_OVR_FRAC_BOTH: {
+      double perc = spec->overlap_frac;  // PercentOverlapMapping ctor, BedDistances.hpp:120-131
+      while (perc > 1) perc /= 10.0;
+      perc -= 2.220446049250313e-16;
+      if (perc <= 0.0) perc = 2.220446049250313e-16;
+      ov.frac = perc;
+      break;
+    }
+    case BK_OVR_EXACT: break;
+    default: return fail(ctx, BK_ERR_ARG, "unknown overlap kind %d", spec->overlap_kind);
+  }
+
+  // reference rows to process and the chromosome pairing table
+  const bool all = !spec->chrom || !*spec->chrom || strcmp(spec->chrom, "all") == 0;
+  std::vector<uint64_t> rrb, rmb, rme;
+  uint64_t row0 = 0, row1 = 0;
+  if (all) {
+    row0 = 0;
+    row1 = ref->nrows;
+    for (auto& r : ref->runs) {
+      rrb.push_back(r.row_begin);
+      int j = find_run(map, r.name);
+      rmb.push_back(j >= 0 ? map->runs[j].row_begin : 0);
+      rme.push_back(j >= 0 ? map->runs[j].row_end : 0);
+    }
+  } else {
+    int jr = find_run(ref, spec->chrom);
+    if (jr >= 0) {
+      row0 = ref->runs[jr].row_begin;
+      row1 = ref->runs[jr].row_end;
+      rrb.push_back(row0);
+      int j = find_run(map, spec->chrom);
+      rmb.push_back(j >= 0 ? map->runs[j].row_begin : 0);
+      rme.push_back(j >= 0 ? map->runs[j].row_end : 0);
+    }
+  }
+  const uint64_t n = row1 - row0;
+  if (n == 0) return finish_text(ctx, nullptr, 0, 0, spec->out_on_device, out);
+  rrb.push_back(row1);
+  const int nruns = (int)rmb.size();
+
+  BK_TRY(ensure_pmax(ctx, map));
+
+  uint64_t* d_tab = dalloc<uint64_t>(ctx, 3 * (size_t)nruns + 1);
+  if (!d_tab) return BK_ERR_NOMEM;
+  std::vector<uint64_t> tab;
+  tab.insert(tab.end(), rrb.begin(), rrb.end());
+  tab.insert(tab.end(), rmb.begin(), rmb.end());
+  tab.insert(tab.end(), rme.begin(), rme.end());
+  BK_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  MapStatsParams sp{};
+  sp.rs = ref->start; sp.re = ref->end; sp.row0 = row0; sp.n = n;
+  sp.run_ref_begin = d_tab; sp.run_map_begin = d_tab + nruns + 1; sp.run_map_end = d_tab + 2 * nruns + 1; sp.nruns = nruns;
+  sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.score = map->score; sp.idspan = map->idspan;
+  sp.ov = ov; sp.need = need; sp.mdelim_len = (uint32_t)strlen(mdelim);
+  sp.count = dalloc<uint32_t>(ctx, n);
+  if (need & NEED_BASES) sp.bases = dalloc<uint64_t>(ctx, n);
+  if (need & NEED_SUM) sp.sum = dalloc<double>(ctx, n);
+  if (need & NEED_MAX) sp.vmax = dalloc<double>(ctx, n);
+  if (need & NEED_MIN) sp.vmin = dalloc<double>(ctx, n);
+  if (need & NEED_IDS) {
+    sp.win_lo = dalloc<uint64_t>(ctx, n);
+    sp.win_n = dalloc<uint32_t>(ctx, n);
+    sp.idbytes = dalloc<uint32_t>(ctx, n);
+  }
+  sp.scratch = ctx->d_scratch;
+  if (!sp.count || ((need & NEED_BASES) && !sp.bases) || ((need & NEED_SUM) && !sp.sum) || ((need & NEED_MAX) && !sp.vmax) ||
+      ((need & NEED_MIN) && !sp.vmin) || ((need & NEED_IDS) && (!sp.win_lo || !sp.win_n || !sp.idbytes)))
+    return BK_ERR_NOMEM;
+  {
+    uint64_t blocks = (n + MS_THREADS - 1) / MS_THREADS;
+    uint64_t cap = (uint64_t)kSMs * 8 * 4;
+    k_map_stats<<<(unsigned)(blocks < cap ? blocks : cap), MS_THREADS, 0, ctx->stream>>>(sp);
+    BK_LAUNCHED(ctx);
+  }
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host table `tab` must outlive its copy
+  dfree(ctx, d_tab);
+
+  // output size bound: echoed reference text + a fixed worst case per numeric column + id lists
+  uint64_t idtotal = 0;
+  if (need & NEED_IDS) {
+    // sum of idbytes: tiny reduction on the host side of a device prefix would cost a pass; reuse the bound
+    // sum_i idbytes[i] <= map id bytes * (windows that contain the row) -- not bounded a priori, so reduce it.
+    std::vector<uint32_t> h(n);
+    BK_CUDA(ctx, cudaMemcpyAsync(h.data(), sp.idbytes, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < n; i++) idtotal += h[i];
+  }
+  const uint64_t dl = strlen(delim);
+  uint64_t per_row = 1 + (uint64_t)spec->n_ops * (dl + 44);
+  uint64_t cap = n * per_row + idtotal + 64;
+  if (need_refline) cap += ref->nbytes + 2 * 11 * n;
+
+  BedmapRow fn{};
+  fn.rtext = ref->d_text; fn.rline = ref->line_off; fn.rs = ref->start; fn.re = ref->end; fn.row0 = row0;
+  fn.mtext = map->d_text; fn.mline = map->line_off; fn.midspan = map->idspan; fn.ms = map->start; fn.me = map->end;
+  fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
+  fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
+  fn.ov = ov; fn.n_ops = spec->n_ops;
+  for (int c = 0; c < spec->n_ops; c++) fn.ops[c] = (unsigned char)spec->ops[c];
+  fn.prec = spec->precision; fn.skip_unmapped = spec->skip_unmapped;
+  fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
+  fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
+  fn.scratch = ctx->d_scratch;
+
+  char*    d_out = nullptr;
+  uint64_t bytes = 0, rows = 0;
+  int rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
+  dfree(ctx, sp.count); dfree(ctx, sp.bases); dfree(ctx, sp.sum); dfree(ctx, sp.vmax); dfree(ctx, sp.vmin);
+  dfree(ctx, sp.win_lo); dfree(ctx, sp.win_n); dfree(ctx, sp.idbytes);
+  if (rc != BK_OK) {
+    dfree(ctx, d_out);
+    return rc;
+  }
+  return finish_text(ctx, d_out, bytes, rows, spec->out_on_device, out);
+}

@@ -1,0 +1,280 @@
+// common.cuh -- context, error plumbing and small device primitives shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/bedkit.h"
+
+namespace bk {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct ChromRun {
+  std::string name;
+  uint64_t    row_begin;
+  uint64_t    row_end;
+};
+
+}  // namespace bk
+
+struct bk_ctx {
+  int          device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string  last_error;
+  uint64_t     launches = 0;
+  // small device scratch reused by every call: error record, counters
+  uint64_t* d_scratch = nullptr;  // 64 x u64
+  uint64_t* h_scratch = nullptr;  // pinned mirror
+  // pinned host staging pool (result text / input upload)
+  struct Pinned {
+    char*  ptr;
+    size_t cap;
+    bool   busy;
+  };
+  std::vector<Pinned> pinned;
+};
+
+struct bk_bed {
+  const char* d_text = nullptr;  // device text (owned iff owns_text)
+  uint64_t    nbytes = 0;        // effective length: up to and including the last '\n'
+  bool        owns_text = false;
+  int         min_fields = 3;
+  unsigned    cols = 0;
+  uint64_t    nrows = 0;
+  uint32_t*   start = nullptr;
+  uint32_t*   end = nullptr;
+  double*     score = nullptr;
+  uint64_t*   line_off = nullptr;  // [nrows+1]; line_off[nrows] = nbytes
+  uint32_t*   idspan = nullptr;    // (rel_off << 16) | len  relative to line_off
+  uint32_t*   pmax_end = nullptr;  // inclusive running max of end within the chromosome run (lazy)
+  std::vector<bk::ChromRun> runs;
+};
+
+namespace bk {
+
+int  fail(bk_ctx* ctx, int code, const char* fmt, ...);
+int  cuda_fail(bk_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+void* dmalloc(bk_ctx* ctx, size_t bytes);  // stream-ordered; returns nullptr and sets last_error on failure
+void  dfree(bk_ctx* ctx, void* p);
+char* pinned_get(bk_ctx* ctx, size_t bytes);
+void  pinned_put(bk_ctx* ctx, char* p);
+
+#define BK_CUDA(ctx, expr)                                                      \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) return bk::cuda_fail((ctx), _e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define BK_LAUNCHED(ctx)                                                        \
+  do {                                                                          \
+    (ctx)->launches++;                                                          \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) return bk::cuda_fail((ctx), _e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define BK_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != BK_OK) return _rc; \
+  } while (0)
+
+template <typename T>
+inline T* dalloc(bk_ctx* ctx, size_t n) {
+  return reinterpret_cast<T*>(dmalloc(ctx, (n ? n : 1) * sizeof(T)));
+}
+
+// device scratch slots (u64 each)
+enum {
+  SC_ERR_CODE = 0,   // first error code seen by any kernel (atomicCAS from 0)
+  SC_ERR_ROW = 1,    // row / byte offset attached to it
+  SC_TICKET = 2,     // dynamic tile ticket for look-back kernels
+  SC_COUNT_A = 3,    // generic counters
+  SC_COUNT_B = 4,
+  SC_COUNT_C = 5,
+  SC_COUNT_D = 6,
+  SC_EFFLEN = 7,    // parser: bytes up to and including the last newline
+  SC_NHEADS = 8,    // parser: chromosome run heads found
+  SC_NROWS = 9,     // parser: total rows
+  SC_OUT_BYTES = 10, // emitters: total bytes written
+  SC_OUT_ROWS = 11,  // emitters: total rows written
+  SC_N = 64
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void dev_set_error(uint64_t* scratch, int code, uint64_t where) {
+  if (atomicCAS(reinterpret_cast<unsigned long long*>(&scratch[SC_ERR_CODE]), 0ull, (unsigned long long)code) == 0ull)
+    scratch[SC_ERR_ROW] = where;
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // streaming 16-byte load, no L1 allocation
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ bool is_ws(unsigned char c) {  // isspace() minus '\n'
+  return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f';
+}
+__device__ __forceinline__ bool is_tok(unsigned char c) { return !(is_ws(c) || c == '\n'); }
+__device__ __forceinline__ bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+
+// warp inclusive scan (sum) of a 32-bit value
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// Block-wide exclusive scan of one u32 per thread (blockDim.x <= 1024, multiple of 32).
+// smem: at least 33 u32.  Returns the exclusive prefix; *total receives the block total (all threads).
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  uint32_t incl = warp_incl_scan(v);
+  if (lane == 31) smem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < nwarp ? smem[lane] : 0;
+    uint32_t wi = warp_incl_scan(w);
+    smem[lane] = wi - w;
+    if (lane == 31) smem[32] = wi;
+  }
+  __syncthreads();
+  uint32_t base = smem[warp];
+  *total = smem[32];
+  __syncthreads();
+  return base + incl - v;
+}
+
+// ---- decoupled look-back over self-contained 64-bit tile words --------------------------------------------
+// word = status(2 bits) << 62 | value(62 bits).  status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
+// Tiles are numbered by a dynamic ticket so that every predecessor is already resident (forward progress).
+constexpr uint64_t kTileValMask = (1ull << 62) - 1;
+
+// Sum look-back.  Call with all 32 lanes of one warp; every lane passes the same agg.  Returns the exclusive
+// prefix of this tile (sum of the aggregates of tiles 0..tile-1) in every lane.
+__device__ __forceinline__ uint64_t lookback_sum(uint64_t* state, uint32_t tile, uint64_t agg) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_relaxed_u64(&state[tile], ((tile == 0 ? 2ull : 1ull) << 62) | agg);
+  if (tile == 0) return 0;
+  uint64_t excl = 0;
+  int64_t  look = (int64_t)tile - 1;
+  while (true) {
+    int64_t  idx = look - lane;
+    uint64_t w = 2ull << 62;  // virtual tiles before 0: inclusive prefix 0
+    if (idx >= 0) {
+      w = ld_relaxed_u64(&state[idx]);
+      while ((w >> 62) == 0) w = ld_relaxed_u64(&state[idx]);
+    }
+    unsigned done = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+    int      first = done ? (__ffs(done) - 1) : 31;
+    uint64_t c = (lane <= first) ? (w & kTileValMask) : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    excl += c;
+    if (done) break;
+    look -= 32;
+  }
+  if (lane == 0) st_relaxed_u64(&state[tile], (2ull << 62) | (excl + agg));
+  return excl;
+}
+
+// Segmented-max look-back.  value = head(1 bit) << 40 | max(40 bits): a tile aggregate is "the max since the
+// tile's last segment head (or since the tile start)" plus whether the tile contains a head.  Returns the running
+// max flowing INTO this tile (0 if the predecessor chain ends in a head with nothing after it is handled by value).
+__device__ __forceinline__ uint64_t lookback_segmax(uint64_t* state, uint32_t tile, bool agg_head, uint64_t agg_max) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t kHead = 1ull << 40, kMax = kHead - 1;
+  // if this tile has a head, its inclusive value is already final
+  uint64_t mine = (agg_head ? kHead : 0) | agg_max;
+  if (lane == 0) st_relaxed_u64(&state[tile], (((tile == 0 || agg_head) ? 2ull : 1ull) << 62) | mine);
+  if (tile == 0) return 0;
+  uint64_t carry = 0;
+  int64_t  look = (int64_t)tile - 1;
+  while (true) {
+    int64_t  idx = look - lane;
+    uint64_t w = (2ull << 62) | kHead;  // virtual predecessor: a head with max 0
+    if (idx >= 0) {
+      w = ld_relaxed_u64(&state[idx]);
+      while ((w >> 62) == 0) w = ld_relaxed_u64(&state[idx]);
+    }
+    // a lane ends the walk if it holds an inclusive prefix or contains a head
+    unsigned stop = __ballot_sync(0xffffffffu, (w >> 62) == 2 || (w & kHead));
+    int      first = stop ? (__ffs(stop) - 1) : 31;
+    uint64_t c = (lane <= first) ? (w & kMax) : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      uint64_t o = __shfl_xor_sync(0xffffffffu, c, d);
+      c = o > c ? o : c;
+    }
+    carry = c > carry ? c : carry;
+    if (stop) break;
+    look -= 32;
+  }
+  if (!agg_head && lane == 0) {
+    uint64_t incl = agg_max > carry ? agg_max : carry;
+    st_relaxed_u64(&state[tile], (2ull << 62) | incl);
+  }
+  return carry;
+}
+
+// dynamic tile ticket: one atomicAdd per tile, broadcast through shared memory
+__device__ __forceinline__ uint32_t next_ticket(uint64_t* scratch, uint32_t* smem_slot) {
+  if (threadIdx.x == 0) *smem_slot = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_TICKET]), 1ull);
+  __syncthreads();
+  uint32_t t = *smem_slot;
+  __syncthreads();
+  return t;
+}
+
+// ---- binary searches over sorted u32 arrays -----------------------------------------------------------------
+// first index in [lo,hi) with a[i] >= key
+__device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t* __restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
+  while (lo < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    if ((uint64_t)__ldg(&a[mid]) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// first index in [lo,hi) with a[i] > key
+__device__ __forceinline__ uint64_t upper_bound_u32(const uint32_t* __restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
+  while (lo < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    if ((uint64_t)__ldg(&a[mid]) <= key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bk

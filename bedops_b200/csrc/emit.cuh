@@ -1,0 +1,129 @@
+// emit.cuh -- the BED writer skeleton shared by every tool: one output row per thread, single pass.
+//
+//   length pass (CountSink) -> block scan -> decoupled look-back over tiles (byte offsets) ->
+//   write pass (MemSink) into a shared-memory stage laid out with the same 16-byte phase as the destination ->
+//   16-byte coalesced streaming stores to HBM.
+//
+// RowFn contract:  template <class Sink> __device__ void operator()(uint64_t i, Sink& s) const;
+//                  writes row i (including its '\n'), or nothing at all if the row is suppressed.
+#pragma once
+#include "common.cuh"
+#include "fmt.cuh"
+
+namespace bk {
+
+constexpr int E_THREADS = 256;
+constexpr int E_STAGE = 32 * 1024;  // bytes of shared staging per tile (tiles that exceed it write straight to HBM)
+
+#ifdef __CUDACC__
+
+template <class RowFn>
+__global__ void __launch_bounds__(E_THREADS) k_emit(RowFn fn, uint64_t n, char* __restrict__ out, uint64_t out_cap,
+                                                    uint64_t* tile_state, uint32_t ntiles, uint64_t* scratch) {
+  __shared__ __align__(16) char stage[E_STAGE + 16];
+  __shared__ uint32_t           scan_sm[34];
+  __shared__ uint32_t           ticket_sm;
+  __shared__ uint64_t           base_sm;
+  const int tid = threadIdx.x;
+  while (true) {
+    const uint32_t tile = next_ticket(scratch, &ticket_sm);
+    if (tile >= ntiles) break;
+    const uint64_t i = (uint64_t)tile * E_THREADS + tid;
+    uint64_t       len64 = 0;
+    if (i < n) {
+      CountSink cs;
+      fn(i, cs);
+      len64 = cs.n;
+    }
+    // rows longer than 4 GiB are not representable in the block scan; rest fields are <= 1 MiB per row
+    uint32_t len = (uint32_t)len64, total;
+    uint32_t off = block_excl_scan(len, scan_sm, &total);
+    uint32_t nz = __syncthreads_count(len != 0);
+    if (tid < 32) {
+      uint64_t b = lookback_sum(tile_state, tile, total);
+      if (tid == 0) {
+        base_sm = b;
+        if (nz) atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_OUT_ROWS]), (unsigned long long)nz);
+        if (tile == ntiles - 1) scratch[SC_OUT_BYTES] = b + total;
+      }
+    }
+    __syncthreads();
+    const uint64_t base = base_sm;
+    if (base + total > out_cap) {
+      if (tid == 0) dev_set_error(scratch, BK_ERR_NOMEM, tile);
+      continue;
+    }
+    const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15);
+    if (total + shift <= E_STAGE) {
+      if (len) {
+        MemSink ms{stage + shift + off};
+        fn(i, ms);
+      }
+      __syncthreads();
+      // stage[0] corresponds to the 16-byte aligned address out + base - shift
+      char*          dst0 = out + base - shift;
+      const uint32_t end = shift + total;
+      const uint32_t nvec = (end + 15) / 16;
+      for (uint32_t v = tid; v < nvec; v += E_THREADS) {
+        const uint32_t b0 = v * 16;
+        if (b0 >= shift && b0 + 16 <= end) {
+          stg_stream16(dst0 + b0, *reinterpret_cast<const uint4*>(stage + b0));
+        } else {
+          for (uint32_t b = (b0 < shift ? shift : b0); b < b0 + 16 && b < end; b++) dst0[b] = stage[b];
+        }
+      }
+    } else if (len) {
+      MemSink ms{out + base + off};
+      fn(i, ms);
+    }
+    __syncthreads();
+  }
+}
+
+#endif
+
+inline int grid_for_kernel(const void* kernel, int threads, uint64_t ntiles) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  uint64_t g = (uint64_t)kSMs * per_sm;
+  return (int)(ntiles < g ? (ntiles ? ntiles : 1) : g);
+}
+
+int reset_scratch(bk_ctx* ctx);
+int read_scratch(bk_ctx* ctx);
+
+#ifdef __CUDACC__
+// host helper: run an emitter over n rows into a freshly allocated device buffer of out_cap bytes.
+// On return *d_out holds the text, *out_bytes / *out_rows its size (the stream has been synchronised).
+template <class RowFn>
+int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** d_out, uint64_t* out_bytes,
+             uint64_t* out_rows) {
+  *out_bytes = 0;
+  *out_rows = 0;
+  *d_out = reinterpret_cast<char*>(dmalloc(ctx, out_cap + 16));
+  if (!*d_out) return BK_ERR_NOMEM;
+  if (n == 0) return BK_OK;
+  const uint32_t ntiles = (uint32_t)((n + E_THREADS - 1) / E_THREADS);
+  uint64_t*      state = dalloc<uint64_t>(ctx, ntiles);
+  if (!state) return BK_ERR_NOMEM;
+  BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
+  BK_TRY(reset_scratch(ctx));
+  k_emit<RowFn><<<grid_for_kernel((const void*)k_emit<RowFn>, E_THREADS, ntiles), E_THREADS, 0, ctx->stream>>>(
+      fn, n, *d_out, out_cap, state, ntiles, ctx->d_scratch);
+  BK_LAUNCHED(ctx);
+  BK_TRY(read_scratch(ctx));
+  dfree(ctx, state);
+  if (ctx->h_scratch[SC_ERR_CODE]) {
+    int code = (int)ctx->h_scratch[SC_ERR_CODE];
+    return fail(ctx, code, code == BK_ERR_NOMEM ? "output exceeds the precomputed bound (tile %llu)"
+                                                 : "value outside the exact device formatter (row block %llu)",
+                (unsigned long long)ctx->h_scratch[SC_ERR_ROW]);
+  }
+  *out_bytes = ctx->h_scratch[SC_OUT_BYTES];
+  *out_rows = ctx->h_scratch[SC_OUT_ROWS];
+  return BK_OK;
+}
+#endif
+
+}  // namespace bk

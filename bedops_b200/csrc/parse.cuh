@@ -1,0 +1,43 @@
+// parse.cuh -- shared declarations of the BED reader kernels
+#pragma once
+#include "common.cuh"
+
+namespace bk {
+
+constexpr int P_THREADS = 256;
+constexpr int P_TILE = 8192;  // bytes of text whose line STARTS one tile owns
+constexpr int P_PRE = 128;    // halo before the tile (previous line's chromosome token)
+constexpr int P_POST = 384;   // halo after the tile (tail of the last line that starts in the tile)
+constexpr int P_BUF = P_PRE + P_TILE + P_POST;
+constexpr int P_MAXROWS = P_TILE / 2;
+
+struct HeadRec {  // first row of a chromosome run, discovered by the parser
+  uint64_t row;
+  uint32_t len;
+  char     name[132];
+};
+
+struct ParseParams {
+  const char* text;
+  uint64_t    nbytes_raw;
+  int         min_fields;
+  unsigned    cols;
+  uint32_t*   start;
+  uint32_t*   end;
+  double*     score;
+  uint64_t*   line_off;
+  uint32_t*   idspan;
+  uint64_t    cap;
+  uint64_t*   tile_state;
+  uint32_t    ntiles;
+  uint64_t*   scratch;
+  HeadRec*    heads;
+  uint32_t    heads_cap;
+};
+
+int reset_scratch(bk_ctx* ctx);
+int read_scratch(bk_ctx* ctx);
+int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw);
+int ensure_pmax(bk_ctx* ctx, const bk_bed* bed);
+
+}  // namespace bk

@@ -1,0 +1,687 @@
+// setops.cu -- bedops --merge / --intersect / --element-of / --not-element-of as scans and binary searches
+// (SURVEY A14).  Replaces the streaming k-way state machines nextMergeAllLines (Bedops.cpp:1186-1243),
+// getNextFileMergedCoords/mergeOverlap (:791-814, :864-886), nextIntersectLine (:1105-1181) and
+// nextElementOfLine (:1023-1100).
+//
+//   union-merge of k sorted files:  rank-merge (each row's output slot = its own rank + lower/upper_bound ranks in
+//       the other files, per chromosome) -> segmented prefix-max of end -> a row opens a segment iff
+//       start > running max end (touching intervals coalesce: "bt->start() <= toRtn->end()", Bedops.cpp:1233) ->
+//       stream compaction of (segment start, segment max end) with a look-back scan.
+//   intersect: every file is self-merged, then folded pairwise; for a segment a of A the overlapping pieces of the
+//       disjoint sorted list B are the index range [lower_bound(B.end, a.start+1), lower_bound(B.start, a.end)).
+//   element-of: overlap bases of each reference row with the union-merge of the other files, compared with the
+//       threshold exactly as Bedops.cpp:1094-1099 does (double arithmetic), then the kept rows are echoed.
+#include <algorithm>
+#include <map>
+#include "common.cuh"
+#include "emit.cuh"
+#include "fmt.cuh"
+#include "parse.cuh"
+
+namespace bk {
+
+constexpr int kMaxFiles = 64;
+
+// a sorted interval list on the device with its chromosome runs (runs may be empty)
+struct IvList {
+  uint32_t* s = nullptr;
+  uint32_t* e = nullptr;
+  uint64_t  n = 0;
+  bool      owned = false;
+  std::vector<ChromRun> runs;
+};
+
+static void free_list(bk_ctx* ctx, IvList& l) {
+  if (l.owned) {
+    dfree(ctx, l.s);
+    dfree(ctx, l.e);
+  }
+  l.s = l.e = nullptr;
+  l.n = 0;
+  l.owned = false;
+}
+
+static IvList view_of(const bk_bed* b, const char* chrom) {
+  IvList l;
+  l.s = b->start;
+  l.e = b->end;
+  l.n = b->nrows;
+  const bool all = !chrom || !*chrom || strcmp(chrom, "all") == 0;
+  for (auto& r : b->runs)
+    if (all || r.name == chrom) l.runs.push_back(r);
+  return l;
+}
+
+// ---- rank-merge -------------------------------------------------------------------------------------------
+struct RankParams {
+  const uint32_t* s;
+  const uint32_t* e;
+  const uint64_t* run_begin;  // [nruns+1] rows of THIS file that take part (selected runs, ascending)
+  const uint32_t* run_g;      // [nruns] global chromosome index of each run
+  int             nruns;
+  int             k, f;
+  const uint32_t* fs[kMaxFiles];  // start columns of every file
+  const uint64_t* g_begin;        // [G*k] row range of chromosome g in file j (begin == end if absent)
+  const uint64_t* g_end;
+  const uint64_t* g_out;          // [G] first output slot of chromosome g
+  uint32_t*       outS;
+  uint32_t*       outE;
+  uint64_t        nsel;       // number of participating rows of this file
+  const uint64_t* sel_prefix; // [nruns+1] prefix of participating rows per run
+};
+
+__global__ void __launch_bounds__(256) k_rank_merge(RankParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.nsel; t += stride) {
+    int lo = 0, hi = p.nruns;  // last run with sel_prefix <= t
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.sel_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint64_t row = p.run_begin[lo] + (t - p.sel_prefix[lo]);
+    const uint32_t g = p.run_g[lo];
+    const uint32_t key = p.s[row];
+    uint64_t       pos = p.g_out[g] + (row - p.g_begin[(uint64_t)g * p.k + p.f]);
+    for (int j = 0; j < p.k; j++) {
+      if (j == p.f) continue;
+      const uint64_t b = p.g_begin[(uint64_t)g * p.k + j], e = p.g_end[(uint64_t)g * p.k + j];
+      if (b == e) continue;
+      // ties: rows of lower-numbered files first (stable)
+      pos += (j < p.f ? upper_bound_u32(p.fs[j], b, e, key) : lower_bound_u32(p.fs[j], b, e, key)) - b;
+    }
+    p.outS[pos] = key;
+    p.outE[pos] = p.e[row];
+  }
+}
+
+// ---- segments from a sorted list + its inclusive prefix-max of end ----------------------------------------
+struct SegParams {
+  const uint32_t* s;
+  const uint32_t* pm;
+  uint64_t        n;
+  const uint64_t* run_begin;  // [nruns] (ascending; empty runs allowed)
+  int             nruns;
+  uint32_t*       outS;
+  uint32_t*       outE;
+  uint64_t*       run_seg_begin;  // [nruns] first output segment of each run (written for non-empty runs)
+  uint64_t*       tile_state;
+  uint32_t        ntiles;
+  uint64_t*       scratch;
+};
+
+// is `row` the first row of a non-empty run?  returns the run index or -1
+__device__ __forceinline__ int run_head_of(const uint64_t* run_begin, int nruns, uint64_t n, uint64_t row) {
+  int lo = 0, hi = nruns;  // first run_begin >= row
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (run_begin[mid] < row) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= nruns || run_begin[lo] != row) return -1;
+  // among equal begins the last one is the non-empty run
+  while (lo + 1 < nruns && run_begin[lo + 1] == row) lo++;
+  return lo;
+}
+
+constexpr int SEG_THREADS = 256;
+__global__ void __launch_bounds__(SEG_THREADS) k_segments(SegParams p) {
+  __shared__ uint32_t scan_sm[34];
+  __shared__ uint32_t ticket_sm;
+  __shared__ uint64_t base_sm;
+  const int tid = threadIdx.x;
+  while (true) {
+    const uint32_t tile = next_ticket(p.scratch, &ticket_sm);
+    if (tile >= p.ntiles) break;
+    const uint64_t i = (uint64_t)tile * SEG_THREADS + tid;
+    bool           head = false, tail = false;
+    int            rh = -1;
+    uint32_t       s = 0, pm = 0;
+    if (i < p.n) {
+      s = p.s[i];
+      pm = p.pm[i];
+      rh = run_head_of(p.run_begin, p.nruns, p.n, i);
+      head = rh >= 0 || s > p.pm[i - 1];
+      if (i + 1 == p.n) tail = true;
+      else tail = run_head_of(p.run_begin, p.nruns, p.n, i + 1) >= 0 || p.s[i + 1] > pm;
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan(head ? 1u : 0u, scan_sm, &total);
+    if (tid < 32) {
+      uint64_t b = lookback_sum(p.tile_state, tile, total);
+      if (tid == 0) {
+        base_sm = b;
+        if (tile == p.ntiles - 1) p.scratch[SC_OUT_ROWS] = b + total;
+      }
+    }
+    __syncthreads();
+    const uint64_t seg = base_sm + ex;  // index of the segment this row opens (if head)
+    if (head) {
+      p.outS[seg] = s;
+      if (rh >= 0) p.run_seg_begin[rh] = seg;
+    }
+    if (tail) p.outE[seg + (head ? 1 : 0) - 1] = pm;
+    __syncthreads();
+  }
+}
+
+// ---- pairwise intersection of two disjoint sorted lists ---------------------------------------------------
+struct IsectParams {
+  const uint32_t* as;
+  const uint32_t* ae;
+  uint64_t        row0, n;        // A rows [row0,row0+n) take part
+  const uint64_t* run_a_begin;    // [nruns+1] A rows per common chromosome (ascending)
+  const uint64_t* run_b_begin;    // [nruns]
+  const uint64_t* run_b_end;
+  int             nruns;
+  const uint32_t* bs;
+  const uint32_t* be;
+  uint32_t*       outS;
+  uint32_t*       outE;
+  uint64_t*       run_out_begin;  // [nruns]
+  uint64_t*       tile_state;
+  uint32_t        ntiles;
+  uint64_t*       scratch;
+  uint64_t        out_cap;
+};
+
+__global__ void __launch_bounds__(SEG_THREADS) k_intersect(IsectParams p) {
+  __shared__ uint32_t scan_sm[34];
+  __shared__ uint32_t ticket_sm;
+  __shared__ uint64_t base_sm;
+  const int tid = threadIdx.x;
+  while (true) {
+    const uint32_t tile = next_ticket(p.scratch, &ticket_sm);
+    if (tile >= p.ntiles) break;
+    const uint64_t i = (uint64_t)tile * SEG_THREADS + tid;
+    uint64_t       lo = 0, hi = 0;
+    uint32_t       a0 = 0, a1 = 0;
+    int            run = 0;
+    bool           runhead = false;
+    if (i < p.n) {
+      const uint64_t row = p.row0 + i;
+      int l = 0, h = p.nruns;
+      while (h - l > 1) {
+        int mid = (l + h) >> 1;
+        if (p.run_a_begin[mid] <= row) l = mid; else h = mid;
+      }
+      run = l;
+      runhead = p.run_a_begin[l] == row;
+      a0 = p.as[row];
+      a1 = p.ae[row];
+      const uint64_t bb = p.run_b_begin[l], bend = p.run_b_end[l];
+      lo = lower_bound_u32(p.be, bb, bend, (uint64_t)a0 + 1);  // first b.end > a.start
+      hi = lower_bound_u32(p.bs, bb, bend, (uint64_t)a1);      // first b.start >= a.end
+      if (hi < lo) hi = lo;
+    }
+    uint32_t total;
+    uint32_t ex = block_excl_scan((uint32_t)(hi - lo), scan_sm, &total);
+    if (tid < 32) {
+      uint64_t b = lookback_sum(p.tile_state, tile, total);
+      if (tid == 0) {
+        base_sm = b;
+        if (tile == p.ntiles - 1) p.scratch[SC_OUT_ROWS] = b + total;
+      }
+    }
+    __syncthreads();
+    uint64_t o = base_sm + ex;
+    if (i < p.n) {
+      if (runhead) p.run_out_begin[run] = o;
+      for (uint64_t k = lo; k < hi; k++, o++) {
+        if (o >= p.out_cap) break;
+        const uint32_t b0 = p.bs[k], b1 = p.be[k];
+        p.outS[o] = a0 > b0 ? a0 : b0;
+        p.outE[o] = a1 < b1 ? a1 : b1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- element-of: keep flag per reference row ---------------------------------------------------------------
+struct ElemParams {
+  const uint32_t* rs;
+  const uint32_t* re;
+  uint64_t        row0, n;
+  const uint64_t* run_ref_begin;  // [nruns+1]
+  const uint64_t* run_u_begin;    // [nruns]
+  const uint64_t* run_u_end;
+  int             nruns;
+  const uint32_t* us;
+  const uint32_t* ue;
+  double          thr;
+  int             use_pct, invert;
+  const uint8_t*  run_has_later;  // [nruns] the union holds an element on a later chromosome
+  uint8_t*        keep;
+};
+
+__global__ void __launch_bounds__(256) k_element_of(ElemParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const uint64_t row = p.row0 + i;
+    int l = 0, h = p.nruns;
+    while (h - l > 1) {
+      int mid = (l + h) >> 1;
+      if (p.run_ref_begin[mid] <= row) l = mid; else h = mid;
+    }
+    const uint32_t a0 = p.rs[row], a1 = p.re[row];
+    const uint64_t ub = p.run_u_begin[l], uend = p.run_u_end[l];
+    uint64_t       lo = lower_bound_u32(p.ue, ub, uend, (uint64_t)a0 + 1);
+    const uint64_t hi = lower_bound_u32(p.us, ub, uend, (uint64_t)a1);
+    double         range_overlap = 0;  // "double rangeOverlap", Bedops.cpp:1062
+    for (; lo < hi; lo++) {
+      const uint32_t b0 = p.us[lo], b1 = p.ue[lo];
+      const uint32_t mn = a0 > b0 ? a0 : b0, mx = a1 < b1 ? a1 : b1;
+      range_overlap += (double)(mx - mn);
+    }
+    const double range = (double)(a1 - a0);
+    bool         is_elem = p.use_pct ? (range_overlap / range >= p.thr) : (range_overlap >= p.thr);
+    // "-e 0": 0 >= 0 holds for every row the streaming loop reaches, but a row with no merged element at or after
+    // it is reported as a non-element before the test (Bedops.cpp:1044-1049, :1053-1062)
+    if (!p.use_pct && p.thr <= 0) is_elem = p.run_has_later[l] || (uend > ub && p.ue[uend - 1] > a0);
+    p.keep[i] = (is_elem != (p.invert != 0)) ? 1 : 0;
+  }
+}
+
+// ---- emitters -------------------------------------------------------------------------------------------------
+struct NameTable {
+  const char*     names;  // [nruns][128]
+  const uint32_t* len;
+  const uint64_t* run_begin;
+  int             nruns;
+};
+
+struct Bed3Row {  // chrom \t start \t end \n   (B3NoRest::println, Bed.hpp:228-232)
+  const uint32_t* s;
+  const uint32_t* e;
+  NameTable       nt;
+  template <class Sink>
+  __device__ void operator()(uint64_t i, Sink& sk) const {
+    int l = 0, h = nt.nruns;
+    while (h - l > 1) {
+      int mid = (l + h) >> 1;
+      if (nt.run_begin[mid] <= i) l = mid; else h = mid;
+    }
+    sk.puts_(nt.names + (size_t)l * 128, (int)nt.len[l]);
+    sk.put('\t');
+    sk.put_u32(s[i]);
+    sk.put('\t');
+    sk.put_u32(e[i]);
+    sk.put('\n');
+  }
+};
+
+template <class Sink>
+__device__ __forceinline__ void echo_b3rest_row(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
+  const char* p = text + off;
+  int         n = 0;
+  while (is_tok((unsigned char)p[n])) n++;
+  s.copy(p, n);
+  s.put('\t');
+  s.put_u32(st);
+  s.put('\t');
+  s.put_u32(en);
+  const char* q = p + n;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  int m = 0;
+  while (q[m] != '\n') m++;
+  s.copy(q, m);
+}
+
+struct EchoKeptRow {  // record(nextRef) for -e/-n: B3Rest::println (Bedops.cpp:148-152, :555-556)
+  const char*     text;
+  const uint64_t* line;
+  const uint32_t* s;
+  const uint32_t* e;
+  const uint8_t*  keep;
+  uint64_t        row0;
+  template <class Sink>
+  __device__ void operator()(uint64_t i, Sink& sk) const {
+    if (!keep[i]) return;
+    const uint64_t row = row0 + i;
+    echo_b3rest_row(sk, text, line[row], s[row], e[row]);
+    sk.put('\n');
+  }
+};
+
+int finish_text(bk_ctx* ctx, char* d_out, uint64_t bytes, uint64_t rows, int on_device, bk_text* out);
+
+// upload a host vector; the caller must sync before the vector dies (all callers below sync via read_scratch)
+template <class T>
+static T* upload(bk_ctx* ctx, const std::vector<T>& v) {
+  T* d = dalloc<T>(ctx, v.size());
+  if (d && !v.empty()) cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+  return d;
+}
+
+// union-merge of k lists -> disjoint sorted segments (touching coalesced)
+static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in, IvList* out) {
+  const int k = (int)in.size();
+  // global chromosome table
+  std::vector<std::string> names;
+  for (auto& l : in)
+    for (auto& r : l.runs)
+      if (r.row_end > r.row_begin) names.push_back(r.name);
+  std::sort(names.begin(), names.end(), [](const std::string& a, const std::string& b) { return strcmp(a.c_str(), b.c_str()) < 0; });
+  names.erase(std::unique(names.begin(), names.end()), names.end());
+  const int G = (int)names.size();
+  out->runs.clear();
+  out->n = 0;
+  out->owned = true;
+  if (G == 0) return BK_OK;
+  std::map<std::string, int> gidx;
+  for (int g = 0; g < G; g++) gidx[names[g]] = g;
+  std::vector<uint64_t> g_begin((size_t)G * k, 0), g_end((size_t)G * k, 0), g_out(G + 1, 0);
+  for (int f = 0; f < k; f++)
+    for (auto& r : in[f].runs) {
+      if (r.row_end == r.row_begin) continue;
+      int g = gidx[r.name];
+      g_begin[(size_t)g * k + f] = r.row_begin;
+      g_end[(size_t)g * k + f] = r.row_end;
+    }
+  for (int g = 0; g < G; g++) {
+    uint64_t c = 0;
+    for (int f = 0; f < k; f++) c += g_end[(size_t)g * k + f] - g_begin[(size_t)g * k + f];
+    g_out[g + 1] = g_out[g] + c;
+  }
+  const uint64_t N = g_out[G];
+  // merged-order columns
+  uint32_t *mS = nullptr, *mE = nullptr;
+  bool      merged_owned = false;
+  if (k == 1) {
+    // a single file is already in order, but only its selected runs take part: they are contiguous iff all
+    // runs were selected or exactly one; otherwise compact through the same rank kernel
+    bool contiguous = true;
+    for (size_t i = 1; i < in[0].runs.size(); i++)
+      if (in[0].runs[i].row_begin != in[0].runs[i - 1].row_end) contiguous = false;
+    if (contiguous) {
+      uint64_t first = UINT64_MAX;
+      for (auto& r : in[0].runs)
+        if (r.row_end > r.row_begin && r.row_begin < first) first = r.row_begin;
+      mS = in[0].s + first;
+      mE = in[0].e + first;
+    }
+  }
+  if (!mS) {
+    if (k > kMaxFiles) return fail(ctx, BK_ERR_UNSUPPORTED, "more than %d input files", kMaxFiles);
+    mS = dalloc<uint32_t>(ctx, N);
+    mE = dalloc<uint32_t>(ctx, N);
+    if (!mS || !mE) return BK_ERR_NOMEM;
+    merged_owned = true;
+    uint64_t* d_gb = upload(ctx, g_begin);
+    uint64_t* d_ge = upload(ctx, g_end);
+    uint64_t* d_go = upload(ctx, g_out);
+    if (!d_gb || !d_ge || !d_go) return BK_ERR_NOMEM;
+    std::vector<void*> tofree{d_gb, d_ge, d_go};
+    std::vector<std::vector<uint64_t>> keep_rb(k), keep_sp(k);
+    std::vector<std::vector<uint32_t>> keep_rg(k);
+    for (int f = 0; f < k; f++) {
+      std::vector<uint64_t>& rb = keep_rb[f];
+      std::vector<uint64_t>& sp = keep_sp[f];
+      std::vector<uint32_t>& rg = keep_rg[f];
+      uint64_t acc = 0;
+      for (auto& r : in[f].runs) {
+        if (r.row_end == r.row_begin) continue;
+        rb.push_back(r.row_begin);
+        rg.push_back((uint32_t)gidx[r.name]);
+        sp.push_back(acc);
+        acc += r.row_end - r.row_begin;
+      }
+      if (acc == 0) continue;
+      rb.push_back(0);
+      sp.push_back(acc);
+      RankParams p{};
+      p.s = in[f].s; p.e = in[f].e;
+      p.run_begin = upload(ctx, rb); p.run_g = upload(ctx, rg); p.sel_prefix = upload(ctx, sp);
+      if (!p.run_begin || !p.run_g || !p.sel_prefix) return BK_ERR_NOMEM;
+      tofree.push_back((void*)p.run_begin); tofree.push_back((void*)p.run_g); tofree.push_back((void*)p.sel_prefix);
+      p.nruns = (int)rg.size(); p.k = k; p.f = f;
+      for (int j = 0; j < k; j++) p.fs[j] = in[j].s;
+      p.g_begin = d_gb; p.g_end = d_ge; p.g_out = d_go;
+      p.outS = mS; p.outE = mE; p.nsel = acc;
+      uint64_t blocks = (acc + 255) / 256, cap = (uint64_t)kSMs * 32;
+      k_rank_merge<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+      BK_LAUNCHED(ctx);
+    }
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (void* q : tofree) dfree(ctx, q);
+  }
+  // runs of the merged list
+  bk_bed tmp;  // borrow ensure_pmax's kernel through a temporary view
+  tmp.end = mE;
+  tmp.nrows = N;
+  for (int g = 0; g < G; g++) tmp.runs.push_back({names[g], g_out[g], g_out[g + 1]});
+  int rc = ensure_pmax(ctx, &tmp);
+  if (rc != BK_OK) return rc;
+  // segments
+  std::vector<uint64_t> rb(G);
+  for (int g = 0; g < G; g++) rb[g] = g_out[g];
+  SegParams sp{};
+  sp.s = mS; sp.pm = tmp.pmax_end; sp.n = N;
+  sp.run_begin = upload(ctx, rb); sp.nruns = G;
+  sp.outS = dalloc<uint32_t>(ctx, N); sp.outE = dalloc<uint32_t>(ctx, N);
+  sp.run_seg_begin = dalloc<uint64_t>(ctx, G);
+  sp.ntiles = (uint32_t)((N + SEG_THREADS - 1) / SEG_THREADS);
+  sp.tile_state = dalloc<uint64_t>(ctx, sp.ntiles);
+  sp.scratch = ctx->d_scratch;
+  if (!sp.run_begin || !sp.outS || !sp.outE || !sp.run_seg_begin || !sp.tile_state) return BK_ERR_NOMEM;
+  BK_CUDA(ctx, cudaMemsetAsync(sp.tile_state, 0, (size_t)sp.ntiles * 8, ctx->stream));
+  BK_TRY(reset_scratch(ctx));
+  k_segments<<<grid_for_kernel((const void*)k_segments, SEG_THREADS, sp.ntiles), SEG_THREADS, 0, ctx->stream>>>(sp);
+  BK_LAUNCHED(ctx);
+  std::vector<uint64_t> rsb(G);
+  BK_CUDA(ctx, cudaMemcpyAsync(rsb.data(), sp.run_seg_begin, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_TRY(read_scratch(ctx));
+  const uint64_t nseg = ctx->h_scratch[SC_OUT_ROWS];
+  dfree(ctx, (void*)sp.run_begin); dfree(ctx, sp.run_seg_begin); dfree(ctx, sp.tile_state); dfree(ctx, tmp.pmax_end);
+  tmp.pmax_end = nullptr;
+  if (merged_owned) { dfree(ctx, mS); dfree(ctx, mE); }
+  out->s = sp.outS; out->e = sp.outE; out->n = nseg; out->owned = true;
+  for (int g = 0; g < G; g++) out->runs.push_back({names[g], rsb[g], g + 1 < G ? rsb[g + 1] : nseg});
+  return BK_OK;
+}
+
+// A ∩ B for disjoint sorted lists
+static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList* out) {
+  out->runs.clear();
+  out->n = 0;
+  out->owned = true;
+  std::vector<uint64_t> ab, bb, be;
+  std::vector<std::string> names;
+  size_t j = 0;
+  for (auto& r : A.runs) {
+    if (r.row_end == r.row_begin) continue;
+    while (j < B.runs.size() && strcmp(B.runs[j].name.c_str(), r.name.c_str()) < 0) j++;
+    if (j < B.runs.size() && B.runs[j].name == r.name && B.runs[j].row_end > B.runs[j].row_begin) {
+      // only chromosomes present on both sides can intersect; A rows of other chromosomes are skipped by
+      // giving them an empty B range
+    }
+    ab.push_back(r.row_begin);
+    names.push_back(r.name);
+    if (j < B.runs.size() && B.runs[j].name == r.name) {
+      bb.push_back(B.runs[j].row_begin);
+      be.push_back(B.runs[j].row_end);
+    } else {
+      bb.push_back(0);
+      be.push_back(0);
+    }
+  }
+  const int nruns = (int)names.size();
+  if (nruns == 0) return BK_OK;
+  // participating A rows: from the first selected run to the end of the last one (runs in between that were not
+  // selected cannot exist: `runs` only ever holds all runs or one run)
+  const uint64_t row0 = ab.front();
+  uint64_t       row1 = 0;
+  for (auto& r : A.runs)
+    if (r.row_end > r.row_begin) row1 = r.row_end;
+  ab.push_back(row1);
+  const uint64_t n = row1 - row0;
+  IsectParams p{};
+  p.as = A.s; p.ae = A.e; p.row0 = row0; p.n = n;
+  p.run_a_begin = upload(ctx, ab); p.run_b_begin = upload(ctx, bb); p.run_b_end = upload(ctx, be); p.nruns = nruns;
+  p.bs = B.s; p.be = B.e;
+  p.out_cap = n + B.n + 1;  // pieces <= |A| + |B|
+  p.outS = dalloc<uint32_t>(ctx, p.out_cap); p.outE = dalloc<uint32_t>(ctx, p.out_cap);
+  p.run_out_begin = dalloc<uint64_t>(ctx, nruns);
+  p.ntiles = (uint32_t)((n + SEG_THREADS - 1) / SEG_THREADS);
+  p.tile_state = dalloc<uint64_t>(ctx, p.ntiles);
+  p.scratch = ctx->d_scratch;
+  if (!p.run_a_begin || !p.run_b_begin || !p.run_b_end || !p.outS || !p.outE || !p.run_out_begin || !p.tile_state)
+    return BK_ERR_NOMEM;
+  BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
+  BK_TRY(reset_scratch(ctx));
+  k_intersect<<<grid_for_kernel((const void*)k_intersect, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
+  BK_LAUNCHED(ctx);
+  std::vector<uint64_t> rob(nruns);
+  BK_CUDA(ctx, cudaMemcpyAsync(rob.data(), p.run_out_begin, (size_t)nruns * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_TRY(read_scratch(ctx));
+  const uint64_t nout = ctx->h_scratch[SC_OUT_ROWS];
+  dfree(ctx, (void*)p.run_a_begin); dfree(ctx, (void*)p.run_b_begin); dfree(ctx, (void*)p.run_b_end);
+  dfree(ctx, p.run_out_begin); dfree(ctx, p.tile_state);
+  out->s = p.outS; out->e = p.outE; out->n = nout;
+  for (int r = 0; r < nruns; r++) out->runs.push_back({names[r], rob[r], r + 1 < nruns ? rob[r + 1] : nout});
+  return BK_OK;
+}
+
+static int emit_bed3(bk_ctx* ctx, const IvList& l, int on_device, bk_text* out) {
+  std::vector<char>     names;
+  std::vector<uint32_t> lens;
+  std::vector<uint64_t> rb;
+  uint64_t              maxname = 0;
+  for (auto& r : l.runs) {
+    if (r.row_end == r.row_begin) continue;
+    size_t o = names.size();
+    names.resize(o + 128, 0);
+    memcpy(&names[o], r.name.c_str(), r.name.size());
+    lens.push_back((uint32_t)r.name.size());
+    rb.push_back(r.row_begin);
+    maxname = std::max<uint64_t>(maxname, r.name.size());
+  }
+  if (l.n == 0 || rb.empty()) return finish_text(ctx, nullptr, 0, 0, on_device, out);
+  Bed3Row fn{};
+  fn.s = l.s; fn.e = l.e;
+  fn.nt.names = upload(ctx, names); fn.nt.len = upload(ctx, lens); fn.nt.run_begin = upload(ctx, rb); fn.nt.nruns = (int)rb.size();
+  if (!fn.nt.names || !fn.nt.len || !fn.nt.run_begin) return BK_ERR_NOMEM;
+  char*    d_out = nullptr;
+  uint64_t bytes = 0, rows = 0;
+  // rows before the first non-empty run cannot exist (lists start at their first run)
+  int rc = run_emit(ctx, fn, l.n, l.n * (maxname + 24) + 64, &d_out, &bytes, &rows);
+  dfree(ctx, (void*)fn.nt.names); dfree(ctx, (void*)fn.nt.len); dfree(ctx, (void*)fn.nt.run_begin);
+  if (rc != BK_OK) {
+    dfree(ctx, d_out);
+    return rc;
+  }
+  return finish_text(ctx, d_out, bytes, rows, on_device, out);
+}
+
+}  // namespace bk
+
+using namespace bk;
+
+extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, double thr, int thr_is_pct,
+                        const char* chrom, int out_on_device, bk_text* out) {
+  if (!ctx || !files || !out || n_files < 1) return BK_ERR_ARG;
+  ctx->last_error.clear();
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < n_files; i++)
+    if (!files[i]) return BK_ERR_ARG;
+  if (n_files > kMaxFiles) return fail(ctx, BK_ERR_UNSUPPORTED, "more than %d input files", kMaxFiles);
+
+  if (op == BK_SETOP_MERGE) {
+    std::vector<IvList> in;
+    for (int i = 0; i < n_files; i++) in.push_back(view_of(files[i], chrom));
+    IvList u;
+    BK_TRY(union_merge(ctx, in, &u));
+    int rc = emit_bed3(ctx, u, out_on_device, out);
+    free_list(ctx, u);
+    return rc;
+  }
+  if (op == BK_SETOP_INTERSECT) {
+    if (n_files < 2) return fail(ctx, BK_ERR_ARG, "Not enough files");
+    IvList acc;
+    for (int i = 0; i < n_files; i++) {
+      std::vector<IvList> one{view_of(files[i], chrom)};
+      IvList m;
+      BK_TRY(union_merge(ctx, one, &m));  // getNextFileMergedCoords: every file is merged within itself first
+      if (i == 0) {
+        acc = m;
+      } else {
+        IvList r;
+        int    rc = intersect_pair(ctx, acc, m, &r);
+        free_list(ctx, acc);
+        free_list(ctx, m);
+        if (rc != BK_OK) return rc;
+        acc = r;
+      }
+    }
+    int rc = emit_bed3(ctx, acc, out_on_device, out);
+    free_list(ctx, acc);
+    return rc;
+  }
+  if (op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF) {
+    if (n_files < 2) return fail(ctx, BK_ERR_ARG, "Not enough files");
+    const bk_bed* ref = files[0];
+    if (!ref->line_off && ref->nrows) return fail(ctx, BK_ERR_ARG, "reference file was loaded without BK_COL_LINE");
+    std::vector<IvList> in;
+    for (int i = 1; i < n_files; i++) in.push_back(view_of(files[i], chrom));
+    IvList u;
+    BK_TRY(union_merge(ctx, in, &u));
+    IvList rv = view_of(ref, chrom);
+    std::vector<uint64_t> rrb, ub, ue;
+    std::vector<uint8_t>  later;
+    std::string           last_u;
+    for (auto& r : u.runs)
+      if (r.row_end > r.row_begin) last_u = r.name;
+    uint64_t row0 = 0, row1 = 0;
+    bool     first = true;
+    size_t   j = 0;
+    for (auto& r : rv.runs) {
+      if (r.row_end == r.row_begin) continue;
+      if (first) { row0 = r.row_begin; first = false; }
+      row1 = r.row_end;
+      rrb.push_back(r.row_begin);
+      later.push_back(!last_u.empty() && strcmp(r.name.c_str(), last_u.c_str()) < 0);
+      while (j < u.runs.size() && strcmp(u.runs[j].name.c_str(), r.name.c_str()) < 0) j++;
+      if (j < u.runs.size() && u.runs[j].name == r.name) {
+        ub.push_back(u.runs[j].row_begin);
+        ue.push_back(u.runs[j].row_end);
+      } else {
+        ub.push_back(0);
+        ue.push_back(0);
+      }
+    }
+    const uint64_t n = row1 - row0;
+    if (n == 0) {
+      free_list(ctx, u);
+      return finish_text(ctx, nullptr, 0, 0, out_on_device, out);
+    }
+    rrb.push_back(row1);
+    ElemParams p{};
+    p.rs = ref->start; p.re = ref->end; p.row0 = row0; p.n = n;
+    p.run_ref_begin = upload(ctx, rrb); p.run_u_begin = upload(ctx, ub); p.run_u_end = upload(ctx, ue); p.nruns = (int)ub.size();
+    p.us = u.s; p.ue = u.e; p.thr = thr; p.use_pct = thr_is_pct; p.invert = op == BK_SETOP_NOT_ELEMENT_OF;
+    p.keep = dalloc<uint8_t>(ctx, n);
+    p.run_has_later = upload(ctx, later);
+    if (!p.run_ref_begin || !p.run_u_begin || !p.run_u_end || !p.keep || !p.run_has_later) return BK_ERR_NOMEM;
+    uint64_t blocks = (n + 255) / 256, cap = (uint64_t)kSMs * 32;
+    k_element_of<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+    BK_LAUNCHED(ctx);
+    EchoKeptRow fn{};
+    fn.text = ref->d_text; fn.line = ref->line_off; fn.s = ref->start; fn.e = ref->end; fn.keep = p.keep; fn.row0 = row0;
+    char*    d_out = nullptr;
+    uint64_t bytes = 0, rows = 0;
+    int rc = run_emit(ctx, fn, n, ref->nbytes + n * 24 + 64, &d_out, &bytes, &rows);  // run_emit syncs: uploads done
+    dfree(ctx, (void*)p.run_ref_begin); dfree(ctx, (void*)p.run_u_begin); dfree(ctx, (void*)p.run_u_end); dfree(ctx, p.keep);
+    dfree(ctx, (void*)p.run_has_later);
+    free_list(ctx, u);
+    if (rc != BK_OK) {
+      dfree(ctx, d_out);
+      return rc;
+    }
+    return finish_text(ctx, d_out, bytes, rows, out_on_device, out);
+  }
+  return fail(ctx, BK_ERR_UNSUPPORTED, "bedops operation %d is outside the device hot path", op);
+}

@@ -1,0 +1,242 @@
+// bedops -- drop-in command line for the B200 engine.  Mirrors the option grammar, output and exit codes of
+// applications/bed/bedops/src/Input.hpp:57-298 / Bedops.cpp:81-127 for the operators on the hot path
+// (--merge, --intersect, --element-of, --not-element-of) and replaces selectWork() (Bedops.cpp:1523-1577)
+// with bk_setop().
+#include <fstream>
+#include <map>
+#include "cli_common.hpp"
+
+namespace {
+
+using cli::UserError;
+
+enum Mode { MERGE, INTERSECTION, ELEMENTOF, NOTELEMENTOF, COMPLEMENT, DIFFERENCE, SYMMDIFF, UNIONALL, PARTITION, CHOP };
+
+struct Options {
+  Mode   mode = MERGE;
+  int    min_files = 1000;
+  double subset = 1;  // Input::subsetPerc_
+  bool   use_pct = true;
+  bool   ec = false, has_range = false;
+  std::string chrom = "all";
+  std::vector<std::string> files;
+};
+
+void require(bool ok, const std::string& msg) {
+  if (!ok) throw UserError(msg);
+}
+
+struct Help {};
+struct Version {};
+struct NoInput {};
+
+void set_mode(Options& o, char t) {  // Input::setModeType, Input.hpp:390-420
+  int min = 1;
+  switch (t) {
+    case 'c': case 'C': o.mode = COMPLEMENT; break;
+    case 'd': case 'D': o.mode = DIFFERENCE; ++min; break;
+    case 'e': case 'E': o.mode = ELEMENTOF; ++min; break;
+    case 'i': case 'I': o.mode = INTERSECTION; ++min; break;
+    case 'm': case 'M': o.mode = MERGE; break;
+    case 'n': case 'N': o.mode = NOTELEMENTOF; ++min; break;
+    case 'p': case 'P': o.mode = PARTITION; break;
+    case 's': case 'S': o.mode = SYMMDIFF; ++min; break;
+    case 'u': case 'U': o.mode = UNIONALL; break;
+    case 'w': case 'W': o.mode = CHOP; break;
+    default: throw UserError(std::string("Unknown operation: -") + t);
+  }
+  o.min_files = min;
+}
+
+void set_subset(Options& o, const std::string& str) {  // Input::setSubsetOption, Input.hpp:344-382
+  const char* nums = ".1234567890";
+  const char* ints = "1234567890";
+  std::string l = str.substr(1);
+  std::string::size_type pos = str.find("%");
+  if (pos != std::string::npos) {
+    require(pos + 1 == str.size(), "Bad placement of %");
+    std::string value = str.substr(0, pos);
+    require(!value.empty(), "Bad % value");
+    if (value[0] == '-') {
+      value = value.substr(1);
+      require(!value.empty(), "Bad % value");
+    }
+    require(cli::only_chars(value, nums), "Bad: % value");
+    o.subset = std::strtod(value.c_str(), nullptr);
+    o.subset /= 100.0;
+    if (o.subset > 1) throw UserError("Expect percentage less than or equal to 100%");
+    o.use_pct = true;
+    if (o.subset == 0) {  // 0% can match everything: convert to 1bp
+      o.subset = 1;
+      o.use_pct = false;
+    }
+  } else if (cli::only_chars(str, ints)) {
+    o.subset = std::atoi(str.c_str());
+    o.use_pct = false;
+  } else if (cli::only_chars(l, ints)) {
+    o.subset = std::atoi(l.c_str());
+    o.use_pct = false;
+  } else if (cli::only_chars(str, nums)) {
+    throw UserError("Fractional amounts require a '%' symbol (e.g.; 5.4% not 5.4 base-pair)");
+  } else {
+    throw UserError("Unknown arg: " + str);
+  }
+}
+
+Options parse_args(int argc, char** argv) {
+  Options o;
+  const std::map<std::string, std::string> longopts = {
+      {"--complement", "-c"}, {"--difference", "-d"}, {"--element-of", "-e"},     {"--intersect", "-i"},  {"--merge", "-m"},
+      {"--not-element-of", "-n"}, {"--partition", "-p"}, {"--symmdiff", "-s"}, {"--everything", "-u"}, {"--chop", "-w"}};
+  try {
+    if (argc <= 1) throw NoInput();
+    bool has_option = false;
+    int  i = 1;
+    bool chr_specific = false;
+    const char* plusints = "0123456789";
+    while (i < argc) {
+      std::string next = argv[i];
+      if (next == "--ec" || next == "--header") {
+        o.ec = true;
+      } else if (next == "--chrom") {
+        require(!chr_specific, "--chrom specified multiple times.");
+        require(++i < argc, "No value for --chrom given.");
+        o.chrom = argv[i];
+        chr_specific = o.chrom != "all";
+      } else if (next == "--range") {
+        require(!o.has_range, "--range specified multiple times.");
+        require(++i < argc, "No value for --range given.");
+        o.has_range = true;
+      } else if (next == "--help") {
+        throw Help();
+      } else if (next.find("--help-") == 0) {
+        throw Help();
+      } else if (next == "--version") {
+        throw Version();
+      } else if (next.find("-") != 0) {
+        break;
+      } else if (next.size() > 1) {
+        require(next.find_first_not_of("-") != std::string::npos, "Bad option: " + next);
+        require(!has_option, "More than one operation specified: " + next);
+        has_option = true;
+        if (next.find("--") == 0) {
+          auto it = longopts.find(next);
+          require(it != longopts.end(), "Unknown operation: " + next);
+          next = it->second;
+        }
+        require(next.size() == 2, "Unknown operation: " + next);
+        set_mode(o, next[1]);
+        if (o.mode == ELEMENTOF || o.mode == NOTELEMENTOF) {  // optional overlap spec, Input.hpp:171-206
+          const char* ints = "1234567890";
+          if (i + 1 < argc) {
+            std::string a = argv[i + 1];
+            if ((a[0] == '-' && a.size() > 1) || cli::only_chars(a, ints) || a.find("%") != std::string::npos) {
+              if (a.find("--") == std::string::npos) {
+                std::ifstream tmpfile(a.c_str());
+                if (!tmpfile) {
+                  set_subset(o, a);
+                  ++i;
+                } else if (cli::only_chars(a, plusints)) {
+                  std::fprintf(stderr,
+                               "Warning: interpreting argument '%s' as a file input and not as an overlap spec,\n"
+                               "         since the file exists.\n"
+                               "You can use the legacy syntax '-%s' if you want to use it as an overlap criterion.\n",
+                               a.c_str(), a.c_str());
+                }
+              }
+            }
+          }
+        } else if (o.mode == COMPLEMENT) {
+          while (i + 1 < argc && std::string(argv[i + 1]) == "-L") ++i;
+        }
+      } else {
+        break;
+      }
+      ++i;
+    }
+    require(i < argc, "No input file given.");
+    require(has_option, "No operation argument given.");
+    bool only_one = true;
+    int  nfiles = 0;
+    for (; i < argc; ++i) {
+      std::string a = argv[i];
+      if (a == "-") {
+        require(only_one, "Too many '-'");
+        only_one = false;
+      } else {
+        require(a[0] != '-', "Bad option: " + a);
+        std::ifstream check(a.c_str());
+        require(static_cast<bool>(check), "Cannot find " + a);
+      }
+      o.files.push_back(a);
+      ++nfiles;
+    }
+    require(nfiles >= o.min_files, "Not enough files");
+  } catch (const UserError& e) {
+    throw UserError(std::string("Bad Input\n") + e.what());  // Input.hpp:292-297
+  }
+  return o;
+}
+
+void usage(FILE* f) {
+  std::fputs(
+      "\n      USAGE: bedops [process-flags] <operation> <File(s)>*\n\n"
+      "          Every input file must be sorted per the sort-bed utility.\n"
+      "          Each operation requires a minimum number of files as shown below.\n"
+      "            There is no fixed maximum number of files that may be used.\n"
+      "          Input files must have at least the first 3 columns of the BED specification.\n"
+      "          '-' may be used to indicate data should be read from standard input.\n\n"
+      "      Process Flags:\n"
+      "          --chrom <chromosome>, --ec, --header, --help, --version\n\n"
+      "      Operations on this build's B200 hot path (choose one):\n"
+      "          -e, --element-of [bp | percentage]    Min: 2 files.\n"
+      "          -i, --intersect                       Min: 2 files.\n"
+      "          -m, --merge                           Min: 1 file.\n"
+      "          -n, --not-element-of [bp | percentage] Min: 2 files.\n\n",
+      f);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Options o = parse_args(argc, argv);
+    int     op = 0;
+    switch (o.mode) {
+      case MERGE: op = BK_SETOP_MERGE; break;
+      case INTERSECTION: op = BK_SETOP_INTERSECT; break;
+      case ELEMENTOF: op = BK_SETOP_ELEMENT_OF; break;
+      case NOTELEMENTOF: op = BK_SETOP_NOT_ELEMENT_OF; break;
+      default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
+    }
+    if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
+    cli::Engine eng;
+    std::vector<bk_bed*> beds;
+    for (size_t f = 0; f < o.files.size(); f++) {
+      std::vector<char> text;
+      if (!cli::slurp(o.files[f], text)) throw UserError("Cannot find " + o.files[f]);
+      const bool is_ref = (op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF) && f == 0;
+      beds.push_back(eng.load(text, 3, is_ref ? BK_COL_LINE : 0));
+    }
+    bk_text out;
+    int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), o.subset, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
+    if (rc != BK_OK) eng.raise(rc);
+    cli::write_all(out.ptr, out.len);
+    bk_free_text(eng.ctx, &out);
+    for (bk_bed* b : beds) bk_free_bed(eng.ctx, b);
+    return EXIT_SUCCESS;
+  } catch (const Help&) {
+    cli::banner(stdout, "bedops");
+    usage(stdout);
+    return EXIT_SUCCESS;
+  } catch (const Version&) {
+    cli::banner(stdout, "bedops");
+    return EXIT_SUCCESS;
+  } catch (const NoInput&) {
+    cli::banner(stderr, "bedops");
+    usage(stderr);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "May use bedops --help for more help.\n\nError: %s\n", e.what());
+  }
+  return EXIT_FAILURE;
+}

@@ -1,0 +1,113 @@
+// closest-features -- drop-in command line for the B200 engine.  Mirrors the option grammar of
+// applications/bed/closestfeats/src/Input.hpp:58-102 and replaces findDistances()
+// (ClosestFeature.cpp:260-413) with bk_closest().
+#include "cli_common.hpp"
+
+namespace {
+using cli::UserError;
+struct Help {};
+struct Version {};
+struct NoInput {};
+
+struct Options {
+  bool ec = false, overlaps = true, closest = false, dist = false, no_ref = false;
+  std::string delim = "|", chrom = "all", ref, query;
+};
+
+void require(bool ok, const std::string& msg) {
+  if (!ok) throw UserError(msg);
+}
+
+Options parse_args(int argc, char** argv) {
+  Options o;
+  if (argc <= 1) throw NoInput();
+  int  i = 1;
+  bool outoption = false;
+  while (i < argc) {
+    std::string next = argv[i];
+    if (next == "--help") throw Help();
+    else if (next == "--version") throw Version();
+    else if (next == "--ec" || next == "--header") o.ec = true;
+    else if (next == "--no-overlaps") o.overlaps = false;
+    else if (next == "--delim") {
+      require(++i < argc, "No value given for --delim.");
+      o.delim = argv[i];
+    } else if (next == "--chrom") {
+      require(++i < argc, "No value given for --chrome.");
+      o.chrom = argv[i];
+    } else if (next == "--closest" || next == "--shortest") {
+      require(!outoption, "Multiple output options not allowed.");
+      o.closest = true;
+      outoption = true;
+    } else if (next == "--dist") o.dist = true;
+    else if (next == "--no-ref") o.no_ref = true;
+    else {
+      require(i + 2 == argc, "Unknown option: " + next + ".");
+      break;
+    }
+    ++i;
+  }
+  require(i + 2 == argc, "Not enough input files given.");
+  o.ref = argv[i++];
+  o.query = argv[i];
+  require(o.ref.find("--") != 0, "Option given where file expected: " + o.ref + ".");
+  require(o.query.find("--") != 0, "Option given where file expected: " + o.query + ".");
+  return o;
+}
+
+void usage(FILE* f) {
+  std::fputs(
+      "\nUSAGE: closest-features [Process-Flags] <input-file> <query-file>\n"
+      "   All input files must be sorted per sort-bed.\n"
+      "   For every element in <input-file>, determine the two elements from <query-file> falling\n"
+      "     nearest to its left and right edges.  By default, output consists of the <input-file> element,\n"
+      "     followed by results from <query-file>.\n\n"
+      "  Process Flags:\n"
+      "    --chrom <chromosome>, --closest, --delim <delim>, --dist, --ec, --header, --help, --no-overlaps,\n"
+      "    --no-ref, --version\n\n",
+      f);
+}
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Options           o = parse_args(argc, argv);
+    std::vector<char> rtext, qtext;
+    if (!cli::slurp(o.ref, rtext)) throw UserError("Unable to find file: " + o.ref);
+    if (!cli::slurp(o.query, qtext)) throw UserError("Unable to find file: " + o.query);
+    cli::Engine eng;
+    bk_bed*     ref = eng.load(rtext, 3, BK_COL_LINE);
+    bk_bed*     qry = eng.load(qtext, 3, BK_COL_LINE);
+    bk_cfspec   spec;
+    bk_cfspec_default(&spec);
+    spec.dist = o.dist;
+    spec.closest = o.closest;
+    spec.no_overlaps = !o.overlaps;
+    spec.no_ref = o.no_ref;
+    std::string delim = o.delim;
+    if (delim == "\t" || delim == "\\t" || delim == "'\t'") delim = "\t";
+    spec.delim = delim.c_str();
+    spec.chrom = o.chrom.c_str();
+    bk_text out;
+    int     rc = bk_closest(eng.ctx, ref, qry, &spec, &out);
+    if (rc != BK_OK) eng.raise(rc);
+    cli::write_all(out.ptr, out.len);
+    bk_free_text(eng.ctx, &out);
+    bk_free_bed(eng.ctx, ref);
+    bk_free_bed(eng.ctx, qry);
+    return EXIT_SUCCESS;
+  } catch (const Help&) {
+    cli::banner(stdout, "closest-features");
+    usage(stdout);
+    return EXIT_SUCCESS;
+  } catch (const Version&) {
+    cli::banner(stdout, "closest-features");
+    return EXIT_SUCCESS;
+  } catch (const NoInput&) {
+    cli::banner(stderr, "closest-features");
+    usage(stderr);
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "May use closest-features --help for more help.\n\nError: %s\n", e.what());
+  }
+  return EXIT_FAILURE;
+}

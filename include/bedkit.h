@@ -1,0 +1,168 @@
+/* bedkit.h -- C ABI of the B200-native sorted-interval engine (libbedkit.so).
+ *
+ * The reference (BEDOPS v2.4.26) has no library boundary: its algorithms are templates compiled into each
+ * tool.  The three seams this ABI replaces are the calls a maintainer would swap out in the reference:
+ *
+ *   bk_load_bed / bk_load_bed_device   replaces  Bed::allocate_iterator_starch_bed<T*> + T::readline(FILE*)
+ *                                      (interfaces/general-headers/data/bed/AllocateIterator_BED_starch.hpp:60-187,
+ *                                       data/bed/Bed.hpp:244-255, 343-360, 577-606, 829-860)
+ *   bk_bedmap                          replaces  WindowSweep::sweep(refI, refEnd, mapI, mapEnd, st, multiv, sweepAll)
+ *                                      (applications/bed/bedmap/src/Bedmap.cpp:288, single-file form :229) together
+ *                                      with the MultiVisitor print chain (visitors/other/MultiVisitor.hpp:83-98)
+ *   bk_setop                           replaces  selectWork(...) -> doMerge/doIntersection/doElementOf
+ *                                      (applications/bed/bedops/src/Bedops.cpp:1523-1577, :538-606)
+ *   bk_closest                         replaces  findDistances(ref, nonRef, allowOverlaps, printer)
+ *                                      (applications/bed/closestfeats/src/ClosestFeature.cpp:260-413)
+ *
+ * Conventions: plain pointers and sizes, integer return codes (0 = ok), never exceptions; the caller owns input
+ * text; the library owns device memory and returns result text as bk_text, released with bk_free_text.  One host
+ * thread per bk_ctx (one ctx per GPU; contexts are independent).  There is no CPU fallback: every entry point
+ * fails with BK_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BEDKIT_H
+#define BEDKIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEDKIT_ABI_VERSION 1
+
+typedef struct bk_ctx bk_ctx; /* one per GPU: stream, memory pool, pinned staging, last error text */
+typedef struct bk_bed bk_bed; /* a parsed, device-resident sorted BED file: SoA columns + chromosome runs */
+
+/* result text; ptr is pinned host memory (on_device == 0) or device memory (on_device == 1) */
+typedef struct bk_text {
+  char*    ptr;
+  uint64_t len;
+  int      on_device;
+  uint64_t rows; /* number of output lines */
+} bk_text;
+
+/* ---- error codes ----------------------------------------------------------------------------------------- */
+enum {
+  BK_OK = 0,
+  BK_ERR_CUDA = 1,        /* CUDA runtime failure or no usable device */
+  BK_ERR_NOMEM = 2,
+  BK_ERR_ARG = 3,         /* bad argument to the ABI */
+  BK_ERR_PARSE = 4,       /* a BED line the device parser does not accept (message names the row) */
+  BK_ERR_COORD_RANGE = 5, /* coordinate >= 2^32 - 1: outside this build's 32-bit device layout */
+  BK_ERR_UNSUPPORTED = 6, /* option combination outside the hot path (named in the message) */
+  BK_ERR_STARCH = 7,      /* input is a Starch archive; only plain BED text is accepted */
+  BK_ERR_UNSORTED = 8,    /* chromosome runs not in strcmp order / repeated chromosome run */
+  BK_ERR_CHECK = 9        /* --ec validation failed (message mirrors BedCheckIterator.hpp:589-593) */
+};
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int         bk_init(bk_ctx** out, int device);
+void        bk_destroy(bk_ctx* ctx);
+/* run all work of this ctx on an existing CUDA stream (cudaStream_t); NULL restores the ctx's own stream */
+int         bk_set_stream(bk_ctx* ctx, void* cuda_stream);
+int         bk_sync(bk_ctx* ctx);
+const char* bk_strerror(int code);
+const char* bk_last_error(const bk_ctx* ctx); /* detail for the last failing call on this ctx ("" if none) */
+int         bk_abi_version(void);
+/* number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches) */
+uint64_t    bk_launch_count(const bk_ctx* ctx);
+
+/* ---- BED reader ------------------------------------------------------------------------------ */
+/* which per-row columns the parser materialises besides start/end */
+enum {
+  BK_COL_LINE = 1,  /* byte offset of each line (needed to echo a row or copy its id) */
+  BK_COL_SCORE = 2, /* column 5 as double (strtod-exact); requires min_fields == 5 */
+  BK_COL_ID = 4     /* (offset,len) of column 4; requires min_fields >= 4 and BK_COL_LINE */
+};
+/* min_fields = 3|4|5 selects the reference record type B3Rest / B4Rest / B5Rest (bedmap/src/Bedmap.cpp:623-654).
+ * host text: copied to the device (pinned staging, async), then parsed.  The text must stay valid until return. */
+int bk_load_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, int min_fields, unsigned cols, bk_bed** out);
+/* device text: borrowed, 16-byte aligned, must outlive the bk_bed */
+int bk_load_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int min_fields, unsigned cols, bk_bed** out);
+void        bk_free_bed(bk_ctx* ctx, bk_bed* bed);
+uint64_t    bk_bed_rows(const bk_bed* bed);
+int         bk_bed_nchrom(const bk_bed* bed);
+const char* bk_bed_chrom_name(const bk_bed* bed, int i);
+uint64_t    bk_bed_chrom_rows(const bk_bed* bed, int i);
+/* test/debug accessor: copy parsed columns to host arrays of bk_bed_rows() elements (any pointer may be NULL) */
+int bk_bed_copy_columns(bk_ctx* ctx, const bk_bed* bed, uint32_t* start, uint32_t* end, double* score,
+                        uint64_t* line_off);
+
+/* ---- bedmap ------------------------------------------------------------------------------ */
+enum { /* operations, printed left to right in the order given (MultiVisitor.hpp:83-98) */
+  BK_OP_ECHO = 1,        /* --echo          EchoVisitor.hpp:39-65 */
+  BK_OP_COUNT = 2,       /* --count         CountVisitor.hpp:34-64 */
+  BK_OP_INDICATOR = 3,   /* --indicator     IndicatorVisitor.hpp:37-56 */
+  BK_OP_BASES = 4,       /* --bases         OvrAggregateVisitor.hpp:41-108 */
+  BK_OP_SUM = 5,         /* --sum           SumVisitor.hpp:36-68 */
+  BK_OP_MEAN = 6,        /* --mean          AverageVisitor.hpp:35-76 */
+  BK_OP_MAX = 7,         /* --max           ExtremeVisitor.hpp:84-134 */
+  BK_OP_MIN = 8,         /* --min */
+  BK_OP_ECHO_MAP_ID = 9, /* --echo-map-id   EchoMapBedVisitor.hpp:39-66 */
+  BK_OP_ECHO_REF_SIZE = 10,  /* --echo-ref-size  */
+  BK_OP_ECHO_REF_NAME = 11,  /* --echo-ref-name  chrom:start-end */
+  BK_OP_ECHO_REF_ROW_ID = 12 /* --echo-ref-row-id  id-<row> */
+};
+enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
+  BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */
+  BK_OVR_RANGE = 1,       /* --range N */
+  BK_OVR_FRAC_REF = 2,    /* --fraction-ref F */
+  BK_OVR_FRAC_MAP = 3,    /* --fraction-map F */
+  BK_OVR_FRAC_EITHER = 4, /* --fraction-either F */
+  BK_OVR_FRAC_BOTH = 5,   /* --fraction-both F */
+  BK_OVR_EXACT = 6        /* --exact */
+};
+#define BK_MAX_OPS 32
+typedef struct bk_mapspec {
+  int         n_ops;
+  int         ops[BK_MAX_OPS];
+  int         overlap_kind;
+  uint64_t    overlap_bp;    /* BK_OVR_BP: required bases; BK_OVR_RANGE: padding */
+  double      overlap_frac;  /* BK_OVR_FRAC_* */
+  int         precision;     /* --prec, default 6 */
+  int         sci;           /* --sci */
+  int         skip_unmapped; /* --skip-unmapped */
+  const char* delim;         /* --delim, default "|" (already unescaped) */
+  const char* multidelim;    /* --multidelim, default ";" */
+  const char* chrom;         /* --chrom, NULL or "all" = every chromosome */
+  int         out_on_device; /* leave result text in HBM (bench: device-resident timing) */
+} bk_mapspec;
+void bk_mapspec_default(bk_mapspec* spec);
+/* map == NULL: single-file mode, ref is mapped onto itself (Input.hpp:359-364) */
+int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, const bk_mapspec* spec, bk_text* out);
+
+/* ---- bedops set operators ------------------------------------------------------------------- */
+enum { BK_SETOP_MERGE = 1, BK_SETOP_INTERSECT = 2, BK_SETOP_ELEMENT_OF = 3, BK_SETOP_NOT_ELEMENT_OF = 4 };
+/* thr / thr_is_pct: -e/-n threshold as Input::Threshold()/UsePercentage() deliver it (bedops/src/Input.hpp:344-382):
+ * a fraction in (0,1] when thr_is_pct, else a base count.  files[0] is the reference file for -e/-n. */
+int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, double thr, int thr_is_pct,
+             const char* chrom, int out_on_device, bk_text* out);
+
+/* ---- closest-features ----------------------------------------------------------------------- */
+typedef struct bk_cfspec {
+  int         dist;        /* --dist */
+  int         closest;     /* --closest */
+  int         no_overlaps; /* --no-overlaps */
+  int         no_ref;      /* --no-ref */
+  int         no_query;    /* --no-query */
+  int         center;      /* --center */
+  const char* delim;       /* --delim, default "|" */
+  const char* chrom;       /* --chrom */
+  int         out_on_device;
+} bk_cfspec;
+void bk_cfspec_default(bk_cfspec* spec);
+int  bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, const bk_cfspec* spec, bk_text* out);
+
+/* ---- BED writer used by the synthetic-input generator and tests -------------------------------------------- */
+/* format n rows "chrom\tstart\tend[\tid<k>\tscore]\n" from device SoA arrays (one chromosome name per call);
+ * id_base < 0 writes BED3.  Result text in HBM (out->on_device = 1). */
+int bk_format_bed_device(bk_ctx* ctx, const char* chrom, const uint32_t* d_start, const uint32_t* d_end,
+                         const uint32_t* d_score, uint64_t n, int64_t id_base, bk_text* out);
+
+void bk_free_text(bk_ctx* ctx, bk_text* text);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEDKIT_H */

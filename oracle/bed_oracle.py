@@ -1,0 +1,433 @@
+"""bed_oracle.py -- CPU restatement of the BEDOPS v2.4.26 sorted-interval hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under bedops_b200/ may import this module; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg use it, and only as the checker.
+
+Parity status: PINNED.  tests/test_oracle.py checks every function here against
+  * the reference's own golden vectors (applications/bed/bedops/test/TestPlan.xml, orders listed in
+    SURVEY.md 8c) and the worked examples in docs/content/reference/statistics/bedmap.rst, committed as
+    fixtures under tests/golden/ by tests/golden/make_golden.py, and
+  * outputs of the unmodified reference binaries built by oracle/build_ref.sh (oracle/_ref/bin), on seeded
+    synthetic inputs (fixtures committed; live differential runs when the binaries are present).
+
+Each function cites the reference code it restates (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import bisect
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+WS = b" \t\r\v\f"
+
+
+@dataclass
+class Row:
+    chrom: bytes
+    start: int
+    end: int
+    rest: bytes          # verbatim remainder of the line after the last parsed field (leading tab included)
+    id: bytes = b""
+    score: float = 0.0
+    rest3: bytes = b""   # remainder after column 3 (what B3Rest keeps)
+
+
+def _token(line: bytes, pos: int) -> Tuple[bytes, int]:
+    n = len(line)
+    while pos < n and line[pos:pos + 1] in (b" ", b"\t", b"\r", b"\v", b"\f"):
+        pos += 1
+    s = pos
+    while pos < n and line[pos:pos + 1] not in (b" ", b"\t", b"\r", b"\v", b"\f"):
+        pos += 1
+    return line[s:pos], pos
+
+
+def _number(line: bytes, pos: int) -> Tuple[bytes, int]:
+    """Longest prefix strtod would accept (decimal form)."""
+    n = len(line)
+    s = pos
+    if pos < n and line[pos:pos + 1] in (b"+", b"-"):
+        pos += 1
+    while pos < n and line[pos:pos + 1].isdigit():
+        pos += 1
+    if pos < n and line[pos:pos + 1] == b".":
+        pos += 1
+        while pos < n and line[pos:pos + 1].isdigit():
+            pos += 1
+    if pos < n and line[pos:pos + 1] in (b"e", b"E"):
+        q = pos + 1
+        if q < n and line[q:q + 1] in (b"+", b"-"):
+            q += 1
+        if q < n and line[q:q + 1].isdigit():
+            while q < n and line[q:q + 1].isdigit():
+                q += 1
+            pos = q
+    return line[s:pos], pos
+
+
+def parse_bed(text: bytes, min_fields: int = 3) -> List[Row]:
+    """Bed::B3Rest/B4Rest/B5Rest::readline(FILE*)  (interfaces/general-headers/data/bed/Bed.hpp:343-360,
+    :577-606, :829-860) with formats "%s\\t%lu\\t%lu%[^\\n]s\\n" etc. (:380-382, :644-646, :901-903).
+    A last line without '\\n' is not a record (allocate_iterator_starch_bed tests feof after the read,
+    data/bed/AllocateIterator_BED_starch.hpp:172-187); blank lines are skipped by %s."""
+    rows: List[Row] = []
+    end = text.rfind(b"\n")
+    if end < 0:
+        return rows
+    for line in text[:end].split(b"\n"):
+        if not line.strip(WS):
+            continue
+        chrom, p = _token(line, 0)
+        st, p = _token(line, p)
+        en, p = _token(line, p)
+        # %lu stops at the first non-digit: the rest starts right there
+        sdig = st.lstrip(b"+")
+        edig_full = en.lstrip(b"+")
+        k = 0
+        while k < len(edig_full) and edig_full[k:k + 1].isdigit():
+            k += 1
+        p -= len(edig_full) - k
+        r = Row(chrom, int(sdig), int(edig_full[:k]), line[p:], rest3=line[p:])
+        if min_fields >= 4:
+            r.id, p = _token(line, p)
+            r.rest = line[p:]
+            if min_fields >= 5:
+                while p < len(line) and line[p:p + 1] in (b" ", b"\t", b"\r", b"\v", b"\f"):
+                    p += 1
+                num, p = _number(line, p)
+                r.score = float(num)
+                r.rest = line[p:]
+        rows.append(r)
+    return rows
+
+
+def by_chrom(rows: Sequence[Row]) -> Dict[bytes, List[Row]]:
+    out: Dict[bytes, List[Row]] = {}
+    for r in rows:
+        out.setdefault(r.chrom, []).append(r)
+    return out
+
+
+def chrom_order(*files: Sequence[Row]) -> List[bytes]:
+    """strcmp order of chromosome names (BedCheckIterator.hpp:596-597)."""
+    names = set()
+    for f in files:
+        for r in f:
+            names.add(r.chrom)
+    return sorted(names)
+
+
+# --------------------------------------------------------------------------------------------------
+# bedmap
+# --------------------------------------------------------------------------------------------------
+DBL_EPS = 2.220446049250313e-16
+
+
+def _perc(p: float) -> float:
+    """PercentOverlapMapping constructor (data/bed/BedDistances.hpp:120-131)."""
+    while p > 1:
+        p /= 10.0
+    p -= DBL_EPS
+    if p <= 0.0:
+        p = DBL_EPS
+    return p
+
+
+def qualifies(kind: str, val, rs: int, re: int, ms: int, me: int) -> Tuple[bool, int]:
+    """dist_.Map2Ref(m, r) == 0 for the overlap criteria of Bedmap.cpp:107-156 / BedDistances.hpp:41-317.
+    Returns (qualifies, overlap bases)."""
+    ov = max(0, min(re, me) - max(rs, ms))
+    if kind == "bp":        # Bed::Overlapping(N), :96-115
+        return ov > 0 and ov >= val, ov
+    if kind == "range":     # Bed::RangedDist(N), :41-67
+        if ms < re:
+            return me + val > rs, ov
+        return re + val > ms, ov
+    if kind == "exact":     # Bed::Exact, :285-308
+        return rs == ms and re == me, ov
+    if ov <= 0:
+        return False, ov
+    p = _perc(val)
+    fm = ov / float(me - ms) >= p   # PercentOverlapMapping::Ref2Map, :136-172
+    fr = ov / float(re - rs) >= p   # PercentOverlapReference, :190-213
+    if kind == "fraction-map":
+        return fm, ov
+    if kind == "fraction-ref":
+        return fr, ov
+    if kind == "fraction-either":
+        return fm or fr, ov
+    if kind == "fraction-both":
+        return fm and fr, ov
+    raise ValueError(kind)
+
+
+def _fmt_score(v: float, prec: int, sci: bool) -> bytes:
+    """Formats::Format(double, precision, scientific) -> "%.<prec>lf" / "%.<prec>e" (utility/Formats.hpp:42-49)."""
+    return (("%%.%de" if sci else "%%.%df") % prec % v).encode()
+
+
+def echo_b3rest(r: Row) -> bytes:
+    """B3Rest::print "%s\\t%lu\\t%lu%s" (Bed.hpp:316-320, :376-378)."""
+    return r.chrom + b"\t" + str(r.start).encode() + b"\t" + str(r.end).encode() + r.rest3
+
+
+def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overlap: Tuple[str, object] = ("bp", 1),
+           prec: int = 6, sci: bool = False, delim: bytes = b"|", multidelim: bytes = b";",
+           skip_unmapped: bool = False, chrom: Optional[bytes] = None) -> bytes:
+    """WindowSweep::sweep + BedBaseVisitor + MultiVisitor (interfaces/src/algorithm/sweep/WindowSweepImpl.cpp:174-256,
+    algorithm/visitors/bed/BedBaseVisitor.hpp:118-225, visitors/other/MultiVisitor.hpp:83-98), restated
+    declaratively: for every reference row the qualifying map rows are {m : dist_.Map2Ref(m, r) == 0}, visited in
+    file order.  Sums are taken fresh per reference row (the reference keeps a rolling double, SumVisitor.hpp:47-51;
+    identical for exactly representable partial sums, see DESIGN.md parity notes)."""
+    need_fields = 3
+    for o in ops:
+        if o in ("sum", "mean", "max", "min"):
+            need_fields = max(need_fields, 5)
+        elif o == "echo-map-id":
+            need_fields = max(need_fields, 4)
+    single = map_text is None
+    maps = parse_bed(ref_text if single else map_text, need_fields)
+    refs = maps if single else parse_bed(ref_text, 3)
+    mchrom = by_chrom(maps)
+    kind, val = overlap
+    pad = val if kind == "range" else 0
+    out: List[bytes] = []
+    cache = {}
+    for ri, r in enumerate(refs):
+        if chrom is not None and chrom != b"all" and r.chrom != chrom:
+            continue
+        if r.chrom not in cache:
+            ml = mchrom.get(r.chrom, [])
+            starts = [m.start for m in ml]
+            pm, cur = [], 0
+            for m in ml:
+                cur = max(cur, m.end)
+                pm.append(cur)
+            cache[r.chrom] = (ml, starts, pm)
+        ml, starts, pm = cache[r.chrom]
+        hi = bisect.bisect_left(starts, r.end + pad)
+        lo = bisect.bisect_left(pm, r.start - pad + 1, 0, hi) if r.start >= pad else 0
+        hits = []
+        bases = 0
+        for k in range(lo, hi):
+            m = ml[k]
+            ok, ov = qualifies(kind, val, r.start, r.end, m.start, m.end)
+            if ok:
+                hits.append(m)
+                bases += ov
+        cnt = len(hits)
+        if skip_unmapped and cnt == 0:   # MultiVisitor.hpp:84-85
+            continue
+        cols: List[bytes] = []
+        for o in ops:
+            if o == "echo":              # EchoVisitor.hpp:39-65
+                cols.append(echo_b3rest(r))
+            elif o == "count":           # CountVisitor.hpp:34-64
+                cols.append(str(cnt).encode())
+            elif o == "indicator":       # IndicatorVisitor.hpp:37-56
+                cols.append(b"1" if cnt else b"0")
+            elif o == "bases":           # OvrAggregateVisitor.hpp:41-108
+                cols.append(str(bases).encode())
+            elif o in ("sum", "mean", "max", "min"):
+                if cnt == 0:
+                    cols.append(b"NAN")  # Signal::NaN (interfaces/src/data/measurement/NaN.cpp:27)
+                else:
+                    if o == "sum":       # SumVisitor.hpp:36-68
+                        s = 0.0
+                        for m in hits:
+                            s += m.score
+                        v = s
+                    elif o == "mean":    # AverageVisitor.hpp:35-76: sum_/counter_
+                        s = 0.0
+                        for m in hits:
+                            s += m.score
+                        v = s / cnt
+                    elif o == "max":     # ExtremeVisitor.hpp:84-134
+                        v = max(m.score for m in hits)
+                    else:
+                        v = min(m.score for m in hits)
+                    cols.append(_fmt_score(v, prec, sci))
+            elif o == "echo-map-id":     # EchoMapBedVisitor.hpp:39-66 (ties in file order, SURVEY hazard 2)
+                cols.append(multidelim.join(m.id for m in hits))
+            elif o == "echo-ref-size":
+                cols.append(str(r.end - r.start).encode())
+            elif o == "echo-ref-name":
+                cols.append(r.chrom + b":" + str(r.start).encode() + b"-" + str(r.end).encode())
+            elif o == "echo-ref-row-id":
+                cols.append(b"id-" + str(ri + 1).encode())
+            else:
+                raise ValueError(o)
+        out.append(delim.join(cols) + b"\n")
+    return b"".join(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# bedops
+# --------------------------------------------------------------------------------------------------
+def _sel(rows: Sequence[Row], chrom: Optional[bytes]) -> List[Row]:
+    if chrom is None or chrom == b"all":
+        return list(rows)
+    return [r for r in rows if r.chrom == chrom]
+
+
+def merged_union(files: Sequence[Sequence[Row]]) -> Dict[bytes, List[Tuple[int, int]]]:
+    """nextMergeAllLines (applications/bed/bedops/src/Bedops.cpp:1186-1243): take the minimum (chrom,start) over
+    all files, extend its end while any file's next element has start <= current end (touching coalesces, :1233)."""
+    out: Dict[bytes, List[Tuple[int, int]]] = {}
+    per: Dict[bytes, List[Tuple[int, int]]] = {}
+    for f in files:
+        for r in f:
+            per.setdefault(r.chrom, []).append((r.start, r.end))
+    for c, iv in per.items():
+        iv.sort(key=lambda t: t[0])
+        res: List[Tuple[int, int]] = []
+        cs, ce = iv[0]
+        for s, e in iv[1:]:
+            if s <= ce:
+                if e > ce:
+                    ce = e
+            else:
+                res.append((cs, ce))
+                cs, ce = s, e
+        res.append((cs, ce))
+        out[c] = res
+    return out
+
+
+def bedops_merge(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doMerge (Bedops.cpp:592-606) -> record() -> B3NoRest::println "%s\\t%lu\\t%lu\\n" (Bed.hpp:228-232)."""
+    files = [_sel(parse_bed(t, 3), chrom) for t in texts]
+    u = merged_union(files)
+    out = []
+    for c in sorted(u):
+        for s, e in u[c]:
+            out.append(c + b"\t%d\t%d\n" % (s, e))
+    return b"".join(out)
+
+
+def bedops_intersect(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doIntersection / nextIntersectLine (Bedops.cpp:574-587, :1105-1181): every file is merged within itself
+    (getNextFileMergedCoords :791-814, mergeOverlap :864-886), then the common coverage of all files is emitted,
+    positive length only."""
+    lists = [merged_union([_sel(parse_bed(t, 3), chrom)]) for t in texts]
+    out = []
+    common = set(lists[0])
+    for l in lists[1:]:
+        common &= set(l)
+    for c in sorted(common):
+        acc = lists[0][c]
+        for l in lists[1:]:
+            b = l[c]
+            res = []
+            i = j = 0
+            while i < len(acc) and j < len(b):
+                lo = max(acc[i][0], b[j][0])
+                hi = min(acc[i][1], b[j][1])
+                if hi > lo:
+                    res.append((lo, hi))
+                if acc[i][1] < b[j][1]:
+                    i += 1
+                else:
+                    j += 1
+            acc = res
+        for s, e in acc:
+            out.append(c + b"\t%d\t%d\n" % (s, e))
+    return b"".join(out)
+
+
+def bedops_element_of(texts: Sequence[bytes], thr: float = 1.0, use_pct: bool = True, invert: bool = False,
+                      chrom: Optional[bytes] = None) -> bytes:
+    """doElementOf / nextElementOfLine (Bedops.cpp:538-566, :1023-1100): overlap bases of each reference row
+    (file 0, unmerged, all columns) with the union-merge of the other files; keep when
+    rangeOverlap/range >= threshold (percent) or rangeOverlap >= threshold (bp) (:1094-1096), inverted for -n."""
+    ref = _sel(parse_bed(texts[0], 3), chrom)
+    u = merged_union([_sel(parse_bed(t, 3), chrom) for t in texts[1:]])
+    out = []
+    last_chrom = max(u) if u else None
+    for r in ref:
+        segs = u.get(r.chrom, [])
+        ends = [e for _, e in segs]
+        k = bisect.bisect_right(ends, r.start)
+        ovl = 0.0
+        while k < len(segs) and segs[k][0] < r.end:
+            ovl += min(r.end, segs[k][1]) - max(r.start, segs[k][0])
+            k += 1
+        rng = float(r.end - r.start)
+        is_elem = (ovl / rng >= thr) if use_pct else (ovl >= thr)
+        if not use_pct and thr <= 0:
+            # "-e 0" / "-n 0": 0 >= 0 holds for every row the loop reaches, but once the merged stream has no element
+            # at or after the row (:1044-1049, :1053-1062) the row is reported as a non-element without the test
+            is_elem = (bool(segs) and segs[-1][1] > r.start) or (last_chrom is not None and r.chrom < last_chrom)
+        if is_elem != invert:
+            out.append(echo_b3rest(r) + b"\n")
+    return b"".join(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# closest-features (declarative rule; see SURVEY.md 8c hazard 3 for where the streaming reference differs)
+# --------------------------------------------------------------------------------------------------
+def closest_features(ref_text: bytes, qry_text: bytes, dist: bool = False, closest: bool = False,
+                     no_overlaps: bool = False, no_ref: bool = False, delim: bytes = b"|",
+                     chrom: Optional[bytes] = None) -> bytes:
+    """findDistances (applications/bed/closestfeats/src/ClosestFeature.cpp:260-413) + PrintAll/PrintShortest
+    (Printers.hpp:46-205)."""
+    refs = _sel(parse_bed(ref_text, 3), chrom)
+    qc = by_chrom(_sel(parse_bed(qry_text, 3), chrom))
+    out = []
+    for b in refs:
+        ql = qc.get(b.chrom, [])
+        left = right = None
+        ldist = rdist = None
+        # nearest non-overlapping neighbours
+        for c in ql:
+            if c.end <= b.start:
+                d = -(b.start - c.end + 1)          # getDistance :244-255
+                if ldist is None or d >= ldist:     # ">=": later row wins ties (:300)
+                    left, ldist = c, d
+            elif c.start >= b.end:
+                d = c.start - b.end + 1
+                if rdist is None or d < rdist:
+                    right, rdist = c, d
+                break
+        if not no_overlaps:
+            lov = False
+            for c in ql:
+                if c.start >= b.end:
+                    break
+                if c.end <= b.start:
+                    continue
+                if c.start <= b.start:              # hangs over the left edge (:335-342)
+                    left, ldist, lov = c, 0, True
+                elif b.end <= c.end:                # hangs over the right edge (:343-350)
+                    right, rdist = c, 0
+                else:                               # contained: centroid rule (:351-388)
+                    centroid = (b.end - 1.0 + b.start) / 2.0
+                    prop = 0.0 if centroid < c.start else (centroid + 1 - c.start) / (c.end - c.start)
+                    if lov:
+                        if prop < 0.5:
+                            right, rdist = c, 0
+                    elif prop >= 0.5:
+                        left, ldist, lov = c, 0, True
+                    else:
+                        right, rdist = c, 0
+        parts: List[bytes] = []
+
+        def show(x, d):
+            parts.append(echo_b3rest(x) if x is not None else b"NA")
+            if dist:
+                parts.append(str(d).encode() if x is not None else b"NA")
+
+        if not no_ref:
+            parts.append(echo_b3rest(b))
+        if closest:                                 # PrintShortest (Printers.hpp:120-205)
+            if left is None and right is None:
+                show(None, None)
+            elif right is None or (left is not None and abs(ldist) <= abs(rdist)):
+                show(left, ldist)
+            else:
+                show(right, rdist)
+        else:
+            show(left, ldist)
+            show(right, rdist)
+        out.append(delim.join(parts) + b"\n")
+    return b"".join(out)

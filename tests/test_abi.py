@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol include/bedkit.h declares,
+has no torch types in its ABI, and the product fails loudly (no CPU fallback) when there is no B200."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "bedkit.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bk_[a-z_0-9]+)\s*\(", src)))
+
+
+def lib_file():
+    import bedops_b200
+    return bedops_b200.lib_path()
+
+
+def gpu_present():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except ImportError:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    import bedops_b200
+    lib = bedops_b200.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libbedkit.so does not export %s" % s
+    from bedops_b200._lib import EXPORTS
+    assert sorted(EXPORTS) == syms
+    assert lib.bk_abi_version() == 1
+
+
+def test_abi_is_plain_c():
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_file()], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    bk = [n for n in names if n.startswith("bk_")]
+    assert len(bk) >= 20
+    assert not any("torch" in n or "at::" in n for n in names)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", lib_file()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import bedops_b200
+    if gpu_present():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bedops_b200.BedKitError) as e:
+        bedops_b200.BedKit()
+    assert e.value.code == 1
+    for tool in ("bedmap", "bedops", "closest-features"):
+        assert os.access(bedops_b200.tool_path(tool), os.X_OK)
+    p = subprocess.run([bedops_b200.tool_path("bedops"), "-m", os.path.join(ROOT, "tests", "golden", "docs.json")],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and p.stdout == "" and "no CPU fallback" in p.stderr
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, names in os.walk(os.path.join(ROOT, "bedops_b200")):
+        for n in names:
+            if n.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                src = open(os.path.join(dirpath, n), errors="ignore").read()
+                assert "bed_oracle" not in src and "oracle/" not in src, n
+
+
+def test_cli_banners_and_errors_match_reference_shape():
+    import bedops_b200
+    p = subprocess.run([bedops_b200.tool_path("bedops"), "--version"], capture_output=True, text=True)
+    assert p.returncode == 0
+    assert p.stdout == ("bedops\n  citation: http://bioinformatics.oxfordjournals.org/content/28/14/1919.abstract\n"
+                        "  version:  2.4.26\n  authors:  Shane Neph & Scott Kuehn\n")
+    p = subprocess.run([bedops_b200.tool_path("bedmap"), "--version"], capture_output=True, text=True)
+    assert p.returncode == 1 and p.stdout.startswith("bedmap\n  citation:")   # Bedmap.cpp:166-170 quirk
+    p = subprocess.run([bedops_b200.tool_path("bedops"), "-m", "/nonexistent.bed"], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert p.stderr == "May use bedops --help for more help.\n\nError: Bad Input\nCannot find /nonexistent.bed\n"
+    p = subprocess.run([bedops_b200.tool_path("bedmap"), "--count", "/nonexistent.bed"], capture_output=True, text=True)
+    assert p.returncode == 1
+    assert p.stderr == "May use bedmap --help for more help.\n\nError: Unable to find file: /nonexistent.bed\n"
+    p = subprocess.run([bedops_b200.tool_path("bedmap"), "--bogus", "a", "b"], capture_output=True, text=True)
+    assert p.stderr == "May use bedmap --help for more help.\n\nError: Unknown option: --bogus\n"

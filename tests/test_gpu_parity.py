@@ -1,0 +1,231 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+  * the reference's own golden vectors (TestPlan.xml in-scope orders, docs worked examples),
+  * the Python oracle on seeded synthetic inputs (and the committed hashes of the reference binaries' output),
+  * the reference binaries themselves (oracle/_ref/bin) through the drop-in command lines,
+plus parser column parity and edge cases (empty / ragged / unterminated input, chromosome handling).
+Bar: byte-identical output."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REFBIN, have_ref, load_golden
+import bed_oracle as O
+import oracle_cli
+
+pytestmark = pytest.mark.gpu
+
+TESTPLAN = load_golden("testplan.json")
+DOCS = load_golden("docs.json")
+SYN = load_golden("synthetic.json")
+
+
+@pytest.fixture(scope="module")
+def kit():
+    import bedops_b200
+    k = bedops_b200.BedKit(0)
+    yield k
+    k.close()
+
+
+def first_diff(a: bytes, b: bytes) -> str:
+    la, lb = a.split(b"\n"), b.split(b"\n")
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return "line %d: got %r expected %r (lens %d/%d lines)" % (i + 1, x[:200], y[:200], len(la), len(lb))
+    return "length differs: %d vs %d lines" % (len(la), len(lb))
+
+
+def assert_same(got: bytes, exp: bytes):
+    assert got == exp, first_diff(got, exp)
+
+
+# ---- reader ------------------------------------------------------------------------------------------------
+def test_parser_columns_match_oracle(kit, synth_files):
+    from bedops_b200._lib import COL_LINE, COL_SCORE
+    text = synth_files["m.bed"]
+    bed = kit.load(text, 5, COL_SCORE | COL_LINE)
+    rows = O.parse_bed(text, 5)
+    st, en, sc, lo = bed.columns(score=True, line=True)
+    assert bed.rows == len(rows)
+    assert np.array_equal(st, np.array([r.start for r in rows], dtype=np.uint32))
+    assert np.array_equal(en, np.array([r.end for r in rows], dtype=np.uint32))
+    assert np.array_equal(sc, np.array([r.score for r in rows], dtype=np.float64))
+    # line offsets point at the chromosome token of each row
+    offs = np.cumsum([0] + [len(l) + 1 for l in text.split(b"\n")[:-1]])[:-1]
+    assert np.array_equal(lo, offs.astype(np.uint64))
+    names = [c for c, _ in bed.chroms()]
+    assert names == sorted({r.chrom.decode() for r in rows})
+    assert sum(n for _, n in bed.chroms()) == len(rows)
+    bed.free()
+
+
+def test_parser_float_scores_are_strtod_exact(kit):
+    from bedops_b200 import synth
+    from bedops_b200._lib import COL_SCORE
+    text = synth.bed_text(20000, 7, fields=5, float_scores=True)
+    extra = b"chrZ\t1\t5\tx\t1e3\nchrZ\t2\t6\tx\t-0.000001\nchrZ\t3\t7\tx\t123456789012345.678\nchrZ\t4\t8\tx\t+.5\nchrZ\t5\t9\tx\t7.\n"
+    text += extra
+    bed = kit.load(text, 5, COL_SCORE)
+    _, _, sc, _ = bed.columns(score=True)
+    exp = np.array([r.score for r in O.parse_bed(text, 5)], dtype=np.float64)
+    assert np.array_equal(sc.view(np.uint64), exp.view(np.uint64))
+    bed.free()
+
+
+def test_parser_edge_cases(kit):
+    # empty input, blank lines, CRLF, unterminated last line (dropped), spaces as separators, leading zeros, '+'
+    assert kit.load(b"", 3).rows == 0
+    assert kit.load(b"\n\n\n", 3).rows == 0
+    assert kit.load(b"chr1\t1\t2", 3).rows == 0
+    t = b"\nchr1 \t 0007  +12\textra stuff\r\n\n  \nchr1\t20\t30\nchr2\t5\t6\nchr2\t7\t9"
+    bed = kit.load(t, 3, 1)
+    st, en, _, lo = bed.columns(line=True)
+    assert bed.rows == 3 and st.tolist() == [7, 20, 5] and en.tolist() == [12, 30, 6]
+    assert bed.chroms() == [("chr1", 2), ("chr2", 1)]
+    out = kit.setop("not-element-of", [bed, kit.load(b"chr9\t1\t2\n", 3)], 1.0, False)
+    assert out == b"chr1\t7\t12\textra stuff\r\nchr1\t20\t30\nchr2\t5\t6\n"
+    assert out == O.bedops_element_of([t, b"chr9\t1\t2\n"], 1.0, False, True)
+
+
+def test_parser_rejects_what_it_cannot_parse_exactly(kit):
+    import bedops_b200
+    for bad, code in ((b"chr1\tx\t5\n", 4), (b"chr1\t1\n", 4), (b"chr1\t1\t4294967295\n", 5),
+                      (b"chr2\t1\t2\nchr1\t1\t2\n", 8)):
+        with pytest.raises(bedops_b200.BedKitError) as e:
+            kit.load(bad, 3)
+        assert e.value.code == code, bad
+    with pytest.raises(bedops_b200.BedKitError) as e:
+        kit.load(b"chr1\t1\t2\tid\n", 5, 2)   # B5Rest needs a score column
+    assert e.value.code == 4
+    with pytest.raises(bedops_b200.BedKitError) as e:
+        kit.load(b"\xca\x5c\xad\xe5\x00\x00", 3)   # starch magic
+    assert e.value.code == 7
+
+
+def test_tile_boundaries_and_long_lines(kit):
+    # lines that straddle the 8 KiB parser tiles, a line longer than a tile, many chromosomes
+    rng = np.random.default_rng(5)
+    lines = []
+    pos = 0
+    for c in range(40):
+        pos = 0
+        for k in range(rng.integers(1, 400)):
+            pos += int(rng.integers(1, 50))
+            rest = b"" if k % 3 else b"\t" + b"x" * int(rng.integers(0, 300))
+            if k == 7 and c == 3:
+                rest = b"\t" + b"y" * 20000
+            lines.append(b"c%03d\t%d\t%d%s" % (c, pos, pos + int(rng.integers(1, 100)), rest))
+    text = b"\n".join(lines) + b"\n"
+    bed = kit.load(text, 3, 1)
+    rows = O.parse_bed(text, 3)
+    st, en, _, _ = bed.columns()
+    assert st.tolist() == [r.start for r in rows] and en.tolist() == [r.end for r in rows]
+    assert [c for c, _ in bed.chroms()] == ["c%03d" % c for c in range(40)]
+    assert_same(kit.bedmap(bed, None, ["echo", "count", "bases"]), O.bedmap(text, None, ["echo", "count", "bases"]))
+    assert_same(kit.setop("merge", [bed]), O.bedops_merge([text]))
+
+
+# ---- golden vectors of the reference ------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", TESTPLAN, ids=lambda c: "order%d" % c["order"])
+def test_testplan_golden(kit, case):
+    files = {k: v.encode() for k, v in case["files"].items()}
+    got = oracle_cli.run_kit(kit, "bedops", case["argv"], files)
+    assert_same(got, case["raw_stdout"].encode())
+
+
+@pytest.mark.parametrize("ex", DOCS["examples"], ids=lambda e: e["source"].split()[0])
+def test_docs_examples(kit, ex):
+    files = {k: v.encode() for k, v in DOCS["files"].items()}
+    stdin = ex["stdin"].encode() if ex["stdin"] else None
+    assert_same(oracle_cli.run_kit(kit, ex["tool"], ex["argv"], files, stdin), ex["expected"].encode())
+
+
+# ---- synthetic inputs: CUDA vs oracle vs hashes of the reference binaries' output ------------------------------------
+@pytest.mark.parametrize("case", [c for c in SYN["cases"] if c["tool"] != "closest-features"],
+                         ids=lambda c: c["tool"] + "_" + "_".join(c["argv"]).replace("\t", "TAB"))
+def test_synthetic_vs_reference_hash(kit, case, synth_files):
+    got = oracle_cli.run_kit(kit, case["tool"], case["argv"], synth_files)
+    assert len(got) == case["nbytes"]
+    assert hashlib.sha256(got).hexdigest() == case["sha256"]
+
+
+def test_synthetic_vs_oracle_bytes(kit, synth_files):
+    for tool, argv in (("bedops", ["-m", "m.bed", "m2.bed"]), ("bedops", ["-i", "m.bed", "m2.bed", "r.bed"]),
+                       ("bedops", ["-e", "30%", "m.bed", "m2.bed"]), ("bedops", ["-n", "10", "m.bed", "r.bed"]),
+                       ("bedmap", ["--echo", "--count", "--mean", "--bases", "--sum", "--max", "--min", "r.bed", "m.bed"]),
+                       ("bedmap", ["--prec", "0", "--mean", "--echo-ref-size", "--echo-ref-name", "--echo-ref-row-id", "r.bed", "m.bed"]),
+                       ("bedmap", ["--prec", "12", "--mean", "r.bed", "m.bed"]),
+                       ("bedmap", ["--multidelim", "::", "--delim", "\t", "--echo-map-id", "--count", "r.bed", "u.bed"])):
+        assert_same(oracle_cli.run_kit(kit, tool, argv, synth_files), oracle_cli.run(tool, argv, synth_files))
+
+
+def test_nested_and_duplicate_intervals(kit):
+    # adversarial nesting: one chromosome-long interval, duplicates, touching and abutting intervals
+    m = [b"chr1\t0\t1000000\tbig\t5"]
+    for k in range(2000):
+        s = 10 + k * 400
+        m.append(b"chr1\t%d\t%d\ta%d\t%d" % (s, s + 150, k, k % 17))
+        if k % 5 == 0:
+            m.append(b"chr1\t%d\t%d\tb%d\t%d" % (s, s + 150, k, k % 11))
+        if k % 7 == 0:
+            m.append(b"chr1\t%d\t%d\tc%d\t%d" % (s + 150, s + 300, k, 3))
+    m.sort(key=lambda l: (int(l.split(b"\t")[1]), int(l.split(b"\t")[2])))
+    mt = b"\n".join(m) + b"\n"
+    r = [b"chr1\t%d\t%d\tr%d" % (k * 333, k * 333 + 1 + (k * 37) % 900, k) for k in range(2500)]
+    rt = b"\n".join(r) + b"\n"
+    files = {"r.bed": rt, "m.bed": mt}
+    for tool, argv in (("bedmap", ["--echo", "--count", "--bases", "--mean", "--max", "--min", "r.bed", "m.bed"]),
+                       ("bedmap", ["--count", "--bases", "m.bed"]), ("bedmap", ["--range", "200", "--count", "r.bed", "m.bed"]),
+                       ("bedops", ["-m", "m.bed", "r.bed"]), ("bedops", ["-i", "m.bed", "r.bed"]),
+                       ("bedops", ["-e", "100%", "r.bed", "m.bed"]), ("bedops", ["-n", "m.bed", "r.bed"])):
+        assert_same(oracle_cli.run_kit(kit, tool, argv, files), oracle_cli.run(tool, argv, files))
+
+
+def test_float_scores_within_tolerance(kit):
+    """--mean/--sum on floating-point scores: <= 1e-12 relative to the exactly rounded per-row sum (math.fsum),
+    before --prec formatting (north_star).  Compared at --prec 15 through the printed text."""
+    import math
+    from bedops_b200 import synth
+    m = synth.bed_text(30000, 11, fields=5, float_scores=True)
+    r = synth.bed_text(3000, 12, synth.REF_SHAPE, fields=5)
+    got = oracle_cli.run_kit(kit, "bedmap", ["--prec", "15", "--sum", "--mean", "r.bed", "m.bed"], {"r.bed": r, "m.bed": m})
+    refs, maps = O.parse_bed(r, 3), O.by_chrom(O.parse_bed(m, 5))
+    lines = got.split(b"\n")[:-1]
+    assert len(lines) == len(refs)
+    worst = 0.0
+    for ref, line in zip(refs, lines):
+        hits = [x.score for x in maps.get(ref.chrom, []) if x.start < ref.end and x.end > ref.start]
+        a, b = line.split(b"|")
+        if not hits:
+            assert a == b == b"NAN"
+            continue
+        exact, scale = math.fsum(hits), math.fsum(abs(h) for h in hits)
+        worst = max(worst, abs(float(a) - exact) / scale, abs(float(b) - exact / len(hits)) / scale * len(hits))
+    assert worst <= 1e-12, worst
+
+
+# ---- the drop-in command lines against the reference binaries ------------------------------------------------------
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
+    import bedops_b200
+    for n, c in synth_files.items():
+        (tmp_path / n).write_bytes(c)
+    runs = [("bedops", ["-m", "m.bed", "r.bed"]), ("bedops", ["--ec", "-i", "m.bed", "m2.bed"]),
+            ("bedops", ["-e", "50%", "r.bed", "m.bed"]), ("bedops", ["--chrom", "chr5", "-n", "1", "r.bed", "m.bed"]),
+            ("bedmap", ["--echo", "--count", "--mean", "--bases", "r.bed", "m.bed"]),
+            ("bedmap", ["--faster", "--delim", "\\t", "--sum", "--max", "--echo-map-id", "r.bed", "u.bed"]),
+            ("bedmap", ["--count", "m3.bed"])]
+    for tool, argv in runs:
+        ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
+        ref = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
+        assert ours.returncode == ref.returncode == 0, ours.stderr
+        assert_same(ours.stdout, ref.stdout)
+    # stdin as the reference file
+    ours = subprocess.run([bedops_b200.tool_path("bedmap"), "--echo", "--indicator", "-", "m.bed"], cwd=tmp_path,
+                          input=synth_files["r.bed"], capture_output=True)
+    ref = subprocess.run([os.path.join(REFBIN, "bedmap"), "--echo", "--indicator", "-", "m.bed"], cwd=tmp_path,
+                         input=synth_files["r.bed"], capture_output=True)
+    assert_same(ours.stdout, ref.stdout)
