@@ -71,6 +71,9 @@ def load_library() -> C.CDLL:
         "bk_last_error": (C.c_char_p, [vp]),
         "bk_abi_version": (i, []),
         "bk_launch_count": (u64, [vp]),
+        "bk_profile": (i, [vp, i]),
+        "bk_profile_query": (i, [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]),
+        "bk_copy": (i, [vp, vp, vp, C.c_size_t]),
         "bk_load_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.c_uint, C.POINTER(vp)]),
         "bk_load_bed_device": (i, [vp, vp, C.c_size_t, i, C.c_uint, C.POINTER(vp)]),
         "bk_free_bed": (None, [vp, vp]),
@@ -96,7 +99,7 @@ def load_library() -> C.CDLL:
 
 
 EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "bk_last_error", "bk_abi_version",
-           "bk_launch_count", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
+           "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text"]
 
@@ -129,9 +132,9 @@ class Bed:
         return st, en, sc, lo
 
     def free(self):
-        if self.h:
+        if self.h and getattr(self.kit, "ctx", None):
             self.kit.lib.bk_free_bed(self.kit.ctx, self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -159,8 +162,9 @@ class DeviceText:
         return self.t.rows
 
     def free(self):
-        if self.t.ptr:
+        if self.t.ptr and getattr(self.kit, "ctx", None):
             self.kit.lib.bk_free_text(self.kit.ctx, C.byref(self.t))
+        self.t.ptr = None
 
     def __del__(self):
         try:
@@ -206,6 +210,19 @@ class BedKit:
     def launches(self) -> int:
         return self.lib.bk_launch_count(self.ctx)
 
+    def profile(self, enable: bool = True):
+        """Enable (and reset) per-kernel CUDA-event timing inside the library."""
+        self._chk(self.lib.bk_profile(self.ctx, int(enable)))
+
+    def profile_query(self, kernel: str):
+        """(total milliseconds, launches) of the named kernel since the last profile() reset."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._chk(self.lib.bk_profile_query(self.ctx, kernel.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def copy(self, dst_ptr: int, src_ptr: int, nbytes: int):
+        self._chk(self.lib.bk_copy(self.ctx, dst_ptr, src_ptr, nbytes))
+
     # ---- reader -----------------------------------------------------------------------------------
     def load(self, text: bytes, min_fields: int = 3, cols: int = 0) -> Bed:
         h = C.c_void_p()
@@ -223,7 +240,12 @@ class BedKit:
         return Bed(self, h, keep)
 
     # ---- tools ------------------------------------------------------------------------------------
-    def _take(self, t: _Text, on_device: bool):
+    def free_text(self, t: _Text):
+        self.lib.bk_free_text(self.ctx, C.byref(t))
+
+    def _take(self, t: _Text, on_device: bool, raw: bool = False):
+        if raw:
+            return t          # caller frees with free_text(); host text stays in the library's pinned buffer
         if on_device:
             return DeviceText(self, t)
         data = C.string_at(t.ptr, t.len) if t.len else b""
@@ -232,7 +254,7 @@ class BedKit:
 
     def bedmap(self, ref: Bed, map_: Optional[Bed], ops: Sequence[str], overlap=("bp", 1), prec: int = 6,
                sci: bool = False, delim: bytes = b"|", multidelim: bytes = b";", skip_unmapped: bool = False,
-               chrom: Optional[bytes] = None, on_device: bool = False):
+               chrom: Optional[bytes] = None, on_device: bool = False, _raw: bool = False):
         spec = _MapSpec()
         self.lib.bk_mapspec_default(C.byref(spec))
         spec.n_ops = len(ops)
@@ -249,7 +271,7 @@ class BedKit:
         spec.out_on_device = int(on_device)
         t = _Text()
         self._chk(self.lib.bk_bedmap(self.ctx, ref.h, map_.h if map_ is not None else None, C.byref(spec), C.byref(t)))
-        return self._take(t, on_device)
+        return self._take(t, on_device, _raw)
 
     def setop(self, op: str, files: Sequence[Bed], thr: float = 1.0, use_pct: bool = True,
               chrom: Optional[bytes] = None, on_device: bool = False):

@@ -73,6 +73,27 @@ void pinned_put(bk_ctx* ctx, char* p) {
     if (b.ptr == p) b.busy = false;
 }
 
+static cudaEvent_t prof_event(bk_ctx* ctx) {
+  if (!ctx->prof_free.empty()) {
+    cudaEvent_t e = ctx->prof_free.back();
+    ctx->prof_free.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(bk_ctx* ctx, const char* name) {
+  if (!ctx->prof_on) return;
+  bk_ctx::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+  cudaEventRecord(r.a, ctx->stream);
+  ctx->prof.push_back(r);
+}
+void prof_end(bk_ctx* ctx) {
+  if (!ctx->prof_on || ctx->prof.empty()) return;
+  cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}
+
 // hand a device result buffer to the caller: either as-is (on_device) or copied into pinned host memory
 int finish_text(bk_ctx* ctx, char* d_out, uint64_t bytes, uint64_t rows, int on_device, bk_text* out) {
   out->len = bytes;
@@ -157,6 +178,11 @@ extern "C" void bk_destroy(bk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->pinned) cudaFreeHost(b.ptr);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto e : ctx->prof_free) cudaEventDestroy(e);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -167,6 +193,43 @@ extern "C" int bk_set_stream(bk_ctx* ctx, void* cuda_stream) {
   if (!ctx) return BK_ERR_ARG;
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return BK_OK;
+}
+
+extern "C" int bk_profile(bk_ctx* ctx, int enable) {
+  if (!ctx) return BK_ERR_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->prof) {
+    ctx->prof_free.push_back(r.a);
+    ctx->prof_free.push_back(r.b);
+  }
+  ctx->prof.clear();
+  ctx->prof_on = enable != 0;
+  return BK_OK;
+}
+
+extern "C" int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches) {
+  if (!ctx || !kernel) return BK_ERR_ARG;
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double   ms = 0;
+  uint64_t n = 0;
+  for (auto& r : ctx->prof) {
+    if (strcmp(r.name, kernel) != 0) continue;
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms += t;
+      n++;
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return BK_OK;
+}
+
+extern "C" int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  if (!ctx) return BK_ERR_ARG;
+  if (nbytes) BK_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, ctx->stream));
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BK_OK;
 }
 
@@ -240,7 +303,7 @@ extern "C" int bk_load_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbyt
 }
 
 extern "C" void bk_free_bed(bk_ctx* ctx, bk_bed* bed) {
-  if (!bed) return;
+  if (!bed || !ctx) return;
   if (bed->owns_text) dfree(ctx, const_cast<char*>(bed->d_text));
   dfree(ctx, bed->start);
   dfree(ctx, bed->end);

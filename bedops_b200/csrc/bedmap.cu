@@ -397,7 +397,9 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   {
     uint64_t blocks = (n + MS_THREADS - 1) / MS_THREADS;
     uint64_t cap = (uint64_t)kSMs * 8 * 4;
+    prof_begin(ctx, "k_map_stats");
     k_map_stats<<<(unsigned)(blocks < cap ? blocks : cap), MS_THREADS, 0, ctx->stream>>>(sp);
+    prof_end(ctx);
     BK_LAUNCHED(ctx);
   }
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host table `tab` must outlive its copy

@@ -39,6 +39,14 @@ struct bk_ctx {
     bool   busy;
   };
   std::vector<Pinned> pinned;
+  // optional per-kernel timing (bk_profile): CUDA event pairs recorded on the launching stream
+  struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  bool                 prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_free;
 };
 
 struct bk_bed {
@@ -84,6 +92,9 @@ void  pinned_put(bk_ctx* ctx, char* p);
     int _rc = (expr);             \
     if (_rc != BK_OK) return _rc; \
   } while (0)
+
+void prof_begin(bk_ctx* ctx, const char* name);
+void prof_end(bk_ctx* ctx);
 
 template <typename T>
 inline T* dalloc(bk_ctx* ctx, size_t n) {

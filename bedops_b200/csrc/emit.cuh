@@ -109,8 +109,10 @@ int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** 
   if (!state) return BK_ERR_NOMEM;
   BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
   BK_TRY(reset_scratch(ctx));
+  prof_begin(ctx, "k_emit");
   k_emit<RowFn><<<grid_for_kernel((const void*)k_emit<RowFn>, E_THREADS, ntiles), E_THREADS, 0, ctx->stream>>>(
       fn, n, *d_out, out_cap, state, ntiles, ctx->d_scratch);
+  prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_TRY(read_scratch(ctx));
   dfree(ctx, state);

@@ -13,12 +13,9 @@
 #include <algorithm>
 #include "common.cuh"
 #include "parse.cuh"
+#include "strtod_exact.cuh"
 
 namespace bk {
-
-// powers of ten exactly representable in double (Clinger fast path)
-__constant__ double kP10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                                1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
 // ---- byte cursor: shared-memory window with a global-memory fallback for lines that leave the window --------
 struct Cursor {
@@ -65,93 +62,6 @@ __device__ __forceinline__ bool parse_u64(const C& c, int64_t& q, uint64_t& v) {
   return true;
 }
 
-// strtod for the decimal literals BED scores use; exact (correctly rounded) whenever it returns 0.
-// Returns BK_ERR_PARSE for "no number", BK_ERR_UNSUPPORTED for literals that need more than the
-// 53-bit x 10^22 exact path (reported, never guessed).
-template <class C>
-__device__ __forceinline__ int parse_f64(const C& c, int64_t& q, double& out) {
-  unsigned char ch = c.at(q);
-  bool          neg = false;
-  if (ch == '+' || ch == '-') {
-    neg = ch == '-';
-    ch = c.at(++q);
-  }
-  uint64_t mant = 0;
-  int      nd = 0, exp10 = 0;
-  bool     any = false, inexact = false;
-  while (ch >= '0' && ch <= '9') {
-    any = true;
-    if (nd < 19) {
-      mant = mant * 10 + (ch - '0');
-      if (mant) nd++;
-    } else {
-      exp10++;
-      inexact |= ch != '0';
-    }
-    ch = c.at(++q);
-  }
-  if (ch == '.') {
-    ch = c.at(++q);
-    while (ch >= '0' && ch <= '9') {
-      any = true;
-      if (nd < 19) {
-        mant = mant * 10 + (ch - '0');
-        if (mant) nd++;
-        exp10--;
-      } else {
-        inexact |= ch != '0';
-      }
-      ch = c.at(++q);
-    }
-  }
-  if (!any) return (ch == 'n' || ch == 'N' || ch == 'i' || ch == 'I') ? BK_ERR_UNSUPPORTED : BK_ERR_PARSE;
-  if (ch == 'e' || ch == 'E') {
-    int64_t       q2 = q + 1;
-    unsigned char c2 = c.at(q2);
-    bool          eneg = false;
-    if (c2 == '+' || c2 == '-') {
-      eneg = c2 == '-';
-      c2 = c.at(++q2);
-    }
-    if (c2 >= '0' && c2 <= '9') {
-      int e = 0;
-      while (c2 >= '0' && c2 <= '9') {
-        if (e < 100000) e = e * 10 + (c2 - '0');
-        c2 = c.at(++q2);
-      }
-      exp10 += eneg ? -e : e;
-      q = q2;
-    }
-  }
-  if (ch == 'x' || ch == 'X') return BK_ERR_UNSUPPORTED;  // hex float
-  double v;
-  if (mant == 0) {
-    v = 0.0;
-  } else {
-    if (inexact) return BK_ERR_UNSUPPORTED;
-    // pull trailing zeros of the mantissa into the exponent so that e.g. 1500000000000000000e-18 stays exact
-    while (mant >= (1ull << 53) && mant % 10 == 0) {
-      mant /= 10;
-      exp10++;
-    }
-    if (mant >= (1ull << 53)) return BK_ERR_UNSUPPORTED;
-    if (exp10 >= 0 && exp10 <= 22) {
-      v = (double)mant * kP10[exp10];
-    } else if (exp10 < 0 && exp10 >= -22) {
-      v = (double)mant / kP10[-exp10];
-    } else if (exp10 > 22 && exp10 <= 22 + 15) {
-      // mant * 10^(exp10-22) may still be exact
-      double m2 = (double)mant * kP10[exp10 - 22];
-      if (m2 > 9007199254740992.0) return BK_ERR_UNSUPPORTED;
-      v = m2 * kP10[22];
-    } else {
-      return BK_ERR_UNSUPPORTED;
-    }
-  }
-  out = neg ? -v : v;
-  return 0;
-}
-
 // tokenise one line starting at window index q0
 template <class C>
 __device__ __forceinline__ void parse_line(const C& c, int64_t q0, int min_fields, unsigned cols, RowOut& r) {
@@ -180,7 +90,7 @@ __device__ __forceinline__ void parse_line(const C& c, int64_t q0, int min_field
       while (is_ws(c.at(q))) q++;
       if (c.at(q) == '\n') { r.err = BK_ERR_PARSE; return; }
       if (cols & BK_COL_SCORE) {
-        int e = parse_f64(c, q, r.score);
+        int e = parse_decimal(c, q, r.score);
         if (e) { r.err = e; return; }
       }
     }
@@ -498,7 +408,9 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     cap = nbytes_raw / 6 + 2;  // shortest legal line "c\t0\t1\n"
   } else {
     uint64_t sample = 16ull << 20;
+    prof_begin(ctx, "k_count_nl");
     k_count_nl<<<(unsigned)(sample / 16 / 256), 256, 0, ctx->stream>>>(text, sample, ctx->d_scratch);
+    prof_end(ctx);
     BK_LAUNCHED(ctx);
     BK_TRY(read_scratch(ctx));
     uint64_t nl = ctx->h_scratch[SC_COUNT_A];
@@ -540,9 +452,13 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     p.tile_state = dalloc<uint64_t>(ctx, p.ntiles);
     if (!p.tile_state) return BK_ERR_NOMEM;
     BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
+    prof_begin(ctx, "k_efflen");
     k_efflen<<<1, 32, 0, ctx->stream>>>(text, nbytes_raw, ctx->d_scratch);
+    prof_end(ctx);
     BK_LAUNCHED(ctx);
+    prof_begin(ctx, "k_parse");
     k_parse<<<grid_for((const void*)k_parse, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p);
+    prof_end(ctx);
     BK_LAUNCHED(ctx);
     BK_TRY(read_scratch(ctx));
     dfree(ctx, p.tile_state);
@@ -614,8 +530,10 @@ int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
   BK_CUDA(ctx, cudaMemcpyAsync(d_rb, rb.data(), nruns * 8, cudaMemcpyHostToDevice, ctx->stream));
   BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
   BK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + SC_TICKET, 0, 8, ctx->stream));
+  prof_begin(ctx, "k_pmax");
   k_pmax<<<grid_for((const void*)k_pmax, PM_THREADS, ntiles), PM_THREADS, 0, ctx->stream>>>(
       bed->end, bed->pmax_end, bed->nrows, d_rb, nruns, state, ntiles, ctx->d_scratch);
+  prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rb (host vector) must outlive the copy
   dfree(ctx, d_rb);

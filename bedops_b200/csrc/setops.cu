@@ -443,7 +443,9 @@ static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in, IvList* out) 
       p.g_begin = d_gb; p.g_end = d_ge; p.g_out = d_go;
       p.outS = mS; p.outE = mE; p.nsel = acc;
       uint64_t blocks = (acc + 255) / 256, cap = (uint64_t)kSMs * 32;
+      prof_begin(ctx, "k_rank_merge");
       k_rank_merge<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+      prof_end(ctx);
       BK_LAUNCHED(ctx);
     }
     BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -470,7 +472,9 @@ static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in, IvList* out) 
   if (!sp.run_begin || !sp.outS || !sp.outE || !sp.run_seg_begin || !sp.tile_state) return BK_ERR_NOMEM;
   BK_CUDA(ctx, cudaMemsetAsync(sp.tile_state, 0, (size_t)sp.ntiles * 8, ctx->stream));
   BK_TRY(reset_scratch(ctx));
+  prof_begin(ctx, "k_segments");
   k_segments<<<grid_for_kernel((const void*)k_segments, SEG_THREADS, sp.ntiles), SEG_THREADS, 0, ctx->stream>>>(sp);
+  prof_end(ctx);
   BK_LAUNCHED(ctx);
   std::vector<uint64_t> rsb(G);
   BK_CUDA(ctx, cudaMemcpyAsync(rsb.data(), sp.run_seg_begin, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -533,7 +537,9 @@ static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList*
     return BK_ERR_NOMEM;
   BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
   BK_TRY(reset_scratch(ctx));
+  prof_begin(ctx, "k_intersect");
   k_intersect<<<grid_for_kernel((const void*)k_intersect, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
+  prof_end(ctx);
   BK_LAUNCHED(ctx);
   std::vector<uint64_t> rob(nruns);
   BK_CUDA(ctx, cudaMemcpyAsync(rob.data(), p.run_out_begin, (size_t)nruns * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -667,7 +673,9 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
     p.run_has_later = upload(ctx, later);
     if (!p.run_ref_begin || !p.run_u_begin || !p.run_u_end || !p.keep || !p.run_has_later) return BK_ERR_NOMEM;
     uint64_t blocks = (n + 255) / 256, cap = (uint64_t)kSMs * 32;
+    prof_begin(ctx, "k_element_of");
     k_element_of<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+    prof_end(ctx);
     BK_LAUNCHED(ctx);
     EchoKeptRow fn{};
     fn.text = ref->d_text; fn.line = ref->line_off; fn.s = ref->start; fn.e = ref->end; fn.keep = p.keep; fn.row0 = row0;

@@ -68,6 +68,14 @@ int         bk_abi_version(void);
 /* number of kernels this ctx has launched since creation (bench.py reports it as gpu_launches) */
 uint64_t    bk_launch_count(const bk_ctx* ctx);
 
+/* per-kernel device timing for bench.py's roofline: enable (and reset) recording of a CUDA event pair around every
+ * kernel launch; query sums the elapsed time of the launches named `kernel` ("k_parse", "k_map_stats", "k_emit", ...)
+ * since the last reset.  Off by default; costs two event records per launch when on. */
+int bk_profile(bk_ctx* ctx, int enable);
+int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
+/* cudaMemcpyAsync(cudaMemcpyDefault) + sync on the ctx stream (bench/test plumbing for device-resident text) */
+int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes);
+
 /* ---- BED reader ------------------------------------------------------------------------------ */
 /* which per-row columns the parser materialises besides start/end */
 enum {
