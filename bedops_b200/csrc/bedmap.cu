@@ -75,52 +75,191 @@ struct MapStatsParams {
 
 constexpr int MS_THREADS = 256;
 
-__global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
-  const uint64_t stride = (uint64_t)gridDim.x * MS_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * MS_THREADS + threadIdx.x; i < p.n; i += stride) {
-    const uint64_t row = p.row0 + i;
-    const uint32_t rs = p.rs[row], re = p.re[row];
-    // chromosome run of this reference row: last run_ref_begin <= row
-    int lo_r = 0, hi_r = p.nruns;
-    while (hi_r - lo_r > 1) {
-      int mid = (lo_r + hi_r) >> 1;
-      if (p.run_ref_begin[mid] <= row) lo_r = mid; else hi_r = mid;
+// First index i in [from, n) with a[i] >= key (n if none); a is non-decreasing and `from` is a lower bound of the
+// answer.  All 32 lanes call it with the same arguments.  Probe 1: 32 consecutive elements (the common case when
+// the answer moved a few rows since the previous reference row).  Probe 2: the last element of each of the next 32
+// blocks of 32 (1024 rows per probe), then one consecutive probe inside the block found.  Far jumps fall back to a
+// binary search.
+__device__ __forceinline__ uint32_t warp_gallop(const uint32_t* __restrict__ a, uint32_t from, uint32_t n, uint32_t key,
+                                                int lane, bool near_first) {
+  if (near_first) {
+    if (from >= n) return n;
+    const uint32_t k = from + lane;
+    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
+    if (m) {
+      const uint32_t r = from + (__ffs(m) - 1);
+      return r < n ? r : n;
     }
-    const uint64_t mb = p.run_map_begin[lo_r], mend = p.run_map_end[lo_r];
-    const uint32_t pad = p.ov.kind == BK_OVR_RANGE ? p.ov.bp : 0;
-    const uint64_t hi = lower_bound_u32(p.ms, mb, mend, (uint64_t)re + pad);
-    const uint64_t lo = rs >= pad ? lower_bound_u32(p.pm, mb, hi, (uint64_t)rs - pad + 1) : mb;
-    uint32_t cnt = 0, idb = 0;
-    uint64_t bases = 0;
-    double   sum = 0.0, vmax = 0.0, vmin = 0.0;
-    for (uint64_t k = lo; k < hi; k++) {
-      const uint32_t ms = __ldg(&p.ms[k]), me = __ldg(&p.me[k]);
-      uint32_t       ov;
-      if (!qualifies(p.ov, rs, re, ms, me, ov)) continue;
-      if (p.need & NEED_BASES) bases += ov;
-      if (p.need & (NEED_SUM | NEED_MAX | NEED_MIN)) {
-        const double v = __ldg(&p.score[k]);
-        sum += v;
-        if (cnt == 0) {
-          vmax = vmin = v;
-        } else {
-          vmax = v > vmax ? v : vmax;
-          vmin = v < vmin ? v : vmin;
+    from += 32;
+  }
+#pragma unroll 1
+  for (int round = 0; round < 2; round++) {
+    if (from >= n) return n;
+    const uint32_t k = from + 32u * lane + 31u;
+    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
+    if (m) {
+      const uint32_t base = from + 32u * (__ffs(m) - 1);
+      const uint32_t k2 = base + lane;
+      const uint32_t v2 = k2 < n ? __ldg(&a[k2]) : 0xFFFFFFFFu;
+      const unsigned m2 = __ballot_sync(0xffffffffu, k2 >= n || v2 >= key);
+      const uint32_t r = base + (__ffs(m2) - 1);
+      return r < n ? r : n;
+    }
+    from += 1024;
+  }
+  uint32_t lo = from, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(&a[mid]) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  const uint64_t r0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), r1 = __reduce_add_sync(0xffffffffu, lo >> 16);
+  const uint64_t r2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), r3 = __reduce_add_sync(0xffffffffu, hi >> 16);
+  return r0 + (r1 << 16) + (r2 << 32) + (r3 << 48);
+}
+
+// One warp per batch of 32 consecutive reference rows.  For each row of the batch (broadcast by shuffle) the 32
+// lanes scan the candidate range [lo,hi) of the map rows of the same chromosome, 32 rows at a time with coalesced
+// loads:  lo = first map row whose running-max end exceeds ref.start (galloped from the previous row's lo, a lower
+// bound because reference rows are sorted by start),  hi = first map row with start >= ref.end (galloped from lo).
+// KIND < 0 selects the generic predicate (runtime overlap kind); FLAGS = NEED_* known at compile time.
+template <int KIND, unsigned FLAGS>
+__global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * MS_THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * MS_THREADS) >> 5;
+  const uint64_t nbatch = (p.n + 31) >> 5;
+  OverlapSpec    ov = p.ov;
+  if (KIND >= 0) ov.kind = KIND;
+  const uint32_t pad = ov.kind == BK_OVR_RANGE ? ov.bp : 0;
+  constexpr bool kScore = (FLAGS & (NEED_SUM | NEED_MAX | NEED_MIN)) != 0;
+  constexpr bool kMinMax = (FLAGS & (NEED_MAX | NEED_MIN)) != 0;
+  for (uint64_t batch = warp0; batch < nbatch; batch += nwarps) {
+    const uint64_t i = (batch << 5) + lane;
+    const bool     valid = i < p.n;
+    const uint64_t row = p.row0 + (valid ? i : p.n - 1);
+    const uint32_t my_rs = p.rs[row], my_re = p.re[row];
+    int my_run = 0;
+    {  // chromosome run of this reference row: last run_ref_begin <= row
+      int hi_r = p.nruns;
+      while (hi_r - my_run > 1) {
+        int mid = (my_run + hi_r) >> 1;
+        if (p.run_ref_begin[mid] <= row) my_run = mid; else hi_r = mid;
+      }
+    }
+    uint32_t out_cnt = 0, out_idb = 0, out_n = 0, out_lo = 0;
+    uint64_t out_bases = 0, out_mb = 0;
+    double   out_sum = 0.0, out_max = 0.0, out_min = 0.0;
+    int      hint_run = -1;
+    uint32_t hint = 0, nr = 0;
+    uint64_t mb = 0;
+    const uint32_t *ms = nullptr, *me = nullptr, *pm = nullptr, *ids = nullptr;
+    const double*   sc = nullptr;
+    const int nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
+#pragma unroll 1
+    for (int j = 0; j < nj; j++) {
+      const uint32_t rs = __shfl_sync(0xffffffffu, my_rs, j), re = __shfl_sync(0xffffffffu, my_re, j);
+      const int      run = __shfl_sync(0xffffffffu, my_run, j);
+      const uint32_t key = rs >= pad ? rs - pad + 1 : 0;  // first pmax_end that reaches the (padded) reference start
+      const bool     fresh = run != hint_run;
+      if (fresh) {
+        mb = p.run_map_begin[run];
+        nr = (uint32_t)(p.run_map_end[run] - mb);
+        ms = p.ms + mb;
+        me = p.me + mb;
+        pm = p.pm + mb;
+        if (kScore) sc = p.score + mb;
+        if (FLAGS & NEED_IDS) ids = p.idspan + mb;
+        hint_run = run;
+        hint = 0;
+      }
+      const uint32_t lo = warp_gallop(pm, hint, nr, key, lane, !fresh);
+      hint = lo;
+      const uint64_t re_pad64 = (uint64_t)re + pad;
+      const uint32_t re_pad = re_pad64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)re_pad64;
+      const uint32_t hi = warp_gallop(ms, lo, nr, re_pad, lane, false);
+      uint32_t cnt = 0, idb = 0;
+      uint64_t bases = 0;
+      double   sum = 0.0, vmax = 0.0, vmin = 0.0;
+      bool     have = false;
+#pragma unroll 1
+      for (uint32_t k = lo + lane; k < hi; k += 32) {
+        const uint32_t s = __ldg(&ms[k]), e = __ldg(&me[k]);
+        uint32_t       ovl;
+        const bool     q = qualifies(ov, rs, re, s, e, ovl);
+        if (q) {
+          cnt++;
+          if (FLAGS & NEED_BASES) bases += ovl;
+          if (kScore) {
+            const double v = __ldg(&sc[k]);
+            sum += v;
+            if (kMinMax) {
+              vmax = have ? (v > vmax ? v : vmax) : v;
+              vmin = have ? (v < vmin ? v : vmin) : v;
+              have = true;
+            }
+          }
+          if (FLAGS & NEED_IDS) idb += __ldg(&ids[k]) & 0xFFFFu;
         }
       }
-      if (p.need & NEED_IDS) idb += (__ldg(&p.idspan[k]) & 0xFFFFu) + (cnt ? p.mdelim_len : 0);
-      cnt++;
+      // warp reductions (fixed order: deterministic)
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (FLAGS & NEED_BASES) bases = warp_sum_u64(bases);
+      if (kScore) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, d);
+          if (kMinMax) {
+            const double omx = __shfl_xor_sync(0xffffffffu, vmax, d);
+            const double omn = __shfl_xor_sync(0xffffffffu, vmin, d);
+            const bool   oh = __shfl_xor_sync(0xffffffffu, (int)have, d);
+            if (oh) {
+              vmax = have ? (omx > vmax ? omx : vmax) : omx;
+              vmin = have ? (omn < vmin ? omn : vmin) : omn;
+              have = true;
+            }
+          }
+        }
+      }
+      if (FLAGS & NEED_IDS) {
+        idb = __reduce_add_sync(0xffffffffu, idb);
+        if (cnt) idb += (cnt - 1) * p.mdelim_len;
+      }
+      if (lane == j) {
+        out_cnt = cnt; out_bases = bases; out_sum = sum; out_max = vmax; out_min = vmin;
+        out_lo = lo; out_mb = mb; out_n = hi - lo; out_idb = idb;
+      }
     }
-    p.count[i] = cnt;
-    if (p.bases) p.bases[i] = bases;
-    if (p.sum) p.sum[i] = sum;
-    if (p.vmax) p.vmax[i] = vmax;
-    if (p.vmin) p.vmin[i] = vmin;
-    if (p.win_lo) {
-      p.win_lo[i] = lo;
-      p.win_n[i] = (uint32_t)(hi - lo);
-      p.idbytes[i] = idb;
+    if (valid) {
+      p.count[i] = out_cnt;
+      if (FLAGS & NEED_BASES) p.bases[i] = out_bases;
+      if (FLAGS & NEED_SUM) p.sum[i] = out_sum;
+      if (FLAGS & NEED_MAX) p.vmax[i] = out_max;
+      if (FLAGS & NEED_MIN) p.vmin[i] = out_min;
+      if (FLAGS & NEED_IDS) {
+        p.win_lo[i] = out_mb + out_lo;
+        p.win_n[i] = out_n;
+        p.idbytes[i] = out_idb;
+      }
     }
+  }
+}
+
+template <int KIND>
+static void launch_map_stats(unsigned need, unsigned blocks, cudaStream_t st, const MapStatsParams& sp) {
+  switch (need & 31u) {
+#define BK_F(F) case F: k_map_stats<KIND, F><<<blocks, MS_THREADS, 0, st>>>(sp); break;
+    BK_F(0) BK_F(1) BK_F(2) BK_F(3) BK_F(4) BK_F(5) BK_F(6) BK_F(7) BK_F(8) BK_F(9) BK_F(10) BK_F(11) BK_F(12) BK_F(13)
+    BK_F(14) BK_F(15) BK_F(16) BK_F(17) BK_F(18) BK_F(19) BK_F(20) BK_F(21) BK_F(22) BK_F(23) BK_F(24) BK_F(25) BK_F(26)
+    BK_F(27) BK_F(28) BK_F(29) BK_F(30) BK_F(31)
+#undef BK_F
   }
 }
 
@@ -395,10 +534,14 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       ((need & NEED_MIN) && !sp.vmin) || ((need & NEED_IDS) && (!sp.win_lo || !sp.win_n || !sp.idbytes)))
     return BK_ERR_NOMEM;
   {
-    uint64_t blocks = (n + MS_THREADS - 1) / MS_THREADS;
-    uint64_t cap = (uint64_t)kSMs * 8 * 4;
+    const uint64_t batches = (n + 31) / 32, per_block = MS_THREADS / 32;
+    uint64_t       blocks = (batches + per_block - 1) / per_block;
+    const uint64_t cap = (uint64_t)kSMs * 8 * 8;  // several resident waves; warps stride over the batches
+    if (blocks > cap) blocks = cap;
     prof_begin(ctx, "k_map_stats");
-    k_map_stats<<<(unsigned)(blocks < cap ? blocks : cap), MS_THREADS, 0, ctx->stream>>>(sp);
+    // the default criterion (--bp-ovr) gets its own instantiation; the other six share the generic predicate
+    if (ov.kind == BK_OVR_BP) launch_map_stats<BK_OVR_BP>(need, (unsigned)blocks, ctx->stream, sp);
+    else launch_map_stats<-1>(need, (unsigned)blocks, ctx->stream, sp);
     prof_end(ctx);
     BK_LAUNCHED(ctx);
   }

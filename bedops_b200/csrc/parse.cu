@@ -121,9 +121,80 @@ __device__ int64_t prev_line_token(const Cursor& c, int64_t p0) {
   }
 }
 
+// ---- fast path helpers: control-byte bitmask + SWAR digit conversion -------------------------------------------
+// ctlp: one bit per text byte, set iff the byte is < 0x21 (TAB, NL, CR, space, ...).  Canonical BED has exactly one
+// such byte after every field, so the set bits of the 64-bit window that starts at a line start ARE the field
+// boundaries; reading the byte found tells TAB from NL from anything that sends the line to the general tokeniser.
+constexpr int P_NW = (P_TILE + P_POST) / 32;  // mask words; word w covers window bytes [P_PRE+32w, P_PRE+32w+32)
+constexpr int P_RCAP = 1408;                  // rows staged per tile (>= P_TILE / 6, the shortest legal line)
+
+__device__ __forceinline__ uint32_t ctl_mask4(uint32_t w) {  // bit 8j+7 set iff byte j < 0x21
+  return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t nl_mask4(uint32_t w, uint32_t ctl) {  // bytes == '\n' (given the ctl mask)
+  return ~(((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & ctl;
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t m) {  // bits 7,15,23,31 -> bits 0..3
+  return ((m >> 7) * 0x01020408u) >> 24;
+}
+
+// unaligned 32-bit read of window bytes [x, x+4)
+__device__ __forceinline__ uint32_t ld32u(const unsigned char* sm, int x) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(sm) + (x >> 2);
+  return __funnelshift_r(w[0], w[1], (x & 3) * 8);
+}
+
+// four ASCII digits (first digit in the lowest byte) -> 0..9999; bad accumulates a non-zero value on a non-digit
+__device__ __forceinline__ uint32_t digits4(uint32_t w, uint32_t& bad) {
+  const uint32_t t = w - 0x30303030u;
+  bad |= ((w + 0x46464646u) | t) & 0x80808080u;
+  const uint32_t u = t * 10u + (t >> 8);
+  return (u & 0xFFu) * 100u + ((u >> 16) & 0xFFu);
+}
+
+// decimal field of len digits (1..9) that ENDS at window byte index e (exclusive) -> value
+__device__ __forceinline__ uint32_t parse_digits_swar(const unsigned char* sm, int e, int len, uint32_t& bad) {
+  uint32_t g0 = ld32u(sm, e - 4), g1 = ld32u(sm, e - 8);
+  // bytes in front of the field (the lower bytes) are replaced by '0':  keep the top min(len,4) bytes of g0 and
+  // the top clamp(len-4,0,4) bytes of g1
+  const uint32_t m0 = len >= 4 ? 0u : (0xFFFFFFFFu >> (8 * len));
+  const uint32_t m1 = len >= 8 ? 0u : (len <= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (len - 4))));
+  g0 = (g0 & ~m0) | (0x30303030u & m0);
+  g1 = (g1 & ~m1) | (0x30303030u & m1);
+  uint32_t v = digits4(g1, bad) * 10000u + digits4(g0, bad);
+  if (len == 9) {
+    const uint32_t d = (uint32_t)sm[e - 9] - '0';
+    bad |= d > 9 ? 1u : 0u;
+    v += d * 100000000u;
+  }
+  return v;
+}
+
+// first 8 bytes of a token of length len (>= 1) at window index x, bytes beyond the token zeroed
+__device__ __forceinline__ uint2 token8(const unsigned char* sm, int x, int len) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(sm) + (x >> 2);
+  const int       sh = (x & 3) * 8;
+  uint32_t        lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);
+  if (len < 4) {
+    lo &= (1u << (8 * len)) - 1u;
+    hi = 0;
+  } else if (len < 8) {
+    hi &= (1u << (8 * (len - 4))) - 1u;  // len == 4 -> 0
+  }
+  return make_uint2(lo, hi);
+}
+
+// NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
+template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
-  __shared__ __align__(16) unsigned char sm[P_BUF];
-  __shared__ uint16_t                    lstart[P_MAXROWS];
+  __shared__ __align__(16) unsigned char sm[P_BUF + 16];
+  __shared__ uint32_t                    ctlp[P_NW + 4];
+  __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
+  __shared__ uint32_t                    s_start[P_RCAP], s_end[P_RCAP];
+  __shared__ uint32_t                    s_id[NSEP >= 4 ? P_RCAP : 1];
+  __shared__ double                      s_score[WANT_SCORE ? P_RCAP : 1];
+  __shared__ uint16_t                    s_tok0[P_RCAP];
+  __shared__ uint8_t                     s_toklen[P_RCAP];  // 0xFF = the line failed to parse (code in s_start)
   __shared__ uint32_t                    scan_sm[34];
   __shared__ uint32_t                    ticket_sm;
   __shared__ uint64_t                    base_sm;
@@ -160,82 +231,214 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
     }
     __syncthreads();
 
-    // ---- line starts: position q starts a line iff q == 0 or byte q-1 is '\n' -----------------------------
-    Cursor cur{sm, g0, text, eff};
-    const int      off = P_PRE + tid * 32;
-    const uint32_t* wv = reinterpret_cast<const uint32_t*>(sm + off);
-    uint32_t       nl = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      uint32_t m = __vcmpeq4(wv[w], 0x0A0A0A0Au) & 0x01010101u;
-      nl |= ((m * 0x01020408u) >> 24) << (4 * w);
-    }
+    // ---- control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' -----------
+    Cursor        cur{sm, g0, text, eff};
+    const int     off = P_PRE + tid * 32;
     const int64_t p0 = ts + tid * 32;  // global offset of this thread's first byte
-    uint32_t      prevnl = (p0 == 0) ? 1u : (sm[off - 1] == '\n');
-    uint32_t      smask = (nl << 1) | prevnl;
-    if ((uint64_t)p0 >= eff) smask = 0;
-    else if ((uint64_t)p0 + 32 > eff) smask &= (1u << (int)(eff - (uint64_t)p0)) - 1u;
-    // drop blank lines (fscanf's %s skips them: whitespace, including '\n', is not a record)
-    for (uint32_t m = smask; m; m &= m - 1) {
-      int     j = __ffs(m) - 1;
-      int64_t q = off + j;
+    uint32_t      smask = 0;           // packed line-start mask of this thread's 32 bytes
+    uint32_t      cm = 0;              // packed control-byte mask of this thread's 32 bytes
+    {
+      const uint4* v4 = reinterpret_cast<const uint4*>(sm + off);
+      const uint4  a = v4[0], c = v4[1];
+      const uint32_t w8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      uint32_t nlp = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const uint32_t ctl = ctl_mask4(w8[i]);
+        cm |= pack4(ctl) << (4 * i);
+        nlp |= pack4(nl_mask4(w8[i], ctl)) << (4 * i);
+      }
+      smask = (nlp << 1) | ((p0 == 0 || sm[off - 1] == '\n') ? 1u : 0u);  // a line starts after every NL
+      ctlp[tid] = cm;
+      nlw[P_PRE / 32 + tid] = nlp;
+      if (tid >= 32 && tid < 32 + P_PRE / 32) {  // head halo: NL mask only (previous line of the tile's first row)
+        const uint4* h4 = reinterpret_cast<const uint4*>(sm + (tid - 32) * 32);
+        const uint4  ha = h4[0], hc = h4[1];
+        const uint32_t h8[8] = {ha.x, ha.y, ha.z, ha.w, hc.x, hc.y, hc.z, hc.w};
+        uint32_t     hm = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) hm |= pack4(nl_mask4(h8[i], ctl_mask4(h8[i]))) << (4 * i);
+        nlw[tid - 32] = hm;
+      }
+      if (tid < P_POST / 32) {  // tail halo
+        const uint4* t4 = reinterpret_cast<const uint4*>(sm + P_PRE + P_TILE + tid * 32);
+        const uint4  ta = t4[0], tc = t4[1];
+        const uint32_t t8[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
+        uint32_t     tm = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tm |= pack4(ctl_mask4(t8[i])) << (4 * i);
+        ctlp[P_TILE / 32 + tid] = tm;
+      } else if (tid < P_POST / 32 + 4) {
+        ctlp[P_TILE / 32 + tid] = 0;  // padding words read by the 64-bit line windows
+      }
+    }
+    if ((uint64_t)p0 + 32 > eff)  // clip to the effective text length (last tile only)
+      smask = (uint64_t)p0 >= eff ? 0u : (smask & ((1u << (int)(eff - (uint64_t)p0)) - 1u));
+    // drop blank lines (fscanf's %s skips them: whitespace, including '\n', is not a record); only a line that
+    // begins with a control byte can be blank
+    for (uint32_t m = smask & cm; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      int64_t   q = off + j;
       while (is_ws(cur.at(q))) q++;
       if (cur.at(q) == '\n') smask &= ~(1u << j);
     }
-    uint32_t cnt = __popc(smask), nrow;
+    const uint32_t cnt = __popc(smask);
+    uint32_t nrow;
     uint32_t ex = block_excl_scan(cnt, scan_sm, &nrow);
-    for (uint32_t m = smask; m; m &= m - 1) lstart[ex++] = (uint16_t)(off + __ffs(m) - 1);
 
-    // ---- global row index of the tile's first row -----------------------------------------------------------
+    // ---- global row index of the tile's first row: warp 0 resolves the look-back while warps 1..7 parse ---------
     if (tid < 32) {
       uint64_t b = lookback_sum(p.tile_state, tile, nrow);
       if (tid == 0) base_sm = b;
     }
+
+    // ---- every thread parses the lines that START in its 32 bytes into the shared staging rows ---------------
+    {
+#pragma unroll 1
+      for (uint32_t m = smask; m; m &= m - 1) {
+        const uint32_t k = ex++;
+        if (k >= P_RCAP) continue;  // more rows than a tile of legal lines can hold: reported below
+        const int q0 = off + __ffs(m) - 1;
+        // 64 line bytes of control-byte mask, starting at the line start
+        const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
+        const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
+        unsigned long long W = ((unsigned long long)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
+        int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
+        bool fast = true;
+#pragma unroll
+        for (int f = 0; f < NSEP; f++) {
+          fast = fast && W != 0;
+          sp[f] = __ffsll((long long)W) - 1;
+          W &= W - 1;
+        }
+        uint32_t v_start = 0, v_end = 0, v_id = 0, bad = 0;
+        double   v_score = 0.0;
+        int      tok0 = q0, toklen = 0;
+        if (fast) {
+          // every separator but the last must be a TAB, the last a TAB or the NL
+#pragma unroll
+          for (int f = 0; f < NSEP; f++) {
+            const unsigned char c = sm[q0 + sp[f]];
+            bad |= (c == '\t' || (f + 1 == NSEP && c == '\n')) ? 0u : 1u;
+          }
+          toklen = sp[0];
+          const int l1 = sp[1] - sp[0] - 1, l2 = sp[2] - sp[1] - 1;
+          bad |= (toklen < 1 || toklen > 127 || l1 < 1 || l1 > 9 || l2 < 1 || l2 > 9) ? 1u : 0u;
+          if (!bad) {
+            v_start = parse_digits_swar(sm, q0 + sp[1], l1, bad);
+            v_end = parse_digits_swar(sm, q0 + sp[2], l2, bad);
+          }
+          if (NSEP >= 4) {
+            const int idlen = sp[NSEP >= 4 ? 3 : 0] - sp[2] - 1;
+            bad |= (idlen < 1 || idlen > 16383) ? 1u : 0u;
+            v_id = ((uint32_t)(sp[2] + 1) << 16) | (uint32_t)idlen;
+          }
+          if (NSEP >= 5) {
+            const int s3 = sp[NSEP >= 5 ? 3 : 0], s4 = sp[NSEP >= 5 ? 4 : 0];
+            const int l4 = s4 - s3 - 1;
+            bad |= l4 < 1 ? 1u : 0u;
+            if (WANT_SCORE && !bad) {
+              uint32_t sbad = l4 > 9 ? 1u : 0u;
+              if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
+              if (sbad) {  // not a short unsigned integer: exact strtod on the field
+                SmCursor sc{sm};
+                int64_t  q = q0 + s3 + 1;
+                bad |= parse_decimal(sc, q, v_score) != 0 ? 1u : 0u;
+              }
+            }
+          }
+          fast = bad == 0;
+        }
+        if (!fast) {  // general path: fscanf-equivalent tokeniser
+          RowOut r;
+          parse_line(cur, q0, p.min_fields, p.cols, r);
+          if (r.err) {
+            s_toklen[k] = 0xFF;
+            s_start[k] = (uint32_t)r.err;
+            continue;
+          }
+          v_start = (uint32_t)r.start;
+          v_end = (uint32_t)r.end;
+          v_score = r.score;
+          v_id = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
+          tok0 = (int)r.tok0;
+          toklen = r.toklen;
+        }
+        s_start[k] = v_start;
+        s_end[k] = v_end;
+        if (NSEP >= 4) s_id[NSEP >= 4 ? k : 0] = v_id;
+        if (WANT_SCORE) s_score[WANT_SCORE ? k : 0] = v_score;
+        s_tok0[k] = (uint16_t)tok0;
+        s_toklen[k] = (uint8_t)toklen;
+      }
+    }
     __syncthreads();
     const uint64_t base = base_sm;
 
-    // ---- one thread per line -----------------------------------------------------------------------------
-    for (uint32_t k = tid; k < nrow; k += P_THREADS) {
-      const int64_t q0 = lstart[k];
-      RowOut        r;
-      bool          head;
-      if (k + 1 < nrow) {  // line ends before the next line start: entirely inside the window
-        SmCursor sc{sm};
-        parse_line(sc, q0, p.min_fields, p.cols, r);
-      } else {
-        parse_line(cur, q0, p.min_fields, p.cols, r);
-      }
-      const uint64_t row = base + k;
-      if (r.err) {
-        dev_set_error(p.scratch, r.err, row);
+    // ---- copy-out in row order (coalesced) + chromosome run heads ---------------------------------------------
+    const uint32_t nst = nrow < P_RCAP ? nrow : P_RCAP;
+    for (uint32_t r = tid; r < nst; r += P_THREADS) {
+      const uint64_t row = base + r;
+      const int      len = s_toklen[r];
+      if (len == 0xFF) {
+        dev_set_error(p.scratch, (int)s_start[r], row);
         continue;
       }
-      if (k > 0) {  // line k-1 lies wholly inside the window
-        int64_t pq = lstart[k - 1];
-        while (is_ws(sm[pq])) pq++;
-        head = !same_token(cur, r.tok0, r.toklen, pq);
+      const int tok0 = s_tok0[r];
+      bool      head;
+      if (r > 0 && s_toklen[r - 1] != 0xFF) {
+        const int plen = s_toklen[r - 1], ptok = s_tok0[r - 1];
+        if (plen != len) {
+          head = true;
+        } else if (len <= 8) {
+          const uint2 a = token8(sm, tok0, len), c = token8(sm, ptok, len);
+          head = a.x != c.x || a.y != c.y;
+        } else {
+          head = !same_token(cur, tok0, len, ptok);
+        }
       } else {
-        int64_t pq = prev_line_token(cur, q0);
-        head = (pq == INT64_MIN) || !same_token(cur, r.tok0, r.toklen, pq);
+        // first row of the tile: the previous line ends at the NL just before this line's start; find the NL before
+        // that one in the window's NL mask, compare the token that follows it
+        bool done = false;
+        const int q0 = tok0;  // a canonical line starts with its token; anything else takes the general path
+        if (len <= 8 && q0 >= 2 && q0 < P_PRE + P_TILE && sm[q0 - 1] == '\n' && g0 + q0 >= 2) {
+          const int x = q0 - 2;
+          int       w = x >> 5;
+          uint32_t  m = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
+          while (!m && w > 0) m = nlw[--w];
+          if (m) {
+            const int ps = 32 * w + 32 - __clz(m);  // first byte after that NL
+            if (ps + len < q0 && sm[ps] > 0x20) {
+              const uint2 a = token8(sm, tok0, len), c = token8(sm, ps, len);
+              head = a.x != c.x || a.y != c.y || sm[ps + len] > 0x20;
+              done = true;
+            }
+          }
+        }
+        if (!done) {
+          int64_t pt = prev_line_token(cur, tok0);
+          head = (pt == INT64_MIN) || !same_token(cur, tok0, len, pt);
+        }
       }
       if (head) {
         uint32_t h = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_NHEADS]), 1ull);
         if (h < p.heads_cap) {
           HeadRec* hr = &p.heads[h];
           hr->row = row;
-          hr->len = r.toklen;
-          for (int i = 0; i < r.toklen; i++) hr->name[i] = cur.at(r.tok0 + i);
-          hr->name[r.toklen] = 0;
+          hr->len = len;
+          for (int i = 0; i < len; i++) hr->name[i] = cur.at(tok0 + i);
+          hr->name[len] = 0;
         }
       }
       if (row < p.cap) {
-        p.start[row] = (uint32_t)r.start;
-        p.end[row] = (uint32_t)r.end;
-        if (p.score) p.score[row] = r.score;
-        if (p.line_off) p.line_off[row] = (uint64_t)(g0 + r.tok0);
-        if (p.idspan) p.idspan[row] = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
+        p.start[row] = s_start[r];
+        p.end[row] = s_end[r];
+        if (WANT_SCORE) p.score[row] = s_score[WANT_SCORE ? r : 0];
+        if (p.line_off) p.line_off[row] = (uint64_t)(g0 + tok0);
+        if (NSEP >= 4 && p.idspan) p.idspan[row] = s_id[NSEP >= 4 ? r : 0];
       }
     }
+    if (nrow > P_RCAP && tid == 0) dev_set_error(p.scratch, BK_ERR_PARSE, base + P_RCAP);
     if (tile == p.ntiles - 1 && tid == 0) p.scratch[SC_NROWS] = base + nrow;
     __syncthreads();
   }
@@ -457,7 +660,15 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     prof_end(ctx);
     BK_LAUNCHED(ctx);
     prof_begin(ctx, "k_parse");
-    k_parse<<<grid_for((const void*)k_parse, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p);
+    {
+      const bool sc = (p.cols & BK_COL_SCORE) != 0;
+#define BK_PARSE(N, S) k_parse<N, S><<<grid_for((const void*)k_parse<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p)
+      if (p.min_fields == 3) BK_PARSE(3, false);
+      else if (p.min_fields == 4) BK_PARSE(4, false);
+      else if (sc) BK_PARSE(5, true);
+      else BK_PARSE(5, false);
+#undef BK_PARSE
+    }
     prof_end(ctx);
     BK_LAUNCHED(ctx);
     BK_TRY(read_scratch(ctx));

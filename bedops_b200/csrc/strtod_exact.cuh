@@ -48,6 +48,12 @@ BK_FN double bits_to_double(uint64_t b) {
 #endif
 }
 
+#ifdef __CUDACC__
+__device__
+#endif
+static const double kPow10d[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
 // Eisel-Lemire: w * 10^q -> IEEE bits.  Returns false when the algorithm cannot decide (caller refuses).
 BK_FN bool eisel_lemire(uint64_t w, int q, uint64_t& bits) {
   if (w == 0 || q < -342) {
@@ -114,8 +120,7 @@ BK_FN int decimal_to_double(uint64_t mant, int exp10, bool truncated, double& ou
     return 0;
   }
   if (!truncated && mant < (1ull << 53)) {  // Clinger
-    const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
-                            1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const double* p10 = kPow10d;
     if (exp10 >= 0 && exp10 <= 22) {
       out = (double)mant * p10[exp10];
       return 0;
