@@ -153,6 +153,7 @@ extern "C" int bk_init(bk_ctx** out, int device) {
   if (cudaSetDevice(device) != cudaSuccess) return BK_ERR_CUDA;
   bk_ctx* ctx = new bk_ctx();
   ctx->device = device;
+  ctx->sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kSMs;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return BK_ERR_CUDA;

@@ -25,6 +25,7 @@ struct ChromRun {
 
 struct bk_ctx {
   int          device = 0;
+  int          sms = 148;  // multiProcessorCount of the device (148 on B200)
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string  last_error;

@@ -185,27 +185,27 @@ __device__ __forceinline__ uint2 token8(const unsigned char* sm, int x, int len)
 }
 
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
+//
+// Per tile: (1) stage the text, (2) every thread builds the control-byte / NL bitmasks of its 32 bytes and counts the
+// lines that START there, (3) block scan -> local row index, warp 0 resolves the look-back (global row index of the
+// tile) while warps 1..7 already parse, (4) every thread parses ITS lines and writes the SoA columns directly (the
+// lanes of a warp hold consecutive rows, so the stores coalesce).  Three block barriers per tile.
 template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
   __shared__ __align__(16) unsigned char sm[P_BUF + 16];
   __shared__ uint32_t                    ctlp[P_NW + 4];
   __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
-  __shared__ uint32_t                    s_start[P_RCAP], s_end[P_RCAP];
-  __shared__ uint32_t                    s_id[NSEP >= 4 ? P_RCAP : 1];
-  __shared__ double                      s_score[WANT_SCORE ? P_RCAP : 1];
-  __shared__ uint16_t                    s_tok0[P_RCAP];
-  __shared__ uint8_t                     s_toklen[P_RCAP];  // 0xFF = the line failed to parse (code in s_start)
-  __shared__ uint32_t                    scan_sm[34];
-  __shared__ uint32_t                    ticket_sm;
+  __shared__ uint32_t                    wsum[P_THREADS / 32];
   __shared__ uint64_t                    base_sm;
 
-  const int      tid = threadIdx.x;
+  const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t eff = p.scratch[SC_EFFLEN];  // bytes up to and including the last '\n'
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
 
-  while (true) {
-    const uint32_t tile = next_ticket(p.scratch, &ticket_sm);
-    if (tile >= p.ntiles) break;
+  // Tiles are dealt round-robin to a grid that is launched cooperatively (every CTA resident), so that the tiles of
+  // one "wave" start together: a tile's predecessors publish their row counts at about the same moment it needs
+  // them, and the look-back chain never waits for a CTA that has not been scheduled.
+  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int64_t ts = (int64_t)tile * P_TILE;
     const int64_t g0 = ts - P_PRE;
 
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
       }
       reinterpret_cast<uint4*>(sm)[v] = w;
     }
-    __syncthreads();
+    __syncthreads();  // [S1] text staged
 
     // ---- control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' -----------
     Cursor        cur{sm, g0, text, eff};
@@ -283,164 +283,159 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
       if (cur.at(q) == '\n') smask &= ~(1u << j);
     }
     const uint32_t cnt = __popc(smask);
-    uint32_t nrow;
-    uint32_t ex = block_excl_scan(cnt, scan_sm, &nrow);
+    const uint32_t incl = warp_incl_scan(cnt);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();  // [S2] masks and warp totals visible
+    uint32_t ex = incl - cnt, nrow = 0;
+#pragma unroll
+    for (int v = 0; v < P_THREADS / 32; v++) {
+      const uint32_t t = wsum[v];
+      if (v < warp) ex += t;
+      nrow += t;
+    }
 
     // ---- global row index of the tile's first row: warp 0 resolves the look-back while warps 1..7 parse ---------
-    if (tid < 32) {
-      uint64_t b = lookback_sum(p.tile_state, tile, nrow);
-      if (tid == 0) base_sm = b;
+    if (warp == 0) {
+      const uint64_t b = lookback_sum(p.tile_state, tile, nrow);
+      if (lane == 0) {
+        base_sm = b;
+        if (tile == p.ntiles - 1) p.scratch[SC_NROWS] = b + nrow;
+      }
+      __threadfence_block();
+      asm volatile("bar.arrive 1, %0;" ::"n"(P_THREADS) : "memory");  // releases warps 1..7 waiting below
     }
 
-    // ---- every thread parses the lines that START in its 32 bytes into the shared staging rows ---------------
-    {
+    // ---- every thread parses the lines that START in its 32 bytes ---------------------------------------------
+    // The loop is warp-uniform: lanes without a (further) line idle.  In the first round warps 1..7 block on named
+    // barrier 1 (no issue slots burnt) until warp 0 has published the tile's first row index.
+    uint64_t base = 0;
+    uint32_t m = smask;
 #pragma unroll 1
-      for (uint32_t m = smask; m; m &= m - 1) {
-        const uint32_t k = ex++;
-        if (k >= P_RCAP) continue;  // more rows than a tile of legal lines can hold: reported below
-        const int q0 = off + __ffs(m) - 1;
-        // 64 line bytes of control-byte mask, starting at the line start
-        const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
-        const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
-        unsigned long long W = ((unsigned long long)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
-        int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
-        bool fast = true;
+    for (int round = 0; round == 0 || __any_sync(0xffffffffu, m != 0); round++) {
+      const bool     has = m != 0;
+      const uint32_t k = ex;
+      const int      q0 = has ? off + __ffs(m) - 1 : off;
+      if (has) {
+        ex++;
+        m &= m - 1;
+      }
+      uint32_t v_start = 0, v_end = 0, v_id = 0;
+      double   v_score = 0.0;
+      int      tok0 = q0, toklen = 0, err = 0;
+      bool     head = false;
+      if (has) {
+      // 64 line bytes of control-byte mask, starting at the line start
+      const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
+      const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
+      unsigned long long W = ((unsigned long long)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
+      int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
+      bool fast = true;
+#pragma unroll
+      for (int f = 0; f < NSEP; f++) {
+        fast = fast && W != 0;
+        sp[f] = __ffsll((long long)W) - 1;
+        W &= W - 1;
+      }
+      uint32_t bad = 0;
+      if (fast) {
+        // every separator but the last must be a TAB, the last a TAB or the NL
 #pragma unroll
         for (int f = 0; f < NSEP; f++) {
-          fast = fast && W != 0;
-          sp[f] = __ffsll((long long)W) - 1;
-          W &= W - 1;
+          const unsigned char c = sm[q0 + sp[f]];
+          bad |= (c == '\t' || (f + 1 == NSEP && c == '\n')) ? 0u : 1u;
         }
-        uint32_t v_start = 0, v_end = 0, v_id = 0, bad = 0;
-        double   v_score = 0.0;
-        int      tok0 = q0, toklen = 0;
-        if (fast) {
-          // every separator but the last must be a TAB, the last a TAB or the NL
-#pragma unroll
-          for (int f = 0; f < NSEP; f++) {
-            const unsigned char c = sm[q0 + sp[f]];
-            bad |= (c == '\t' || (f + 1 == NSEP && c == '\n')) ? 0u : 1u;
-          }
-          toklen = sp[0];
-          const int l1 = sp[1] - sp[0] - 1, l2 = sp[2] - sp[1] - 1;
-          bad |= (toklen < 1 || toklen > 127 || l1 < 1 || l1 > 9 || l2 < 1 || l2 > 9) ? 1u : 0u;
-          if (!bad) {
-            v_start = parse_digits_swar(sm, q0 + sp[1], l1, bad);
-            v_end = parse_digits_swar(sm, q0 + sp[2], l2, bad);
-          }
-          if (NSEP >= 4) {
-            const int idlen = sp[NSEP >= 4 ? 3 : 0] - sp[2] - 1;
-            bad |= (idlen < 1 || idlen > 16383) ? 1u : 0u;
-            v_id = ((uint32_t)(sp[2] + 1) << 16) | (uint32_t)idlen;
-          }
-          if (NSEP >= 5) {
-            const int s3 = sp[NSEP >= 5 ? 3 : 0], s4 = sp[NSEP >= 5 ? 4 : 0];
-            const int l4 = s4 - s3 - 1;
-            bad |= l4 < 1 ? 1u : 0u;
-            if (WANT_SCORE && !bad) {
-              uint32_t sbad = l4 > 9 ? 1u : 0u;
-              if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
-              if (sbad) {  // not a short unsigned integer: exact strtod on the field
-                SmCursor sc{sm};
-                int64_t  q = q0 + s3 + 1;
-                bad |= parse_decimal(sc, q, v_score) != 0 ? 1u : 0u;
-              }
+        toklen = sp[0];
+        const int l1 = sp[1] - sp[0] - 1, l2 = sp[2] - sp[1] - 1;
+        bad |= (toklen < 1 || toklen > 127 || l1 < 1 || l1 > 9 || l2 < 1 || l2 > 9) ? 1u : 0u;
+        if (!bad) {
+          v_start = parse_digits_swar(sm, q0 + sp[1], l1, bad);
+          v_end = parse_digits_swar(sm, q0 + sp[2], l2, bad);
+        }
+        if (NSEP >= 4) {
+          const int idlen = sp[NSEP >= 4 ? 3 : 0] - sp[2] - 1;
+          bad |= (idlen < 1 || idlen > 16383) ? 1u : 0u;
+          v_id = ((uint32_t)(sp[2] + 1) << 16) | (uint32_t)idlen;
+        }
+        if (NSEP >= 5) {
+          const int s3 = sp[NSEP >= 5 ? 3 : 0], s4 = sp[NSEP >= 5 ? 4 : 0];
+          const int l4 = s4 - s3 - 1;
+          bad |= l4 < 1 ? 1u : 0u;
+          if (WANT_SCORE && !bad) {
+            uint32_t sbad = l4 > 9 ? 1u : 0u;
+            if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
+            if (sbad) {  // not a short unsigned integer: exact strtod on the field
+              SmCursor sc{sm};
+              int64_t  q = q0 + s3 + 1;
+              bad |= parse_decimal(sc, q, v_score) != 0 ? 1u : 0u;
             }
           }
-          fast = bad == 0;
         }
-        if (!fast) {  // general path: fscanf-equivalent tokeniser
-          RowOut r;
-          parse_line(cur, q0, p.min_fields, p.cols, r);
-          if (r.err) {
-            s_toklen[k] = 0xFF;
-            s_start[k] = (uint32_t)r.err;
-            continue;
-          }
-          v_start = (uint32_t)r.start;
-          v_end = (uint32_t)r.end;
-          v_score = r.score;
-          v_id = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
-          tok0 = (int)r.tok0;
-          toklen = r.toklen;
-        }
-        s_start[k] = v_start;
-        s_end[k] = v_end;
-        if (NSEP >= 4) s_id[NSEP >= 4 ? k : 0] = v_id;
-        if (WANT_SCORE) s_score[WANT_SCORE ? k : 0] = v_score;
-        s_tok0[k] = (uint16_t)tok0;
-        s_toklen[k] = (uint8_t)toklen;
+        fast = bad == 0;
       }
-    }
-    __syncthreads();
-    const uint64_t base = base_sm;
-
-    // ---- copy-out in row order (coalesced) + chromosome run heads ---------------------------------------------
-    const uint32_t nst = nrow < P_RCAP ? nrow : P_RCAP;
-    for (uint32_t r = tid; r < nst; r += P_THREADS) {
-      const uint64_t row = base + r;
-      const int      len = s_toklen[r];
-      if (len == 0xFF) {
-        dev_set_error(p.scratch, (int)s_start[r], row);
-        continue;
+      if (!fast) {  // general path: fscanf-equivalent tokeniser
+        RowOut r;
+        parse_line(cur, q0, p.min_fields, p.cols, r);
+        err = r.err;
+        v_start = (uint32_t)r.start;
+        v_end = (uint32_t)r.end;
+        v_score = r.score;
+        v_id = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
+        tok0 = (int)r.tok0;
+        toklen = r.toklen;
       }
-      const int tok0 = s_tok0[r];
-      bool      head;
-      if (r > 0 && s_toklen[r - 1] != 0xFF) {
-        const int plen = s_toklen[r - 1], ptok = s_tok0[r - 1];
-        if (plen != len) {
-          head = true;
-        } else if (len <= 8) {
-          const uint2 a = token8(sm, tok0, len), c = token8(sm, ptok, len);
-          head = a.x != c.x || a.y != c.y;
-        } else {
-          head = !same_token(cur, tok0, len, ptok);
-        }
-      } else {
-        // first row of the tile: the previous line ends at the NL just before this line's start; find the NL before
-        // that one in the window's NL mask, compare the token that follows it
+      // chromosome run head?  the previous line ends at the NL just before this line's start; the NL before that one
+      // (found in the window's NL mask) is where the previous line starts
+      if (!err) {
         bool done = false;
-        const int q0 = tok0;  // a canonical line starts with its token; anything else takes the general path
-        if (len <= 8 && q0 >= 2 && q0 < P_PRE + P_TILE && sm[q0 - 1] == '\n' && g0 + q0 >= 2) {
+        if (toklen <= 8 && tok0 == q0 && q0 >= 2 && g0 + q0 >= 2) {
           const int x = q0 - 2;
           int       w = x >> 5;
-          uint32_t  m = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
-          while (!m && w > 0) m = nlw[--w];
-          if (m) {
-            const int ps = 32 * w + 32 - __clz(m);  // first byte after that NL
-            if (ps + len < q0 && sm[ps] > 0x20) {
-              const uint2 a = token8(sm, tok0, len), c = token8(sm, ps, len);
-              head = a.x != c.x || a.y != c.y || sm[ps + len] > 0x20;
-              done = true;
-            }
+          uint32_t  pm = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
+          while (!pm && w > 0) pm = nlw[--w];
+          int ps = -1;
+          if (pm) ps = 32 * w + 32 - __clz(pm);   // first byte after that NL
+          else if (g0 <= 0) ps = (int)(-g0);      // the previous line is the first line of the file
+          if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
+            const uint2 a = token8(sm, tok0, toklen), c = token8(sm, ps, toklen);
+            head = a.x != c.x || a.y != c.y || sm[ps + toklen] > 0x20;
+            done = true;
           }
         }
         if (!done) {
-          int64_t pt = prev_line_token(cur, tok0);
-          head = (pt == INT64_MIN) || !same_token(cur, tok0, len, pt);
+          int64_t pt = prev_line_token(cur, q0);
+          head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
         }
+      }
+      }  // has
+      if (round == 0) {
+        if (warp != 0) asm volatile("bar.sync 1, %0;" ::"n"(P_THREADS) : "memory");
+        base = *reinterpret_cast<volatile uint64_t*>(&base_sm);
+      }
+      if (!has) continue;
+      const uint64_t row = base + k;
+      if (err) {
+        dev_set_error(p.scratch, err, row);
+        continue;
       }
       if (head) {
         uint32_t h = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_NHEADS]), 1ull);
         if (h < p.heads_cap) {
           HeadRec* hr = &p.heads[h];
           hr->row = row;
-          hr->len = len;
-          for (int i = 0; i < len; i++) hr->name[i] = cur.at(tok0 + i);
-          hr->name[len] = 0;
+          hr->len = toklen;
+          for (int i = 0; i < toklen; i++) hr->name[i] = cur.at(tok0 + i);
+          hr->name[toklen] = 0;
         }
       }
       if (row < p.cap) {
-        p.start[row] = s_start[r];
-        p.end[row] = s_end[r];
-        if (WANT_SCORE) p.score[row] = s_score[WANT_SCORE ? r : 0];
+        p.start[row] = v_start;
+        p.end[row] = v_end;
+        if (WANT_SCORE) p.score[row] = v_score;
         if (p.line_off) p.line_off[row] = (uint64_t)(g0 + tok0);
-        if (NSEP >= 4 && p.idspan) p.idspan[row] = s_id[NSEP >= 4 ? r : 0];
+        if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
       }
     }
-    if (nrow > P_RCAP && tid == 0) dev_set_error(p.scratch, BK_ERR_PARSE, base + P_RCAP);
-    if (tile == p.ntiles - 1 && tid == 0) p.scratch[SC_NROWS] = base + nrow;
-    __syncthreads();
+    __syncthreads();  // [S3] everyone is done with this tile's text and masks
   }
 }
 
@@ -589,11 +584,11 @@ int read_scratch(bk_ctx* ctx) {
   return BK_OK;
 }
 
-static int grid_for(const void* kernel, int threads, uint32_t ntiles) {
+static int grid_for(const bk_ctx* ctx, const void* kernel, int threads, uint32_t ntiles) {
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
   if (per_sm < 1) per_sm = 1;
-  uint64_t g = (uint64_t)kSMs * per_sm;
+  uint64_t g = (uint64_t)ctx->sms * per_sm;
   return (int)(ntiles < g ? (ntiles ? ntiles : 1) : g);
 }
 
@@ -662,7 +657,11 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     prof_begin(ctx, "k_parse");
     {
       const bool sc = (p.cols & BK_COL_SCORE) != 0;
-#define BK_PARSE(N, S) k_parse<N, S><<<grid_for((const void*)k_parse<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p)
+      void* args[] = {&p};
+#define BK_PARSE(N, S)                                                                                             \
+  BK_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_parse<N, S>,                                              \
+                                           dim3(grid_for(ctx, (const void*)k_parse<N, S>, P_THREADS, p.ntiles)),          \
+                                           dim3(P_THREADS), args, 0, ctx->stream))
       if (p.min_fields == 3) BK_PARSE(3, false);
       else if (p.min_fields == 4) BK_PARSE(4, false);
       else if (sc) BK_PARSE(5, true);
@@ -742,7 +741,7 @@ int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
   BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
   BK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + SC_TICKET, 0, 8, ctx->stream));
   prof_begin(ctx, "k_pmax");
-  k_pmax<<<grid_for((const void*)k_pmax, PM_THREADS, ntiles), PM_THREADS, 0, ctx->stream>>>(
+  k_pmax<<<grid_for(ctx, (const void*)k_pmax, PM_THREADS, ntiles), PM_THREADS, 0, ctx->stream>>>(
       bed->end, bed->pmax_end, bed->nrows, d_rb, nruns, state, ntiles, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);

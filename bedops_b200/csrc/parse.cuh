@@ -4,8 +4,8 @@
 
 namespace bk {
 
-constexpr int P_THREADS = 256;
-constexpr int P_TILE = 8192;  // bytes of text whose line STARTS one tile owns
+constexpr int P_THREADS = 512;
+constexpr int P_TILE = P_THREADS * 32;  // bytes of text whose line STARTS one tile owns
 constexpr int P_PRE = 128;    // halo before the tile (previous line's chromosome token)
 constexpr int P_POST = 384;   // halo after the tile (tail of the last line that starts in the tile)
 constexpr int P_BUF = P_PRE + P_TILE + P_POST;
