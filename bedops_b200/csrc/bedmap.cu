@@ -75,56 +75,6 @@ struct MapStatsParams {
 
 constexpr int MS_THREADS = 256;
 
-// First index i in [from, n) with a[i] >= key (n if none); a is non-decreasing and `from` is a lower bound of the
-// answer.  All 32 lanes call it with the same arguments.  Probe 1: 32 consecutive elements (the common case when
-// the answer moved a few rows since the previous reference row).  Probe 2: the last element of each of the next 32
-// blocks of 32 (1024 rows per probe), then one consecutive probe inside the block found.  Far jumps fall back to a
-// binary search.
-__device__ __forceinline__ uint32_t warp_gallop(const uint32_t* __restrict__ a, uint32_t from, uint32_t n, uint32_t key,
-                                                int lane, bool near_first) {
-  if (near_first) {
-    if (from >= n) return n;
-    const uint32_t k = from + lane;
-    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
-    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
-    if (m) {
-      const uint32_t r = from + (__ffs(m) - 1);
-      return r < n ? r : n;
-    }
-    from += 32;
-  }
-#pragma unroll 1
-  for (int round = 0; round < 2; round++) {
-    if (from >= n) return n;
-    const uint32_t k = from + 32u * lane + 31u;
-    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
-    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
-    if (m) {
-      const uint32_t base = from + 32u * (__ffs(m) - 1);
-      const uint32_t k2 = base + lane;
-      const uint32_t v2 = k2 < n ? __ldg(&a[k2]) : 0xFFFFFFFFu;
-      const unsigned m2 = __ballot_sync(0xffffffffu, k2 >= n || v2 >= key);
-      const uint32_t r = base + (__ffs(m2) - 1);
-      return r < n ? r : n;
-    }
-    from += 1024;
-  }
-  uint32_t lo = from, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (__ldg(&a[mid]) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)
-__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
-  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-  const uint64_t r0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), r1 = __reduce_add_sync(0xffffffffu, lo >> 16);
-  const uint64_t r2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), r3 = __reduce_add_sync(0xffffffffu, hi >> 16);
-  return r0 + (r1 << 16) + (r2 << 32) + (r3 << 48);
-}
-
 // One warp per batch of 32 consecutive reference rows.  For each row of the batch (broadcast by shuffle) the 32
 // lanes scan the candidate range [lo,hi) of the map rows of the same chromosome, 32 rows at a time with coalesced
 // loads:  lo = first map row whose running-max end exceeds ref.start (galloped from the previous row's lo, a lower
@@ -261,30 +211,6 @@ static void launch_map_stats(unsigned need, unsigned blocks, cudaStream_t st, co
     BK_F(27) BK_F(28) BK_F(29) BK_F(30) BK_F(31)
 #undef BK_F
   }
-}
-
-// echo a B3Rest row: chrom \t start \t end <rest>   (Bed.hpp:316-320, :376-378): numbers are re-printed from the
-// parsed values, the rest of the line (including its leading tab) is copied verbatim.
-template <class Sink>
-__device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
-  const char* p = text + off;
-  int         n = 0;
-  while (is_tok((unsigned char)p[n])) n++;
-  s.copy(p, n);
-  s.put('\t');
-  s.put_u32(st);
-  s.put('\t');
-  s.put_u32(en);
-  const char* q = p + n;
-  while (is_ws((unsigned char)*q)) q++;
-  if (*q == '+') q++;
-  while (is_digit((unsigned char)*q)) q++;
-  while (is_ws((unsigned char)*q)) q++;
-  if (*q == '+') q++;
-  while (is_digit((unsigned char)*q)) q++;
-  int m = 0;
-  while (q[m] != '\n') m++;
-  s.copy(q, m);
 }
 
 struct BedmapRow {

@@ -287,6 +287,56 @@ __device__ __forceinline__ uint64_t upper_bound_u32(const uint32_t* __restrict__
   return lo;
 }
 
+// First index i in [from, n) with a[i] >= key (n if none); a is non-decreasing and `from` is a lower bound of the
+// answer.  All 32 lanes call it with the same arguments.  Probe 1: 32 consecutive elements (the common case when
+// the answer moved a few rows since the previous reference row).  Probe 2: the last element of each of the next 32
+// blocks of 32 (1024 rows per probe), then one consecutive probe inside the block found.  Far jumps fall back to a
+// binary search.
+__device__ __forceinline__ uint32_t warp_gallop(const uint32_t* __restrict__ a, uint32_t from, uint32_t n, uint32_t key,
+                                                int lane, bool near_first) {
+  if (near_first) {
+    if (from >= n) return n;
+    const uint32_t k = from + lane;
+    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
+    if (m) {
+      const uint32_t r = from + (__ffs(m) - 1);
+      return r < n ? r : n;
+    }
+    from += 32;
+  }
+#pragma unroll 1
+  for (int round = 0; round < 2; round++) {
+    if (from >= n) return n;
+    const uint32_t k = from + 32u * lane + 31u;
+    const uint32_t v = k < n ? __ldg(&a[k]) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(0xffffffffu, k >= n || v >= key);
+    if (m) {
+      const uint32_t base = from + 32u * (__ffs(m) - 1);
+      const uint32_t k2 = base + lane;
+      const uint32_t v2 = k2 < n ? __ldg(&a[k2]) : 0xFFFFFFFFu;
+      const unsigned m2 = __ballot_sync(0xffffffffu, k2 >= n || v2 >= key);
+      const uint32_t r = base + (__ffs(m2) - 1);
+      return r < n ? r : n;
+    }
+    from += 1024;
+  }
+  uint32_t lo = from, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(&a[mid]) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+  const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  const uint64_t r0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu), r1 = __reduce_add_sync(0xffffffffu, lo >> 16);
+  const uint64_t r2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu), r3 = __reduce_add_sync(0xffffffffu, hi >> 16);
+  return r0 + (r1 << 16) + (r2 << 32) + (r3 << 48);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace bk

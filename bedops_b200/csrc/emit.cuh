@@ -17,6 +17,30 @@ constexpr int E_STAGE = 32 * 1024;  // bytes of shared staging per tile (tiles t
 
 #ifdef __CUDACC__
 
+// echo a B3Rest row: chrom \t start \t end <rest>   (Bed.hpp:316-320, :376-378): numbers are re-printed from the
+// parsed values, the rest of the line (including its leading tab) is copied verbatim.
+template <class Sink>
+__device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
+  const char* p = text + off;
+  int         n = 0;
+  while (is_tok((unsigned char)p[n])) n++;
+  s.copy(p, n);
+  s.put('\t');
+  s.put_u32(st);
+  s.put('\t');
+  s.put_u32(en);
+  const char* q = p + n;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  int m = 0;
+  while (q[m] != '\n') m++;
+  s.copy(q, m);
+}
+
 template <class RowFn>
 __global__ void __launch_bounds__(E_THREADS) k_emit(RowFn fn, uint64_t n, char* __restrict__ out, uint64_t out_cap,
                                                     uint64_t* tile_state, uint32_t ntiles, uint64_t* scratch) {

@@ -725,16 +725,14 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   return BK_OK;
 }
 
-int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
-  bk_bed* bed = const_cast<bk_bed*>(cbed);
-  if (bed->pmax_end || bed->nrows == 0) return BK_OK;
-  bed->pmax_end = dalloc<uint32_t>(ctx, bed->nrows);
-  if (!bed->pmax_end) return BK_ERR_NOMEM;
-  int                   nruns = (int)bed->runs.size();
+// out[k] = max(in[j] : j <= k, j in the same chromosome run as k)
+int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, const std::vector<ChromRun>& runs) {
+  if (n == 0) return BK_OK;
+  int                   nruns = (int)runs.size();
   std::vector<uint64_t> rb(nruns);
-  for (int i = 0; i < nruns; i++) rb[i] = bed->runs[i].row_begin;
+  for (int i = 0; i < nruns; i++) rb[i] = runs[i].row_begin;
   uint64_t* d_rb = dalloc<uint64_t>(ctx, nruns);
-  uint32_t  ntiles = (uint32_t)((bed->nrows + PM_TILE - 1) / PM_TILE);
+  uint32_t  ntiles = (uint32_t)((n + PM_TILE - 1) / PM_TILE);
   uint64_t* state = dalloc<uint64_t>(ctx, ntiles);
   if (!d_rb || !state) return BK_ERR_NOMEM;
   BK_CUDA(ctx, cudaMemcpyAsync(d_rb, rb.data(), nruns * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -742,13 +740,21 @@ int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
   BK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + SC_TICKET, 0, 8, ctx->stream));
   prof_begin(ctx, "k_pmax");
   k_pmax<<<grid_for(ctx, (const void*)k_pmax, PM_THREADS, ntiles), PM_THREADS, 0, ctx->stream>>>(
-      bed->end, bed->pmax_end, bed->nrows, d_rb, nruns, state, ntiles, ctx->d_scratch);
+      in, out, n, d_rb, nruns, state, ntiles, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rb (host vector) must outlive the copy
   dfree(ctx, d_rb);
   dfree(ctx, state);
   return BK_OK;
+}
+
+int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
+  bk_bed* bed = const_cast<bk_bed*>(cbed);
+  if (bed->pmax_end || bed->nrows == 0) return BK_OK;
+  bed->pmax_end = dalloc<uint32_t>(ctx, bed->nrows);
+  if (!bed->pmax_end) return BK_ERR_NOMEM;
+  return seg_prefix_max(ctx, bed->end, bed->pmax_end, bed->nrows, bed->runs);
 }
 
 }  // namespace bk

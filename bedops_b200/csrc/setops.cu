@@ -309,28 +309,6 @@ struct Bed3Row {  // chrom \t start \t end \n   (B3NoRest::println, Bed.hpp:228-
   }
 };
 
-template <class Sink>
-__device__ __forceinline__ void echo_b3rest_row(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
-  const char* p = text + off;
-  int         n = 0;
-  while (is_tok((unsigned char)p[n])) n++;
-  s.copy(p, n);
-  s.put('\t');
-  s.put_u32(st);
-  s.put('\t');
-  s.put_u32(en);
-  const char* q = p + n;
-  while (is_ws((unsigned char)*q)) q++;
-  if (*q == '+') q++;
-  while (is_digit((unsigned char)*q)) q++;
-  while (is_ws((unsigned char)*q)) q++;
-  if (*q == '+') q++;
-  while (is_digit((unsigned char)*q)) q++;
-  int m = 0;
-  while (q[m] != '\n') m++;
-  s.copy(q, m);
-}
-
 struct EchoKeptRow {  // record(nextRef) for -e/-n: B3Rest::println (Bedops.cpp:148-152, :555-556)
   const char*     text;
   const uint64_t* line;
@@ -342,7 +320,7 @@ struct EchoKeptRow {  // record(nextRef) for -e/-n: B3Rest::println (Bedops.cpp:
   __device__ void operator()(uint64_t i, Sink& sk) const {
     if (!keep[i]) return;
     const uint64_t row = row0 + i;
-    echo_b3rest_row(sk, text, line[row], s[row], e[row]);
+    echo_b3rest(sk, text, line[row], s[row], e[row]);
     sk.put('\n');
   }
 };

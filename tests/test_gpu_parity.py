@@ -144,7 +144,7 @@ def test_docs_examples(kit, ex):
 
 
 # ---- synthetic inputs: CUDA vs oracle vs hashes of the reference binaries' output ------------------------------------
-@pytest.mark.parametrize("case", [c for c in SYN["cases"] if c["tool"] != "closest-features"],
+@pytest.mark.parametrize("case", SYN["cases"],
                          ids=lambda c: c["tool"] + "_" + "_".join(c["argv"]).replace("\t", "TAB"))
 def test_synthetic_vs_reference_hash(kit, case, synth_files):
     got = oracle_cli.run_kit(kit, case["tool"], case["argv"], synth_files)
@@ -184,6 +184,22 @@ def test_nested_and_duplicate_intervals(kit):
         assert_same(oracle_cli.run_kit(kit, tool, argv, files), oracle_cli.run(tool, argv, files))
 
 
+def test_closest_features_vs_oracle(kit, synth_files):
+    """Declarative closest-features rule (non-nested reference rows: the case where the reference's streaming state
+    machine and the rule agree, SURVEY 8c hazard 3), every output mode, plus nested QUERY rows and --chrom."""
+    for argv in (["r.bed", "m.bed"], ["--dist", "r.bed", "m.bed"], ["--closest", "--dist", "r.bed", "m.bed"],
+                 ["--no-ref", "--delim", "\t", "r.bed", "m3.bed"], ["--chrom", "chr8", "--dist", "r.bed", "m.bed"],
+                 ["--dist", "r.bed", "r.bed"]):
+        assert_same(oracle_cli.run_kit(kit, "closest-features", argv, synth_files),
+                    oracle_cli.run("closest-features", argv, synth_files))
+    # hand-made: ties on the left end (later row wins), containment by centroid, touching neighbours, no neighbours
+    q = b"chr1\t5\t10\ta\nchr1\t7\t10\tb\nchr1\t20\t30\tc\nchr1\t22\t24\td\nchr1\t26\t28\te\nchr1\t40\t50\tf\nchr3\t1\t2\tg\n"
+    r = b"chr1\t12\t15\tr1\nchr1\t21\t29\tr2\nchr1\t30\t40\tr3\nchr1\t60\t70\tr4\nchr2\t1\t5\tr5\nchr3\t0\t1\tr6\n"
+    files = {"q.bed": q, "r.bed": r}
+    for argv in (["--dist", "r.bed", "q.bed"], ["--closest", "r.bed", "q.bed"], ["--dist", "q.bed", "q.bed"]):
+        assert_same(oracle_cli.run_kit(kit, "closest-features", argv, files), oracle_cli.run("closest-features", argv, files))
+
+
 def test_float_scores_within_tolerance(kit):
     """--mean/--sum on floating-point scores: <= 1e-12 relative to the exactly rounded per-row sum (math.fsum),
     before --prec formatting (north_star).  Compared at --prec 15 through the printed text."""
@@ -217,7 +233,8 @@ def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
             ("bedops", ["-e", "50%", "r.bed", "m.bed"]), ("bedops", ["--chrom", "chr5", "-n", "1", "r.bed", "m.bed"]),
             ("bedmap", ["--echo", "--count", "--mean", "--bases", "r.bed", "m.bed"]),
             ("bedmap", ["--faster", "--delim", "\\t", "--sum", "--max", "--echo-map-id", "r.bed", "u.bed"]),
-            ("bedmap", ["--count", "m3.bed"])]
+            ("bedmap", ["--count", "m3.bed"]), ("closest-features", ["--dist", "r.bed", "m.bed"]),
+            ("closest-features", ["--closest", "--delim", "\\t", "r.bed", "m3.bed"])]
     for tool, argv in runs:
         ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
         ref = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
