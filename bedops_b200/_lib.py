@@ -101,7 +101,7 @@ def load_library() -> C.CDLL:
 EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "bk_last_error", "bk_abi_version",
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
-           "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text"]
+           "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards"]
 
 
 class Bed:

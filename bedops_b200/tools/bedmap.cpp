@@ -242,22 +242,39 @@ int main(int argc, char** argv) {
     spec.multidelim = mdelim.c_str();
     spec.chrom = o.chrom.c_str();
 
-    cli::Engine eng;
-    bk_bed *    ref = nullptr, *map = nullptr;
     const unsigned map_cols = (need_score ? BK_COL_SCORE : 0) | (need_id ? (BK_COL_ID | BK_COL_LINE) : 0);
-    if (o.num_files == 2) {
-      ref = eng.load(rtext, 3, need_line ? BK_COL_LINE : 0);
-      map = eng.load(mtext, o.min_map_fields, map_cols);
+    auto run_one = [&](cli::Engine& eng, const char* rp, size_t rn, const char* mp, size_t mn) {
+      bk_bed *ref = nullptr, *map = nullptr;
+      if (o.num_files == 2) {
+        ref = eng.load(rp, rn, 3, need_line ? BK_COL_LINE : 0);
+        map = eng.load(mp, mn, o.min_map_fields, map_cols);
+      } else {
+        ref = eng.load(rp, rn, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));
+      }
+      bk_text out;
+      int     rc = bk_bedmap(eng.ctx, ref, map, &spec, &out);
+      if (rc != BK_OK) eng.raise(rc);
+      std::string text(out.ptr ? out.ptr : "", out.len);
+      bk_free_text(eng.ctx, &out);
+      bk_free_bed(eng.ctx, ref);
+      bk_free_bed(eng.ctx, map);
+      return text;
+    };
+    bool row_ids = false;
+    for (int op : o.ops) row_ids |= op == BK_OP_ECHO_REF_ROW_ID;
+    const int gpus = cli::gpus_requested();
+    if (gpus > 1 && o.chrom == "all" && !row_ids) {
+      std::vector<const std::vector<char>*> files{&rtext};
+      if (o.num_files == 2) files.push_back(&mtext);
+      auto slices = cli::plan_slices(files, gpus);
+      cli::run_sharded(slices, [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
+        return run_one(eng, sl[0].ptr, sl[0].len, o.num_files == 2 ? sl[1].ptr : nullptr, o.num_files == 2 ? sl[1].len : 0);
+      });
     } else {
-      ref = eng.load(rtext, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));
+      cli::Engine eng;
+      std::string text = run_one(eng, rtext.data(), rtext.size(), mtext.data(), mtext.size());
+      cli::write_all(text.data(), text.size());
     }
-    bk_text out;
-    int     rc = bk_bedmap(eng.ctx, ref, map, &spec, &out);
-    if (rc != BK_OK) eng.raise(rc);
-    cli::write_all(out.ptr, out.len);
-    bk_free_text(eng.ctx, &out);
-    bk_free_bed(eng.ctx, ref);
-    bk_free_bed(eng.ctx, map);
     return EXIT_SUCCESS;
   } catch (const Help&) {
     cli::banner(stdout, "bedmap");

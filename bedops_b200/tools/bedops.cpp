@@ -210,20 +210,34 @@ int main(int argc, char** argv) {
       default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
     if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
-    cli::Engine eng;
-    std::vector<bk_bed*> beds;
-    for (size_t f = 0; f < o.files.size(); f++) {
-      std::vector<char> text;
-      if (!cli::slurp(o.files[f], text)) throw UserError("Cannot find " + o.files[f]);
-      const bool is_ref = (op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF) && f == 0;
-      beds.push_back(eng.load(text, 3, is_ref ? BK_COL_LINE : 0));
+    std::vector<std::vector<char>> texts(o.files.size());
+    for (size_t f = 0; f < o.files.size(); f++)
+      if (!cli::slurp(o.files[f], texts[f])) throw UserError("Cannot find " + o.files[f]);
+    const bool has_ref = op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF;
+    auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
+      std::vector<bk_bed*> beds;
+      for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, (has_ref && f == 0) ? BK_COL_LINE : 0));
+      bk_text out;
+      int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), o.subset, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
+      if (rc != BK_OK) eng.raise(rc);
+      std::string text(out.ptr ? out.ptr : "", out.len);
+      bk_free_text(eng.ctx, &out);
+      for (bk_bed* b : beds) bk_free_bed(eng.ctx, b);
+      return text;
+    };
+    const int gpus = cli::gpus_requested();
+    // "-e 0" / "-n 0" look at later chromosomes (Bedops.cpp:1044-1049): keep those runs on one GPU
+    if (gpus > 1 && o.chrom == "all" && !(has_ref && !o.use_pct && o.subset <= 0)) {
+      std::vector<const std::vector<char>*> files;
+      for (auto& t : texts) files.push_back(&t);
+      cli::run_sharded(cli::plan_slices(files, gpus), run_one);
+    } else {
+      cli::Engine eng;
+      std::vector<cli::Slice> sl;
+      for (auto& t : texts) sl.push_back(cli::Slice{t.data(), t.size()});
+      std::string text = run_one(eng, sl);
+      cli::write_all(text.data(), text.size());
     }
-    bk_text out;
-    int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), o.subset, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
-    if (rc != BK_OK) eng.raise(rc);
-    cli::write_all(out.ptr, out.len);
-    bk_free_text(eng.ctx, &out);
-    for (bk_bed* b : beds) bk_free_bed(eng.ctx, b);
     return EXIT_SUCCESS;
   } catch (const Help&) {
     cli::banner(stdout, "bedops");

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 #include <fcntl.h>
@@ -67,9 +69,10 @@ inline void write_all(const char* p, size_t n) {
 
 struct Engine {
   bk_ctx* ctx = nullptr;
-  Engine() {
+  explicit Engine(int shard = 0) {
     const char* dev = std::getenv("BEDKIT_DEVICE");
-    int         rc = bk_init(&ctx, dev ? std::atoi(dev) : 0);
+    if (std::getenv("BEDKIT_SHARE_DEVICE")) shard = 0;  // all shards on one GPU (tests on a single-GPU box)
+    int         rc = bk_init(&ctx, (dev ? std::atoi(dev) : 0) + shard);
     if (rc != BK_OK) throw std::runtime_error(bk_strerror(rc));
   }
   ~Engine() { bk_destroy(ctx); }
@@ -78,11 +81,95 @@ struct Engine {
     throw std::runtime_error(detail && *detail ? std::string(detail) : std::string(bk_strerror(rc)));
   }
   bk_bed* load(const std::vector<char>& text, int min_fields, unsigned cols) const {
+    return load(text.data(), text.size(), min_fields, cols);
+  }
+  bk_bed* load(const char* p, size_t n, int min_fields, unsigned cols) const {
     bk_bed* b = nullptr;
-    int     rc = bk_load_bed(ctx, text.data(), text.size(), min_fields, cols, &b);
+    int     rc = bk_load_bed(ctx, p, n, min_fields, cols, &b);
     if (rc != BK_OK) raise(rc);
     return b;
   }
 };
+
+// ---- multi-GPU: BEDKIT_GPUS=N shards the inputs by contiguous chromosome groups, one host thread + one bk_ctx per
+// GPU, outputs concatenated in shard order (byte-identical to the unsharded run) -------------------------
+struct Slice {
+  const char* ptr;
+  size_t      len;
+};
+
+inline int gpus_requested() {
+  const char* g = std::getenv("BEDKIT_GPUS");
+  int         n = g ? std::atoi(g) : 1;
+  return n < 1 ? 1 : n;
+}
+
+// slices[shard][file]
+inline std::vector<std::vector<Slice>> plan_slices(const std::vector<const std::vector<char>*>& files, int n_shards) {
+  std::vector<std::vector<bk_chrom_span>> idx(files.size());
+  std::vector<std::string>                names;
+  for (size_t f = 0; f < files.size(); f++) {
+    int n = 0, cap = 64;
+    while (true) {
+      idx[f].resize(cap);
+      int rc = bk_chrom_index(files[f]->data(), files[f]->size(), idx[f].data(), cap, &n);
+      if (rc == BK_OK) break;
+      if (rc != BK_ERR_NOMEM) throw std::runtime_error("chromosome index failed");
+      cap = n + 8;
+    }
+    idx[f].resize(n);
+    for (auto& s : idx[f]) names.push_back(s.name);
+  }
+  std::sort(names.begin(), names.end(), [](const std::string& a, const std::string& b) { return std::strcmp(a.c_str(), b.c_str()) < 0; });
+  names.erase(std::unique(names.begin(), names.end()), names.end());
+  std::vector<uint64_t> load(names.size(), 0);
+  auto pos_of = [&](const char* nm) {
+    return (size_t)(std::lower_bound(names.begin(), names.end(), std::string(nm),
+                                     [](const std::string& a, const std::string& b) { return std::strcmp(a.c_str(), b.c_str()) < 0; }) -
+                    names.begin());
+  };
+  for (auto& ix : idx)
+    for (auto& s : ix) load[pos_of(s.name)] += s.end - s.begin;
+  std::vector<int> first(n_shards + 1, 0);
+  if (bk_plan_shards(load.data(), (int)load.size(), n_shards, first.data()) != BK_OK) throw std::runtime_error("shard plan failed");
+  std::vector<std::vector<Slice>> out(n_shards, std::vector<Slice>(files.size(), Slice{nullptr, 0}));
+  for (int s = 0; s < n_shards; s++)
+    for (size_t f = 0; f < files.size(); f++) {
+      uint64_t b = 0, e = 0;
+      bool     any = false;
+      for (auto& sp : idx[f]) {
+        size_t p = pos_of(sp.name);
+        if ((int)p >= first[s] && (int)p < first[s + 1]) {
+          if (!any) b = sp.begin;
+          e = sp.end;
+          any = true;
+        }
+      }
+      out[s][f] = Slice{files[f]->data() + b, (size_t)(e - b)};
+    }
+  return out;
+}
+
+// run fn(engine, slices_of_this_shard) -> result text on n_shards GPUs concurrently; write the outputs in shard order
+template <class Fn>
+inline void run_sharded(const std::vector<std::vector<Slice>>& slices, Fn fn) {
+  const int                n = (int)slices.size();
+  std::vector<std::string> outs(n), errs(n);
+  std::vector<std::thread> th;
+  for (int s = 0; s < n; s++)
+    th.emplace_back([&, s]() {
+      try {
+        Engine eng(s);
+        outs[s] = fn(eng, slices[s]);
+      } catch (const std::exception& e) {
+        errs[s] = e.what();
+        if (errs[s].empty()) errs[s] = "unknown error";
+      }
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : errs)
+    if (!e.empty()) throw std::runtime_error(e);
+  for (auto& o : outs) write_all(o.data(), o.size());
+}
 
 }  // namespace cli

@@ -75,10 +75,7 @@ int main(int argc, char** argv) {
     std::vector<char> rtext, qtext;
     if (!cli::slurp(o.ref, rtext)) throw UserError("Unable to find file: " + o.ref);
     if (!cli::slurp(o.query, qtext)) throw UserError("Unable to find file: " + o.query);
-    cli::Engine eng;
-    bk_bed*     ref = eng.load(rtext, 3, BK_COL_LINE);
-    bk_bed*     qry = eng.load(qtext, 3, BK_COL_LINE);
-    bk_cfspec   spec;
+    bk_cfspec spec;
     bk_cfspec_default(&spec);
     spec.dist = o.dist;
     spec.closest = o.closest;
@@ -88,13 +85,26 @@ int main(int argc, char** argv) {
     if (delim == "\t" || delim == "\\t" || delim == "'\t'") delim = "\t";
     spec.delim = delim.c_str();
     spec.chrom = o.chrom.c_str();
-    bk_text out;
-    int     rc = bk_closest(eng.ctx, ref, qry, &spec, &out);
-    if (rc != BK_OK) eng.raise(rc);
-    cli::write_all(out.ptr, out.len);
-    bk_free_text(eng.ctx, &out);
-    bk_free_bed(eng.ctx, ref);
-    bk_free_bed(eng.ctx, qry);
+    auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
+      bk_bed* ref = eng.load(sl[0].ptr, sl[0].len, 3, BK_COL_LINE);
+      bk_bed* qry = eng.load(sl[1].ptr, sl[1].len, 3, BK_COL_LINE);
+      bk_text out;
+      int     rc = bk_closest(eng.ctx, ref, qry, &spec, &out);
+      if (rc != BK_OK) eng.raise(rc);
+      std::string text(out.ptr ? out.ptr : "", out.len);
+      bk_free_text(eng.ctx, &out);
+      bk_free_bed(eng.ctx, ref);
+      bk_free_bed(eng.ctx, qry);
+      return text;
+    };
+    const int gpus = cli::gpus_requested();
+    if (gpus > 1 && o.chrom == "all") {
+      cli::run_sharded(cli::plan_slices({&rtext, &qtext}, gpus), run_one);
+    } else {
+      cli::Engine eng;
+      std::string text = run_one(eng, {cli::Slice{rtext.data(), rtext.size()}, cli::Slice{qtext.data(), qtext.size()}});
+      cli::write_all(text.data(), text.size());
+    }
     return EXIT_SUCCESS;
   } catch (const Help&) {
     cli::banner(stdout, "closest-features");

@@ -170,6 +170,22 @@ int bk_format_bed_device(bk_ctx* ctx, const char* chrom, const uint32_t* d_start
 
 void bk_free_text(bk_ctx* ctx, bk_text* text);
 
+/* ---- multi-GPU planning (host only, no device needed) ------------------------------------------------ */
+/* The path shards by genomic range with no data-path collective: cut the sorted inputs at chromosome boundaries,
+ * give every GPU (one bk_ctx each) a contiguous group of chromosomes, concatenate the outputs in shard order.
+ * Replaces the reference's per-chromosome seek (AllocateIterator_BED_starch.hpp:113-160 -> FindBedRange.hpp:68). */
+typedef struct bk_chrom_span {
+  char     name[128];
+  uint64_t begin; /* byte offset of the chromosome's first line */
+  uint64_t end;   /* byte offset one past its last line */
+} bk_chrom_span;
+/* chromosome byte ranges of a sorted BED text by galloping + bisection on line-aligned probes (O(#chrom log n)).
+ * Returns BK_ERR_NOMEM (and the needed count in *n_out) when cap is too small. */
+int bk_chrom_index(const char* host_text, size_t nbytes, bk_chrom_span* out, int cap, int* n_out);
+/* contiguous partition of n_items loads into n_shards groups minimising the largest group;
+ * first_item[0..n_shards] receives the group boundaries */
+int bk_plan_shards(const uint64_t* load, int n_items, int n_shards, int* first_item);
+
 #ifdef __cplusplus
 }
 #endif

@@ -246,3 +246,23 @@ def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
     ref = subprocess.run([os.path.join(REFBIN, "bedmap"), "--echo", "--indicator", "-", "m.bed"], cwd=tmp_path,
                          input=synth_files["r.bed"], capture_output=True)
     assert_same(ours.stdout, ref.stdout)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_cli_sharded_mode_is_byte_identical(tmp_path, synth_files):
+    """BEDKIT_GPUS=N: contiguous chromosome groups, one host thread + ctx per shard, outputs concatenated in shard
+    order.  On a single-GPU box the shards share device 0 (BEDKIT_SHARE_DEVICE); on a multi-GPU box they spread."""
+    import bedops_b200
+    import torch
+    for n, c in synth_files.items():
+        (tmp_path / n).write_bytes(c)
+    env = dict(os.environ, BEDKIT_GPUS="3")
+    if torch.cuda.device_count() < 3:
+        env["BEDKIT_SHARE_DEVICE"] = "1"
+    for tool, argv in (("bedmap", ["--echo", "--count", "--mean", "--bases", "r.bed", "m.bed"]),
+                       ("bedops", ["-m", "m.bed", "m2.bed", "r.bed"]), ("bedops", ["-e", "1", "r.bed", "m.bed"]),
+                       ("closest-features", ["--dist", "r.bed", "m.bed"])):
+        ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True, env=env)
+        ref = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
+        assert ours.returncode == 0, ours.stderr
+        assert_same(ours.stdout, ref.stdout)
