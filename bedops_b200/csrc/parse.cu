@@ -97,6 +97,15 @@ __device__ __forceinline__ void parse_line(const C& c, int64_t q0, int min_field
   }
 }
 
+__device__ __noinline__ void parse_line_slow(const Cursor& c, int64_t q0, int min_fields, unsigned cols, RowOut& r) {
+  parse_line(c, q0, min_fields, cols, r);
+}
+__device__ __noinline__ int parse_score_slow(const unsigned char* sm, int q, double& out) {
+  SmCursor sc{sm};
+  int64_t  qq = q;
+  return parse_decimal(sc, qq, out);
+}
+
 // compare the chromosome token at window index a (length la) with the token starting at window index b
 template <class C>
 __device__ __forceinline__ bool same_token(const C& c, int64_t a, int la, int64_t b) {
@@ -107,7 +116,7 @@ __device__ __forceinline__ bool same_token(const C& c, int64_t a, int la, int64_
 
 // window index of the first token of the last non-blank line that ends before window index p0 (p0 = a line start);
 // INT64_MIN if there is none.  Rare path (first row of a tile only): walks backwards through the window/global text.
-__device__ int64_t prev_line_token(const Cursor& c, int64_t p0) {
+__device__ __noinline__ int64_t prev_line_token(const Cursor& c, int64_t p0) {
   int64_t q = p0 - 1;  // the '\n' that terminates the previous line
   while (true) {
     if (c.g0 + q < 0) return INT64_MIN;
@@ -184,27 +193,130 @@ __device__ __forceinline__ uint2 token8(const unsigned char* sm, int x, int len)
   return make_uint2(lo, hi);
 }
 
+// packed control-byte mask and NL mask (bit i = byte i) of 32 text bytes held in 8 words
+__device__ __forceinline__ void pack_masks32(const uint32_t (&w8)[8], uint32_t& cm, uint32_t& nlp) {
+  cm = 0;
+  nlp = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t ctl = ctl_mask4(w8[i]);
+    cm |= pack4(ctl) << (4 * i);
+    nlp |= pack4(nl_mask4(w8[i], ctl)) << (4 * i);
+  }
+}
+
+// ---- pass 1: rows per tile ---------------------------------------------------------------------------------------
+// A row starts at p iff (p == 0 or byte p-1 is NL), p < eff, and the line is not blank.  Same definition, same helper
+// functions as the parser below, so the two passes always agree on the row numbering.  Streams the text once
+// (pure bandwidth); the exclusive scan of the counts gives every tile its first row, which removes any ordering
+// between tiles from the parser (no look-back chain to wait for) and makes the row count -- hence the column
+// allocation -- exact.
+// One WARP owns a contiguous range of `tiles_per_warp` tiles and walks it 1 KiB at a time (32 lanes x 32 bytes,
+// two 16-byte streaming loads per lane), so there is no block barrier and no atomics: local_prefix[tile] = rows of the
+// warp's earlier tiles, warp_total[warp] = rows of its whole range.  The NL that precedes a lane's span comes from the
+// neighbouring lane by shuffle (and from the previous step's lane 31).
+constexpr int CR_THREADS = 256;
+__global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* __restrict__ text, uint64_t nbytes_raw,
+                                                           const uint64_t* __restrict__ scratch,
+                                                           uint32_t* __restrict__ local_prefix, uint64_t* __restrict__ warp_total,
+                                                           uint32_t ntiles, uint32_t tiles_per_warp, uint32_t nwarps) {
+  const int      lane = threadIdx.x & 31;
+  const uint32_t wid = (blockIdx.x * CR_THREADS + threadIdx.x) >> 5;
+  if (wid >= nwarps) return;
+  const uint64_t eff = scratch[SC_EFFLEN];
+  const uint32_t t0 = wid * tiles_per_warp, t1 = (t0 + tiles_per_warp < ntiles) ? t0 + tiles_per_warp : ntiles;
+  uint64_t       run = 0;
+  uint32_t       carry = 0;  // was the byte just before this step's first byte a NL?
+  if (t0 < t1) {
+    const uint64_t g = (uint64_t)t0 * P_TILE;
+    carry = (g == 0 || (g - 1 < nbytes_raw && text[g - 1] == '\n')) ? 1u : 0u;
+  }
+  for (uint32_t tile = t0; tile < t1; tile++) {
+    if (lane == 0) local_prefix[tile] = (uint32_t)run;  // a warp range holds far fewer than 2^32 rows
+    uint32_t cnt = 0;
+#pragma unroll 2
+    for (int step = 0; step < P_TILE / 1024; step++) {
+      const uint64_t p0 = (uint64_t)tile * P_TILE + (uint64_t)step * 1024 + (uint64_t)lane * 32;
+      uint32_t       w8[8];
+      if (p0 + 32 <= nbytes_raw) {
+        const uint4 a = ldg_stream16(text + p0), c = ldg_stream16(text + p0 + 16);
+        w8[0] = a.x; w8[1] = a.y; w8[2] = a.z; w8[3] = a.w; w8[4] = c.x; w8[5] = c.y; w8[6] = c.z; w8[7] = c.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint64_t g = p0 + 4 * i + j;
+            w |= (uint32_t)(g < nbytes_raw ? text[g] : 0) << (8 * j);
+          }
+          w8[i] = w;
+        }
+      }
+      uint32_t cm, nlp;
+      pack_masks32(w8, cm, nlp);
+      uint32_t prev = __shfl_up_sync(0xffffffffu, nlp >> 31, 1);
+      if (lane == 0) prev = carry;
+      carry = __shfl_sync(0xffffffffu, nlp >> 31, 31);
+      uint32_t smask = (nlp << 1) | prev;
+      if (p0 >= eff) smask = 0;
+      else if (p0 + 32 > eff) smask &= (1u << (int)(eff - p0)) - 1u;
+      for (uint32_t m = smask & cm; m; m &= m - 1) {  // a line that begins with a control byte may be blank
+        const int j = __ffs(m) - 1;
+        uint64_t  q = p0 + j;
+        while (q < eff && is_ws(text[q])) q++;
+        if (q >= eff || text[q] == '\n') smask &= ~(1u << j);
+      }
+      cnt += __popc(smask);
+    }
+    run += __reduce_add_sync(0xffffffffu, cnt);
+  }
+  if (lane == 0) warp_total[wid] = run;
+}
+
+// exclusive scan of the per-warp totals (one CTA; n <= a few thousand): base[i] = sum total[0..i), base[n] = all rows
+__global__ void __launch_bounds__(1024) k_scan_warps(const uint64_t* __restrict__ total, uint64_t* __restrict__ base, uint32_t n,
+                                                     uint64_t* scratch) {
+  __shared__ uint64_t part[1024];
+  const uint32_t tid = threadIdx.x, per = (n + 1023) / 1024;
+  const uint32_t b = tid * per, e = b + per < n ? b + per : n;
+  uint64_t       s = 0;
+  for (uint32_t i = b; i < e; i++) s += total[i];
+  part[tid] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele over the 1024 partials
+    uint64_t v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint64_t runv = tid ? part[tid - 1] : 0;
+  for (uint32_t i = b; i < e; i++) {
+    base[i] = runv;
+    runv += total[i];
+  }
+  if (tid == 1023) {
+    base[n] = part[1023];
+    scratch[SC_NROWS] = part[1023];
+  }
+}
+
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
 //
-// Per tile: (1) stage the text, (2) every thread builds the control-byte / NL bitmasks of its 32 bytes and counts the
-// lines that START there, (3) block scan -> local row index, warp 0 resolves the look-back (global row index of the
-// tile) while warps 1..7 already parse, (4) every thread parses ITS lines and writes the SoA columns directly (the
-// lanes of a warp hold consecutive rows, so the stores coalesce).  Three block barriers per tile.
+// Per tile (tiles are independent: the first row of each tile comes from pass 1): (1) stage the text, (2) every
+// thread builds the control-byte / NL bitmasks of its 32 bytes and counts the lines that START there, (3) block scan
+// -> row index, (4) every thread parses ITS lines and writes the SoA columns directly (the lanes of a warp hold
+// consecutive rows, so the stores coalesce).  Three block barriers per tile.
 template <int NSEP, bool WANT_SCORE>
-__global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
+__global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p) {
   __shared__ __align__(16) unsigned char sm[P_BUF + 16];
   __shared__ uint32_t                    ctlp[P_NW + 4];
   __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
   __shared__ uint32_t                    wsum[P_THREADS / 32];
-  __shared__ uint64_t                    base_sm;
-
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t eff = p.scratch[SC_EFFLEN];  // bytes up to and including the last '\n'
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
 
-  // Tiles are dealt round-robin to a grid that is launched cooperatively (every CTA resident), so that the tiles of
-  // one "wave" start together: a tile's predecessors publish their row counts at about the same moment it needs
-  // them, and the look-back chain never waits for a CTA that has not been scheduled.
   for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     const int64_t ts = (int64_t)tile * P_TILE;
     const int64_t g0 = ts - P_PRE;
@@ -241,13 +353,8 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
       const uint4* v4 = reinterpret_cast<const uint4*>(sm + off);
       const uint4  a = v4[0], c = v4[1];
       const uint32_t w8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-      uint32_t nlp = 0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const uint32_t ctl = ctl_mask4(w8[i]);
-        cm |= pack4(ctl) << (4 * i);
-        nlp |= pack4(nl_mask4(w8[i], ctl)) << (4 * i);
-      }
+      uint32_t nlp;
+      pack_masks32(w8, cm, nlp);
       smask = (nlp << 1) | ((p0 == 0 || sm[off - 1] == '\n') ? 1u : 0u);  // a line starts after every NL
       ctlp[tid] = cm;
       nlw[P_PRE / 32 + tid] = nlp;
@@ -294,21 +401,11 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
       nrow += t;
     }
 
-    // ---- global row index of the tile's first row: warp 0 resolves the look-back while warps 1..7 parse ---------
-    if (warp == 0) {
-      const uint64_t b = lookback_sum(p.tile_state, tile, nrow);
-      if (lane == 0) {
-        base_sm = b;
-        if (tile == p.ntiles - 1) p.scratch[SC_NROWS] = b + nrow;
-      }
-      __threadfence_block();
-      asm volatile("bar.arrive 1, %0;" ::"n"(P_THREADS) : "memory");  // releases warps 1..7 waiting below
-    }
+    const uint64_t base = p.warp_base[tile / p.tiles_per_warp] + p.local_prefix[tile];  // first row of this tile (pass 1)
+    (void)nrow;
 
     // ---- every thread parses the lines that START in its 32 bytes ---------------------------------------------
-    // The loop is warp-uniform: lanes without a (further) line idle.  In the first round warps 1..7 block on named
-    // barrier 1 (no issue slots burnt) until warp 0 has published the tile's first row index.
-    uint64_t base = 0;
+    // The loop is warp-uniform: lanes without a (further) line idle.
     uint32_t m = smask;
 #pragma unroll 1
     for (int round = 0; round == 0 || __any_sync(0xffffffffu, m != 0); round++) {
@@ -363,18 +460,14 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
           if (WANT_SCORE && !bad) {
             uint32_t sbad = l4 > 9 ? 1u : 0u;
             if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
-            if (sbad) {  // not a short unsigned integer: exact strtod on the field
-              SmCursor sc{sm};
-              int64_t  q = q0 + s3 + 1;
-              bad |= parse_decimal(sc, q, v_score) != 0 ? 1u : 0u;
-            }
+            if (sbad) bad |= parse_score_slow(sm, q0 + s3 + 1, v_score) ? 1u : 0u;  // exact strtod on the field
           }
         }
         fast = bad == 0;
       }
-      if (!fast) {  // general path: fscanf-equivalent tokeniser
+      if (!fast) {  // general path: fscanf-equivalent tokeniser (out of line: keeps the fast path's registers low)
         RowOut r;
-        parse_line(cur, q0, p.min_fields, p.cols, r);
+        parse_line_slow(cur, q0, p.min_fields, p.cols, r);
         err = r.err;
         v_start = (uint32_t)r.start;
         v_end = (uint32_t)r.end;
@@ -383,33 +476,46 @@ __global__ void __launch_bounds__(P_THREADS) k_parse(ParseParams p) {
         tok0 = (int)r.tok0;
         toklen = r.toklen;
       }
-      // chromosome run head?  the previous line ends at the NL just before this line's start; the NL before that one
-      // (found in the window's NL mask) is where the previous line starts
-      if (!err) {
-        bool done = false;
-        if (toklen <= 8 && tok0 == q0 && q0 >= 2 && g0 + q0 >= 2) {
-          const int x = q0 - 2;
-          int       w = x >> 5;
-          uint32_t  pm = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
-          while (!pm && w > 0) pm = nlw[--w];
-          int ps = -1;
-          if (pm) ps = 32 * w + 32 - __clz(pm);   // first byte after that NL
-          else if (g0 <= 0) ps = (int)(-g0);      // the previous line is the first line of the file
-          if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
-            const uint2 a = token8(sm, tok0, toklen), c = token8(sm, ps, toklen);
-            head = a.x != c.x || a.y != c.y || sm[ps + toklen] > 0x20;
-            done = true;
+      }  // has
+      // chromosome run head?  Compare the token with the previous row's.  Shortcut: the previous row is usually the one
+      // the nearest lower lane with a line parsed in this very round (each lane owns 32 bytes, a line is longer),
+      // so its token arrives by shuffle.
+      {
+        const bool     cand = has && !err && toklen <= 8 && tok0 == q0;
+        const uint2    t8 = cand ? token8(sm, tok0, toklen) : make_uint2(0u, 0u);
+        const unsigned act = __ballot_sync(0xffffffffu, has);
+        const unsigned below = act & ((1u << lane) - 1u);
+        const int      src = below ? 31 - __clz(below) : lane;
+        const uint32_t pk = __shfl_sync(0xffffffffu, k, src);
+        const uint32_t px = __shfl_sync(0xffffffffu, t8.x, src), py = __shfl_sync(0xffffffffu, t8.y, src);
+        const int      plen = __shfl_sync(0xffffffffu, cand ? toklen : -1, src);
+        bool           done = false;
+        if (cand && below && pk + 1 == k && plen >= 0) {
+          head = plen != toklen || px != t8.x || py != t8.y;
+          done = true;
+        }
+        if (has && !err && !done) {
+          // the previous line ends at the NL just before this line's start; the NL before that one (found in the
+          // window's NL mask) is where the previous line starts
+          if (cand && q0 >= 2 && g0 + q0 >= 2) {
+            const int x = q0 - 2;
+            int       w = x >> 5;
+            uint32_t  pm = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
+            while (!pm && w > 0) pm = nlw[--w];
+            int ps = -1;
+            if (pm) ps = 32 * w + 32 - __clz(pm);   // first byte after that NL
+            else if (g0 <= 0) ps = (int)(-g0);      // the previous line is the first line of the file
+            if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
+              const uint2 c = token8(sm, ps, toklen);
+              head = t8.x != c.x || t8.y != c.y || sm[ps + toklen] > 0x20;
+              done = true;
+            }
+          }
+          if (!done) {
+            int64_t pt = prev_line_token(cur, q0);
+            head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
           }
         }
-        if (!done) {
-          int64_t pt = prev_line_token(cur, q0);
-          head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
-        }
-      }
-      }  // has
-      if (round == 0) {
-        if (warp != 0) asm volatile("bar.sync 1, %0;" ::"n"(P_THREADS) : "memory");
-        base = *reinterpret_cast<volatile uint64_t*>(&base_sm);
       }
       if (!has) continue;
       const uint64_t row = base + k;
@@ -600,29 +706,37 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     bed->nbytes = 0;
     return BK_OK;
   }
-  // row-capacity estimate: exact bound for small inputs, sampled line length for large ones
-  uint64_t cap;
-  if (nbytes_raw <= (64ull << 20)) {
-    cap = nbytes_raw / 6 + 2;  // shortest legal line "c\t0\t1\n"
-  } else {
-    uint64_t sample = 16ull << 20;
-    prof_begin(ctx, "k_count_nl");
-    k_count_nl<<<(unsigned)(sample / 16 / 256), 256, 0, ctx->stream>>>(text, sample, ctx->d_scratch);
-    prof_end(ctx);
-    BK_LAUNCHED(ctx);
-    BK_TRY(read_scratch(ctx));
-    uint64_t nl = ctx->h_scratch[SC_COUNT_A];
-    if (nl < 16) nl = 16;
-    double per = (double)sample / (double)nl;
-    cap = (uint64_t)((double)nbytes_raw / per * 1.10) + 4096;
-    if (cap > nbytes_raw / 6 + 2) cap = nbytes_raw / 6 + 2;
-    BK_TRY(reset_scratch(ctx));
-  }
+  const uint32_t ntiles = (uint32_t)((nbytes_raw + P_TILE - 1) / P_TILE);
   const uint32_t heads_cap = 1u << 16;
   HeadRec*       d_heads = dalloc<HeadRec>(ctx, heads_cap);
-  if (!d_heads) return BK_ERR_NOMEM;
-
-  for (int attempt = 0; attempt < 2; attempt++) {
+  // pass 1 geometry: one warp per contiguous range of tiles
+  const uint32_t max_warps = (uint32_t)ctx->sms * 8 * (CR_THREADS / 32);
+  const uint32_t tiles_per_warp = (ntiles + max_warps - 1) / max_warps;
+  const uint32_t nwarps = (ntiles + tiles_per_warp - 1) / tiles_per_warp;
+  uint32_t*      d_lpre = dalloc<uint32_t>(ctx, ntiles);
+  uint64_t*      d_wtot = dalloc<uint64_t>(ctx, nwarps);
+  uint64_t*      d_wbase = dalloc<uint64_t>(ctx, (size_t)nwarps + 1);
+  if (!d_heads || !d_lpre || !d_wtot || !d_wbase) return BK_ERR_NOMEM;
+  // pass 1: effective length, rows per tile, exclusive scan -> exact row count
+  prof_begin(ctx, "k_efflen");
+  k_efflen<<<1, 32, 0, ctx->stream>>>(text, nbytes_raw, ctx->d_scratch);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  prof_begin(ctx, "k_count_rows");
+  k_count_rows<<<(nwarps * 32 + CR_THREADS - 1) / CR_THREADS, CR_THREADS, 0, ctx->stream>>>(
+      text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  prof_begin(ctx, "k_scan_warps");
+  k_scan_warps<<<1, 1024, 0, ctx->stream>>>(d_wtot, d_wbase, nwarps, ctx->d_scratch);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  BK_TRY(read_scratch(ctx));
+  bed->nrows = ctx->h_scratch[SC_NROWS];
+  bed->nbytes = ctx->h_scratch[SC_EFFLEN];
+  dfree(ctx, d_wtot);
+  const uint64_t cap = bed->nrows;
+  {
     bed->start = dalloc<uint32_t>(ctx, cap);
     bed->end = dalloc<uint32_t>(ctx, cap);
     if (bed->cols & BK_COL_SCORE) bed->score = dalloc<double>(ctx, cap);
@@ -632,6 +746,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
         ((bed->cols & BK_COL_LINE) && !bed->line_off) || ((bed->cols & BK_COL_ID) && !bed->idspan))
       return BK_ERR_NOMEM;
 
+    // pass 2: tokenise
     ParseParams p{};
     p.text = bed->d_text;
     p.nbytes_raw = nbytes_raw;
@@ -643,25 +758,18 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     p.line_off = bed->line_off;
     p.idspan = bed->idspan;
     p.cap = cap;
-    p.ntiles = (uint32_t)((nbytes_raw + P_TILE - 1) / P_TILE);
+    p.ntiles = ntiles;
     p.scratch = ctx->d_scratch;
     p.heads = d_heads;
     p.heads_cap = heads_cap;
-    p.tile_state = dalloc<uint64_t>(ctx, p.ntiles);
-    if (!p.tile_state) return BK_ERR_NOMEM;
-    BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
-    prof_begin(ctx, "k_efflen");
-    k_efflen<<<1, 32, 0, ctx->stream>>>(text, nbytes_raw, ctx->d_scratch);
-    prof_end(ctx);
-    BK_LAUNCHED(ctx);
+    p.local_prefix = d_lpre;
+    p.warp_base = d_wbase;
+    p.tiles_per_warp = tiles_per_warp;
     prof_begin(ctx, "k_parse");
     {
       const bool sc = (p.cols & BK_COL_SCORE) != 0;
-      void* args[] = {&p};
-#define BK_PARSE(N, S)                                                                                             \
-  BK_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_parse<N, S>,                                              \
-                                           dim3(grid_for(ctx, (const void*)k_parse<N, S>, P_THREADS, p.ntiles)),          \
-                                           dim3(P_THREADS), args, 0, ctx->stream))
+#define BK_PARSE(N, S) \
+  k_parse<N, S><<<grid_for(ctx, (const void*)k_parse<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p)
       if (p.min_fields == 3) BK_PARSE(3, false);
       else if (p.min_fields == 4) BK_PARSE(4, false);
       else if (sc) BK_PARSE(5, true);
@@ -671,7 +779,8 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     prof_end(ctx);
     BK_LAUNCHED(ctx);
     BK_TRY(read_scratch(ctx));
-    dfree(ctx, p.tile_state);
+    dfree(ctx, d_lpre);
+    dfree(ctx, d_wbase);
     const uint64_t* h = ctx->h_scratch;
     if (h[SC_ERR_CODE]) {
       int code = (int)h[SC_ERR_CODE];
@@ -681,14 +790,6 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
                                                       : "line is not chrom<ws>start<ws>end[...] with enough fields";
       return fail(ctx, code, "BED parse error at row %llu: %s", (unsigned long long)h[SC_ERR_ROW] + 1, what);
     }
-    bed->nrows = h[SC_NROWS];
-    bed->nbytes = h[SC_EFFLEN];
-    if (bed->nrows <= cap) break;
-    // the estimate was too small: the exact row count is now known; free and redo once
-    dfree(ctx, bed->start); dfree(ctx, bed->end); dfree(ctx, bed->score); dfree(ctx, bed->line_off); dfree(ctx, bed->idspan);
-    bed->start = bed->end = nullptr; bed->score = nullptr; bed->line_off = nullptr; bed->idspan = nullptr;
-    cap = bed->nrows;
-    BK_TRY(reset_scratch(ctx));
   }
   if (bed->line_off && bed->nrows) {
     uint64_t endoff = bed->nbytes;

@@ -4,7 +4,8 @@
 
 namespace bk {
 
-constexpr int P_THREADS = 512;
+constexpr int P_THREADS = 256;
+constexpr int P_MINBLOCKS = 6;  // resident CTAs per SM the compiler must leave registers for
 constexpr int P_TILE = P_THREADS * 32;  // bytes of text whose line STARTS one tile owns
 constexpr int P_PRE = 128;    // halo before the tile (previous line's chromosome token)
 constexpr int P_POST = 384;   // halo after the tile (tail of the last line that starts in the tile)
@@ -28,7 +29,9 @@ struct ParseParams {
   uint64_t*   line_off;
   uint32_t*   idspan;
   uint64_t    cap;
-  uint64_t*   tile_state;
+  const uint32_t* local_prefix;  // [ntiles] rows of the earlier tiles of the same pass-1 warp range
+  const uint64_t* warp_base;     // [nwarps+1] first row of each pass-1 warp range
+  uint32_t        tiles_per_warp;
   uint32_t    ntiles;
   uint64_t*   scratch;
   HeadRec*    heads;
