@@ -134,21 +134,27 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
       hint = lo;
       const uint64_t re_pad64 = (uint64_t)re + pad;
       const uint32_t re_pad = re_pad64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)re_pad64;
-      const uint32_t hi = warp_gallop(ms, lo, nr, re_pad, lane, false);
-      uint32_t cnt = 0, idb = 0;
+      uint32_t cnt = 0, idb = 0, nwin = 0;
       uint64_t bases = 0;
       double   sum = 0.0, vmax = 0.0, vmin = 0.0;
       bool     have = false;
+      // Scan 64 map rows per step (two coalesced 32-row chunks whose loads are issued together).  Map starts are
+      // sorted, so the window ends in the first step in which some lane of the second chunk sees start >= ref.end.
 #pragma unroll 1
-      for (uint32_t k = lo + lane; k < hi; k += 32) {
-        const uint32_t s = __ldg(&ms[k]), e = __ldg(&me[k]);
-        uint32_t       ovl;
-        const bool     q = qualifies(ov, rs, re, s, e, ovl);
-        if (q) {
+      for (uint32_t k0 = lo; k0 < nr; k0 += 64) {
+        const uint32_t ka = k0 + lane, kb = ka + 32;
+        const bool     va = ka < nr, vb = kb < nr;
+        const uint32_t sa = va ? __ldg(&ms[ka]) : 0xFFFFFFFFu, sb = vb ? __ldg(&ms[kb]) : 0xFFFFFFFFu;
+        const uint32_t ea = va ? __ldg(&me[ka]) : 0u, eb = vb ? __ldg(&me[kb]) : 0u;
+        const bool     ina = va && sa < re_pad, inb = vb && sb < re_pad;
+        uint32_t       ova = 0, ovb = 0;
+        const bool     qa = ina && qualifies(ov, rs, re, sa, ea, ova);
+        const bool     qb = inb && qualifies(ov, rs, re, sb, eb, ovb);
+        if (qa) {
           cnt++;
-          if (FLAGS & NEED_BASES) bases += ovl;
+          if (FLAGS & NEED_BASES) bases += ova;
           if (kScore) {
-            const double v = __ldg(&sc[k]);
+            const double v = __ldg(&sc[ka]);
             sum += v;
             if (kMinMax) {
               vmax = have ? (v > vmax ? v : vmax) : v;
@@ -156,9 +162,27 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
               have = true;
             }
           }
-          if (FLAGS & NEED_IDS) idb += __ldg(&ids[k]) & 0xFFFFu;
+          if (FLAGS & NEED_IDS) idb += __ldg(&ids[ka]) & 0xFFFFu;
         }
+        if (qb) {
+          cnt++;
+          if (FLAGS & NEED_BASES) bases += ovb;
+          if (kScore) {
+            const double v = __ldg(&sc[kb]);
+            sum += v;
+            if (kMinMax) {
+              vmax = have ? (v > vmax ? v : vmax) : v;
+              vmin = have ? (v < vmin ? v : vmin) : v;
+              have = true;
+            }
+          }
+          if (FLAGS & NEED_IDS) idb += __ldg(&ids[kb]) & 0xFFFFu;
+        }
+        const unsigned mb_ = __ballot_sync(0xffffffffu, inb);
+        if (FLAGS & NEED_IDS) nwin += __popc(__ballot_sync(0xffffffffu, ina)) + __popc(mb_);
+        if (mb_ != 0xffffffffu) break;
       }
+      const uint32_t hi = lo + nwin;
       // warp reductions (fixed order: deterministic)
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (FLAGS & NEED_BASES) bases = warp_sum_u64(bases);
