@@ -340,6 +340,8 @@ extern "C" int bk_bed_copy_columns(bk_ctx* ctx, const bk_bed* bed, uint32_t* sta
     BK_CUDA(ctx, cudaMemcpyAsync(line_off, bed->line_off, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (line_off)
+    for (uint64_t i = 0; i < n; i++) line_off[i] &= kLineOffMask;  // the high 16 bits carry the echo fast-path length
   return BK_OK;
 }
 

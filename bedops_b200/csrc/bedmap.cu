@@ -315,13 +315,13 @@ struct BedmapRow {
             if (!first) s.puts_(mdelim, mdelim_len);
             first = false;
             const uint32_t sp = midspan[k];
-            s.copy(mtext + mline[k] + (sp >> 16), sp & 0xFFFFu);
+            s.copy(mtext + (mline[k] & kLineOffMask) + (sp >> 16), sp & 0xFFFFu);
           }
           break;
         }
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
-          const char* p = rtext + rline[row];
+          const char* p = rtext + (rline[row] & kLineOffMask);
           int         n = 0;
           while (is_tok((unsigned char)p[n])) n++;
           s.copy(p, n);

@@ -10,7 +10,8 @@
 
 namespace bk {
 
-constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kSMs = 148;
+constexpr uint64_t kLineOffMask = (1ull << 48) - 1;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 // ---------------------------------------------------------------------------------------------------------
 // host side
@@ -60,7 +61,8 @@ struct bk_bed {
   uint32_t*   start = nullptr;
   uint32_t*   end = nullptr;
   double*     score = nullptr;
-  uint64_t*   line_off = nullptr;  // [nrows+1]; line_off[nrows] = nbytes
+  uint64_t*   line_off = nullptr;  // [nrows+1]; low 48 bits = offset of the row's chromosome token, high 16 = line length
+                                   // (bytes up to the NL) when echoing the row is a verbatim copy, else 0xFFFF
   uint32_t*   idspan = nullptr;    // (rel_off << 16) | len  relative to line_off
   uint32_t*   pmax_end = nullptr;  // inclusive running max of end within the chromosome run (lazy)
   std::vector<bk::ChromRun> runs;

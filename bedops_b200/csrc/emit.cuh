@@ -20,9 +20,14 @@ constexpr int E_STAGE = 32 * 1024;  // bytes of shared staging per tile (tiles t
 // echo a B3Rest row: chrom \t start \t end <rest>   (Bed.hpp:316-320, :376-378): numbers are re-printed from the
 // parsed values, the rest of the line (including its leading tab) is copied verbatim.
 template <class Sink>
-__device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t off, uint32_t st, uint32_t en) {
-  const char* p = text + off;
-  int         n = 0;
+__device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t packed_off, uint32_t st, uint32_t en) {
+  const char*    p = text + (packed_off & kLineOffMask);
+  const uint32_t len = (uint32_t)(packed_off >> 48);
+  if (len != 0xFFFFu) {  // canonical line: re-printing reproduces the input bytes (decided by the parser)
+    s.copy(p, len);
+    return;
+  }
+  int n = 0;
   while (is_tok((unsigned char)p[n])) n++;
   s.copy(p, n);
   s.put('\t');
@@ -42,7 +47,7 @@ __device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ te
 }
 
 template <class RowFn>
-__global__ void __launch_bounds__(E_THREADS) k_emit(RowFn fn, uint64_t n, char* __restrict__ out, uint64_t out_cap,
+__global__ void __launch_bounds__(E_THREADS, 4) k_emit(RowFn fn, uint64_t n, char* __restrict__ out, uint64_t out_cap,
                                                     uint64_t* tile_state, uint32_t ntiles, uint64_t* scratch) {
   __shared__ __align__(16) char stage[E_STAGE + 16];
   __shared__ uint32_t           scan_sm[34];

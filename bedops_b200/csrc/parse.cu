@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       uint32_t v_start = 0, v_end = 0, v_id = 0;
       double   v_score = 0.0;
       int      tok0 = q0, toklen = 0, err = 0;
+      uint32_t linelen = 0xFFFFu;  // bytes up to the NL when the line is canonical (echo = verbatim copy), else 0xFFFF
       bool     head = false;
       if (has) {
       // 64 line bytes of control-byte mask, starting at the line start
@@ -464,6 +465,19 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           }
         }
         fast = bad == 0;
+        if (fast && p.line_off) {
+          // canonical for echo: single TABs (checked above), no leading zeros -> re-printing the numbers reproduces the
+          // input bytes, so the whole line can be copied.  Find the NL among the remaining control bytes.
+          int nlpos = -1;
+          if (sm[q0 + sp[NSEP - 1]] == '\n') nlpos = sp[NSEP - 1];
+          for (int it = 0; nlpos < 0 && W != 0 && it < 8; it++) {
+            const int r = __ffsll((long long)W) - 1;
+            if (sm[q0 + r] == '\n') nlpos = r;
+            W &= W - 1;
+          }
+          const bool lz = (sm[q0 + sp[0] + 1] == '0' && sp[1] - sp[0] > 2) || (sm[q0 + sp[1] + 1] == '0' && sp[2] - sp[1] > 2);
+          if (nlpos >= 0 && !lz) linelen = (uint32_t)nlpos;
+        }
       }
       if (!fast) {  // general path: fscanf-equivalent tokeniser (out of line: keeps the fast path's registers low)
         RowOut r;
@@ -537,7 +551,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         p.start[row] = v_start;
         p.end[row] = v_end;
         if (WANT_SCORE) p.score[row] = v_score;
-        if (p.line_off) p.line_off[row] = (uint64_t)(g0 + tok0);
+        if (p.line_off) p.line_off[row] = ((uint64_t)linelen << 48) | (uint64_t)(g0 + tok0);
         if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
       }
     }
