@@ -14,7 +14,7 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4}
-COL_LINE, COL_SCORE, COL_ID = 1, 2, 4
+COL_LINE, COL_SCORE, COL_ID, LOAD_HEADERS = 1, 2, 4, 8
 
 
 class BedKitError(RuntimeError):
@@ -89,6 +89,8 @@ def load_library() -> C.CDLL:
         "bk_closest": (i, [vp, vp, vp, C.POINTER(_CfSpec), C.POINTER(_Text)]),
         "bk_format_bed_device": (i, [vp, C.c_char_p, vp, vp, vp, u64, C.c_int64, C.POINTER(_Text)]),
         "bk_free_text": (None, [vp, C.POINTER(_Text)]),
+        "bk_check_text": (i, [vp, C.c_char_p, C.c_size_t, i, i, i]),
+        "bk_check_text_device": (i, [vp, vp, C.c_size_t, i, i, i]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
@@ -101,7 +103,8 @@ def load_library() -> C.CDLL:
 EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "bk_last_error", "bk_abi_version",
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
-           "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards"]
+           "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
+           "bk_check_text_device"]
 
 
 class Bed:
@@ -238,6 +241,10 @@ class BedKit:
         h = C.c_void_p()
         self._chk(self.lib.bk_load_bed_device(self.ctx, dev_ptr, nbytes, min_fields, cols, C.byref(h)))
         return Bed(self, h, keep)
+
+    def check_text(self, text: bytes, n_fields: int = 3, has_rest: bool = True, nest_check: bool = False):
+        """--ec validation; raises BedKitError(code 9) with the reference's message text on the first bad line."""
+        self._chk(self.lib.bk_check_text(self.ctx, text, len(text), n_fields, int(has_rest), int(nest_check)))
 
     # ---- tools ------------------------------------------------------------------------------------
     def free_text(self, t: _Text):

@@ -244,6 +244,8 @@ struct BedmapRow {
   const uint32_t* rs;
   const uint32_t* re;
   uint64_t        row0;
+  int             ref_fields;  // record type of the reference file: 3 = B3Rest; 4/5 only in single-file mode
+  const double*   rscore;
   // map side (echo-map-id)
   const char*     mtext;
   const uint64_t* mline;
@@ -263,6 +265,7 @@ struct BedmapRow {
   int             n_ops;
   unsigned char   ops[BK_MAX_OPS];
   int             prec;
+  int             sci;
   int             skip_unmapped;
   char            delim[24];
   int             delim_len;
@@ -274,6 +277,31 @@ struct BedmapRow {
   __device__ __forceinline__ void put_score(Sink& s, double v, uint32_t cnt, uint64_t i) const {
     if (cnt == 0) {
       s.puts_("NAN", 3);  // Signal::NaN::nan_ (interfaces/src/data/measurement/NaN.cpp:27)
+      return;
+    }
+    if (sci) {  // "%.<prec>e" (Formats.hpp:42-49)
+      Sci e;
+      if (!to_sci(v, prec, e)) {
+        dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);
+        s.put('?');
+        return;
+      }
+      if (e.neg) s.put('-');
+      if (e.special) {
+        if (e.special == 1) s.puts_("nan", 3); else s.puts_("inf", 3);
+        return;
+      }
+      const uint64_t pw = pow10_u64(prec);
+      s.put((char)('0' + (int)(e.digits / pw)));
+      if (prec > 0) {
+        s.put('.');
+        s.put_padded(e.digits % pw, prec);
+      }
+      s.put('e');
+      s.put(e.exp10 < 0 ? '-' : '+');
+      const uint32_t ae = (uint32_t)(e.exp10 < 0 ? -e.exp10 : e.exp10);
+      if (ae < 10) s.put('0');
+      s.put_u32(ae);
       return;
     }
     Fixed f;
@@ -293,7 +321,10 @@ struct BedmapRow {
     for (int c = 0; c < n_ops; c++) {
       if (c) s.puts_(delim, delim_len);
       switch (ops[c]) {
-        case BK_OP_ECHO: echo_b3rest(s, rtext, rline[row], rs[row], re[row]); break;
+        case BK_OP_ECHO:
+          if (ref_fields <= 3) echo_b3rest(s, rtext, rline[row], rs[row], re[row]);
+          else echo_b45rest(s, rtext, rline[row], rs[row], re[row], ref_fields, ref_fields >= 5 ? rscore[row] : 0.0, scratch, i);
+          break;
         case BK_OP_COUNT: s.put_u32(cnt); break;
         case BK_OP_INDICATOR: s.put(cnt ? '1' : '0'); break;
         case BK_OP_BASES: s.put_u64(bases[i]); break;
@@ -375,9 +406,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   memset(out, 0, sizeof(*out));
   if (!map) map = ref;
   if (spec->n_ops <= 0 || spec->n_ops > BK_MAX_OPS) return fail(ctx, BK_ERR_ARG, "No processing option specified (ie; --max).");
-  if (spec->sci) return fail(ctx, BK_ERR_UNSUPPORTED, "--sci output is not implemented on the device formatter yet");
-  if (spec->precision < 0 || spec->precision > 18)
-    return fail(ctx, BK_ERR_UNSUPPORTED, "--prec %d: the exact device formatter supports 0..18", spec->precision);
+  if (spec->precision < 0 || spec->precision > (spec->sci ? 17 : 18))
+    return fail(ctx, BK_ERR_UNSUPPORTED, "--prec %d: the exact device formatter supports 0..%d", spec->precision, spec->sci ? 17 : 18);
   const char* delim = spec->delim ? spec->delim : "|";
   const char* mdelim = spec->multidelim ? spec->multidelim : ";";
   if (strlen(delim) > 23 || strlen(mdelim) > 23) return fail(ctx, BK_ERR_UNSUPPORTED, "delimiter longer than 23 bytes");
@@ -515,12 +545,14 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
 
   BedmapRow fn{};
   fn.rtext = ref->d_text; fn.rline = ref->line_off; fn.rs = ref->start; fn.re = ref->end; fn.row0 = row0;
+  fn.ref_fields = (ref->min_fields >= 5 && !ref->score) ? 4 : ref->min_fields;
+  fn.rscore = ref->score;
   fn.mtext = map->d_text; fn.mline = map->line_off; fn.midspan = map->idspan; fn.ms = map->start; fn.me = map->end;
   fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
   fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
   fn.ov = ov; fn.n_ops = spec->n_ops;
   for (int c = 0; c < spec->n_ops; c++) fn.ops[c] = (unsigned char)spec->ops[c];
-  fn.prec = spec->precision; fn.skip_unmapped = spec->skip_unmapped;
+  fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
   fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
   fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
   fn.scratch = ctx->d_scratch;

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "fmt.cuh"
+#include "strtod_exact.cuh"
 
 namespace bk {
 
@@ -41,6 +42,62 @@ __device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ te
   while (is_ws((unsigned char)*q)) q++;
   if (*q == '+') q++;
   while (is_digit((unsigned char)*q)) q++;
+  int m = 0;
+  while (q[m] != '\n') m++;
+  s.copy(q, m);
+}
+
+// echo a B4Rest / B5Rest row (single-file bedmap, where the reference file has the map's record type,
+// Bedmap.cpp:676-700): "%s\t%lu\t%lu\t%s%s" / "%s\t%lu\t%lu\t%s\t%lf%s" (Bed.hpp:640-646, :740-743, :896-903):
+// id re-printed, column 5 re-printed with "%lf" (six decimals, whatever --prec says), the remainder verbatim.
+struct GlobalCursor {
+  const char* p;
+  __device__ __forceinline__ unsigned char at(int64_t q) const { return (unsigned char)p[q]; }
+};
+template <class Sink>
+__device__ __forceinline__ void echo_b45rest(Sink& s, const char* __restrict__ text, uint64_t packed_off, uint32_t st, uint32_t en,
+                                             int fields, double score, uint64_t* scratch, uint64_t row) {
+  const char* p = text + (packed_off & kLineOffMask);
+  if (fields == 4 && (uint32_t)(packed_off >> 48) != 0xFFFFu) {
+    s.copy(p, (uint32_t)(packed_off >> 48));
+    return;
+  }
+  int n = 0;
+  while (is_tok((unsigned char)p[n])) n++;
+  s.copy(p, n);
+  s.put('\t');
+  s.put_u32(st);
+  s.put('\t');
+  s.put_u32(en);
+  const char* q = p + n;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  while (is_ws((unsigned char)*q)) q++;
+  if (*q == '+') q++;
+  while (is_digit((unsigned char)*q)) q++;
+  while (is_ws((unsigned char)*q)) q++;
+  int idn = 0;
+  while (is_tok((unsigned char)q[idn])) idn++;
+  s.put('\t');
+  s.copy(q, idn);
+  q += idn;
+  if (fields >= 5) {
+    while (is_ws((unsigned char)*q)) q++;
+    GlobalCursor gc{q};
+    int64_t      adv = 0;
+    double       dummy;
+    parse_decimal(gc, adv, dummy);  // only to find where strtod stops
+    q += adv;
+    s.put('\t');
+    Fixed f;
+    if (!to_fixed(score, 6, f)) {
+      dev_set_error(scratch, BK_ERR_UNSUPPORTED, row);
+      s.put('?');
+    } else {
+      put_fixed(s, f, 6);
+    }
+  }
   int m = 0;
   while (q[m] != '\n') m++;
   s.copy(q, m);

@@ -193,6 +193,29 @@ __device__ __forceinline__ uint2 token8(const unsigned char* sm, int x, int len)
   return make_uint2(lo, hi);
 }
 
+// --ec/--header: is the line that starts at q a header (UCSC "browser"/"track" keyword, or first byte '@' / '#')?
+// (BedCheckIterator.hpp:315-360).  C::at(q) returns the byte at q.
+template <class C>
+__device__ __forceinline__ bool is_header_line(const C& c, int64_t q) {
+  unsigned char ch = c.at(q);
+  if (ch == '@' || ch == '#') return true;
+  if ((ch | 32) != 'b' && (ch | 32) != 't') return false;
+  const char* w = (ch | 32) == 'b' ? "browser" : "track";
+  const int   wl = (ch | 32) == 'b' ? 7 : 5;
+  for (int i = 0; i < wl; i++) {
+    unsigned char x = c.at(q + i);
+    if (x >= 'A' && x <= 'Z') x += 32;
+    if (x != (unsigned char)w[i]) return false;
+  }
+  const unsigned char e = c.at(q + wl);
+  return e == ' ' || e == '\t' || e == '\n';
+}
+struct TextCursor {  // global text with the parser's end-of-text convention
+  const unsigned char* t;
+  uint64_t             eff;
+  __device__ __forceinline__ unsigned char at(int64_t q) const { return (q < 0 || (uint64_t)q >= eff) ? '\n' : t[q]; }
+};
+
 // packed control-byte mask and NL mask (bit i = byte i) of 32 text bytes held in 8 words
 __device__ __forceinline__ void pack_masks32(const uint32_t (&w8)[8], uint32_t& cm, uint32_t& nlp) {
   cm = 0;
@@ -219,7 +242,8 @@ constexpr int CR_THREADS = 256;
 __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* __restrict__ text, uint64_t nbytes_raw,
                                                            const uint64_t* __restrict__ scratch,
                                                            uint32_t* __restrict__ local_prefix, uint64_t* __restrict__ warp_total,
-                                                           uint32_t ntiles, uint32_t tiles_per_warp, uint32_t nwarps) {
+                                                           uint32_t ntiles, uint32_t tiles_per_warp, uint32_t nwarps,
+                                                           int skip_headers) {
   const int      lane = threadIdx.x & 31;
   const uint32_t wid = (blockIdx.x * CR_THREADS + threadIdx.x) >> 5;
   if (wid >= nwarps) return;
@@ -266,6 +290,13 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
         uint64_t  q = p0 + j;
         while (q < eff && is_ws(text[q])) q++;
         if (q >= eff || text[q] == '\n') smask &= ~(1u << j);
+      }
+      if (skip_headers) {
+        const TextCursor tc{text, eff};
+        for (uint32_t m = smask; m; m &= m - 1) {
+          const int j = __ffs(m) - 1;
+          if (is_header_line(tc, (int64_t)(p0 + j))) smask &= ~(1u << j);
+        }
       }
       cnt += __popc(smask);
     }
@@ -389,6 +420,11 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       while (is_ws(cur.at(q))) q++;
       if (cur.at(q) == '\n') smask &= ~(1u << j);
     }
+    if (p.cols & BK_LOAD_HEADERS)
+      for (uint32_t m = smask; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        if (is_header_line(cur, off + j)) smask &= ~(1u << j);
+      }
     const uint32_t cnt = __popc(smask);
     const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31) wsum[warp] = incl;
@@ -738,7 +774,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_count_rows");
   k_count_rows<<<(nwarps * 32 + CR_THREADS - 1) / CR_THREADS, CR_THREADS, 0, ctx->stream>>>(
-      text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps);
+      text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps, (bed->cols & BK_LOAD_HEADERS) ? 1 : 0);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_scan_warps");

@@ -242,11 +242,23 @@ int main(int argc, char** argv) {
     spec.multidelim = mdelim.c_str();
     spec.chrom = o.chrom.c_str();
 
-    const unsigned map_cols = (need_score ? BK_COL_SCORE : 0) | (need_id ? (BK_COL_ID | BK_COL_LINE) : 0);
+    const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
+    const unsigned map_cols = (need_score ? BK_COL_SCORE : 0) | (need_id ? (BK_COL_ID | BK_COL_LINE) : 0) | hdr;
+    if (o.ec) {  // validate first (Bedmap.cpp:229-253, :292-329 use bed_check_iterator under --ec)
+      cli::ec_prepare(rtext);
+      cli::ec_prepare(mtext);
+      cli::Engine eng;
+      if (o.num_files == 2) {
+        cli::ec_check(eng, rtext, o.ref, 3, true, o.fast);
+        cli::ec_check(eng, mtext, o.map, o.min_map_fields, true, o.fast);
+      } else {
+        cli::ec_check(eng, rtext, o.ref, o.min_ref_fields, true, o.fast);
+      }
+    }
     auto run_one = [&](cli::Engine& eng, const char* rp, size_t rn, const char* mp, size_t mn) {
       bk_bed *ref = nullptr, *map = nullptr;
       if (o.num_files == 2) {
-        ref = eng.load(rp, rn, 3, need_line ? BK_COL_LINE : 0);
+        ref = eng.load(rp, rn, 3, (need_line ? BK_COL_LINE : 0) | hdr);
         map = eng.load(mp, mn, o.min_map_fields, map_cols);
       } else {
         ref = eng.load(rp, rn, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));

@@ -214,9 +214,17 @@ int main(int argc, char** argv) {
     for (size_t f = 0; f < o.files.size(); f++)
       if (!cli::slurp(o.files[f], texts[f])) throw UserError("Cannot find " + o.files[f]);
     const bool has_ref = op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF;
+    const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
+    if (o.ec) {  // Bedops.cpp:259-286: BedPadReader over bed_check_iterator; B3Rest for the -e/-n reference, B3NoRest otherwise
+      cli::Engine eng;
+      for (size_t f = 0; f < texts.size(); f++) {
+        cli::ec_prepare(texts[f]);
+        cli::ec_check(eng, texts[f], o.files[f], 3, has_ref && f == 0, false);
+      }
+    }
     auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
       std::vector<bk_bed*> beds;
-      for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, (has_ref && f == 0) ? BK_COL_LINE : 0));
+      for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, ((has_ref && f == 0) ? BK_COL_LINE : 0) | hdr));
       bk_text out;
       int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), o.subset, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
       if (rc != BK_OK) eng.raise(rc);

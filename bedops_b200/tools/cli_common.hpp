@@ -91,6 +91,18 @@ struct Engine {
   }
 };
 
+// --ec / --header: the checking iterator also reads an unterminated last line, so give the text its final NL, then run
+// the device validation (bk_check_text); failures are reported the way BedCheckIterator.hpp:589-593 words them.
+inline void ec_prepare(std::vector<char>& text) {
+  if (!text.empty() && text.back() != '\n') text.push_back('\n');
+}
+inline void ec_check(const Engine& eng, const std::vector<char>& text, const std::string& name, int n_fields, bool has_rest,
+                     bool nest_check) {
+  int rc = bk_check_text(eng.ctx, text.data(), text.size(), n_fields, has_rest ? 1 : 0, nest_check ? 1 : 0);
+  if (rc == BK_ERR_CHECK) throw std::runtime_error("in " + name + "\n" + bk_last_error(eng.ctx));
+  if (rc != BK_OK) eng.raise(rc);
+}
+
 // ---- multi-GPU: BEDKIT_GPUS=N shards the inputs by contiguous chromosome groups, one host thread + one bk_ctx per
 // GPU, outputs concatenated in shard order (byte-identical to the unsharded run) -------------------------
 struct Slice {

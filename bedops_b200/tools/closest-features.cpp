@@ -85,9 +85,17 @@ int main(int argc, char** argv) {
     if (delim == "\t" || delim == "\\t" || delim == "'\t'") delim = "\t";
     spec.delim = delim.c_str();
     spec.chrom = o.chrom.c_str();
+    const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
+    if (o.ec) {
+      cli::ec_prepare(rtext);
+      cli::ec_prepare(qtext);
+      cli::Engine eng;
+      cli::ec_check(eng, rtext, o.ref, 3, true, false);
+      cli::ec_check(eng, qtext, o.query, 3, true, false);
+    }
     auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
-      bk_bed* ref = eng.load(sl[0].ptr, sl[0].len, 3, BK_COL_LINE);
-      bk_bed* qry = eng.load(sl[1].ptr, sl[1].len, 3, BK_COL_LINE);
+      bk_bed* ref = eng.load(sl[0].ptr, sl[0].len, 3, BK_COL_LINE | hdr);
+      bk_bed* qry = eng.load(sl[1].ptr, sl[1].len, 3, BK_COL_LINE | hdr);
       bk_text out;
       int     rc = bk_closest(eng.ctx, ref, qry, &spec, &out);
       if (rc != BK_OK) eng.raise(rc);

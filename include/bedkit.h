@@ -81,7 +81,9 @@ int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes);
 enum {
   BK_COL_LINE = 1,  /* byte offset of each line (needed to echo a row or copy its id) */
   BK_COL_SCORE = 2, /* column 5 as double (strtod-exact); requires min_fields == 5 */
-  BK_COL_ID = 4     /* (offset,len) of column 4; requires min_fields >= 4 and BK_COL_LINE */
+  BK_COL_ID = 4,    /* (offset,len) of column 4; requires min_fields >= 4 and BK_COL_LINE */
+  BK_LOAD_HEADERS = 8 /* --ec/--header: UCSC browser/track lines and lines starting with '@' or '#' are not records
+                         (BedCheckIterator.hpp:315-360) */
 };
 /* min_fields = 3|4|5 selects the reference record type B3Rest / B4Rest / B5Rest (bedmap/src/Bedmap.cpp:623-654).
  * host text: copied to the device (pinned staging, async), then parsed.  The text must stay valid until return. */
@@ -96,6 +98,15 @@ uint64_t    bk_bed_chrom_rows(const bk_bed* bed, int i);
 /* test/debug accessor: copy parsed columns to host arrays of bk_bed_rows() elements (any pointer may be NULL) */
 int bk_bed_copy_columns(bk_ctx* ctx, const bk_bed* bed, uint32_t* start, uint32_t* end, double* score,
                         uint64_t* line_off);
+
+/* ---- --ec input validation -------------------------------------------------------------------------- */
+/* Replaces Bed::bed_check_iterator<T*>::check (data/bed/BedCheckIterator.hpp:326-634): format rules per line, then
+ * sort order against the previous data line, "fully nested" (nest_check, bedmap --faster) and end > start.
+ * n_fields = NumFields of the reference record type (3|4|5), has_rest = its UseRest.  The text must end with '\n'
+ * (the checking iterator also reads an unterminated last line; callers append the '\n').  On failure returns
+ * BK_ERR_CHECK and bk_last_error() = "<message>\nSee row: <n>"; the caller prefixes "in <file>\n" (:589-593). */
+int bk_check_text(bk_ctx* ctx, const char* host_text, size_t nbytes, int n_fields, int has_rest, int nest_check);
+int bk_check_text_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int n_fields, int has_rest, int nest_check);
 
 /* ---- bedmap ------------------------------------------------------------------------------ */
 enum { /* operations, printed left to right in the order given (MultiVisitor.hpp:83-98) */

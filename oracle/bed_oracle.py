@@ -166,6 +166,17 @@ def _fmt_score(v: float, prec: int, sci: bool) -> bytes:
     return (("%%.%de" if sci else "%%.%df") % prec % v).encode()
 
 
+def echo_row(r: Row, fields: int) -> bytes:
+    """B4Rest/B5Rest::print (Bed.hpp:640-646 "%s\\t%lu\\t%lu\\t%s%s", :740-743/:896-903 "...\\t%s\\t%lf%s"): used when the
+    reference file has the map's record type, i.e. single-file bedmap (Bedmap.cpp:676-700)."""
+    if fields <= 3:
+        return echo_b3rest(r)
+    out = r.chrom + b"\t" + str(r.start).encode() + b"\t" + str(r.end).encode() + b"\t" + r.id
+    if fields >= 5:
+        out += b"\t" + (b"%f" % r.score)
+    return out + r.rest
+
+
 def echo_b3rest(r: Row) -> bytes:
     """B3Rest::print "%s\\t%lu\\t%lu%s" (Bed.hpp:316-320, :376-378)."""
     return r.chrom + b"\t" + str(r.start).encode() + b"\t" + str(r.end).encode() + r.rest3
@@ -221,7 +232,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
         cols: List[bytes] = []
         for o in ops:
             if o == "echo":              # EchoVisitor.hpp:39-65
-                cols.append(echo_b3rest(r))
+                cols.append(echo_row(r, need_fields if single else 3))
             elif o == "count":           # CountVisitor.hpp:34-64
                 cols.append(str(cnt).encode())
             elif o == "indicator":       # IndicatorVisitor.hpp:37-56

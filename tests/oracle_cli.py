@@ -38,7 +38,7 @@ def parse_argv(tool, argv, known_files):
                 d["names"].append(a)
             i += 1
     elif tool == "bedmap":
-        d.update(ops=[], overlap=("bp", 1), prec=6, delim=b"|", multidelim=b";", skip_unmapped=False)
+        d.update(ops=[], overlap=("bp", 1), prec=6, sci=False, delim=b"|", multidelim=b";", skip_unmapped=False)
         while i < len(argv):
             a = argv[i]
             if a.startswith("--") and a[2:] in BEDMAP_OPS:
@@ -57,6 +57,8 @@ def parse_argv(tool, argv, known_files):
                 d["chrom"] = argv[i].encode()
             elif a == "--skip-unmapped":
                 d["skip_unmapped"] = True
+            elif a == "--sci":
+                d["sci"] = True
             elif a in ("--bp-ovr", "--range"):
                 i += 1
                 d["overlap"] = ("bp" if a == "--bp-ovr" else "range", int(argv[i]))
@@ -110,7 +112,7 @@ def run(tool, argv, files, stdin=None):
         return O.bedops_element_of(texts, d["thr"], d["pct"], d["op"] == "not-element-of", d["chrom"])
     if tool == "bedmap":
         return O.bedmap(texts[0], texts[1] if len(texts) > 1 else None, ops=d["ops"], overlap=d["overlap"],
-                        prec=d["prec"], delim=d["delim"], multidelim=d["multidelim"],
+                        prec=d["prec"], sci=d["sci"], delim=d["delim"], multidelim=d["multidelim"],
                         skip_unmapped=d["skip_unmapped"], chrom=d["chrom"])
     return O.closest_features(texts[0], texts[1], dist=d["dist"], closest=d["closest"], no_overlaps=d["no_overlaps"],
                               no_ref=d["no_ref"], delim=d["delim"], chrom=d["chrom"])
@@ -140,7 +142,7 @@ def run_kit(kit, tool, argv, files, stdin=None):
         else:
             ref = kit.load(texts[0], mf, mcols | (COL_LINE if line else 0))
             mp = None
-        out = kit.bedmap(ref, mp, ops, overlap=d["overlap"], prec=d["prec"], delim=d["delim"],
+        out = kit.bedmap(ref, mp, ops, overlap=d["overlap"], prec=d["prec"], sci=d["sci"], delim=d["delim"],
                          multidelim=d["multidelim"], skip_unmapped=d["skip_unmapped"], chrom=d["chrom"])
         ref.free()
         if mp is not None:

@@ -158,6 +158,9 @@ def test_synthetic_vs_oracle_bytes(kit, synth_files):
                        ("bedmap", ["--echo", "--count", "--mean", "--bases", "--sum", "--max", "--min", "r.bed", "m.bed"]),
                        ("bedmap", ["--prec", "0", "--mean", "--echo-ref-size", "--echo-ref-name", "--echo-ref-row-id", "r.bed", "m.bed"]),
                        ("bedmap", ["--prec", "12", "--mean", "r.bed", "m.bed"]),
+                       ("bedmap", ["--sci", "--mean", "--sum", "--max", "r.bed", "m.bed"]),
+                       ("bedmap", ["--sci", "--prec", "17", "--mean", "--min", "r.bed", "m.bed"]),
+                       ("bedmap", ["--sci", "--prec", "0", "--mean", "r.bed", "m.bed"]),
                        ("bedmap", ["--multidelim", "::", "--delim", "\t", "--echo-map-id", "--count", "r.bed", "u.bed"])):
         assert_same(oracle_cli.run_kit(kit, tool, argv, synth_files), oracle_cli.run(tool, argv, synth_files))
 
@@ -182,6 +185,21 @@ def test_nested_and_duplicate_intervals(kit):
                        ("bedops", ["-m", "m.bed", "r.bed"]), ("bedops", ["-i", "m.bed", "r.bed"]),
                        ("bedops", ["-e", "100%", "r.bed", "m.bed"]), ("bedops", ["-n", "m.bed", "r.bed"])):
         assert_same(oracle_cli.run_kit(kit, tool, argv, files), oracle_cli.run(tool, argv, files))
+
+
+def test_single_file_mode_echo_uses_the_map_record_type(kit, synth_files):
+    """bedmap with one file: the reference row is a B4Rest/B5Rest, so --echo re-prints the id and, with a score
+    operation, column 5 as "%lf" (Bedmap.cpp:676-700, Bed.hpp:740-743)."""
+    t = b"chr1\t10\t20\tz\t1\textra\nchr1\t15\t30\ty\t2.5\nchr2\t5\t9\tx\t-3e2\tq\n"
+    exp = {("echo", "mean"): b"chr1\t10\t20\tz\t1.000000\textra|1.750000\nchr1\t15\t30\ty\t2.500000|1.750000\nchr2\t5\t9\tx\t-300.000000\tq|-300.000000\n",
+           ("echo", "echo-map-id"): b"chr1\t10\t20\tz\t1\textra|z;y\nchr1\t15\t30\ty\t2.5|z;y\nchr2\t5\t9\tx\t-3e2\tq|x\n",
+           ("echo", "count"): b"chr1\t10\t20\tz\t1\textra|2\nchr1\t15\t30\ty\t2.5|2\nchr2\t5\t9\tx\t-3e2\tq|1\n"}
+    for ops, want in exp.items():   # `want` is the reference binary's output for this input
+        argv = ["--" + o for o in ops] + ["s.bed"]
+        assert_same(oracle_cli.run("bedmap", argv, {"s.bed": t}), want)
+        assert_same(oracle_cli.run_kit(kit, "bedmap", argv, {"s.bed": t}), want)
+    argv = ["--echo", "--sum", "--count", "m.bed"]
+    assert_same(oracle_cli.run_kit(kit, "bedmap", argv, synth_files), oracle_cli.run("bedmap", argv, synth_files))
 
 
 def test_closest_features_vs_oracle(kit, synth_files):
@@ -266,3 +284,49 @@ def test_cli_sharded_mode_is_byte_identical(tmp_path, synth_files):
         ref = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
         assert ours.returncode == 0, ours.stderr
         assert_same(ours.stdout, ref.stdout)
+
+
+EC_CASES = {
+    "unsorted_start.bed": b"chr1\t10\t20\nchr1\t5\t9\n",
+    "unsorted_end.bed": b"chr1\t10\t20\tb\nchr1\t10\t15\ta\n",
+    "unsorted_rest.bed": b"chr1\t10\t20\tb\t1\nchr1\t10\t20\ta\t1\n",
+    "unsorted_chrom.bed": b"chr2\t10\t20\nchr1\t5\t9\n",
+    "space_chrom.bed": b"track name=x\n#c\nchr1\t10\t20\tid\t3\nchr1 \t12\t30\n",
+    "space_start.bed": b"chr1\t1 0\t20\n",
+    "nonnum_end.bed": b"chr1\t10\t2x0\tid\t3\n",
+    "neg_start.bed": b"chr1\t-10\t20\n",
+    "two_tabs.bed": b"chr1\t\t20\t30\n",
+    "no_tabs.bed": b"chr1\n",
+    "empty_line.bed": b"chr1\t1\t2\n\nchr1\t3\t4\n",
+    "end_le_start.bed": b"chr1\t10\t20\tid\t1\nchr1\t30\t30\tid\t1\n",
+    "too_many_digits.bed": b"chr1\t1234567890123\t1234567890124\n",
+    "short_cols.bed": b"chr1\t10\t20\tid\t3\nchr1\t12\t30\tid\n",
+    "bad_score.bed": b"chr1\t10\t20\tid\t3.4.5\n",
+    "bad_score2.bed": b"chr1\t10\t20\tid\t3-\n",
+    "nested.bed": b"chr1\t10\t100\tid\t1\nchr1\t20\t30\tid\t2\n",
+    "headers_ok.bed": b"browser x\ntrack y\n@hd\n#c\nchr1\t10\t20\tid\t3\nchr1\t12\t30\tid\t5",
+}
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_ec_validation_matches_reference_messages(tmp_path):
+    """--ec: same stdout, same stderr text (message + row number), same exit code as the reference tools."""
+    import bedops_b200
+    for n, c in EC_CASES.items():
+        (tmp_path / n).write_bytes(c)
+    (tmp_path / "good.bed").write_bytes(b"chr1\t1\t50\tg\t2\nchr1\t40\t90\th\t4\n")
+    runs = []
+    for n in EC_CASES:
+        runs.append(("bedmap", ["--ec", "--echo", "--count", "--mean", n]))
+        runs.append(("bedmap", ["--ec", "--count", "good.bed", n]))
+        runs.append(("bedops", ["--ec", "-m", n]))
+        runs.append(("bedops", ["--ec", "-e", "1", n, "good.bed"]))
+    runs.append(("bedmap", ["--ec", "--faster", "--count", "nested.bed"]))
+    runs.append(("closest-features", ["--ec", "--dist", "space_chrom.bed", "good.bed"]))
+    runs.append(("closest-features", ["--ec", "good.bed", "headers_ok.bed"]))
+    for tool, argv in runs:
+        ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
+        ref = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
+        assert ours.returncode == ref.returncode, (tool, argv, ours.stderr, ref.stderr)
+        assert ours.stdout == ref.stdout, (tool, argv, ours.stdout, ref.stdout)
+        assert ours.stderr == ref.stderr, (tool, argv, ours.stderr, ref.stderr)
