@@ -237,6 +237,9 @@ static void launch_map_stats(unsigned need, unsigned blocks, cudaStream_t st, co
   }
 }
 
+// RARE bit 0: --sci output; bit 1: the reference file is a B4Rest/B5Rest (single-file mode) -- compile-time so that the
+// common instantiation carries none of that code (the emitter is register-bound).
+template <int RARE>
 struct BedmapRow {
   // reference rows
   const char*     rtext;
@@ -279,7 +282,22 @@ struct BedmapRow {
       s.puts_("NAN", 3);  // Signal::NaN::nan_ (interfaces/src/data/measurement/NaN.cpp:27)
       return;
     }
-    if (sci) {  // "%.<prec>e" (Formats.hpp:42-49)
+    if ((RARE & 1) && sci) {  // "%.<prec>e" (Formats.hpp:42-49)
+      put_sci(s, v, i);
+      return;
+    }
+    Fixed f;
+    if (!to_fixed(v, prec, f)) {
+      dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);
+      s.put('?');
+      return;
+    }
+    put_fixed(s, f, prec);
+  }
+
+  template <class Sink>
+  __device__ __noinline__ void put_sci(Sink& s, double v, uint64_t i) const {
+    {
       Sci e;
       if (!to_sci(v, prec, e)) {
         dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);
@@ -302,15 +320,7 @@ struct BedmapRow {
       const uint32_t ae = (uint32_t)(e.exp10 < 0 ? -e.exp10 : e.exp10);
       if (ae < 10) s.put('0');
       s.put_u32(ae);
-      return;
     }
-    Fixed f;
-    if (!to_fixed(v, prec, f)) {
-      dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);
-      s.put('?');
-      return;
-    }
-    put_fixed(s, f, prec);
   }
 
   template <class Sink>
@@ -322,7 +332,7 @@ struct BedmapRow {
       if (c) s.puts_(delim, delim_len);
       switch (ops[c]) {
         case BK_OP_ECHO:
-          if (ref_fields <= 3) echo_b3rest(s, rtext, rline[row], rs[row], re[row]);
+          if (!(RARE & 2) || ref_fields <= 3) echo_b3rest(s, rtext, rline[row], rs[row], re[row]);
           else echo_b45rest(s, rtext, rline[row], rs[row], re[row], ref_fields, ref_fields >= 5 ? rscore[row] : 0.0, scratch, i);
           break;
         case BK_OP_COUNT: s.put_u32(cnt); break;
@@ -427,7 +437,6 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }
   }
-  (void)need_echo;
   if (need_refline && !ref->line_off && ref->nrows)
     return fail(ctx, BK_ERR_ARG, "reference file was loaded without BK_COL_LINE but --echo needs it");
   if ((need & (NEED_SUM | NEED_MAX | NEED_MIN)) && !map->score && map->nrows)
@@ -543,23 +552,29 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   uint64_t cap = n * per_row + idtotal + 64;
   if (need_refline) cap += ref->nbytes + 2 * 11 * n;
 
-  BedmapRow fn{};
-  fn.rtext = ref->d_text; fn.rline = ref->line_off; fn.rs = ref->start; fn.re = ref->end; fn.row0 = row0;
-  fn.ref_fields = (ref->min_fields >= 5 && !ref->score) ? 4 : ref->min_fields;
-  fn.rscore = ref->score;
-  fn.mtext = map->d_text; fn.mline = map->line_off; fn.midspan = map->idspan; fn.ms = map->start; fn.me = map->end;
-  fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
-  fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
-  fn.ov = ov; fn.n_ops = spec->n_ops;
-  for (int c = 0; c < spec->n_ops; c++) fn.ops[c] = (unsigned char)spec->ops[c];
-  fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
-  fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
-  fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
-  fn.scratch = ctx->d_scratch;
-
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
-  int rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
+  int      rc = BK_OK;
+  auto emit = [&](auto fn) {
+    fn.rtext = ref->d_text; fn.rline = ref->line_off; fn.rs = ref->start; fn.re = ref->end; fn.row0 = row0;
+    fn.ref_fields = (ref->min_fields >= 5 && !ref->score) ? 4 : ref->min_fields;
+    fn.rscore = ref->score;
+    fn.mtext = map->d_text; fn.mline = map->line_off; fn.midspan = map->idspan; fn.ms = map->start; fn.me = map->end;
+    fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
+    fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
+    fn.ov = ov; fn.n_ops = spec->n_ops;
+    for (int c = 0; c < spec->n_ops; c++) fn.ops[c] = (unsigned char)spec->ops[c];
+    fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
+    fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
+    fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
+    fn.scratch = ctx->d_scratch;
+    rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
+  };
+  const bool rare_fields = need_echo && ref->min_fields > 3;
+  if (!spec->sci && !rare_fields) emit(BedmapRow<0>{});
+  else if (spec->sci && !rare_fields) emit(BedmapRow<1>{});
+  else if (!spec->sci) emit(BedmapRow<2>{});
+  else emit(BedmapRow<3>{});
   dfree(ctx, sp.count); dfree(ctx, sp.bases); dfree(ctx, sp.sum); dfree(ctx, sp.vmax); dfree(ctx, sp.vmin);
   dfree(ctx, sp.win_lo); dfree(ctx, sp.win_n); dfree(ctx, sp.idbytes);
   if (rc != BK_OK) {

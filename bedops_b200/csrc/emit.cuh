@@ -21,6 +21,9 @@ constexpr int E_STAGE = 32 * 1024;  // bytes of shared staging per tile (tiles t
 // echo a B3Rest row: chrom \t start \t end <rest>   (Bed.hpp:316-320, :376-378): numbers are re-printed from the
 // parsed values, the rest of the line (including its leading tab) is copied verbatim.
 template <class Sink>
+__device__ __noinline__ void echo_b3rest_slow(Sink& s, const char* __restrict__ p, uint32_t st, uint32_t en);
+
+template <class Sink>
 __device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ text, uint64_t packed_off, uint32_t st, uint32_t en) {
   const char*    p = text + (packed_off & kLineOffMask);
   const uint32_t len = (uint32_t)(packed_off >> 48);
@@ -28,6 +31,11 @@ __device__ __forceinline__ void echo_b3rest(Sink& s, const char* __restrict__ te
     s.copy(p, len);
     return;
   }
+  echo_b3rest_slow(s, p, st, en);
+}
+
+template <class Sink>
+__device__ __noinline__ void echo_b3rest_slow(Sink& s, const char* __restrict__ p, uint32_t st, uint32_t en) {
   int n = 0;
   while (is_tok((unsigned char)p[n])) n++;
   s.copy(p, n);
@@ -55,7 +63,7 @@ struct GlobalCursor {
   __device__ __forceinline__ unsigned char at(int64_t q) const { return (unsigned char)p[q]; }
 };
 template <class Sink>
-__device__ __forceinline__ void echo_b45rest(Sink& s, const char* __restrict__ text, uint64_t packed_off, uint32_t st, uint32_t en,
+__device__ __noinline__ void echo_b45rest(Sink& s, const char* __restrict__ text, uint64_t packed_off, uint32_t st, uint32_t en,
                                              int fields, double score, uint64_t* scratch, uint64_t row) {
   const char* p = text + (packed_off & kLineOffMask);
   if (fields == 4 && (uint32_t)(packed_off >> 48) != 0xFFFFu) {

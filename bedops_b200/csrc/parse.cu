@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
   __shared__ uint32_t                    ctlp[P_NW + 4];
   __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
   __shared__ uint32_t                    wsum[P_THREADS / 32];
+  __shared__ uint64_t                    base_sm;
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t eff = p.scratch[SC_EFFLEN];  // bytes up to and including the last '\n'
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     const uint32_t cnt = __popc(smask);
     const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31) wsum[warp] = incl;
-    __syncthreads();  // [S2] masks and warp totals visible
+    if (tid == 0) base_sm = p.warp_base[tile / p.tiles_per_warp] + p.local_prefix[tile];  // first row of this tile (pass 1)
+    __syncthreads();  // [S2] masks, warp totals and the tile's first row visible
     uint32_t ex = incl - cnt, nrow = 0;
 #pragma unroll
     for (int v = 0; v < P_THREADS / 32; v++) {
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       nrow += t;
     }
 
-    const uint64_t base = p.warp_base[tile / p.tiles_per_warp] + p.local_prefix[tile];  // first row of this tile (pass 1)
+    const uint64_t base = base_sm;
     (void)nrow;
 
     // ---- every thread parses the lines that START in its 32 bytes ---------------------------------------------
@@ -461,15 +463,21 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       // 64 line bytes of control-byte mask, starting at the line start
       const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
       const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
-      unsigned long long W = ((unsigned long long)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
+      uint32_t Wlo = __funnelshift_r(c0, c1, sh), Whi = __funnelshift_r(c1, c2, sh);  // bytes 0..31 / 32..63 of the line
       int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
       bool fast = true;
 #pragma unroll
       for (int f = 0; f < NSEP; f++) {
-        fast = fast && W != 0;
-        sp[f] = __ffsll((long long)W) - 1;
-        W &= W - 1;
+        if (Wlo) {
+          sp[f] = __ffs(Wlo) - 1;
+          Wlo &= Wlo - 1;
+        } else {
+          fast = fast && Whi != 0;
+          sp[f] = 31 + __ffs(Whi);
+          Whi &= Whi - 1;
+        }
       }
+      unsigned long long W = ((unsigned long long)Whi << 32) | Wlo;  // the remaining control bytes
       uint32_t bad = 0;
       if (fast) {
         // every separator but the last must be a TAB, the last a TAB or the NL
