@@ -131,6 +131,14 @@ __device__ __forceinline__ void dev_set_error(uint64_t* scratch, int code, uint6
     scratch[SC_ERR_ROW] = where;
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // streaming 16-byte load, no L1 allocation
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -135,7 +135,6 @@ __device__ __noinline__ int64_t prev_line_token(const Cursor& c, int64_t p0) {
 // such byte after every field, so the set bits of the 64-bit window that starts at a line start ARE the field
 // boundaries; reading the byte found tells TAB from NL from anything that sends the line to the general tokeniser.
 constexpr int P_NW = (P_TILE + P_POST) / 32;  // mask words; word w covers window bytes [P_PRE+32w, P_PRE+32w+32)
-constexpr int P_RCAP = 1408;                  // rows staged per tile (>= P_TILE / 6, the shortest legal line)
 
 __device__ __forceinline__ uint32_t ctl_mask4(uint32_t w) {  // bit 8j+7 set iff byte j < 0x21
   return ~(((w & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | w) & 0x80808080u;
@@ -340,7 +339,7 @@ __global__ void __launch_bounds__(1024) k_scan_warps(const uint64_t* __restrict_
 // consecutive rows, so the stores coalesce).  Three block barriers per tile.
 template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p) {
-  __shared__ __align__(16) unsigned char sm[P_BUF + 16];
+  __shared__ __align__(16) unsigned char smbuf[2][P_BUF + 16];  // double-buffered text window
   __shared__ uint32_t                    ctlp[P_NW + 4];
   __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
   __shared__ uint32_t                    wsum[P_THREADS / 32];
@@ -349,31 +348,38 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
   const uint64_t eff = p.scratch[SC_EFFLEN];  // bytes up to and including the last '\n'
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
 
-  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+  // stage [ts-PRE, ts+TILE+POST) of a tile into a window buffer: 16-byte asynchronous copies (global -> shared
+  // without passing through registers), issued one tile ahead so that the copy of tile t+1 overlaps the parse of t
+  auto stage = [&](uint32_t tile, unsigned char* dst) {
+    const int64_t g0 = (int64_t)tile * P_TILE - P_PRE;
+    for (int v = tid; v < P_BUF / 16; v += P_THREADS) {
+      const int64_t g = g0 + (int64_t)v * 16;
+      if (g >= 0 && (uint64_t)g + 16 <= p.nbytes_raw) {
+        cp_async16(dst + v * 16, text + g);
+      } else {  // window edge: before the text, or across its end -- zero-filled, byte by byte
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < p.nbytes_raw) {
+#pragma unroll 1
+          for (int i = 0; i < 16; i++) {
+            const int64_t gi = g + i;
+            if (gi >= 0 && (uint64_t)gi < p.nbytes_raw) w[i >> 2] |= (uint32_t)text[gi] << (8 * (i & 3));
+          }
+        }
+        reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  if (blockIdx.x < p.ntiles) stage(blockIdx.x, smbuf[0]);
+  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, buf ^= 1) {
     const int64_t ts = (int64_t)tile * P_TILE;
     const int64_t g0 = ts - P_PRE;
-
-    // ---- stage [ts-PRE, ts+TILE+POST) into shared memory, 16 bytes per request ---------------------------
-    for (int v = tid; v < P_BUF / 16; v += P_THREADS) {
-      int64_t g = g0 + (int64_t)v * 16;
-      uint4   w = make_uint4(0, 0, 0, 0);
-      if (g >= 0 && (uint64_t)g + 16 <= p.nbytes_raw) {
-        w = ldg_stream16(text + g);
-      } else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < p.nbytes_raw) {
-        unsigned char b[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          int64_t gi = g + i;
-          b[i] = (gi >= 0 && (uint64_t)gi < p.nbytes_raw) ? text[gi] : 0;
-        }
-        w.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
-        w.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
-        w.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
-        w.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
-      }
-      reinterpret_cast<uint4*>(sm)[v] = w;
-    }
-    __syncthreads();  // [S1] text staged
+    unsigned char* const sm = smbuf[buf];
+    cp_async_wait_all();
+    __syncthreads();  // [S1] this tile's text staged (the other buffer is free: everyone passed [S3] of the previous tile)
+    if (tile + gridDim.x < p.ntiles) stage(tile + gridDim.x, smbuf[buf ^ 1]);
 
     // ---- control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' -----------
     Cursor        cur{sm, g0, text, eff};
@@ -431,16 +437,13 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     if (lane == 31) wsum[warp] = incl;
     if (tid == 0) base_sm = p.warp_base[tile / p.tiles_per_warp] + p.local_prefix[tile];  // first row of this tile (pass 1)
     __syncthreads();  // [S2] masks, warp totals and the tile's first row visible
-    uint32_t ex = incl - cnt, nrow = 0;
-#pragma unroll
-    for (int v = 0; v < P_THREADS / 32; v++) {
-      const uint32_t t = wsum[v];
-      if (v < warp) ex += t;
-      nrow += t;
+    uint32_t ex = incl - cnt;  // rows of this tile that start before this thread's bytes
+    {
+      const uint32_t t = (lane < warp && lane < P_THREADS / 32) ? wsum[lane] : 0u;
+      ex += __reduce_add_sync(0xffffffffu, t);
     }
 
     const uint64_t base = base_sm;
-    (void)nrow;
 
     // ---- every thread parses the lines that START in its 32 bytes ---------------------------------------------
     // The loop is warp-uniform: lanes without a (further) line idle.
