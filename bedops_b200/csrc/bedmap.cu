@@ -104,34 +104,53 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
         if (p.run_ref_begin[mid] <= row) my_run = mid; else hi_r = mid;
       }
     }
+    // Window starts of the whole batch at once: lo = first map row whose running-max end reaches the (padded) reference
+    // start.  Reference rows are sorted by start, so lo is non-decreasing within a chromosome: two warp-cooperative
+    // searches bracket the batch (first and last row), then every lane bisects its own key inside the bracket.
+    const int      nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
+    const uint32_t my_key = my_rs >= pad ? my_rs - pad + 1 : 0;
+    uint32_t       my_lo;
+    {
+      const int run_a = __shfl_sync(0xffffffffu, my_run, 0);
+      if (__all_sync(0xffffffffu, my_run == run_a)) {
+        const uint64_t  mb0 = p.run_map_begin[run_a];
+        const uint32_t  nr0 = (uint32_t)(p.run_map_end[run_a] - mb0);
+        const uint32_t* pm0 = p.pm + mb0;
+        const uint32_t  key_a = __shfl_sync(0xffffffffu, my_key, 0), key_b = __shfl_sync(0xffffffffu, my_key, nj - 1);
+        uint32_t        a = warp_search32(pm0, nr0, key_a, lane);
+        uint32_t        b = warp_gallop(pm0, a, nr0, key_b, lane, true);
+        while (a < b) {  // same trip count on every lane
+          const uint32_t mid = a + ((b - a) >> 1);
+          if (__ldg(&pm0[mid]) < my_key) a = mid + 1; else b = mid;
+        }
+        my_lo = a;
+      } else {  // the batch straddles a chromosome boundary: every lane searches its own chromosome
+        const uint64_t mbl = p.run_map_begin[my_run];
+        my_lo = (uint32_t)lower_bound_u32(p.pm + mbl, 0, p.run_map_end[my_run] - mbl, my_key);
+      }
+    }
     uint32_t out_cnt = 0, out_idb = 0, out_n = 0, out_lo = 0;
     uint64_t out_bases = 0, out_mb = 0;
     double   out_sum = 0.0, out_max = 0.0, out_min = 0.0;
     int      hint_run = -1;
-    uint32_t hint = 0, nr = 0;
+    uint32_t nr = 0;
     uint64_t mb = 0;
-    const uint32_t *ms = nullptr, *me = nullptr, *pm = nullptr, *ids = nullptr;
+    const uint32_t *ms = nullptr, *me = nullptr, *ids = nullptr;
     const double*   sc = nullptr;
-    const int nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
 #pragma unroll 1
     for (int j = 0; j < nj; j++) {
       const uint32_t rs = __shfl_sync(0xffffffffu, my_rs, j), re = __shfl_sync(0xffffffffu, my_re, j);
       const int      run = __shfl_sync(0xffffffffu, my_run, j);
-      const uint32_t key = rs >= pad ? rs - pad + 1 : 0;  // first pmax_end that reaches the (padded) reference start
-      const bool     fresh = run != hint_run;
-      if (fresh) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, j);
+      if (run != hint_run) {
         mb = p.run_map_begin[run];
         nr = (uint32_t)(p.run_map_end[run] - mb);
         ms = p.ms + mb;
         me = p.me + mb;
-        pm = p.pm + mb;
         if (kScore) sc = p.score + mb;
         if (FLAGS & NEED_IDS) ids = p.idspan + mb;
         hint_run = run;
-        hint = 0;
       }
-      const uint32_t lo = warp_gallop(pm, hint, nr, key, lane, !fresh);
-      hint = lo;
       const uint64_t re_pad64 = (uint64_t)re + pad;
       const uint32_t re_pad = re_pad64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)re_pad64;
       uint32_t cnt = 0, idb = 0, nwin = 0;

@@ -339,6 +339,26 @@ __device__ __forceinline__ uint32_t warp_gallop(const uint32_t* __restrict__ a, 
   return lo;
 }
 
+// First index i in [0, n) with a[i] >= key (n if none), a non-decreasing: 32-ary search, every round the 32 lanes
+// probe the last element of 32 equal sub-ranges (5 rounds for 2^25 rows instead of 25 dependent binary-search loads).
+__device__ __forceinline__ uint32_t warp_search32(const uint32_t* __restrict__ a, uint32_t n, uint32_t key, int lane) {
+  // invariant: the answer is in [from, from+len]; from+len means "every element of [from, from+len) is < key"
+  uint32_t from = 0, len = n;
+  while (len) {
+    const uint32_t step = (len + 31u) >> 5;
+    const uint32_t k = from + step * (uint32_t)(lane + 1) - 1u;  // last element of sub-range `lane`
+    const bool     in = k < from + len;
+    const uint32_t v = in ? __ldg(&a[k]) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(0xffffffffu, !in || v >= key);
+    if (m == 0) return from + len;
+    const uint32_t j = (uint32_t)(__ffs(m) - 1);
+    const uint32_t ub = min(from + step * (j + 1u) - 1u, from + len);  // a[ub] >= key, or ub is the old bound
+    from += step * j;
+    len = ub - from;
+  }
+  return from;
+}
+
 // sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
   const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
