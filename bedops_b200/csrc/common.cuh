@@ -231,45 +231,6 @@ __device__ __forceinline__ uint64_t lookback_sum(uint64_t* state, uint32_t tile,
   return excl;
 }
 
-// Segmented-max look-back.  value = head(1 bit) << 40 | max(40 bits): a tile aggregate is "the max since the
-// tile's last segment head (or since the tile start)" plus whether the tile contains a head.  Returns the running
-// max flowing INTO this tile (0 if the predecessor chain ends in a head with nothing after it is handled by value).
-__device__ __forceinline__ uint64_t lookback_segmax(uint64_t* state, uint32_t tile, bool agg_head, uint64_t agg_max) {
-  const int      lane = threadIdx.x & 31;
-  const uint64_t kHead = 1ull << 40, kMax = kHead - 1;
-  // if this tile has a head, its inclusive value is already final
-  uint64_t mine = (agg_head ? kHead : 0) | agg_max;
-  if (lane == 0) st_relaxed_u64(&state[tile], (((tile == 0 || agg_head) ? 2ull : 1ull) << 62) | mine);
-  if (tile == 0) return 0;
-  uint64_t carry = 0;
-  int64_t  look = (int64_t)tile - 1;
-  while (true) {
-    int64_t  idx = look - lane;
-    uint64_t w = (2ull << 62) | kHead;  // virtual predecessor: a head with max 0
-    if (idx >= 0) {
-      w = ld_relaxed_u64(&state[idx]);
-      while ((w >> 62) == 0) w = ld_relaxed_u64(&state[idx]);
-    }
-    // a lane ends the walk if it holds an inclusive prefix or contains a head
-    unsigned stop = __ballot_sync(0xffffffffu, (w >> 62) == 2 || (w & kHead));
-    int      first = stop ? (__ffs(stop) - 1) : 31;
-    uint64_t c = (lane <= first) ? (w & kMax) : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      uint64_t o = __shfl_xor_sync(0xffffffffu, c, d);
-      c = o > c ? o : c;
-    }
-    carry = c > carry ? c : carry;
-    if (stop) break;
-    look -= 32;
-  }
-  if (!agg_head && lane == 0) {
-    uint64_t incl = agg_max > carry ? agg_max : carry;
-    st_relaxed_u64(&state[tile], (2ull << 62) | incl);
-  }
-  return carry;
-}
-
 // dynamic tile ticket: one atomicAdd per tile, broadcast through shared memory
 __device__ __forceinline__ uint32_t next_ticket(uint64_t* scratch, uint32_t* smem_slot) {
   if (threadIdx.x == 0) *smem_slot = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_TICKET]), 1ull);

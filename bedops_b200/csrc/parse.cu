@@ -624,116 +624,80 @@ __global__ void k_efflen(const unsigned char* text, uint64_t nbytes, uint64_t* s
   if (lane == 0) scratch[SC_EFFLEN] = 0;
 }
 
-// count '\n' in a prefix of the text (row-capacity estimate)
-__global__ void k_count_nl(const unsigned char* text, uint64_t n, uint64_t* scratch) {
-  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  uint32_t c = 0;
-  if (i + 16 <= n) {
-    uint4 w = ldg_stream16(text + i);
-    c = __popc(__vcmpeq4(w.x, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(w.y, 0x0A0A0A0Au) & 0x01010101u) +
-        __popc(__vcmpeq4(w.z, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(w.w, 0x0A0A0A0Au) & 0x01010101u);
+// inclusive running max of `in` within each chromosome run (the index that bounds candidate windows for nested
+// intervals, north_star item 3).  max is idempotent, so no carry chain between tiles is needed: rows are cut into
+// warp ranges of PM_RANGE rows that never cross a chromosome boundary; pass 1 reduces every range to its maximum,
+// pass 2 gives a range the maximum of the earlier ranges of its chromosome as carry (a short reduction over the
+// pass-1 array, L2 resident) and scans its own rows, 32 at a time with coalesced loads and stores.
+constexpr int PM_THREADS = 256, PM_RANGE = 2048;
+struct PmRun {
+  uint64_t row_begin, row_end, first_range;  // first_range: index of the chromosome's first warp range
+};
+
+__device__ __forceinline__ void pm_locate(const PmRun* __restrict__ runs, int nruns, uint64_t r, uint64_t& a, uint64_t& b,
+                                          uint64_t& first) {
+  int lo = 0, hi = nruns;  // last run with first_range <= r (empty runs own no range and are skipped by "last")
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (runs[mid].first_range <= r) lo = mid; else hi = mid;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_COUNT_A]), (unsigned long long)c);
+  first = runs[lo].first_range;
+  a = runs[lo].row_begin + (r - first) * PM_RANGE;
+  b = a + PM_RANGE < runs[lo].row_end ? a + PM_RANGE : runs[lo].row_end;
 }
 
-// inclusive running max of end within each chromosome run (the index that bounds candidate windows for nested
-// intervals, north_star item 3).  Tiles of 256*8 rows; segmented-max look-back across tiles.
-constexpr int PM_THREADS = 256, PM_ITEMS = 8, PM_TILE = PM_THREADS * PM_ITEMS;
-__global__ void __launch_bounds__(PM_THREADS) k_pmax(const uint32_t* __restrict__ end, uint32_t* __restrict__ pmax,
-                                                     uint64_t n, const uint64_t* __restrict__ run_begin, int nruns,
-                                                     uint64_t* tile_state, uint32_t ntiles, uint64_t* scratch) {
-  __shared__ uint32_t ticket_sm;
-  __shared__ uint64_t wmax[PM_THREADS / 32];
-  __shared__ uint32_t whead[PM_THREADS / 32];
-  __shared__ uint64_t carry_sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  while (true) {
-    const uint32_t tile = next_ticket(scratch, &ticket_sm);
-    if (tile >= ntiles) break;
-    const uint64_t r0 = (uint64_t)tile * PM_TILE + (uint64_t)tid * PM_ITEMS;
-    // which rows of this thread's 8 are run heads?  run_begin is sorted; find the first run_begin >= r0
-    int lo = 0, hi = nruns;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (run_begin[mid] < r0) lo = mid + 1; else hi = mid;
+__global__ void __launch_bounds__(PM_THREADS) k_pmax_reduce(const uint32_t* __restrict__ in, const PmRun* __restrict__ runs,
+                                                            int nruns, uint64_t nranges, uint32_t* __restrict__ range_max) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * PM_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * PM_THREADS) >> 5;
+  for (uint64_t r = w0; r < nranges; r += nw) {
+    uint64_t a, b, first;
+    pm_locate(runs, nruns, r, a, b, first);
+    uint32_t m = 0;
+    for (uint64_t k = a + lane; k < b; k += 128) {  // four independent loads in flight per lane
+      const uint32_t v0 = __ldg(&in[k]);
+      const uint32_t v1 = k + 32 < b ? __ldg(&in[k + 32]) : 0u;
+      const uint32_t v2 = k + 64 < b ? __ldg(&in[k + 64]) : 0u;
+      const uint32_t v3 = k + 96 < b ? __ldg(&in[k + 96]) : 0u;
+      m = max(max(m, v0), max(max(v1, v2), v3));
     }
-    uint32_t v[PM_ITEMS];
-    uint32_t headmask = 0;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) range_max[r] = m;
+  }
+}
+
+__global__ void __launch_bounds__(PM_THREADS) k_pmax(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                     const PmRun* __restrict__ runs, int nruns, uint64_t nranges,
+                                                     const uint32_t* __restrict__ range_max) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * PM_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * PM_THREADS) >> 5;
+  for (uint64_t r = w0; r < nranges; r += nw) {
+    uint64_t a, b, first;
+    pm_locate(runs, nruns, r, a, b, first);
+    uint32_t carry = 0;
+    for (uint64_t q = first + lane; q < r; q += 32) carry = max(carry, __ldg(&range_max[q]));
+    carry = __reduce_max_sync(0xffffffffu, carry);
+    for (uint64_t k0 = a; k0 < b; k0 += 128) {
+      uint32_t v[4];
 #pragma unroll
-    for (int i = 0; i < PM_ITEMS; i++) {
-      uint64_t r = r0 + i;
-      v[i] = r < n ? end[r] : 0;
-      while (lo < nruns && run_begin[lo] < r) lo++;
-      if (lo < nruns && run_begin[lo] == r) headmask |= 1u << i;
-    }
-    // thread-local segmented inclusive max
-    uint32_t run = 0;
-    bool     seen = false;
+      for (int u = 0; u < 4; u++) {
+        const uint64_t k = k0 + 32 * u + lane;
+        v[u] = k < b ? __ldg(&in[k]) : 0u;
+      }
 #pragma unroll
-    for (int i = 0; i < PM_ITEMS; i++) {
-      if (headmask & (1u << i)) { run = 0; seen = true; }
-      run = v[i] > run ? v[i] : run;
-      v[i] = run;
-    }
-    // warp-level segmented scan of (seen, run): value flowing into each thread
-    uint32_t agg = run;
-    bool     aggh = seen;
-    uint32_t inflow = 0;  // max flowing into this thread from earlier threads of the warp (until a head)
-    {
-      uint32_t a = agg;
-      bool     h = aggh;
+      for (int u = 0; u < 4; u++) {
+        uint32_t x = v[u];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t oa = __shfl_up_sync(0xffffffffu, a, d);
-        bool     oh = __shfl_up_sync(0xffffffffu, (int)h, d);
-        if (lane >= d) {
-          if (!h) a = oa > a ? oa : a;
-          h = h || oh;
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+          if (lane >= d) x = max(x, y);
         }
-      }
-      // a,h = inclusive segmented aggregate up to this thread; exclusive = previous lane's
-      uint32_t pa = __shfl_up_sync(0xffffffffu, a, 1);
-      bool     ph = __shfl_up_sync(0xffffffffu, (int)h, 1);
-      inflow = lane ? pa : 0;
-      bool inflow_h = lane ? ph : false;
-      if (lane == 31) { wmax[warp] = a; whead[warp] = h; }
-      __syncthreads();
-      // cross-warp: combine earlier warps (right to left until a head)
-      uint32_t winflow = 0;
-      bool     wh = false;
-      for (int w = warp - 1; w >= 0 && !wh; w--) {
-        winflow = wmax[w] > winflow ? (uint32_t)wmax[w] : winflow;
-        wh = whead[w];
-      }
-      // tile-level look-back (warp 0 publishes the tile aggregate)
-      if (warp == 0) {
-        uint32_t ta = 0;
-        bool     th = false;
-        for (int w = PM_THREADS / 32 - 1; w >= 0 && !th; w--) {
-          ta = wmax[w] > ta ? (uint32_t)wmax[w] : ta;
-          th = whead[w];
-        }
-        uint64_t c = lookback_segmax(tile_state, tile, th, ta);
-        if (lane == 0) carry_sm = c;
-      }
-      __syncthreads();
-      uint32_t carry = (uint32_t)carry_sm;
-      // total inflow for this thread
-      if (!inflow_h) {
-        inflow = winflow > inflow ? winflow : inflow;
-        if (!wh) inflow = carry > inflow ? carry : inflow;
+        x = max(x, carry);
+        const uint64_t k = k0 + 32 * u + lane;
+        if (k < b) out[k] = x;
+        carry = __shfl_sync(0xffffffffu, x, 31);
       }
     }
-    // apply inflow to the items before this thread's first head
-#pragma unroll
-    for (int i = 0; i < PM_ITEMS; i++) {
-      if (headmask & (1u << i)) inflow = 0;
-      uint32_t o = v[i] > inflow ? v[i] : inflow;
-      if (r0 + i < n) pmax[r0 + i] = o;
-    }
-    __syncthreads();
   }
 }
 
@@ -890,24 +854,31 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
 // out[k] = max(in[j] : j <= k, j in the same chromosome run as k)
 int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, const std::vector<ChromRun>& runs) {
   if (n == 0) return BK_OK;
-  int                   nruns = (int)runs.size();
-  std::vector<uint64_t> rb(nruns);
-  for (int i = 0; i < nruns; i++) rb[i] = runs[i].row_begin;
-  uint64_t* d_rb = dalloc<uint64_t>(ctx, nruns);
-  uint32_t  ntiles = (uint32_t)((n + PM_TILE - 1) / PM_TILE);
-  uint64_t* state = dalloc<uint64_t>(ctx, ntiles);
-  if (!d_rb || !state) return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemcpyAsync(d_rb, rb.data(), nruns * 8, cudaMemcpyHostToDevice, ctx->stream));
-  BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
-  BK_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + SC_TICKET, 0, 8, ctx->stream));
-  prof_begin(ctx, "k_pmax");
-  k_pmax<<<grid_for(ctx, (const void*)k_pmax, PM_THREADS, ntiles), PM_THREADS, 0, ctx->stream>>>(
-      in, out, n, d_rb, nruns, state, ntiles, ctx->d_scratch);
+  std::vector<PmRun> pr;
+  uint64_t           nranges = 0;
+  for (const ChromRun& r : runs) {
+    pr.push_back({r.row_begin, r.row_end, nranges});
+    nranges += (r.row_end - r.row_begin + PM_RANGE - 1) / PM_RANGE;
+  }
+  if (nranges == 0) return BK_OK;
+  PmRun*    d_runs = dalloc<PmRun>(ctx, pr.size());
+  uint32_t* d_rmax = dalloc<uint32_t>(ctx, nranges);
+  if (!d_runs || !d_rmax) return BK_ERR_NOMEM;
+  BK_CUDA(ctx, cudaMemcpyAsync(d_runs, pr.data(), pr.size() * sizeof(PmRun), cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t want = (nranges + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
+  const uint32_t ga = (uint32_t)std::min<uint64_t>(want, (uint64_t)grid_for(ctx, (const void*)k_pmax_reduce, PM_THREADS, 0xFFFFFFFFu));
+  const uint32_t gb = (uint32_t)std::min<uint64_t>(want, (uint64_t)grid_for(ctx, (const void*)k_pmax, PM_THREADS, 0xFFFFFFFFu));
+  prof_begin(ctx, "k_pmax_reduce");
+  k_pmax_reduce<<<ga, PM_THREADS, 0, ctx->stream>>>(in, d_runs, (int)pr.size(), nranges, d_rmax);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
-  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rb (host vector) must outlive the copy
-  dfree(ctx, d_rb);
-  dfree(ctx, state);
+  prof_begin(ctx, "k_pmax");
+  k_pmax<<<gb, PM_THREADS, 0, ctx->stream>>>(in, out, d_runs, (int)pr.size(), nranges, d_rmax);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pr (host vector) must outlive the copy
+  dfree(ctx, d_runs);
+  dfree(ctx, d_rmax);
   return BK_OK;
 }
 
