@@ -1,15 +1,15 @@
-// parse.cu -- the BED reader as one single-pass sm_100a kernel.
+// parse.cu -- the BED reader as two sm_100a passes over the text.
 //
 // Replaces Bed::allocate_iterator_starch_bed<T*>::operator++ -> T::readline(FILE*) with fscanf formats
 // "%s\t%lu\t%lu%[^\n]s\n" (B3Rest, Bed.hpp:380-382), "...\t%s%[^\n]s\n" (B4Rest, :644-646) and
 // "...\t%s\t%lf%[^\n]s\n" (B5Rest, :901-903).
 //
-// Design (B200): a persistent grid (multiple of 148 CTAs) takes 8 KiB text tiles by dynamic ticket.  A tile is
-// staged into shared memory with 16-byte coalesced streaming loads (plus a small halo either side), newlines
-// are found with SWAR compares, the number of rows that START in the tile is published through a decoupled
-// look-back chain (one 64-bit word per tile) to obtain the global row index, and then one thread per line
-// tokenises its line out of shared memory and writes the SoA columns with coalesced 4/8-byte stores.
-// Text is read from HBM exactly once; nothing but the SoA columns is written.
+// Design (B200): pass 1 (k_count_rows) streams the text once and counts the rows that start in every 8 KiB tile;
+// a one-CTA scan turns the counts into the first row of every tile, so the tiles of pass 2 are independent (no
+// look-back chain) and the columns are allocated exactly.  Pass 2 (k_parse) stages a tile plus a small halo in
+// shared memory with 16-byte cp.async copies issued one tile ahead (double buffer), finds field boundaries with
+// SWAR byte masks, and one thread per line tokenises its line out of shared memory and writes the SoA columns
+// with coalesced 4/8-byte stores.  Nothing but the SoA columns is written.
 #include <algorithm>
 #include "common.cuh"
 #include "parse.cuh"
@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(1024) k_scan_warps(const uint64_t* __restrict_
 // Per tile (tiles are independent: the first row of each tile comes from pass 1): (1) stage the text, (2) every
 // thread builds the control-byte / NL bitmasks of its 32 bytes and counts the lines that START there, (3) block scan
 // -> row index, (4) every thread parses ITS lines and writes the SoA columns directly (the lanes of a warp hold
-// consecutive rows, so the stores coalesce).  Three block barriers per tile.
+// consecutive rows, so the stores coalesce).  Two block barriers per tile; the text of the next tile is copied
+// into the other window buffer (cp.async) while this one is parsed.
 template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p) {
   __shared__ __align__(16) unsigned char smbuf[2][P_BUF + 16];  // double-buffered text window
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
       }
     }
-    __syncthreads();  // [S3] everyone is done with this tile's text and masks
+    // no barrier here: nothing in shared memory is written again before [S1] of the next tile, which every thread
+    // reaches only after it has finished this tile's lines
   }
 }
 
