@@ -320,6 +320,35 @@ __device__ __forceinline__ uint32_t warp_search32(const uint32_t* __restrict__ a
   return from;
 }
 
+// exclusive scan of per-warp-range totals (one CTA of 1024 threads; n is a few thousand):
+// base[i] = sum total[0..i), base[n] = scratch[SLOT] = the grand total
+template <int SLOT>
+__global__ void __launch_bounds__(1024) k_scan_totals(const uint64_t* __restrict__ total, uint64_t* __restrict__ base,
+                                                      uint32_t n, uint64_t* scratch) {
+  __shared__ uint64_t part[1024];
+  const uint32_t tid = threadIdx.x, per = (n + 1023) / 1024;
+  const uint32_t b = tid * per < n ? tid * per : n, e = b + per < n ? b + per : n;
+  uint64_t       s = 0;
+  for (uint32_t i = b; i < e; i++) s += total[i];
+  part[tid] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele over the 1024 partials
+    uint64_t v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint64_t runv = tid ? part[tid - 1] : 0;
+  for (uint32_t i = b; i < e; i++) {
+    base[i] = runv;
+    runv += total[i];
+  }
+  if (tid == 1023) {
+    base[n] = part[1023];
+    scratch[SLOT] = part[1023];
+  }
+}
+
 // sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)
 __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
   const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);

@@ -1,8 +1,9 @@
-// emit.cuh -- the BED writer skeleton shared by every tool: one output row per thread, single pass.
+// emit.cuh -- the BED writer skeleton shared by every tool: one output row per thread, two passes.
 //
-//   length pass (CountSink) -> block scan -> decoupled look-back over tiles (byte offsets) ->
-//   write pass (MemSink) into a shared-memory stage laid out with the same 16-byte phase as the destination ->
-//   16-byte coalesced streaming stores to HBM.
+//   k_emit_len:  length of every row (CountSink), warp-local prefix sums over contiguous row ranges
+//   k_scan_totals: one CTA, range totals -> range bases (and the output size)
+//   k_emit:      write pass (MemSink) into a shared-memory stage laid out with the same 16-byte phase as the
+//                destination -> 16-byte coalesced streaming stores to HBM.  Tiles are independent (no look-back).
 //
 // RowFn contract:  template <class Sink> __device__ void operator()(uint64_t i, Sink& s) const;
 //                  writes row i (including its '\n'), or nothing at all if the row is suppressed.
@@ -111,38 +112,64 @@ __device__ __noinline__ void echo_b45rest(Sink& s, const char* __restrict__ text
   s.copy(q, m);
 }
 
+// Pass 1: byte length of every row.  A warp owns `rows_per_warp` consecutive rows (a multiple of E_THREADS, so an
+// output tile never straddles two warp ranges), 32 rows per step; local_off[i] = bytes of the earlier rows of the
+// same warp range, warp_total[w] = bytes of the range.  No block barrier, no atomics on the data path.
+template <class RowFn>
+__global__ void __launch_bounds__(E_THREADS) k_emit_len(RowFn fn, uint64_t n, uint32_t rows_per_warp,
+                                                        uint32_t* __restrict__ local_off, uint64_t* __restrict__ warp_total,
+                                                        uint32_t nwarps, uint64_t* scratch) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * E_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * E_THREADS) >> 5;
+  for (uint64_t w = w0; w < nwarps; w += nw) {
+    const uint64_t a = w * rows_per_warp, b = a + rows_per_warp < n ? a + rows_per_warp : n;
+    uint64_t       run = 0;
+    uint32_t       nz = 0;
+    for (uint64_t r0 = a; r0 < b; r0 += 32) {
+      const uint64_t i = r0 + lane;
+      uint64_t       len64 = 0;
+      if (i < b) {
+        CountSink cs;
+        fn(i, cs);
+        len64 = cs.n;
+      }
+      if (len64 >> 32) dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);  // a single row of 4 GiB: not representable
+      const uint32_t len = (uint32_t)len64;
+      const uint32_t incl = warp_incl_scan(len);
+      if (i < b) local_off[i] = (uint32_t)run + (incl - len);
+      run += __shfl_sync(0xffffffffu, incl, 31);
+      nz += __popc(__ballot_sync(0xffffffffu, len != 0));
+    }
+    if (lane == 0) {
+      warp_total[w] = run;
+      if (run >> 32) dev_set_error(scratch, BK_ERR_UNSUPPORTED, a);
+      if (nz) atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_OUT_ROWS]), (unsigned long long)nz);
+    }
+  }
+}
+
+// Pass 2: the byte offset of every row is known (warp_base[range] + local_off[row]), so tiles are independent: every
+// thread formats its row into the shared-memory stage at its final position, then the tile leaves with 16-byte stores.
 template <class RowFn>
 __global__ void __launch_bounds__(E_THREADS, 4) k_emit(RowFn fn, uint64_t n, char* __restrict__ out, uint64_t out_cap,
-                                                    uint64_t* tile_state, uint32_t ntiles, uint64_t* scratch) {
+                                                       int range_shift, const uint32_t* __restrict__ local_off,
+                                                       const uint64_t* __restrict__ warp_base, uint32_t nwarps,
+                                                       uint32_t ntiles, uint64_t* scratch) {
   __shared__ __align__(16) char stage[E_STAGE + 16];
-  __shared__ uint32_t           scan_sm[34];
-  __shared__ uint32_t           ticket_sm;
-  __shared__ uint64_t           base_sm;
   const int tid = threadIdx.x;
-  while (true) {
-    const uint32_t tile = next_ticket(scratch, &ticket_sm);
-    if (tile >= ntiles) break;
-    const uint64_t i = (uint64_t)tile * E_THREADS + tid;
-    uint64_t       len64 = 0;
+  auto offset_of = [&](uint64_t r) -> uint64_t {  // first output byte of row r (r == n: the total)
+    return r >= n ? warp_base[nwarps] : warp_base[r >> range_shift] + local_off[r];
+  };
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t row0 = (uint64_t)tile * E_THREADS, i = row0 + tid;
+    const uint64_t base = offset_of(row0);
+    const uint32_t total = (uint32_t)(offset_of(row0 + E_THREADS) - base);  // a tile lies inside one range: < 4 GiB
+    uint32_t       off = 0, len = 0;
     if (i < n) {
-      CountSink cs;
-      fn(i, cs);
-      len64 = cs.n;
+      const uint64_t o = offset_of(i);
+      off = (uint32_t)(o - base);
+      len = (uint32_t)(offset_of(i + 1) - o);
     }
-    // rows longer than 4 GiB are not representable in the block scan; rest fields are <= 1 MiB per row
-    uint32_t len = (uint32_t)len64, total;
-    uint32_t off = block_excl_scan(len, scan_sm, &total);
-    uint32_t nz = __syncthreads_count(len != 0);
-    if (tid < 32) {
-      uint64_t b = lookback_sum(tile_state, tile, total);
-      if (tid == 0) {
-        base_sm = b;
-        if (nz) atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_OUT_ROWS]), (unsigned long long)nz);
-        if (tile == ntiles - 1) scratch[SC_OUT_BYTES] = b + total;
-      }
-    }
-    __syncthreads();
-    const uint64_t base = base_sm;
     if (base + total > out_cap) {
       if (tid == 0) dev_set_error(scratch, BK_ERR_NOMEM, tile);
       continue;
@@ -166,11 +193,11 @@ __global__ void __launch_bounds__(E_THREADS, 4) k_emit(RowFn fn, uint64_t n, cha
           for (uint32_t b = (b0 < shift ? shift : b0); b < b0 + 16 && b < end; b++) dst0[b] = stage[b];
         }
       }
+      __syncthreads();  // the stage is rewritten by the next tile
     } else if (len) {
       MemSink ms{out + base + off};
       fn(i, ms);
     }
-    __syncthreads();
   }
 }
 
@@ -199,17 +226,32 @@ int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** 
   if (!*d_out) return BK_ERR_NOMEM;
   if (n == 0) return BK_OK;
   const uint32_t ntiles = (uint32_t)((n + E_THREADS - 1) / E_THREADS);
-  uint64_t*      state = dalloc<uint64_t>(ctx, ntiles);
-  if (!state) return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * 8, ctx->stream));
+  // warp ranges of 2^range_shift rows (>= one tile): about 64 warps per SM
+  int range_shift = 8;
+  while (((n + (1ull << range_shift) - 1) >> range_shift) > (uint64_t)kSMs * 64 && range_shift < 20) range_shift++;
+  const uint32_t nwarps = (uint32_t)((n + (1ull << range_shift) - 1) >> range_shift);
+  uint32_t*      local_off = dalloc<uint32_t>(ctx, n);
+  uint64_t*      wtot = dalloc<uint64_t>(ctx, nwarps);
+  uint64_t*      wbase = dalloc<uint64_t>(ctx, (size_t)nwarps + 1);
+  if (!local_off || !wtot || !wbase) return BK_ERR_NOMEM;
   BK_TRY(reset_scratch(ctx));
+  const uint64_t len_ctas = ((uint64_t)nwarps * 32 + E_THREADS - 1) / E_THREADS;
+  prof_begin(ctx, "k_emit_len");
+  k_emit_len<RowFn><<<grid_for_kernel((const void*)k_emit_len<RowFn>, E_THREADS, len_ctas), E_THREADS, 0, ctx->stream>>>(
+      fn, n, 1u << range_shift, local_off, wtot, nwarps, ctx->d_scratch);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  k_scan_totals<SC_OUT_BYTES><<<1, 1024, 0, ctx->stream>>>(wtot, wbase, nwarps, ctx->d_scratch);
+  BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_emit");
   k_emit<RowFn><<<grid_for_kernel((const void*)k_emit<RowFn>, E_THREADS, ntiles), E_THREADS, 0, ctx->stream>>>(
-      fn, n, *d_out, out_cap, state, ntiles, ctx->d_scratch);
+      fn, n, *d_out, out_cap, range_shift, local_off, wbase, nwarps, ntiles, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_TRY(read_scratch(ctx));
-  dfree(ctx, state);
+  dfree(ctx, local_off);
+  dfree(ctx, wtot);
+  dfree(ctx, wbase);
   if (ctx->h_scratch[SC_ERR_CODE]) {
     int code = (int)ctx->h_scratch[SC_ERR_CODE];
     return fail(ctx, code, code == BK_ERR_NOMEM ? "output exceeds the precomputed bound (tile %llu)"

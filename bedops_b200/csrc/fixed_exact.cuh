@@ -21,11 +21,14 @@ BK_FN uint64_t double_bits(double x) {
 #endif
 }
 
-BK_FN uint64_t pow10_u64(int k) {  // 10^k, 0 <= k <= 19
-  uint64_t p = 1;
-  for (int i = 0; i < k; i++) p *= 10;
-  return p;
-}
+#ifdef __CUDACC__
+__device__
+#endif
+static const uint64_t kPow10u[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull,
+                                     100000000ull, 1000000000ull, 10000000000ull, 100000000000ull, 1000000000000ull,
+                                     10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
+                                     100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull};
+BK_FN uint64_t pow10_u64(int k) { return kPow10u[k]; }  // 10^k, 0 <= k <= 19
 
 struct Fixed {
   bool     neg;

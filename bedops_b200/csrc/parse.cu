@@ -304,33 +304,6 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
   if (lane == 0) warp_total[wid] = run;
 }
 
-// exclusive scan of the per-warp totals (one CTA; n <= a few thousand): base[i] = sum total[0..i), base[n] = all rows
-__global__ void __launch_bounds__(1024) k_scan_warps(const uint64_t* __restrict__ total, uint64_t* __restrict__ base, uint32_t n,
-                                                     uint64_t* scratch) {
-  __shared__ uint64_t part[1024];
-  const uint32_t tid = threadIdx.x, per = (n + 1023) / 1024;
-  const uint32_t b = tid * per, e = b + per < n ? b + per : n;
-  uint64_t       s = 0;
-  for (uint32_t i = b; i < e; i++) s += total[i];
-  part[tid] = s;
-  __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {  // Hillis-Steele over the 1024 partials
-    uint64_t v = tid >= d ? part[tid - d] : 0;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
-  }
-  uint64_t runv = tid ? part[tid - 1] : 0;
-  for (uint32_t i = b; i < e; i++) {
-    base[i] = runv;
-    runv += total[i];
-  }
-  if (tid == 1023) {
-    base[n] = part[1023];
-    scratch[SC_NROWS] = part[1023];
-  }
-}
-
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
 //
 // Per tile (tiles are independent: the first row of each tile comes from pass 1): (1) stage the text, (2) every
@@ -755,7 +728,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_scan_warps");
-  k_scan_warps<<<1, 1024, 0, ctx->stream>>>(d_wtot, d_wbase, nwarps, ctx->d_scratch);
+  k_scan_totals<SC_NROWS><<<1, 1024, 0, ctx->stream>>>(d_wtot, d_wbase, nwarps, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_TRY(read_scratch(ctx));

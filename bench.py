@@ -285,6 +285,7 @@ def main():
     parse_ms, parse_n = kit.profile_query("k_parse")
     stats_ms, stats_n = kit.profile_query("k_map_stats")
     emit_ms, emit_n = kit.profile_query("k_emit")
+    emit_len_ms, _ = kit.profile_query("k_emit_len")
     pmax_ms, pmax_n = kit.profile_query("k_pmax")
     pmax_ms += kit.profile_query("k_pmax_reduce")[0]
     count_ms, _ = kit.profile_query("k_count_rows")
@@ -350,7 +351,7 @@ def main():
                 "algorithmic_bytes_per_step": alg_bytes_step,
                 "kernel_ms_per_step": {"k_count_rows": count_ms / args.steps, "k_scan_warps": scan_ms / args.steps,
                                        "k_parse": parse_ms / args.steps, "k_pmax_reduce+k_pmax": pmax_ms / args.steps,
-                                       "k_map_stats": stats_ms / args.steps, "k_emit": emit_ms / args.steps},
+                                       "k_map_stats": stats_ms / args.steps, "k_emit_len": emit_len_ms / args.steps, "k_emit": emit_ms / args.steps},
                 "whole_step_text_GBps": (ref_bytes + map_bytes + out_bytes) * args.steps / (ms_max * 1e-3) / 1e9}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
