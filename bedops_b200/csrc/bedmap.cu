@@ -305,6 +305,13 @@ struct BedmapRow {
       put_sci(s, v, i);
       return;
     }
+    if (Sink::counting) {
+      const int L = fixed_len_fast(v, prec);
+      if (L >= 0) {
+        s.copy(nullptr, (uint64_t)L);
+        return;
+      }
+    }
     Fixed f;
     if (!to_fixed(v, prec, f)) {
       dev_set_error(scratch, BK_ERR_UNSUPPORTED, i);

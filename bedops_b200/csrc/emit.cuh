@@ -226,9 +226,9 @@ int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** 
   if (!*d_out) return BK_ERR_NOMEM;
   if (n == 0) return BK_OK;
   const uint32_t ntiles = (uint32_t)((n + E_THREADS - 1) / E_THREADS);
-  // warp ranges of 2^range_shift rows (>= one tile): about 64 warps per SM
+  // warp ranges of 2^range_shift rows (>= one tile): up to four waves of 64 warps per SM
   int range_shift = 8;
-  while (((n + (1ull << range_shift) - 1) >> range_shift) > (uint64_t)kSMs * 64 && range_shift < 20) range_shift++;
+  while (((n + (1ull << range_shift) - 1) >> range_shift) > (uint64_t)kSMs * 256 && range_shift < 20) range_shift++;
   const uint32_t nwarps = (uint32_t)((n + (1ull << range_shift) - 1) >> range_shift);
   uint32_t*      local_off = dalloc<uint32_t>(ctx, n);
   uint64_t*      wtot = dalloc<uint64_t>(ctx, nwarps);

@@ -101,6 +101,20 @@ BK_FN bool to_fixed(double x, int prec, Fixed& f) {
   return true;
 }
 
+// Length of the "%.<prec>f" text without producing a digit, for the emitter's length pass.  -1 = not decidable
+// cheaply (a carry into the integer part is possible, or the value is large/special): the caller runs to_fixed.
+// A carry needs fraction >= 1 - 0.5*10^-prec >= 0.95 when prec >= 1.
+BK_FN int fixed_len_fast(double x, int prec) {
+  const uint64_t bits = double_bits(x);
+  const double   ax = bits_to_double(bits & 0x7FFFFFFFFFFFFFFFull);
+  if (prec < 1 || prec > 18 || !(ax < 4.0e9)) return -1;
+  const uint32_t ip = (uint32_t)ax;          // truncation
+  if (ax - (double)ip >= 0.9) return -1;     // exact subtraction
+  int nd = 1;
+  for (uint32_t t = ip; t >= 10u; t /= 10u) nd++;
+  return (int)(bits >> 63) + nd + 1 + prec;
+}
+
 // ---- exact "%.<prec>e" -----------------------------------------------------------------------------------------------
 // d.ddd...e+XX of the exact binary value, rounded half-to-even like glibc.  Supported: 0 <= prec <= 17 and
 // 2^-75 <= |x| < 2^63 (or x == 0); returns false otherwise (caller raises BK_ERR_UNSUPPORTED).

@@ -27,6 +27,11 @@ int main(int argc, char** argv) {
     checked++;
     if (render(x, prec, a) < 0) { refused++; return; }
     snprintf(b, sizeof b, "%.*f", prec, x);
+    const int fl = bk::fixed_len_fast(x, prec);  // the length pass's shortcut must agree whenever it answers
+    if (fl >= 0 && fl != (int)strlen(b)) {
+      if (bad < 20) fprintf(stderr, "LENGTH MISMATCH x=%.17g prec=%d: got %d ref %s\n", x, prec, fl, b);
+      bad++;
+    }
     if (strcmp(a, b) != 0) {
       if (bad < 20) fprintf(stderr, "MISMATCH x=%.17g prec=%d: got %s ref %s\n", x, prec, a, b);
       bad++;
