@@ -255,7 +255,8 @@ class BedKit:
             return t          # caller frees with free_text(); host text stays in the library's pinned buffer
         if on_device:
             return DeviceText(self, t)
-        data = C.string_at(t.ptr, t.len) if t.len else b""
+        # not C.string_at: its size argument is a C int, results can exceed 2 GiB
+        data = bytes((C.c_char * t.len).from_address(t.ptr)) if t.len else b""
         self.lib.bk_free_text(self.ctx, C.byref(t))
         return data
 

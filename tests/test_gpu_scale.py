@@ -274,8 +274,12 @@ def test_config3_setops_four_large_files(env, tmp_path):
     pm, pi = kit.setop("merge", tb), kit.setop("intersect", tb)
     pe = kit.setop("element-of", tb, 1, False)
     assert full_m.endswith(pm) and full_i.endswith(pi)
-    fe = kit.setop("element-of", beds, 1, False)
-    assert fe.endswith(pe)
+    fe = kit.setop("element-of", beds, 1, False, on_device=True)   # ~9 GB of echoed rows: compare the tail in HBM
+    tail = torch.empty(len(pe), dtype=torch.uint8, device="cuda:0")
+    kit.copy(tail.data_ptr(), fe.ptr + fe.nbytes - len(pe), len(pe))
+    torch.cuda.synchronize()
+    assert bytes(tail.cpu().numpy()) == pe
+    fe.free()
     if have_ref() and SCALE <= 0.2:   # ~18 M rows per file at full size: minutes of CPU for the reference; sampled runs only
         assert pm == run_ref("bedops", ["-m"], tails, tmp_path)
         assert pi == run_ref("bedops", ["-i"], tails, tmp_path)
@@ -314,9 +318,8 @@ def test_config4_closest_features_large(env, tmp_path):
     Sh, Esh = S.cpu().numpy(), Es.cpu().numpy()
     assert len(lines) == len(rs)
     checked = 0
-    for i in range(0, len(lines), max(1, len(lines) // 20000)):
-        if cnt[i] != 0:
-            continue
+    free_rows = np.nonzero(cnt == 0)[0]          # reference rows that no query row overlaps
+    for i in free_rows[:: max(1, len(free_rows) // 20000)]:
         f = lines[i].split(b"|")
         assert len(f) == 4
         if nxt[i] < len(Sh):
@@ -328,24 +331,26 @@ def test_config4_closest_features_large(env, tmp_path):
         else:
             assert f[0] == b"NA" and f[1] == b"NA"
         checked += 1
-    assert checked > 0
+    assert checked == len(free_rows[:: max(1, len(free_rows) // 20000)])
     if have_ref():
-        # Nested reference rows: the reference's streaming state has sometimes already deleted the true neighbour
-        # (ClosestFeature.cpp:301-304, :369-378; SURVEY 8c hazard 3) and prints NA or a farther element; we report the
-        # nearest one (checked against torch above).  That is the only admissible difference: wherever the outputs
-        # differ ours must be at least as close on both sides, and such rows must stay rare.
+        # Byte parity with the reference is not attainable at this density (SURVEY 8c hazard 3): when several query
+        # rows overlap one edge of a reference row, the element the reference prints depends on the order in which its
+        # push-back list re-queued them for earlier reference rows (ClosestFeature.cpp:296-304, :335-397), and under
+        # nested reference rows it has sometimes already deleted the true neighbour and prints NA or a farther one.
+        # What must hold on every row: the DISTANCES agree, or ours is the closer one (checked against torch above).
         exp = run_ref("closest-features", ["--dist", "--no-ref"], [rt, qt], tmp_path).split(b"\n")[:-1]
         assert len(exp) == len(lines)
 
         def absdist(x):
             return float("inf") if x == b"NA" else abs(int(x))
-        lost = 0
+        closer = 0
         for a, b in zip(exp, lines):
             if a != b:
                 fa, fb = a.split(b"|"), b.split(b"|")
-                assert absdist(fb[1]) <= absdist(fa[1]) and absdist(fb[3]) <= absdist(fa[3]), (a, b)
-                lost += 1
-        assert lost <= 0.05 * len(lines), lost
+                dl, dr = absdist(fb[1]) - absdist(fa[1]), absdist(fb[3]) - absdist(fa[3])
+                assert not dl > 0 and not dr > 0, (a, b)
+                closer += (dl < 0) or (dr < 0)
+        assert closer <= 0.05 * len(lines), closer
     out.free()
     for b in (rb, qb, r1, q1):
         b.free()
