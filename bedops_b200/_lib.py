@@ -74,6 +74,7 @@ def load_library() -> C.CDLL:
         "bk_profile": (i, [vp, i]),
         "bk_profile_query": (i, [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]),
         "bk_copy": (i, [vp, vp, vp, C.c_size_t]),
+        "bk_release_cached": (i, [vp]),
         "bk_load_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.c_uint, C.POINTER(vp)]),
         "bk_load_bed_device": (i, [vp, vp, C.c_size_t, i, C.c_uint, C.POINTER(vp)]),
         "bk_free_bed": (None, [vp, vp]),
@@ -104,7 +105,7 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
-           "bk_check_text_device"]
+           "bk_check_text_device", "bk_release_cached"]
 
 
 class Bed:
@@ -222,6 +223,10 @@ class BedKit:
         ms, n = C.c_double(), C.c_uint64()
         self._chk(self.lib.bk_profile_query(self.ctx, kernel.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def release_cached(self):
+        """hand the context's idle device blocks back to the driver"""
+        self._chk(self.lib.bk_release_cached(self.ctx))
 
     def copy(self, dst_ptr: int, src_ptr: int, nbytes: int):
         self._chk(self.lib.bk_copy(self.ctx, dst_ptr, src_ptr, nbytes))

@@ -1,4 +1,5 @@
 // api.cu -- context, memory and the load/free half of the C ABI (include/bedkit.h).
+#include <chrono>
 #include <stdarg.h>
 #include "common.cuh"
 #include "emit.cuh"
@@ -22,19 +23,67 @@ int cuda_fail(bk_ctx* ctx, cudaError_t e, const char* what, const char* file, in
               cudaGetErrorString(e), what, base ? base + 1 : file, line);
 }
 
+// ---- device memory: a per-context caching allocator -------------------------------------------------------------
+// Every call allocates the same handful of (large) blocks again: text, columns, result.  The driver's stream-ordered
+// pool re-maps multi-GB blocks on most requests (measured: 10 ms .. 3 s per cudaMallocAsync of 3-16 GB in steady
+// state), so freed blocks are kept here, keyed by a size class (8 classes per octave, <= 12.5 % slack), and handed out
+// again without a driver call.  All work of a context is ordered on one stream, so immediate reuse is safe.
+// cudaMalloc is called only for a class with no cached block; when it fails the cache is released and it is retried.
+static size_t size_class(size_t b) {
+  if (b < 512) return 512;
+  int top = 63 - __builtin_clzll((unsigned long long)b);
+  const size_t unit = (size_t)1 << (top - 3);
+  return (b + unit - 1) & ~(unit - 1);
+}
+
+void release_cached(bk_ctx* ctx) {
+  if (ctx->dev_free.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->dev_free) cudaFree(kv.second);
+  ctx->dev_free.clear();
+  ctx->dev_cached_bytes = 0;
+}
+
 void* dmalloc(bk_ctx* ctx, size_t bytes) {
-  void*       p = nullptr;
-  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream);
+  const size_t sz = size_class(bytes);
+  auto         it = ctx->dev_free.find(sz);
+  if (it != ctx->dev_free.end()) {
+    void* p = it->second;
+    ctx->dev_free.erase(it);
+    ctx->dev_cached_bytes -= sz;
+    ctx->dev_live[p] = sz;
+    return p;
+  }
+  static const bool trace = getenv("BEDKIT_TRACE") != nullptr;  // host-side cost of new blocks, to stderr
+  const auto        t0 = std::chrono::steady_clock::now();
+  void*             p = nullptr;
+  cudaError_t       e = cudaMalloc(&p, sz);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    release_cached(ctx);
+    e = cudaMalloc(&p, sz);
+  }
+  if (trace) {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[bedkit] cudaMalloc(%zu bytes, class %zu) took %.2f ms; cached %zu bytes\n", bytes, sz, ms,
+            ctx->dev_cached_bytes);
+  }
   if (e != cudaSuccess) {
-    cuda_fail(ctx, e, "cudaMallocAsync", __FILE__, __LINE__);
+    cuda_fail(ctx, e, "cudaMalloc", __FILE__, __LINE__);
     cudaGetLastError();
     return nullptr;
   }
+  ctx->dev_live[p] = sz;
   return p;
 }
 
 void dfree(bk_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->dev_live.find(p);
+  if (it == ctx->dev_live.end()) return;  // not ours (borrowed text)
+  ctx->dev_free.emplace(it->second, p);
+  ctx->dev_cached_bytes += it->second;
+  ctx->dev_live.erase(it);
 }
 
 char* pinned_get(bk_ctx* ctx, size_t bytes) {
@@ -159,12 +208,6 @@ extern "C" int bk_init(bk_ctx** out, int device) {
     return BK_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
-  // keep freed blocks in the pool: the same shapes recur call after call
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_scratch), SC_N * sizeof(uint64_t)) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_scratch), SC_N * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
     bk_destroy(ctx);
@@ -178,6 +221,8 @@ extern "C" void bk_destroy(bk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  release_cached(ctx);
+  for (auto& kv : ctx->dev_live) cudaFree(kv.first);  // blocks of handles the caller never freed
   for (auto& b : ctx->pinned) cudaFreeHost(b.ptr);
   for (auto& r : ctx->prof) {
     cudaEventDestroy(r.a);
@@ -194,6 +239,12 @@ extern "C" int bk_set_stream(bk_ctx* ctx, void* cuda_stream) {
   if (!ctx) return BK_ERR_ARG;
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return BK_OK;
+}
+
+extern "C" int bk_release_cached(bk_ctx* ctx) {
+  if (!ctx) return BK_ERR_ARG;
+  release_cached(ctx);
   return BK_OK;
 }
 

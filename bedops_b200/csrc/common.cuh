@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/bedkit.h"
 
@@ -41,6 +43,10 @@ struct bk_ctx {
     bool   busy;
   };
   std::vector<Pinned> pinned;
+  // device block cache (api.cu): freed blocks by size class, live blocks by address
+  std::multimap<size_t, void*>      dev_free;
+  std::unordered_map<void*, size_t> dev_live;
+  size_t                            dev_cached_bytes = 0;
   // optional per-kernel timing (bk_profile): CUDA event pairs recorded on the launching stream
   struct ProfRec {
     const char* name;
@@ -72,6 +78,7 @@ namespace bk {
 
 int  fail(bk_ctx* ctx, int code, const char* fmt, ...);
 int  cuda_fail(bk_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+void  release_cached(bk_ctx* ctx);         // give every cached device block back to the driver
 void* dmalloc(bk_ctx* ctx, size_t bytes);  // stream-ordered; returns nullptr and sets last_error on failure
 void  dfree(bk_ctx* ctx, void* p);
 char* pinned_get(bk_ctx* ctx, size_t bytes);

@@ -75,6 +75,10 @@ int bk_profile(bk_ctx* ctx, int enable);
 int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
 /* cudaMemcpyAsync(cudaMemcpyDefault) + sync on the ctx stream (bench/test plumbing for device-resident text) */
 int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes);
+/* Device memory is cached per ctx: blocks freed by bk_free_bed / bk_free_text / internal temporaries are kept (by size
+ * class) and reused by later calls without a driver call.  bk_release_cached hands every idle block back to the driver
+ * (bk_destroy does it too); the library does it by itself when an allocation fails. */
+int bk_release_cached(bk_ctx* ctx);
 
 /* ---- BED reader ------------------------------------------------------------------------------ */
 /* which per-row columns the parser materialises besides start/end */

@@ -1,0 +1,96 @@
+#!/usr/bin/env python3
+"""Device-resident timings of BASELINE.json configurations 3-5 (bench.py covers configuration 2).
+
+One JSON line per operation: wall time by CUDA events around the C-ABI calls (text already in HBM, result left in HBM)
+and the per-kernel split from the library's own event pairs (bk_profile).  Not a bench line -- supporting numbers for
+DESIGN.md section 6."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+KERNELS = ["k_efflen", "k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_rank_merge", "k_segments",
+           "k_intersect", "k_element_of", "k_argmark", "k_closest", "k_map_stats", "k_emit_len", "k_emit"]
+
+
+def main():
+    import torch
+    import bedops_b200
+    from bedops_b200._lib import COL_LINE, COL_SCORE
+    from test_gpu_scale import SynthFile, MAP_SHAPE, REF_SHAPE
+    scale = float(os.environ.get("BEDKIT_SCALE", "1.0"))
+    kit = bedops_b200.BedKit(0)
+    torch.cuda.set_device(0)
+
+    def timed(name, units, fn, reps=3):
+        fn()  # warm-up (also sizes the memory pool)
+        kit.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        split = {}
+        for k in KERNELS:
+            t, n = kit.profile_query(k)
+            if n:
+                split[k] = round(t / reps, 4)
+        kit.profile(False)
+        print(json.dumps({"op": name, "input_rows": units, "ms": round(ms, 3), "rows_per_s": units / (ms * 1e-3),
+                          "kernel_ms": split}), flush=True)
+
+    # configuration 3: bedops over 4 files of 250 M rows (load + operation, as the tools do)
+    files = [SynthFile(kit, torch, int(250_000_000 * scale), s, MAP_SHAPE) for s in (1, 3, 4, 5)]
+    rows = sum(f.rows for f in files)
+
+    def setop(op, thr=1.0, pct=True):
+        def run():
+            beds = [f.load(kit, 3, COL_LINE if (k == 0 and "element" in op) else 0) for k, f in enumerate(files)]
+            out = kit.setop(op, beds, thr, pct, on_device=True)
+            out.free()
+            for b in beds:
+                b.free()
+        return run
+    timed("bedops --merge, 4 x 250M", rows, setop("merge"))
+    timed("bedops --intersect, 4 x 250M", rows, setop("intersect"))
+    timed("bedops --element-of 1, 4 x 250M", rows, setop("element-of", 1, False))
+    timed("bedops --not-element-of 100%, 4 x 250M", rows, setop("not-element-of", 1.0, True))
+    del files
+    torch.cuda.empty_cache()
+
+    # configuration 4: closest-features 50 M x 200 M
+    ref = SynthFile(kit, torch, int(50_000_000 * scale), 2, REF_SHAPE)
+    qry = SynthFile(kit, torch, int(200_000_000 * scale), 1, MAP_SHAPE)
+
+    def closest():
+        rb, qb = ref.load(kit, 3, COL_LINE), qry.load(kit, 3, COL_LINE)
+        out = kit.closest(rb, qb, dist=True, on_device=True)
+        out.free()
+        rb.free()
+        qb.free()
+    timed("closest-features --dist, 50M x 200M", ref.rows + qry.rows, closest)
+    del ref, qry
+    torch.cuda.empty_cache()
+
+    # configuration 5: bedmap --mean over 1 B map rows on one GPU
+    ref = SynthFile(kit, torch, int(10_000_000 * scale), 2, REF_SHAPE)
+    mp = SynthFile(kit, torch, int(1_000_000_000 * scale), 1, MAP_SHAPE)
+
+    def bedmap():
+        rb, mb = ref.load(kit, 3, COL_LINE), mp.load(kit, 5, COL_SCORE)
+        out = kit.bedmap(rb, mb, ["echo", "mean"], on_device=True)
+        out.free()
+        rb.free()
+        mb.free()
+    timed("bedmap --echo --mean, 10M x 1B", ref.rows + mp.rows, bedmap)
+    kit.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,9 +42,11 @@ def release_cached_blocks(env):
     """torch's caching allocator and the library's stream-ordered pool share the HBM: hand cached blocks back"""
     import gc
     gc.collect()
+    env[0].release_cached()
     env[1].cuda.empty_cache()
     yield
     gc.collect()
+    env[0].release_cached()
     env[1].cuda.empty_cache()
 
 
