@@ -84,6 +84,7 @@ void dfree(bk_ctx* ctx, void* p) {
   ctx->dev_free.emplace(it->second, p);
   ctx->dev_cached_bytes += it->second;
   ctx->dev_live.erase(it);
+  if (ctx->dev_cached_bytes > ctx->dev_cache_limit) release_cached(ctx);  // do not hoard: other tenants share the HBM
 }
 
 char* pinned_get(bk_ctx* ctx, size_t bytes) {
@@ -208,6 +209,8 @@ extern "C" int bk_init(bk_ctx** out, int device) {
     return BK_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->dev_cache_limit = total_b / 4;
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_scratch), SC_N * sizeof(uint64_t)) != cudaSuccess ||
       cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_scratch), SC_N * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
     bk_destroy(ctx);

@@ -47,6 +47,7 @@ struct bk_ctx {
   std::multimap<size_t, void*>      dev_free;
   std::unordered_map<void*, size_t> dev_live;
   size_t                            dev_cached_bytes = 0;
+  size_t                            dev_cache_limit = (size_t)32 << 30;  // idle bytes kept at most (bk_init: a quarter of the HBM)
   // optional per-kernel timing (bk_profile): CUDA event pairs recorded on the launching stream
   struct ProfRec {
     const char* name;
@@ -354,6 +355,27 @@ __global__ void __launch_bounds__(1024) k_scan_totals(const uint64_t* __restrict
     base[n] = part[1023];
     scratch[SLOT] = part[1023];
   }
+}
+
+// ---- warp ranges inside chromosome runs (prefix-max index, segment compaction) ----------------------------------
+// Rows are cut into ranges of PM_RANGE rows that never cross a chromosome boundary; one warp owns a range.
+constexpr int PM_THREADS = 256, PM_RANGE = 2048;
+struct PmRun {
+  uint64_t row_begin, row_end, first_range;  // first_range: index of the chromosome's first warp range
+};
+
+// range r -> its rows [a,b), the first range of its chromosome, and the index of that chromosome in runs[]
+__device__ __forceinline__ int pm_locate(const PmRun* __restrict__ runs, int nruns, uint64_t r, uint64_t& a, uint64_t& b,
+                                         uint64_t& first) {
+  int lo = 0, hi = nruns;  // last run with first_range <= r (empty runs own no range and are skipped by "last")
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (runs[mid].first_range <= r) lo = mid; else hi = mid;
+  }
+  first = runs[lo].first_range;
+  a = runs[lo].row_begin + (r - first) * PM_RANGE;
+  b = a + PM_RANGE < runs[lo].row_end ? a + PM_RANGE : runs[lo].row_end;
+  return lo;
 }
 
 // sum of a 64-bit value over the warp from four 16-bit limbs (REDUX is 32-bit)

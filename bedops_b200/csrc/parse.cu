@@ -604,23 +604,6 @@ __global__ void k_efflen(const unsigned char* text, uint64_t nbytes, uint64_t* s
 // warp ranges of PM_RANGE rows that never cross a chromosome boundary; pass 1 reduces every range to its maximum,
 // pass 2 gives a range the maximum of the earlier ranges of its chromosome as carry (a short reduction over the
 // pass-1 array, L2 resident) and scans its own rows, 32 at a time with coalesced loads and stores.
-constexpr int PM_THREADS = 256, PM_RANGE = 2048;
-struct PmRun {
-  uint64_t row_begin, row_end, first_range;  // first_range: index of the chromosome's first warp range
-};
-
-__device__ __forceinline__ void pm_locate(const PmRun* __restrict__ runs, int nruns, uint64_t r, uint64_t& a, uint64_t& b,
-                                          uint64_t& first) {
-  int lo = 0, hi = nruns;  // last run with first_range <= r (empty runs own no range and are skipped by "last")
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (runs[mid].first_range <= r) lo = mid; else hi = mid;
-  }
-  first = runs[lo].first_range;
-  a = runs[lo].row_begin + (r - first) * PM_RANGE;
-  b = a + PM_RANGE < runs[lo].row_end ? a + PM_RANGE : runs[lo].row_end;
-}
-
 __global__ void __launch_bounds__(PM_THREADS) k_pmax_reduce(const uint32_t* __restrict__ in, const PmRun* __restrict__ runs,
                                                             int nruns, uint64_t nranges, uint32_t* __restrict__ range_max) {
   const int      lane = threadIdx.x & 31;

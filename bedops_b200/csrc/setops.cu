@@ -95,71 +95,67 @@ __global__ void __launch_bounds__(256) k_rank_merge(RankParams p) {
 }
 
 // ---- segments from a sorted list + its inclusive prefix-max of end ----------------------------------------
+// Merged segments of a start-sorted list with its running-max-end index: row i opens a segment iff it is the first
+// row of its chromosome or start[i] > pmax[i-1] (touching intervals coalesce: Bedops.cpp:872, :1233); the segment ends
+// at the pmax of its last row.  Two passes over warp ranges that never cross a chromosome (same cut as the prefix-max
+// index): count the heads of every range, scan, then write -- no carry chain between tiles.
 struct SegParams {
   const uint32_t* s;
   const uint32_t* pm;
-  uint64_t        n;
-  const uint64_t* run_begin;  // [nruns] (ascending; empty runs allowed)
+  const PmRun*    runs;   // [nruns] non-empty chromosome runs
   int             nruns;
+  uint64_t        nranges;
+  uint64_t*       range_heads;       // [nranges] pass 1 out
+  const uint64_t* range_base;        // [nranges+1] exclusive scan of range_heads
   uint32_t*       outS;
   uint32_t*       outE;
-  uint64_t*       run_seg_begin;  // [nruns] first output segment of each run (written for non-empty runs)
-  uint64_t*       tile_state;
-  uint32_t        ntiles;
-  uint64_t*       scratch;
+  uint64_t*       run_seg_begin;     // [nruns] first output segment of each run
 };
 
-// is `row` the first row of a non-empty run?  returns the run index or -1
-__device__ __forceinline__ int run_head_of(const uint64_t* run_begin, int nruns, uint64_t n, uint64_t row) {
-  int lo = 0, hi = nruns;  // first run_begin >= row
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (run_begin[mid] < row) lo = mid + 1; else hi = mid;
+constexpr int SEG_THREADS = 256;
+__global__ void __launch_bounds__(SEG_THREADS) k_segment_heads(SegParams p) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * SEG_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * SEG_THREADS) >> 5;
+  for (uint64_t r = w0; r < p.nranges; r += nw) {
+    uint64_t a, b, first;
+    pm_locate(p.runs, p.nruns, r, a, b, first);
+    const bool run_start = r == first;  // row a is the first row of its chromosome
+    uint32_t   heads = 0;
+    for (uint64_t k = a + lane; k < b; k += 32) {
+      const bool head = (k == a && run_start) || (!(k == a && run_start) && __ldg(&p.s[k]) > __ldg(&p.pm[k - 1]));
+      heads += head ? 1u : 0u;
+    }
+    heads = __reduce_add_sync(0xffffffffu, heads);
+    if (lane == 0) p.range_heads[r] = heads;
   }
-  if (lo >= nruns || run_begin[lo] != row) return -1;
-  // among equal begins the last one is the non-empty run
-  while (lo + 1 < nruns && run_begin[lo + 1] == row) lo++;
-  return lo;
 }
 
-constexpr int SEG_THREADS = 256;
 __global__ void __launch_bounds__(SEG_THREADS) k_segments(SegParams p) {
-  __shared__ uint32_t scan_sm[34];
-  __shared__ uint32_t ticket_sm;
-  __shared__ uint64_t base_sm;
-  const int tid = threadIdx.x;
-  while (true) {
-    const uint32_t tile = next_ticket(p.scratch, &ticket_sm);
-    if (tile >= p.ntiles) break;
-    const uint64_t i = (uint64_t)tile * SEG_THREADS + tid;
-    bool           head = false, tail = false;
-    int            rh = -1;
-    uint32_t       s = 0, pm = 0;
-    if (i < p.n) {
-      s = p.s[i];
-      pm = p.pm[i];
-      rh = run_head_of(p.run_begin, p.nruns, p.n, i);
-      head = rh >= 0 || s > p.pm[i - 1];
-      if (i + 1 == p.n) tail = true;
-      else tail = run_head_of(p.run_begin, p.nruns, p.n, i + 1) >= 0 || p.s[i + 1] > pm;
-    }
-    uint32_t total;
-    uint32_t ex = block_excl_scan(head ? 1u : 0u, scan_sm, &total);
-    if (tid < 32) {
-      uint64_t b = lookback_sum(p.tile_state, tile, total);
-      if (tid == 0) {
-        base_sm = b;
-        if (tile == p.ntiles - 1) p.scratch[SC_OUT_ROWS] = b + total;
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * SEG_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * SEG_THREADS) >> 5;
+  for (uint64_t r = w0; r < p.nranges; r += nw) {
+    uint64_t  a, b, first;
+    const int run = pm_locate(p.runs, p.nruns, r, a, b, first);
+    const bool     run_start = r == first;
+    const uint64_t run_end = p.runs[run].row_end;
+    uint64_t       seg = p.range_base[r];  // segments opened before this range
+    if (run_start && lane == 0) p.run_seg_begin[run] = seg;
+    for (uint64_t k0 = a; k0 < b; k0 += 32) {
+      const uint64_t k = k0 + lane;
+      bool           head = false, tail = false;
+      uint32_t       sv = 0, pv = 0;
+      if (k < b) {
+        sv = __ldg(&p.s[k]);
+        pv = __ldg(&p.pm[k]);
+        head = (k == a && run_start) || (!(k == a && run_start) && sv > __ldg(&p.pm[k - 1]));
+        tail = k + 1 == run_end || __ldg(&p.s[k + 1]) > pv;  // the next row opens a segment (k+1 < run_end: same run)
       }
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      const uint64_t mine = seg + __popc(hm & ((2u << lane) - 1u));  // heads up to and including this row
+      if (head) p.outS[mine - 1] = sv;
+      if (tail) p.outE[mine - 1] = pv;
+      seg += __popc(hm);
     }
-    __syncthreads();
-    const uint64_t seg = base_sm + ex;  // index of the segment this row opens (if head)
-    if (head) {
-      p.outS[seg] = s;
-      if (rh >= 0) p.run_seg_begin[rh] = seg;
-    }
-    if (tail) p.outE[seg + (head ? 1 : 0) - 1] = pm;
-    __syncthreads();
   }
 }
 
@@ -336,7 +332,84 @@ static T* upload(bk_ctx* ctx, const std::vector<T>& v) {
 }
 
 // union-merge of k lists -> disjoint sorted segments (touching coalesced)
-static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in, IvList* out) {
+// start-sorted rows (S, E) with their chromosome runs -> the disjoint merged segments
+static int merge_list(bk_ctx* ctx, const uint32_t* S, const uint32_t* E, uint64_t N, const std::vector<ChromRun>& runs,
+                      IvList* out) {
+  out->runs.clear();
+  out->n = 0;
+  out->owned = true;
+  out->s = out->e = nullptr;
+  std::vector<PmRun>       pr;
+  std::vector<std::string> names;
+  uint64_t                 nranges = 0;
+  for (const ChromRun& r : runs) {
+    if (r.row_end == r.row_begin) continue;
+    pr.push_back({r.row_begin, r.row_end, nranges});
+    names.push_back(r.name);
+    nranges += (r.row_end - r.row_begin + PM_RANGE - 1) / PM_RANGE;
+  }
+  if (N == 0 || nranges == 0) return BK_OK;
+  const int G = (int)pr.size();
+  uint32_t* pm = dalloc<uint32_t>(ctx, N);
+  if (!pm) return BK_ERR_NOMEM;
+  BK_TRY(seg_prefix_max(ctx, E, pm, N, runs));
+  SegParams sp{};
+  sp.s = S; sp.pm = pm; sp.nruns = G; sp.nranges = nranges;
+  PmRun*    d_runs = dalloc<PmRun>(ctx, pr.size());
+  uint64_t* d_heads = dalloc<uint64_t>(ctx, nranges);
+  uint64_t* d_base = dalloc<uint64_t>(ctx, nranges + 1);
+  sp.run_seg_begin = dalloc<uint64_t>(ctx, G);
+  if (!d_runs || !d_heads || !d_base || !sp.run_seg_begin) return BK_ERR_NOMEM;
+  if (nranges >> 32) return fail(ctx, BK_ERR_UNSUPPORTED, "more than 2^32 row ranges");
+  BK_CUDA(ctx, cudaMemcpyAsync(d_runs, pr.data(), pr.size() * sizeof(PmRun), cudaMemcpyHostToDevice, ctx->stream));
+  sp.runs = d_runs; sp.range_heads = d_heads; sp.range_base = d_base;
+  const uint64_t want = (nranges + SEG_THREADS / 32 - 1) / (SEG_THREADS / 32);
+  BK_TRY(reset_scratch(ctx));
+  prof_begin(ctx, "k_segment_heads");
+  k_segment_heads<<<grid_for_kernel((const void*)k_segment_heads, SEG_THREADS, want), SEG_THREADS, 0, ctx->stream>>>(sp);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  k_scan_totals<SC_OUT_ROWS><<<1, 1024, 0, ctx->stream>>>(d_heads, d_base, (uint32_t)nranges, ctx->d_scratch);
+  BK_LAUNCHED(ctx);
+  BK_TRY(read_scratch(ctx));  // also: pr (host vector) has been copied
+  const uint64_t nseg = ctx->h_scratch[SC_OUT_ROWS];
+  sp.outS = dalloc<uint32_t>(ctx, nseg);
+  sp.outE = dalloc<uint32_t>(ctx, nseg);
+  if (!sp.outS || !sp.outE) return BK_ERR_NOMEM;
+  prof_begin(ctx, "k_segments");
+  k_segments<<<grid_for_kernel((const void*)k_segments, SEG_THREADS, want), SEG_THREADS, 0, ctx->stream>>>(sp);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  std::vector<uint64_t> rsb(G);
+  BK_CUDA(ctx, cudaMemcpyAsync(rsb.data(), sp.run_seg_begin, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  dfree(ctx, d_runs); dfree(ctx, d_heads); dfree(ctx, d_base); dfree(ctx, sp.run_seg_begin); dfree(ctx, pm);
+  out->s = sp.outS; out->e = sp.outE; out->n = nseg;
+  for (int g = 0; g < G; g++) out->runs.push_back({names[g], rsb[g], g + 1 < G ? rsb[g + 1] : nseg});
+  return BK_OK;
+}
+
+static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in_files, IvList* out) {
+  // Several files: merge every file within itself first (what getNextFileMergedCoords does for --intersect,
+  // Bedops.cpp:791-814) and interleave the -- usually far fewer -- segments; the union is the same.
+  std::vector<IvList> merged_files;
+  if (in_files.size() > 1) {
+    merged_files.resize(in_files.size());
+    for (size_t f = 0; f < in_files.size(); f++) {
+      std::vector<IvList> one{in_files[f]};
+      int rc = union_merge(ctx, one, &merged_files[f]);
+      if (rc != BK_OK) {
+        for (auto& m : merged_files) free_list(ctx, m);
+        return rc;
+      }
+    }
+  }
+  struct Cleanup {
+    bk_ctx* ctx;
+    std::vector<IvList>& v;
+    ~Cleanup() { for (auto& m : v) free_list(ctx, m); }
+  } cleanup{ctx, merged_files};
+  const std::vector<IvList>& in = in_files.size() > 1 ? merged_files : in_files;
   const int k = (int)in.size();
   // global chromosome table
   std::vector<std::string> names;
@@ -429,41 +502,11 @@ static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in, IvList* out) 
     BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (void* q : tofree) dfree(ctx, q);
   }
-  // runs of the merged list
-  bk_bed tmp;  // borrow ensure_pmax's kernel through a temporary view
-  tmp.end = mE;
-  tmp.nrows = N;
-  for (int g = 0; g < G; g++) tmp.runs.push_back({names[g], g_out[g], g_out[g + 1]});
-  int rc = ensure_pmax(ctx, &tmp);
-  if (rc != BK_OK) return rc;
-  // segments
-  std::vector<uint64_t> rb(G);
-  for (int g = 0; g < G; g++) rb[g] = g_out[g];
-  SegParams sp{};
-  sp.s = mS; sp.pm = tmp.pmax_end; sp.n = N;
-  sp.run_begin = upload(ctx, rb); sp.nruns = G;
-  sp.outS = dalloc<uint32_t>(ctx, N); sp.outE = dalloc<uint32_t>(ctx, N);
-  sp.run_seg_begin = dalloc<uint64_t>(ctx, G);
-  sp.ntiles = (uint32_t)((N + SEG_THREADS - 1) / SEG_THREADS);
-  sp.tile_state = dalloc<uint64_t>(ctx, sp.ntiles);
-  sp.scratch = ctx->d_scratch;
-  if (!sp.run_begin || !sp.outS || !sp.outE || !sp.run_seg_begin || !sp.tile_state) return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemsetAsync(sp.tile_state, 0, (size_t)sp.ntiles * 8, ctx->stream));
-  BK_TRY(reset_scratch(ctx));
-  prof_begin(ctx, "k_segments");
-  k_segments<<<grid_for_kernel((const void*)k_segments, SEG_THREADS, sp.ntiles), SEG_THREADS, 0, ctx->stream>>>(sp);
-  prof_end(ctx);
-  BK_LAUNCHED(ctx);
-  std::vector<uint64_t> rsb(G);
-  BK_CUDA(ctx, cudaMemcpyAsync(rsb.data(), sp.run_seg_begin, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_TRY(read_scratch(ctx));
-  const uint64_t nseg = ctx->h_scratch[SC_OUT_ROWS];
-  dfree(ctx, (void*)sp.run_begin); dfree(ctx, sp.run_seg_begin); dfree(ctx, sp.tile_state); dfree(ctx, tmp.pmax_end);
-  tmp.pmax_end = nullptr;
+  std::vector<ChromRun> mruns;
+  for (int g = 0; g < G; g++) mruns.push_back({names[g], g_out[g], g_out[g + 1]});
+  int rc = merge_list(ctx, mS, mE, N, mruns, out);
   if (merged_owned) { dfree(ctx, mS); dfree(ctx, mE); }
-  out->s = sp.outS; out->e = sp.outE; out->n = nseg; out->owned = true;
-  for (int g = 0; g < G; g++) out->runs.push_back({names[g], rsb[g], g + 1 < G ? rsb[g + 1] : nseg});
-  return BK_OK;
+  return rc;
 }
 
 // A ∩ B for disjoint sorted lists

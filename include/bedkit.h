@@ -77,7 +77,8 @@ int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_ms, uint64_t
 int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes);
 /* Device memory is cached per ctx: blocks freed by bk_free_bed / bk_free_text / internal temporaries are kept (by size
  * class) and reused by later calls without a driver call.  bk_release_cached hands every idle block back to the driver
- * (bk_destroy does it too); the library does it by itself when an allocation fails. */
+ * (bk_destroy does it too); the library does it by itself when an allocation fails or when the idle blocks exceed a
+ * quarter of the device memory. */
 int bk_release_cached(bk_ctx* ctx);
 
 /* ---- BED reader ------------------------------------------------------------------------------ */

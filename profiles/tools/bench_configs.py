@@ -62,6 +62,7 @@ def main():
     timed("bedops --element-of 1, 4 x 250M", rows, setop("element-of", 1, False))
     timed("bedops --not-element-of 100%, 4 x 250M", rows, setop("not-element-of", 1.0, True))
     del files
+    kit.release_cached()
     torch.cuda.empty_cache()
 
     # configuration 4: closest-features 50 M x 200 M
@@ -76,6 +77,7 @@ def main():
         qb.free()
     timed("closest-features --dist, 50M x 200M", ref.rows + qry.rows, closest)
     del ref, qry
+    kit.release_cached()
     torch.cuda.empty_cache()
 
     # configuration 5: bedmap --mean over 1 B map rows on one GPU
