@@ -345,9 +345,15 @@ def main():
     # k_parse per launch: the ref text and the map text are each parsed once per step
     alg_bytes_step = (map_bytes + 16 * nmap) + (ref_bytes + 16 * nref)   # text in + (start,end,score|line_off) out
     achieved = alg_bytes_step * args.steps / (parse_ms * 1e-3) / 1e9 if parse_ms > 0 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of the two k_parse launches of one step (reference file + map file),
+    # from the ncu --set full capture of this very command (profiles/r01_final_ncu_raw.csv); only valid for the default workload
+    traffic = None
+    if args.ref_rows == 10_000_000 and args.map_rows == 100_000_000:
+        traffic = int((0.376925 + 0.143766 + 3.869676 + 1.611783) * 1e9)
     roofline = {"bound": "hbm", "kernel": "k_parse", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "traffic_source": "ncu dram bytes, both k_parse launches of a step (profiles/r01_final_ncu_raw.csv)" if traffic else None,
                 "algorithmic_bytes_per_step": alg_bytes_step,
                 "kernel_ms_per_step": {"k_count_rows": count_ms / args.steps, "k_scan_warps": scan_ms / args.steps,
                                        "k_parse": parse_ms / args.steps, "k_pmax_reduce+k_pmax": pmax_ms / args.steps,
