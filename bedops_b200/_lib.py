@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
         "bk_bed_copy_columns": (i, [vp, vp, vp, vp, vp, vp]),
         "bk_mapspec_default": (None, [C.POINTER(_MapSpec)]),
         "bk_bedmap": (i, [vp, vp, vp, C.POINTER(_MapSpec), C.POINTER(_Text)]),
+        "bk_bedmap_host": (i, [vp, vp, C.c_size_t, i, C.c_uint, vp, C.c_size_t, i, C.c_uint, C.POINTER(_MapSpec),
+                               C.POINTER(_Text)]),
         "bk_setop": (i, [vp, i, C.POINTER(vp), i, C.c_double, i, C.c_char_p, i, C.POINTER(_Text)]),
         "bk_cfspec_default": (None, [C.POINTER(_CfSpec)]),
         "bk_closest": (i, [vp, vp, vp, C.POINTER(_CfSpec), C.POINTER(_Text)]),
@@ -105,7 +107,7 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
-           "bk_check_text_device", "bk_release_cached"]
+           "bk_check_text_device", "bk_release_cached", "bk_bedmap_host"]
 
 
 class Bed:
@@ -265,9 +267,26 @@ class BedKit:
         self.lib.bk_free_text(self.ctx, C.byref(t))
         return data
 
+    def bedmap_host(self, ref_ptr: int, ref_len: int, ref_fields: int, ref_cols: int, map_ptr: int, map_len: int,
+                    map_fields: int, map_cols: int, ops: Sequence[str], _raw: bool = False, **kw):
+        """bk_bedmap_host: the whole call over host buffers (addresses), transfers overlapped with the kernels."""
+        spec = self._mapspec(ops, **kw)
+        t = _Text()
+        self._chk(self.lib.bk_bedmap_host(self.ctx, ref_ptr, ref_len, ref_fields, ref_cols, map_ptr, map_len, map_fields,
+                                          map_cols, C.byref(spec), C.byref(t)))
+        return self._take(t, False, _raw)
+
     def bedmap(self, ref: Bed, map_: Optional[Bed], ops: Sequence[str], overlap=("bp", 1), prec: int = 6,
                sci: bool = False, delim: bytes = b"|", multidelim: bytes = b";", skip_unmapped: bool = False,
                chrom: Optional[bytes] = None, on_device: bool = False, _raw: bool = False):
+        spec = self._mapspec(ops, overlap, prec, sci, delim, multidelim, skip_unmapped, chrom, on_device)
+        t = _Text()
+        self._chk(self.lib.bk_bedmap(self.ctx, ref.h, map_.h if map_ is not None else None, C.byref(spec), C.byref(t)))
+        return self._take(t, on_device, _raw)
+
+    def _mapspec(self, ops: Sequence[str], overlap=("bp", 1), prec: int = 6, sci: bool = False, delim: bytes = b"|",
+                 multidelim: bytes = b";", skip_unmapped: bool = False, chrom: Optional[bytes] = None,
+                 on_device: bool = False):
         spec = _MapSpec()
         self.lib.bk_mapspec_default(C.byref(spec))
         spec.n_ops = len(ops)
@@ -282,9 +301,8 @@ class BedKit:
         spec.precision, spec.sci, spec.skip_unmapped = prec, int(sci), int(skip_unmapped)
         spec.delim, spec.multidelim, spec.chrom = delim, multidelim, chrom
         spec.out_on_device = int(on_device)
-        t = _Text()
-        self._chk(self.lib.bk_bedmap(self.ctx, ref.h, map_.h if map_ is not None else None, C.byref(spec), C.byref(t)))
-        return self._take(t, on_device, _raw)
+        self._keep_spec_strings = (delim, multidelim, chrom)
+        return spec
 
     def setop(self, op: str, files: Sequence[Bed], thr: float = 1.0, use_pct: bool = True,
               chrom: Optional[bytes] = None, on_device: bool = False):

@@ -1,0 +1,220 @@
+// pipeline.cu -- bk_bedmap_host: bedmap over HOST text with the PCIe transfers overlapped with the kernels.
+//
+// The path shards by chromosome, so one call can be cut into independent chromosome groups:
+//   copy stream    : H2D of every group's slices of the two files, back to back (enqueued up front)
+//   compute stream : for each group, as soon as its slices have arrived: parse both, map, emit (result stays in HBM)
+//   result stream  : D2H of each group's output text into one pinned host buffer at its final offset
+// PCIe is full duplex, the kernels take ~10 % of the transfer time, so the call approaches the H2D time of the inputs.
+// Output = the groups' outputs in chromosome order = the output of one unsplit call (same contract as the reference's
+// per-chromosome scale-out, bedmap/src/Input.hpp:117-122).  Inputs should be pinned for the overlap to happen.
+#include <algorithm>
+#include "common.cuh"
+
+using namespace bk;
+
+namespace {
+
+struct Group {
+  uint64_t rb, re, mb, me;  // byte ranges in the reference / map text
+  uint64_t d_ref, d_map;    // offsets of the slices in the device staging buffer (256-byte aligned)
+};
+
+bool strictly_sorted(const std::vector<bk_chrom_span>& ix) {
+  for (size_t i = 1; i < ix.size(); i++)
+    if (strcmp(ix[i - 1].name, ix[i].name) >= 0) return false;
+  return true;
+}
+
+int index_of(const char* text, size_t n, std::vector<bk_chrom_span>* out) {
+  int cnt = 0, cap = 64;
+  while (true) {
+    out->assign(cap, bk_chrom_span{});
+    int rc = bk_chrom_index(text, n, out->data(), cap, &cnt);
+    if (rc == BK_OK) {
+      out->resize(cnt);
+      return BK_OK;
+    }
+    if (rc != BK_ERR_NOMEM) return rc;
+    cap = cnt + 8;
+  }
+}
+
+int plain(bk_ctx* ctx, const char* ref_text, size_t ref_len, const char* map_text, size_t map_len, int ref_fields,
+          unsigned ref_cols, int map_fields, unsigned map_cols, const bk_mapspec* spec, bk_text* out) {
+  bk_bed *ref = nullptr, *map = nullptr;
+  int     rc = bk_load_bed(ctx, ref_text, ref_len, ref_fields, ref_cols, &ref);
+  if (rc == BK_OK) rc = bk_load_bed(ctx, map_text, map_len, map_fields, map_cols, &map);
+  if (rc == BK_OK) rc = bk_bedmap(ctx, ref, map, spec, out);
+  bk_free_bed(ctx, ref);
+  bk_free_bed(ctx, map);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len, int ref_fields, unsigned ref_cols,
+                              const char* map_text, size_t map_len, int map_fields, unsigned map_cols,
+                              const bk_mapspec* spec, bk_text* out) {
+  if (!ctx || !spec || !out || (!ref_text && ref_len) || (!map_text && map_len)) return BK_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  const bool one_chrom = spec->chrom && strcmp(spec->chrom, "all") != 0;
+  std::vector<bk_chrom_span> rix, mix;
+  if (one_chrom || spec->out_on_device || index_of(ref_text, ref_len, &rix) != BK_OK ||
+      index_of(map_text, map_len, &mix) != BK_OK || !strictly_sorted(rix) || !strictly_sorted(mix) || rix.size() < 2)
+    return plain(ctx, ref_text, ref_len, map_text, map_len, ref_fields, ref_cols, map_fields, map_cols, spec, out);
+
+  // chromosome groups of roughly 1/16 of the bytes each (>= 32 MiB); chromosomes without reference rows are not uploaded
+  uint64_t total = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> mspan(rix.size(), {0, 0});
+  {
+    size_t j = 0;
+    for (size_t i = 0; i < rix.size(); i++) {
+      while (j < mix.size() && strcmp(mix[j].name, rix[i].name) < 0) j++;
+      if (j < mix.size() && strcmp(mix[j].name, rix[i].name) == 0) mspan[i] = {mix[j].begin, mix[j].end};
+      total += (rix[i].end - rix[i].begin) + (mspan[i].second - mspan[i].first);
+    }
+  }
+  const uint64_t     target = std::max<uint64_t>(total / 16, 32ull << 20);
+  std::vector<Group> groups;
+  uint64_t           dev_bytes = 0;
+  for (size_t i = 0; i < rix.size();) {
+    Group    g{rix[i].begin, rix[i].end, 0, 0, 0, 0};
+    uint64_t load = 0;
+    bool     have_map = false;
+    size_t   k = i;
+    for (; k < rix.size(); k++) {
+      const uint64_t add = (rix[k].end - rix[k].begin) + (mspan[k].second - mspan[k].first);
+      if (k > i && load + add > target) break;
+      // the map slice of a group must be one contiguous byte range: stop in front of a gap made by chromosomes that
+      // exist only in the map file
+      if (mspan[k].second > mspan[k].first) {
+        if (have_map && mspan[k].first != g.me) break;
+        if (!have_map) g.mb = mspan[k].first;
+        g.me = mspan[k].second;
+        have_map = true;
+      }
+      g.re = rix[k].end;
+      load += add;
+    }
+    auto up = [](uint64_t x) { return (x + 255) & ~255ull; };
+    g.d_ref = dev_bytes;
+    dev_bytes = up(dev_bytes + (g.re - g.rb)) + 256;
+    g.d_map = dev_bytes;
+    dev_bytes = up(dev_bytes + (g.me - g.mb)) + 256;
+    groups.push_back(g);
+    i = k;
+  }
+
+  ctx->last_error.clear();
+  char* d_stage = reinterpret_cast<char*>(dmalloc(ctx, dev_bytes + 256));
+  if (!d_stage) return BK_ERR_NOMEM;
+  cudaStream_t copy_s = nullptr, out_s = nullptr;
+  std::vector<cudaEvent_t> ev_in(groups.size(), nullptr), ev_done(groups.size(), nullptr);
+  std::vector<bk_text>     parts(groups.size());
+  for (auto& t : parts) memset(&t, 0, sizeof(t));
+  int  rc = BK_OK;
+  auto cuda_ok = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == BK_OK) rc = cuda_fail(ctx, e, what, __FILE__, __LINE__);
+    return e == cudaSuccess;
+  };
+  cuda_ok(cudaStreamCreateWithFlags(&copy_s, cudaStreamNonBlocking), "cudaStreamCreate");
+  cuda_ok(cudaStreamCreateWithFlags(&out_s, cudaStreamNonBlocking), "cudaStreamCreate");
+  // the staging block may still be in use by earlier work of this ctx (cached allocator, stream order): start the
+  // copies after everything already queued on the compute stream
+  cudaEvent_t ev_start = nullptr;
+  cuda_ok(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming), "cudaEventCreate");
+  if (rc == BK_OK) {
+    cuda_ok(cudaEventRecord(ev_start, ctx->stream), "cudaEventRecord");
+    cuda_ok(cudaStreamWaitEvent(copy_s, ev_start, 0), "cudaStreamWaitEvent");
+  }
+  for (size_t g = 0; g < groups.size() && rc == BK_OK; g++) {
+    const Group& G = groups[g];
+    cuda_ok(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming), "cudaEventCreate");
+    cuda_ok(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming), "cudaEventCreate");
+    if (G.re > G.rb) cuda_ok(cudaMemcpyAsync(d_stage + G.d_ref, ref_text + G.rb, G.re - G.rb, cudaMemcpyHostToDevice, copy_s), "H2D");
+    if (G.me > G.mb) cuda_ok(cudaMemcpyAsync(d_stage + G.d_map, map_text + G.mb, G.me - G.mb, cudaMemcpyHostToDevice, copy_s), "H2D");
+    cuda_ok(cudaEventRecord(ev_in[g], copy_s), "cudaEventRecord");
+  }
+
+  // compute, group by group; results stay in HBM until their D2H has been queued with a known offset
+  bk_mapspec dspec = *spec;
+  dspec.out_on_device = 1;
+  char*    h_out = nullptr;
+  uint64_t h_cap = 0, h_off = 0, rows = 0;
+  size_t   flushed = 0;  // parts [0, flushed) have their D2H queued
+  uint64_t ref_done = 0, out_done = 0;
+  auto     flush = [&](size_t upto) {
+    for (; flushed < upto && rc == BK_OK; flushed++) {
+      bk_text& t = parts[flushed];
+      if (t.len && h_off + t.len <= h_cap) {
+        cuda_ok(cudaStreamWaitEvent(out_s, ev_done[flushed], 0), "cudaStreamWaitEvent");
+        cuda_ok(cudaMemcpyAsync(h_out + h_off, t.ptr, t.len, cudaMemcpyDeviceToHost, out_s), "D2H");
+      } else if (t.len) {
+        break;  // does not fit the estimate: the tail is copied after the final size is known
+      }
+      h_off += t.len;
+    }
+  };
+  for (size_t g = 0; g < groups.size() && rc == BK_OK; g++) {
+    const Group& G = groups[g];
+    cuda_ok(cudaStreamWaitEvent(ctx->stream, ev_in[g], 0), "cudaStreamWaitEvent");
+    bk_bed *ref = nullptr, *map = nullptr;
+    if (rc == BK_OK) rc = bk_load_bed_device(ctx, d_stage + G.d_ref, G.re - G.rb, ref_fields, ref_cols, &ref);
+    if (rc == BK_OK) rc = bk_load_bed_device(ctx, d_stage + G.d_map, G.me - G.mb, map_fields, map_cols, &map);
+    if (rc == BK_OK) rc = bk_bedmap(ctx, ref, map, &dspec, &parts[g]);
+    if (rc == BK_OK) cuda_ok(cudaEventRecord(ev_done[g], ctx->stream), "cudaEventRecord");
+    bk_free_bed(ctx, ref);
+    bk_free_bed(ctx, map);
+    if (rc != BK_OK) break;
+    rows += parts[g].rows;
+    ref_done += G.re - G.rb;
+    out_done += parts[g].len;
+    if (!h_out && (out_done || g + 1 == groups.size())) {  // size the host buffer from the output density so far, +25 %
+      const double per_byte = (double)out_done / (double)std::max<uint64_t>(1, ref_done);
+      h_cap = (uint64_t)(per_byte * 1.25 * (double)ref_len) + (1u << 20);
+      h_out = pinned_get(ctx, h_cap);
+      if (!h_out) rc = BK_ERR_NOMEM;
+    }
+    if (rc == BK_OK && h_out) flush(g + 1);
+  }
+  if (rc == BK_OK) {
+    uint64_t need = 0;
+    for (auto& t : parts) need += t.len;
+    if (flushed < parts.size()) {  // the estimate was too small: move to an exact buffer
+      cuda_ok(cudaStreamSynchronize(out_s), "cudaStreamSynchronize");
+      char* exact = pinned_get(ctx, need);
+      if (!exact) rc = BK_ERR_NOMEM;
+      if (rc == BK_OK) {
+        memcpy(exact, h_out, h_off);
+        pinned_put(ctx, h_out);
+        h_out = exact;
+        h_cap = need;
+        flush(parts.size());
+      }
+    }
+    cuda_ok(cudaStreamSynchronize(out_s), "cudaStreamSynchronize");
+    if (rc == BK_OK) {
+      out->ptr = h_out;
+      out->len = need;
+      out->rows = rows;
+      out->on_device = 0;
+    }
+  }
+  // teardown: nothing may be reused while a stream still reads it
+  if (copy_s) cudaStreamSynchronize(copy_s);
+  if (out_s) cudaStreamSynchronize(out_s);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& t : parts)
+    if (t.ptr) bk_free_text(ctx, &t);
+  dfree(ctx, d_stage);
+  for (auto e : ev_in) if (e) cudaEventDestroy(e);
+  for (auto e : ev_done) if (e) cudaEventDestroy(e);
+  if (ev_start) cudaEventDestroy(ev_start);
+  if (copy_s) cudaStreamDestroy(copy_s);
+  if (out_s) cudaStreamDestroy(out_s);
+  if (rc != BK_OK && h_out) pinned_put(ctx, h_out);
+  // a failing group reports row numbers relative to its slice: let the unsplit path produce the message
+  if (rc != BK_OK && rc != BK_ERR_NOMEM && rc != BK_ERR_CUDA)
+    return plain(ctx, ref_text, ref_len, map_text, map_len, ref_fields, ref_cols, map_fields, map_cols, spec, out);
+  return rc;
+}

@@ -307,13 +307,12 @@ def main():
         torch.cuda.synchronize()
 
         def step_host():
-            ref = kit.load_host_ptr(ref_host.data_ptr(), ref_bytes, 3, COL_LINE)
-            mp = kit.load_host_ptr(map_host.data_ptr(), map_bytes, 5, COL_SCORE)
-            text = kit.bedmap(ref, mp, OPS, on_device=False, _raw=True)
+            # the reference-facing call with HOST buffers: bk_bedmap_host uploads, parses, maps and downloads chromosome
+            # group by chromosome group (H2D, kernels and D2H overlapped); result text lands in pinned host memory
+            text = kit.bedmap_host(ref_host.data_ptr(), ref_bytes, 3, COL_LINE, map_host.data_ptr(), map_bytes, 5,
+                                   COL_SCORE, OPS, _raw=True)
             n = text.len
             kit.free_text(text)
-            ref.free()
-            mp.free()
             return n
 
         for _ in range(max(1, min(args.warmup, 2))):

@@ -156,6 +156,15 @@ void bk_mapspec_default(bk_mapspec* spec);
 /* map == NULL: single-file mode, ref is mapped onto itself (Input.hpp:359-364) */
 int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, const bk_mapspec* spec, bk_text* out);
 
+/* The whole bedmap call over HOST text (what the tool does: read two files, map, print), cut into chromosome groups so
+ * that the host->device copies of later groups and the device->host copies of earlier results overlap the kernels
+ * (PCIe is full duplex; pin the inputs for the overlap to happen).  Same output as
+ * bk_load_bed x2 + bk_bedmap; falls back to exactly that for --chrom, single-chromosome or unsorted input, and to
+ * produce error messages.  ref_fields/ref_cols/map_fields/map_cols as for bk_load_bed.  Result: host text. */
+int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len, int ref_fields, unsigned ref_cols,
+                   const char* map_text, size_t map_len, int map_fields, unsigned map_cols, const bk_mapspec* spec,
+                   bk_text* out);
+
 /* ---- bedops set operators ------------------------------------------------------------------- */
 enum { BK_SETOP_MERGE = 1, BK_SETOP_INTERSECT = 2, BK_SETOP_ELEMENT_OF = 3, BK_SETOP_NOT_ELEMENT_OF = 4 };
 /* thr / thr_is_pct: -e/-n threshold as Input::Threshold()/UsePercentage() deliver it (bedops/src/Input.hpp:344-382):

@@ -242,6 +242,34 @@ def test_float_scores_within_tolerance(kit):
 
 
 # ---- the drop-in command lines against the reference binaries ------------------------------------------------------
+def test_pipelined_host_call_equals_the_unsplit_call(kit, synth_files):
+    """bk_bedmap_host (chromosome groups, transfers overlapped with kernels) == bk_load_bed x2 + bk_bedmap, including
+    chromosomes that exist in only one of the files."""
+    from bedops_b200._lib import COL_ID, COL_LINE, COL_SCORE
+    ref, mp = synth_files["r.bed"], synth_files["m.bed"]
+    extra_ref = b"chrZ\t5\t50\tonly_in_ref\t1\n"
+    mp_gap = b"".join(l + b"\n" for l in mp.split(b"\n")[:-1] if not l.startswith(b"chr11\t")) + b"chrZZ\t1\t9\tx\t2\n"
+    for r, m in ((ref, mp), (ref + extra_ref, mp_gap)):
+        rn, mn = np.frombuffer(r, dtype=np.uint8), np.frombuffer(m, dtype=np.uint8)
+        for ops, mf, mc in ((["echo", "count", "mean", "bases"], 5, COL_SCORE),
+                            (["count", "echo-map-id"], 4, COL_ID | COL_LINE)):
+            rb, mb = kit.load(r, 3, COL_LINE), kit.load(m, mf, mc)
+            exp = kit.bedmap(rb, mb, ops)
+            got = kit.bedmap_host(rn.ctypes.data, len(r), 3, COL_LINE, mn.ctypes.data, len(m), mf, mc, ops)
+            assert_same(got, exp)
+            rb.free()
+            mb.free()
+    # errors come from the unsplit path: same message, row numbers of the whole file
+    bad = ref + b"chrZ\t10\tnot_a_number\n"
+    bn = np.frombuffer(bad, dtype=np.uint8)
+    mn = np.frombuffer(mp, dtype=np.uint8)
+    with pytest.raises(Exception) as e1:
+        kit.bedmap_host(bn.ctypes.data, len(bad), 3, COL_LINE, mn.ctypes.data, len(mp), 5, COL_SCORE, ["count"])
+    with pytest.raises(Exception) as e2:
+        kit.load(bad, 3, COL_LINE)
+    assert str(e1.value) == str(e2.value)
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
 def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
     import bedops_b200
