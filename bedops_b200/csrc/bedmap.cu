@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
         ms = p.ms + mb;
         me = p.me + mb;
         if (kScore) sc = p.score + mb;
-        if (FLAGS & NEED_IDS) ids = p.idspan + mb;
+        if ((FLAGS & NEED_IDS) && p.idspan) ids = p.idspan + mb;
         hint_run = run;
       }
       const uint64_t re_pad64 = (uint64_t)re + pad;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
               have = true;
             }
           }
-          if (FLAGS & NEED_IDS) idb += __ldg(&ids[ka]) & 0xFFFFu;
+          if ((FLAGS & NEED_IDS) && ids) idb += __ldg(&ids[ka]) & 0xFFFFu;
         }
         if (qb) {
           cnt++;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
               have = true;
             }
           }
-          if (FLAGS & NEED_IDS) idb += __ldg(&ids[kb]) & 0xFFFFu;
+          if ((FLAGS & NEED_IDS) && ids) idb += __ldg(&ids[kb]) & 0xFFFFu;
         }
         const unsigned mb_ = __ballot_sync(0xffffffffu, inb);
         if (FLAGS & NEED_IDS) nwin += __popc(__ballot_sync(0xffffffffu, ina)) + __popc(mb_);
@@ -256,7 +256,8 @@ static void launch_map_stats(unsigned need, unsigned blocks, cudaStream_t st, co
   }
 }
 
-// RARE bit 0: --sci output; bit 1: the reference file is a B4Rest/B5Rest (single-file mode) -- compile-time so that the
+// RARE bit 0: --sci output; bit 1: the reference file is a B4Rest/B5Rest (single-file mode); bit 2: per-hit list /
+// unique-bases operations other than --echo-map-id -- compile-time so that the
 // common instantiation carries none of that code (the emitter is register-bound).
 template <int RARE>
 struct BedmapRow {
@@ -274,6 +275,8 @@ struct BedmapRow {
   const uint32_t* midspan;
   const uint32_t* ms;
   const uint32_t* me;
+  const double*   mscore;
+  int             map_fields;  // record type of the map file (3|4|5): how --echo-map prints a row
   // per-row results (indexed by i = row - row0)
   const uint32_t* count;
   const uint64_t* bases;
@@ -349,6 +352,76 @@ struct BedmapRow {
     }
   }
 
+  // the operations that walk the qualifying map rows of reference row `row` in file order (= the order of the
+  // reference's std::set<MapType*, GenomicAddressCompare>, EchoMapBedVisitor.hpp:62)
+  template <class Sink>
+  __device__ __noinline__ void window_op(Sink& s, int op, uint64_t i, uint64_t row) const {
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    bool           first = true;
+    uint32_t       mn = 0xFFFFFFFFu, mx = 0;   // --echo-map-range
+    uint32_t       cs = 0, ce = 0;             // --bases-uniq: the open union run
+    uint64_t       uniq = 0;
+    for (uint64_t k = lo; k < hi; k++) {
+      uint32_t       ovl;
+      const uint32_t s0 = ms[k], e0 = me[k];
+      if (!qualifies(ov, a, b, s0, e0, ovl)) continue;
+      if (op == BK_OP_ECHO_MAP_RANGE) {
+        mn = s0 < mn ? s0 : mn;
+        mx = e0 > mx ? e0 : mx;
+        first = false;
+        continue;
+      }
+      if (op == BK_OP_BASES_UNIQ || op == BK_OP_BASES_UNIQ_F) {
+        if (first) {
+          cs = s0; ce = e0;
+        } else if ((ce < e0 ? ce : e0) > (cs > s0 ? cs : s0)) {  // Bed.hpp:172-191 overlap() > 0 -> eunion (:202-210)
+          cs = cs < s0 ? cs : s0;
+          ce = ce > e0 ? ce : e0;
+        } else {
+          const uint32_t x = ce < b ? ce : b, y = cs > a ? cs : a;
+          uniq += x > y ? x - y : 0;
+          cs = s0; ce = e0;
+        }
+        first = false;
+        continue;
+      }
+      if (!first) s.puts_(mdelim, mdelim_len);
+      first = false;
+      switch (op) {
+        case BK_OP_ECHO_MAP:
+          if (map_fields <= 3) echo_b3rest(s, mtext, mline[k], s0, e0);
+          else echo_b45rest(s, mtext, mline[k], s0, e0, map_fields, map_fields >= 5 ? mscore[k] : 0.0, scratch, i);
+          break;
+        case BK_OP_ECHO_MAP_SCORE: put_score(s, mscore[k], 1, i); break;
+        case BK_OP_ECHO_MAP_SIZE: s.put_u32(e0 - s0); break;
+        case BK_OP_ECHO_OVERLAP_SIZE: {
+          const uint32_t x = e0 < b ? e0 : b, y = s0 > a ? s0 : a;
+          s.put_u32(x > y ? x - y : 0);
+          break;
+        }
+      }
+    }
+    if (op == BK_OP_ECHO_MAP_RANGE && !first) {
+      const char* p = rtext + (rline[row] & kLineOffMask);  // the chromosome name: the reference row's token
+      int         n = 0;
+      while (is_tok((unsigned char)p[n])) n++;
+      s.copy(p, n);
+      s.put('\t');
+      s.put_u32(mn);
+      s.put('\t');
+      s.put_u32(mx);
+    }
+    if (op == BK_OP_BASES_UNIQ || op == BK_OP_BASES_UNIQ_F) {
+      if (!first) {
+        const uint32_t x = ce < b ? ce : b, y = cs > a ? cs : a;
+        uniq += x > y ? x - y : 0;
+      }
+      if (op == BK_OP_BASES_UNIQ) s.put_u64(uniq);
+      else put_score(s, (double)(uint32_t)uniq / (double)(b - a), 1, i);
+    }
+  }
+
   template <class Sink>
   __device__ void operator()(uint64_t i, Sink& s) const {
     const uint32_t cnt = count[i];
@@ -386,6 +459,10 @@ struct BedmapRow {
           }
           break;
         }
+        case BK_OP_ECHO_MAP: case BK_OP_ECHO_MAP_SCORE: case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE:
+        case BK_OP_ECHO_MAP_RANGE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
+          if (RARE & 4) window_op(s, ops[c], i, row);
+          break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
           const char* p = rtext + (rline[row] & kLineOffMask);
@@ -449,7 +526,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   if (strlen(delim) > 23 || strlen(mdelim) > 23) return fail(ctx, BK_ERR_UNSUPPORTED, "delimiter longer than 23 bytes");
 
   unsigned need = 0;
-  bool     need_echo = false, need_refline = false;
+  bool     need_echo = false, need_refline = false, need_ids = false, need_mapline = false, need_mapscore = false;
+  bool     window_ops = false;
   for (int c = 0; c < spec->n_ops; c++) {
     switch (spec->ops[c]) {
       case BK_OP_ECHO: need_echo = true; need_refline = true; break;
@@ -459,7 +537,12 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       case BK_OP_SUM: case BK_OP_MEAN: need |= NEED_SUM; break;
       case BK_OP_MAX: need |= NEED_MAX; break;
       case BK_OP_MIN: need |= NEED_MIN; break;
-      case BK_OP_ECHO_MAP_ID: need |= NEED_IDS; break;
+      case BK_OP_ECHO_MAP_ID: need |= NEED_IDS; need_ids = true; break;
+      case BK_OP_ECHO_MAP: need |= NEED_IDS; need_mapline = true; window_ops = true; break;
+      case BK_OP_ECHO_MAP_SCORE: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      case BK_OP_ECHO_MAP_RANGE: need |= NEED_IDS; need_refline = true; window_ops = true; break;
+      case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
+        need |= NEED_IDS; window_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }
   }
@@ -467,8 +550,12 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     return fail(ctx, BK_ERR_ARG, "reference file was loaded without BK_COL_LINE but --echo needs it");
   if ((need & (NEED_SUM | NEED_MAX | NEED_MIN)) && !map->score && map->nrows)
     return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_SCORE but a score operation needs it");
-  if ((need & NEED_IDS) && (!map->idspan || !map->line_off) && map->nrows)
+  if (need_ids && (!map->idspan || !map->line_off) && map->nrows)
     return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_ID|BK_COL_LINE but --echo-map-id needs it");
+  if (need_mapline && !map->line_off && map->nrows)
+    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_LINE but --echo-map needs it");
+  if (need_mapscore && !map->score && map->nrows)
+    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_SCORE but --echo-map-score needs it");
 
   OverlapSpec ov{};
   ov.kind = spec->overlap_kind;
@@ -563,20 +650,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host table `tab` must outlive its copy
   dfree(ctx, d_tab);
 
-  // output size bound: echoed reference text + a fixed worst case per numeric column + id lists
-  uint64_t idtotal = 0;
-  if (need & NEED_IDS) {
-    // sum of idbytes: tiny reduction on the host side of a device prefix would cost a pass; reuse the bound
-    // sum_i idbytes[i] <= map id bytes * (windows that contain the row) -- not bounded a priori, so reduce it.
-    std::vector<uint32_t> h(n);
-    BK_CUDA(ctx, cudaMemcpyAsync(h.data(), sp.idbytes, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (uint64_t i = 0; i < n; i++) idtotal += h[i];
-  }
   const uint64_t dl = strlen(delim);
-  uint64_t per_row = 1 + (uint64_t)spec->n_ops * (dl + 44);
-  uint64_t cap = n * per_row + idtotal + 64;
-  if (need_refline) cap += ref->nbytes + 2 * 11 * n;
+  const uint64_t cap = 0;  // the emitter sizes the result itself (length pass)
 
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
@@ -586,6 +661,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     fn.ref_fields = (ref->min_fields >= 5 && !ref->score) ? 4 : ref->min_fields;
     fn.rscore = ref->score;
     fn.mtext = map->d_text; fn.mline = map->line_off; fn.midspan = map->idspan; fn.ms = map->start; fn.me = map->end;
+    fn.mscore = map->score;
+    fn.map_fields = (map->min_fields >= 5 && !map->score) ? 4 : map->min_fields;
     fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
     fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
     fn.ov = ov; fn.n_ops = spec->n_ops;
@@ -597,7 +674,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
   };
   const bool rare_fields = need_echo && ref->min_fields > 3;
-  if (!spec->sci && !rare_fields) emit(BedmapRow<0>{});
+  if (window_ops) emit(BedmapRow<7>{});  // the list operations are not the hot path: one instantiation carries everything
+  else if (!spec->sci && !rare_fields) emit(BedmapRow<0>{});
   else if (spec->sci && !rare_fields) emit(BedmapRow<1>{});
   else if (!spec->sci) emit(BedmapRow<2>{});
   else emit(BedmapRow<3>{});

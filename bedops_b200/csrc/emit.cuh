@@ -220,11 +220,14 @@ int read_scratch(bk_ctx* ctx);
 template <class RowFn>
 int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** d_out, uint64_t* out_bytes,
              uint64_t* out_rows) {
+  (void)out_cap;  // historical: the result is allocated exactly, after the length pass
   *out_bytes = 0;
   *out_rows = 0;
-  *d_out = reinterpret_cast<char*>(dmalloc(ctx, out_cap + 16));
-  if (!*d_out) return BK_ERR_NOMEM;
-  if (n == 0) return BK_OK;
+  *d_out = nullptr;
+  if (n == 0) {
+    *d_out = reinterpret_cast<char*>(dmalloc(ctx, 16));
+    return *d_out ? BK_OK : BK_ERR_NOMEM;
+  }
   const uint32_t ntiles = (uint32_t)((n + E_THREADS - 1) / E_THREADS);
   // warp ranges of 2^range_shift rows (>= one tile): up to four waves of 64 warps per SM
   int range_shift = 8;
@@ -243,9 +246,20 @@ int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** 
   BK_LAUNCHED(ctx);
   k_scan_totals<SC_OUT_BYTES><<<1, 1024, 0, ctx->stream>>>(wtot, wbase, nwarps, ctx->d_scratch);
   BK_LAUNCHED(ctx);
+  BK_TRY(read_scratch(ctx));  // the output size: allocate exactly
+  const uint64_t total = ctx->h_scratch[SC_OUT_BYTES];
+  if (!ctx->h_scratch[SC_ERR_CODE]) *d_out = reinterpret_cast<char*>(dmalloc(ctx, total + 16));
+  if (ctx->h_scratch[SC_ERR_CODE] || !*d_out) {
+    dfree(ctx, local_off);
+    dfree(ctx, wtot);
+    dfree(ctx, wbase);
+    if (!ctx->h_scratch[SC_ERR_CODE]) return BK_ERR_NOMEM;
+    return fail(ctx, (int)ctx->h_scratch[SC_ERR_CODE], "output row too long for the device writer (row %llu)",
+                (unsigned long long)ctx->h_scratch[SC_ERR_ROW]);
+  }
   prof_begin(ctx, "k_emit");
   k_emit<RowFn><<<grid_for_kernel((const void*)k_emit<RowFn>, E_THREADS, ntiles), E_THREADS, 0, ctx->stream>>>(
-      fn, n, *d_out, out_cap, range_shift, local_off, wbase, nwarps, ntiles, ctx->d_scratch);
+      fn, n, *d_out, total, range_shift, local_off, wbase, nwarps, ntiles, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   BK_TRY(read_scratch(ctx));
@@ -254,7 +268,9 @@ int run_emit(bk_ctx* ctx, const RowFn& fn, uint64_t n, uint64_t out_cap, char** 
   dfree(ctx, wbase);
   if (ctx->h_scratch[SC_ERR_CODE]) {
     int code = (int)ctx->h_scratch[SC_ERR_CODE];
-    return fail(ctx, code, code == BK_ERR_NOMEM ? "output exceeds the precomputed bound (tile %llu)"
+    dfree(ctx, *d_out);
+    *d_out = nullptr;
+    return fail(ctx, code, code == BK_ERR_NOMEM ? "output writer ran past the length pass (tile %llu)"
                                                  : "value outside the exact device formatter (row block %llu)",
                 (unsigned long long)ctx->h_scratch[SC_ERR_ROW]);
   }

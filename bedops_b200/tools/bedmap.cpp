@@ -15,12 +15,12 @@ struct OpInfo {
   int         nargs;       // fixed extra arguments (only the out-of-scope ops take any)
 };
 const OpInfo kOps[] = {
-    {"bases", BK_OP_BASES, 3, 0},          {"bases-uniq", 0, 3, 0},           {"bases-uniq-f", 0, 3, 0},
+    {"bases", BK_OP_BASES, 3, 0},          {"bases-uniq", BK_OP_BASES_UNIQ, 3, 0},           {"bases-uniq-f", BK_OP_BASES_UNIQ_F, 3, 0},
     {"echo", BK_OP_ECHO, 3, 0},            {"echo-ref-size", BK_OP_ECHO_REF_SIZE, 3, 0},
     {"echo-ref-name", BK_OP_ECHO_REF_NAME, 3, 0},                             {"echo-ref-row-id", BK_OP_ECHO_REF_ROW_ID, 3, 0},
-    {"echo-map", 0, 3, 0},                 {"echo-map-id", BK_OP_ECHO_MAP_ID, 4, 0},
-    {"echo-map-id-uniq", 0, 4, 0},         {"echo-map-size", 0, 3, 0},        {"echo-overlap-size", 0, 3, 0},
-    {"echo-map-range", 0, 3, 0},           {"echo-map-score", 0, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
+    {"echo-map", BK_OP_ECHO_MAP, 3, 0},                 {"echo-map-id", BK_OP_ECHO_MAP_ID, 4, 0},
+    {"echo-map-id-uniq", 0, 4, 0},         {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, 0},        {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, 0},
+    {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, 0},           {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
     {"indicator", BK_OP_INDICATOR, 3, 0},  {"max", BK_OP_MAX, 5, 0},          {"max-element-rand", 0, 5, 0},
     {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
     {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", 0, 5, 0},
@@ -206,7 +206,8 @@ void usage(FILE* f) {
       "      --bp-ovr <int>, --exact, --fraction-both <val>, --fraction-either <val>, --fraction-map <val>,\n"
       "      --fraction-ref <val>, --range <int>\n\n"
       "     Operations on this build's B200 hot path:\n"
-      "      --bases --count --echo --echo-map-id --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
+      "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-range\n"
+      "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
       "      --indicator --max --mean --min --sum\n\n",
       f);
 }
@@ -224,12 +225,13 @@ int main(int argc, char** argv) {
 
     bk_mapspec spec;
     bk_mapspec_default(&spec);
-    bool need_line = false, need_score = false, need_id = false;
+    bool need_line = false, need_score = false, need_id = false, need_mapline = false;
     for (int op : o.ops) {
       spec.ops[spec.n_ops++] = op;
-      need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME;
-      need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN;
+      need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
+      need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE;
       need_id |= op == BK_OP_ECHO_MAP_ID;
+      need_mapline |= op == BK_OP_ECHO_MAP;
     }
     spec.overlap_kind = o.overlap_kind;
     spec.overlap_bp = o.overlap_kind == BK_OVR_RANGE ? (uint64_t)o.range_bp : (uint64_t)o.overlap_bp;
@@ -243,7 +245,8 @@ int main(int argc, char** argv) {
     spec.chrom = o.chrom.c_str();
 
     const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
-    const unsigned map_cols = (need_score ? BK_COL_SCORE : 0) | (need_id ? (BK_COL_ID | BK_COL_LINE) : 0) | hdr;
+    const unsigned map_cols = (need_score ? BK_COL_SCORE : 0) | (need_id ? (BK_COL_ID | BK_COL_LINE) : 0) |
+                              (need_mapline ? BK_COL_LINE : 0) | hdr;
     if (o.ec) {  // validate first (Bedmap.cpp:229-253, :292-329 use bed_check_iterator under --ec)
       cli::ec_prepare(rtext);
       cli::ec_prepare(mtext);

@@ -126,7 +126,15 @@ enum { /* operations, printed left to right in the order given (MultiVisitor.hpp
   BK_OP_ECHO_MAP_ID = 9, /* --echo-map-id   EchoMapBedVisitor.hpp:39-66 */
   BK_OP_ECHO_REF_SIZE = 10,  /* --echo-ref-size  */
   BK_OP_ECHO_REF_NAME = 11,  /* --echo-ref-name  chrom:start-end */
-  BK_OP_ECHO_REF_ROW_ID = 12 /* --echo-ref-row-id  id-<row> */
+  BK_OP_ECHO_REF_ROW_ID = 12, /* --echo-ref-row-id  id-<row> */
+  /* lists over the qualifying map rows, joined by --multidelim (EchoMapBedVisitor.hpp:39-66, helpers :140-170) */
+  BK_OP_ECHO_MAP = 13,          /* --echo-map           the rows as their record type prints them (map needs BK_COL_LINE) */
+  BK_OP_ECHO_MAP_SCORE = 14,    /* --echo-map-score     scores with --prec/--sci (map needs BK_COL_SCORE) */
+  BK_OP_ECHO_MAP_SIZE = 15,     /* --echo-map-size      end - start */
+  BK_OP_ECHO_OVERLAP_SIZE = 16, /* --echo-overlap-size  EchoMapIntersectLengthVisitor.hpp:64-73 */
+  BK_OP_ECHO_MAP_RANGE = 17,    /* --echo-map-range     one chrom<TAB>min start<TAB>max end (ProcessBedVisitorRow.hpp:433-456) */
+  BK_OP_BASES_UNIQ = 18,        /* --bases-uniq         OvrUniqueVisitor.hpp:62-77 */
+  BK_OP_BASES_UNIQ_F = 19       /* --bases-uniq-f       OvrUniqueFractionVisitor.hpp:47-50 */
 };
 enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */

@@ -192,8 +192,8 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     identical for exactly representable partial sums, see DESIGN.md parity notes)."""
     need_fields = 3
     for o in ops:
-        if o in ("sum", "mean", "max", "min"):
-            need_fields = max(need_fields, 5)
+        if o in ("sum", "mean", "max", "min", "echo-map-score"):
+            need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
         elif o == "echo-map-id":
             need_fields = max(need_fields, 4)
     single = map_text is None
@@ -260,6 +260,34 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                     cols.append(_fmt_score(v, prec, sci))
             elif o == "echo-map-id":     # EchoMapBedVisitor.hpp:39-66 (ties in file order, SURVEY hazard 2)
                 cols.append(multidelim.join(m.id for m in hits))
+            elif o == "echo-map":        # EchoMapBed<PrintRangeDelim<PrintAll>>: the map rows as their record type prints them
+                cols.append(multidelim.join(echo_row(m, need_fields) for m in hits))
+            elif o == "echo-map-score":  # PrintRangeDelim<PrintScorePrecision> (ProcessBedVisitorRow.hpp:152-176)
+                cols.append(multidelim.join(_fmt_score(m.score, prec, sci) for m in hits))
+            elif o == "echo-map-size":   # PrintRangeDelim<PrintLength> (:309-316)
+                cols.append(multidelim.join(str(m.end - m.start).encode() for m in hits))
+            elif o == "echo-overlap-size":  # EchoMapIntersectLengthVisitor.hpp:64-73: length of ref.intersection(map), 0 if disjoint
+                cols.append(multidelim.join(str(max(0, min(r.end, m.end) - max(r.start, m.start))).encode() for m in hits))
+            elif o == "echo-map-range":  # PrintGenomicRange<PrintBED3> (:433-456): one range spanning every hit
+                if hits:
+                    cols.append(r.chrom + b"\t%d\t%d" % (min(m.start for m in hits), max(m.end for m in hits)))
+                else:
+                    cols.append(b"")
+            elif o in ("bases-uniq", "bases-uniq-f"):  # OvrUniqueVisitor.hpp:62-77, OvrUniqueFractionVisitor.hpp:47-50
+                ovr = 0
+                if hits:
+                    cs, ce = hits[0].start, hits[0].end
+                    for m in hits[1:]:
+                        if min(ce, m.end) > max(cs, m.start):       # Bed.hpp:172-191 overlap() > 0
+                            cs, ce = min(cs, m.start), max(ce, m.end)
+                        else:
+                            ovr += max(0, min(ce, r.end) - max(cs, r.start))
+                            cs, ce = m.start, m.end
+                    ovr += max(0, min(ce, r.end) - max(cs, r.start))
+                if o == "bases-uniq":
+                    cols.append(str(ovr).encode())
+                else:
+                    cols.append(_fmt_score(float(ovr) / float(r.end - r.start), prec, sci))
             elif o == "echo-ref-size":
                 cols.append(str(r.end - r.start).encode())
             elif o == "echo-ref-name":

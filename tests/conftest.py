@@ -31,5 +31,6 @@ def synth_files():
     spec = load_golden("synthetic.json")["files"]
     out = {}
     for name, a in spec.items():
-        out[name] = synth.bed_text(a[0], a[1], tuple(a[2]), a[3], unique=len(a) > 4)
+        out[name] = synth.bed_text(a[0], a[1], tuple(a[2]), a[3], unique=len(a) > 4 and bool(a[4]),
+                                   chroms=a[5] if len(a) > 5 else None)
     return out

@@ -139,9 +139,13 @@ def synthetic():
     with tempfile.TemporaryDirectory() as td:
         spec = {"m.bed": (60000, 1, synth.MAP_SHAPE, 5), "m2.bed": (60000, 3, synth.MAP_SHAPE, 5),
                 "r.bed": (6000, 2, synth.REF_SHAPE, 5), "m3.bed": (40000, 4, synth.MAP_SHAPE, 3),
-                "u.bed": (60000, 1, synth.MAP_SHAPE, 5, True)}
+                "u.bed": (60000, 1, synth.MAP_SHAPE, 5, True),
+                # dense pair on two chromosomes (about 5 hits per reference row) for the per-hit list operations
+                "dm.bed": (6000000, 1, synth.MAP_SHAPE, 5, True, ["chr21", "chrY"]),
+                "dr.bed": (200000, 2, synth.REF_SHAPE, 5, False, ["chr21", "chrY"])}
         for n, a in spec.items():
-            open(os.path.join(td, n), "wb").write(synth.bed_text(a[0], a[1], a[2], a[3], unique=len(a) > 4))
+            open(os.path.join(td, n), "wb").write(synth.bed_text(a[0], a[1], a[2], a[3], unique=len(a) > 4 and a[4],
+                                                                 chroms=a[5] if len(a) > 5 else None))
         runs = [
             ("bedops", ["-m", "m.bed"]), ("bedops", ["-m", "m.bed", "m2.bed", "r.bed", "m3.bed"]),
             ("bedops", ["-i", "r.bed", "m.bed"]), ("bedops", ["-i", "r.bed", "m.bed", "m2.bed"]),
@@ -160,6 +164,17 @@ def synthetic():
             ("bedmap", ["--fraction-both", "0.5", "--count", "r.bed", "m.bed"]),
             ("bedmap", ["--exact", "--count", "m.bed", "m.bed"]),
             ("bedmap", ["--chrom", "chr2", "--skip-unmapped", "--echo", "--count", "r.bed", "m.bed"]),
+            ("bedmap", ["--echo", "--echo-map", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--echo-map", "--mean", "--echo-map-score", "--prec", "2", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--echo-map", "--echo-map-id", "--multidelim", ",", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--echo-map-size", "--echo-overlap-size", "--echo-map-range", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--bases", "--bases-uniq", "--bases-uniq-f", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--range", "300", "--count", "--echo-overlap-size", "--bases-uniq", "--bases-uniq-f", "--echo-map-range",
+                        "dr.bed", "dm.bed"]),
+            ("bedmap", ["--fraction-map", "0.5", "--skip-unmapped", "--echo", "--echo-map", "--bases-uniq", "--delim", "\t",
+                        "dr.bed", "dm.bed"]),
+            ("bedmap", ["--sci", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--echo-map-size", "--bases-uniq", "dm.bed"]),
             ("closest-features", ["--dist", "r.bed", "m.bed"]),
             ("closest-features", ["--closest", "r.bed", "m.bed"]),
             ("closest-features", ["--no-ref", "--dist", "--closest", "r.bed", "m3.bed"]),
@@ -169,7 +184,7 @@ def synthetic():
             assert p.returncode == 0, (tool, argv, p.stderr)
             cases.append(dict(tool=tool, argv=argv, sha256=hashlib.sha256(p.stdout).hexdigest(), nbytes=len(p.stdout)))
     print("synthetic: %d reference outputs hashed" % len(cases))
-    return dict(files={k: list(v[:2]) + [list(v[2]), v[3]] + ([True] if len(v) > 4 else []) for k, v in spec.items()}, cases=cases)
+    return dict(files={k: list(v[:2]) + [list(v[2]), v[3]] + list(v[4:]) for k, v in spec.items()}, cases=cases)
 
 
 if __name__ == "__main__":

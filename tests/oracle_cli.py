@@ -3,7 +3,8 @@ then run it either through the Python oracle (checker) or through the CUDA libra
 import bed_oracle as O
 
 BEDMAP_OPS = {"echo", "count", "indicator", "bases", "sum", "mean", "max", "min", "echo-map-id", "echo-ref-size",
-              "echo-ref-name", "echo-ref-row-id"}
+              "echo-ref-name", "echo-ref-row-id", "echo-map", "echo-map-score", "echo-map-size", "echo-overlap-size",
+              "echo-map-range", "bases-uniq", "bases-uniq-f"}
 
 
 def parse_argv(tool, argv, known_files):
@@ -131,11 +132,11 @@ def run_kit(kit, tool, argv, files, stdin=None):
         return out
     if tool == "bedmap":
         ops = d["ops"]
-        score = any(o in ("sum", "mean", "max", "min") for o in ops)
+        score = any(o in ("sum", "mean", "max", "min", "echo-map-score") for o in ops)
         ids = "echo-map-id" in ops
-        line = any(o in ("echo", "echo-ref-name") for o in ops)
+        line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)
         mf = 5 if score else (4 if ids else 3)
-        mcols = (COL_SCORE if score else 0) | ((COL_ID | COL_LINE) if ids else 0)
+        mcols = (COL_SCORE if score else 0) | ((COL_ID | COL_LINE) if ids else 0) | (COL_LINE if "echo-map" in ops else 0)
         if len(texts) > 1:
             ref = kit.load(texts[0], 3, COL_LINE if line else 0)
             mp = kit.load(texts[1], mf, mcols)

@@ -280,6 +280,8 @@ def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
             ("bedmap", ["--echo", "--count", "--mean", "--bases", "r.bed", "m.bed"]),
             ("bedmap", ["--faster", "--delim", "\\t", "--sum", "--max", "--echo-map-id", "r.bed", "u.bed"]),
             ("bedmap", ["--count", "m3.bed"]), ("closest-features", ["--dist", "r.bed", "m.bed"]),
+            ("bedmap", ["--echo", "--echo-map", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--range", "200", "--echo-map-range", "--echo-map-size", "--echo-overlap-size", "--bases-uniq", "dr.bed", "dm.bed"]),
             ("closest-features", ["--closest", "--delim", "\\t", "r.bed", "m3.bed"])]
     for tool, argv in runs:
         ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
