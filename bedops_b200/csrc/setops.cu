@@ -179,6 +179,9 @@ struct IsectParams {
   uint64_t        out_cap;
 };
 
+// DIFF = false: pieces of A covered by B (intersection).  DIFF = true: pieces of A that B does NOT cover (difference,
+// nextDifferenceLine, Bedops.cpp:948-1018); B's segments [lo,hi) all overlap the A segment, are disjoint and sorted.
+template <bool DIFF>
 __global__ void __launch_bounds__(SEG_THREADS) k_intersect(IsectParams p) {
   __shared__ uint32_t scan_sm[34];
   __shared__ uint32_t ticket_sm;
@@ -208,8 +211,16 @@ __global__ void __launch_bounds__(SEG_THREADS) k_intersect(IsectParams p) {
       hi = lower_bound_u32(p.bs, bb, bend, (uint64_t)a1);      // first b.start >= a.end
       if (hi < lo) hi = lo;
     }
+    uint32_t npieces = (uint32_t)(hi - lo);
+    if (DIFF && i < p.n) {
+      npieces = (uint32_t)(hi - lo) + 1;
+      if (hi > lo) {
+        if (p.bs[lo] <= a0) npieces--;       // no piece in front of the first covering segment
+        if (p.be[hi - 1] >= a1) npieces--;   // none behind the last
+      }
+    }
     uint32_t total;
-    uint32_t ex = block_excl_scan((uint32_t)(hi - lo), scan_sm, &total);
+    uint32_t ex = block_excl_scan(npieces, scan_sm, &total);
     if (tid < 32) {
       uint64_t b = lookback_sum(p.tile_state, tile, total);
       if (tid == 0) {
@@ -221,11 +232,28 @@ __global__ void __launch_bounds__(SEG_THREADS) k_intersect(IsectParams p) {
     uint64_t o = base_sm + ex;
     if (i < p.n) {
       if (runhead) p.run_out_begin[run] = o;
-      for (uint64_t k = lo; k < hi; k++, o++) {
-        if (o >= p.out_cap) break;
-        const uint32_t b0 = p.bs[k], b1 = p.be[k];
-        p.outS[o] = a0 > b0 ? a0 : b0;
-        p.outE[o] = a1 < b1 ? a1 : b1;
+      if (DIFF) {
+        uint32_t cur = a0;
+        for (uint64_t k = lo; k < hi; k++) {
+          const uint32_t b0 = p.bs[k], b1 = p.be[k];
+          if (b0 > cur && o < p.out_cap) {
+            p.outS[o] = cur;
+            p.outE[o] = b0;
+            o++;
+          }
+          cur = b1 > cur ? b1 : cur;
+        }
+        if (cur < a1 && o < p.out_cap) {
+          p.outS[o] = cur;
+          p.outE[o] = a1;
+        }
+      } else {
+        for (uint64_t k = lo; k < hi; k++, o++) {
+          if (o >= p.out_cap) break;
+          const uint32_t b0 = p.bs[k], b1 = p.be[k];
+          p.outS[o] = a0 > b0 ? a0 : b0;
+          p.outE[o] = a1 < b1 ? a1 : b1;
+        }
       }
     }
     __syncthreads();
@@ -510,7 +538,7 @@ static int union_merge(bk_ctx* ctx, const std::vector<IvList>& in_files, IvList*
 }
 
 // A ∩ B for disjoint sorted lists
-static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList* out) {
+static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList* out, bool diff = false) {
   out->runs.clear();
   out->n = 0;
   out->owned = true;
@@ -558,8 +586,9 @@ static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList*
     return BK_ERR_NOMEM;
   BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
   BK_TRY(reset_scratch(ctx));
-  prof_begin(ctx, "k_intersect");
-  k_intersect<<<grid_for_kernel((const void*)k_intersect, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
+  prof_begin(ctx, diff ? "k_difference" : "k_intersect");
+  if (diff) k_intersect<true><<<grid_for_kernel((const void*)k_intersect<true>, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
+  else k_intersect<false><<<grid_for_kernel((const void*)k_intersect<false>, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   std::vector<uint64_t> rob(nruns);
@@ -570,6 +599,91 @@ static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList*
   dfree(ctx, p.run_out_begin); dfree(ctx, p.tile_state);
   out->s = p.outS; out->e = p.outE; out->n = nout;
   for (int r = 0; r < nruns; r++) out->runs.push_back({names[r], rob[r], r + 1 < nruns ? rob[r + 1] : nout});
+  return BK_OK;
+}
+
+// ---- complement: the gaps between consecutive segments of a merged list (nextComplementLine, Bedops.cpp:891-943) ----
+struct ComplParams {
+  const uint32_t* us;
+  const uint32_t* ue;
+  const uint64_t* seg_begin;  // [nruns] first segment of the run
+  const uint64_t* out_begin;  // [nruns+1] first output row of the run
+  const uint8_t*  has_left;   // [nruns] -L and the run's first segment does not start at 0: one more row, [0, first start)
+  int             nruns;
+  uint64_t        nout;
+  uint32_t*       outS;
+  uint32_t*       outE;
+};
+__global__ void k_complement(ComplParams p) {
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.nout; o += (uint64_t)gridDim.x * blockDim.x) {
+    int l = 0, h = p.nruns;
+    while (h - l > 1) {
+      const int mid = (l + h) >> 1;
+      if (p.out_begin[mid] <= o) l = mid; else h = mid;
+    }
+    uint64_t       j = o - p.out_begin[l];
+    const uint64_t b = p.seg_begin[l];
+    if (p.has_left[l]) {
+      if (j == 0) {
+        p.outS[o] = 0;
+        p.outE[o] = p.us[b];
+        continue;
+      }
+      j--;
+    }
+    p.outS[o] = p.ue[b + j];
+    p.outE[o] = p.us[b + j + 1];
+  }
+}
+
+static int complement_of(bk_ctx* ctx, const IvList& U, bool full_left, IvList* out) {
+  out->runs.clear();
+  out->n = 0;
+  out->owned = true;
+  out->s = out->e = nullptr;
+  std::vector<uint64_t>    sb, ob;
+  std::vector<uint8_t>     left;
+  std::vector<std::string> names;
+  std::vector<uint32_t>    first_start;
+  for (auto& r : U.runs)
+    if (r.row_end > r.row_begin) {
+      sb.push_back(r.row_begin);
+      names.push_back(r.name);
+    }
+  const int nruns = (int)sb.size();
+  if (nruns == 0) return BK_OK;
+  first_start.assign(nruns, 1);
+  if (full_left) {
+    for (int g = 0; g < nruns; g++)
+      BK_CUDA(ctx, cudaMemcpyAsync(&first_start[g], U.s + sb[g], 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  uint64_t nout = 0;
+  int      g = 0;
+  for (auto& r : U.runs) {
+    if (r.row_end == r.row_begin) continue;
+    const bool l = full_left && first_start[g] != 0;
+    left.push_back(l ? 1 : 0);
+    ob.push_back(nout);
+    nout += (r.row_end - r.row_begin - 1) + (l ? 1 : 0);
+    g++;
+  }
+  ob.push_back(nout);
+  if (nout == 0) return BK_OK;
+  ComplParams p{};
+  p.us = U.s; p.ue = U.e; p.nruns = nruns; p.nout = nout;
+  p.seg_begin = upload(ctx, sb); p.out_begin = upload(ctx, ob); p.has_left = upload(ctx, left);
+  p.outS = dalloc<uint32_t>(ctx, nout); p.outE = dalloc<uint32_t>(ctx, nout);
+  if (!p.seg_begin || !p.out_begin || !p.has_left || !p.outS || !p.outE) return BK_ERR_NOMEM;
+  const uint64_t blocks = (nout + 255) / 256, cap = (uint64_t)kSMs * 16;
+  prof_begin(ctx, "k_complement");
+  k_complement<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the uploaded host vectors go out of scope
+  dfree(ctx, (void*)p.seg_begin); dfree(ctx, (void*)p.out_begin); dfree(ctx, (void*)p.has_left);
+  out->s = p.outS; out->e = p.outE; out->n = nout;
+  for (int r = 0; r < nruns; r++) out->runs.push_back({names[r], ob[r], ob[r + 1]});
   return BK_OK;
 }
 
@@ -646,6 +760,57 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
     }
     int rc = emit_bed3(ctx, acc, out_on_device, out);
     free_list(ctx, acc);
+    return rc;
+  }
+  if (op == BK_SETOP_COMPLEMENT) {
+    std::vector<IvList> in;
+    for (int i = 0; i < n_files; i++) in.push_back(view_of(files[i], chrom));
+    IvList u, c;
+    BK_TRY(union_merge(ctx, in, &u));
+    int rc = complement_of(ctx, u, thr != 0.0, &c);
+    free_list(ctx, u);
+    if (rc == BK_OK) rc = emit_bed3(ctx, c, out_on_device, out);
+    free_list(ctx, c);
+    return rc;
+  }
+  if (op == BK_SETOP_DIFFERENCE) {
+    if (n_files < 2) return fail(ctx, BK_ERR_ARG, "Not enough files");
+    std::vector<IvList> first{view_of(files[0], chrom)}, rest;
+    for (int i = 1; i < n_files; i++) rest.push_back(view_of(files[i], chrom));
+    IvList a, b, d;
+    BK_TRY(union_merge(ctx, first, &a));
+    int rc = union_merge(ctx, rest, &b);
+    if (rc == BK_OK) rc = intersect_pair(ctx, a, b, &d, true);
+    free_list(ctx, a);
+    free_list(ctx, b);
+    if (rc == BK_OK) rc = emit_bed3(ctx, d, out_on_device, out);
+    free_list(ctx, d);
+    return rc;
+  }
+  if (op == BK_SETOP_SYMMDIFF) {
+    if (n_files < 2) return fail(ctx, BK_ERR_ARG, "Not enough files");
+    // bases covered by exactly one file = union of all files minus the union of the pairwise intersections
+    std::vector<IvList> per(n_files), pairs;
+    int                 rc = BK_OK;
+    for (int i = 0; i < n_files && rc == BK_OK; i++) {
+      std::vector<IvList> one{view_of(files[i], chrom)};
+      rc = union_merge(ctx, one, &per[i]);
+    }
+    for (int i = 0; i < n_files && rc == BK_OK; i++)
+      for (int j = i + 1; j < n_files && rc == BK_OK; j++) {
+        pairs.emplace_back();
+        rc = intersect_pair(ctx, per[i], per[j], &pairs.back());
+      }
+    IvList u, twice, d;
+    if (rc == BK_OK) rc = union_merge(ctx, per, &u);
+    if (rc == BK_OK) rc = union_merge(ctx, pairs, &twice);
+    if (rc == BK_OK) rc = intersect_pair(ctx, u, twice, &d, true);
+    for (auto& l : per) free_list(ctx, l);
+    for (auto& l : pairs) free_list(ctx, l);
+    free_list(ctx, u);
+    free_list(ctx, twice);
+    if (rc == BK_OK) rc = emit_bed3(ctx, d, out_on_device, out);
+    free_list(ctx, d);
     return rc;
   }
   if (op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF) {

@@ -17,7 +17,7 @@ struct Options {
   int    min_files = 1000;
   double subset = 1;  // Input::subsetPerc_
   bool   use_pct = true;
-  bool   ec = false, has_range = false;
+  bool   ec = false, has_range = false, full_left = false;
   std::string chrom = "all";
   std::vector<std::string> files;
 };
@@ -147,7 +147,10 @@ Options parse_args(int argc, char** argv) {
             }
           }
         } else if (o.mode == COMPLEMENT) {
-          while (i + 1 < argc && std::string(argv[i + 1]) == "-L") ++i;
+          while (i + 1 < argc && std::string(argv[i + 1]) == "-L") {
+            o.full_left = true;
+            ++i;
+          }
         }
       } else {
         break;
@@ -189,10 +192,13 @@ void usage(FILE* f) {
       "      Process Flags:\n"
       "          --chrom <chromosome>, --ec, --header, --help, --version\n\n"
       "      Operations on this build's B200 hot path (choose one):\n"
+      "          -c, --complement [-L]                 Min: 1 file.\n"
+      "          -d, --difference                      Min: 2 files.\n"
       "          -e, --element-of [bp | percentage]    Min: 2 files.\n"
       "          -i, --intersect                       Min: 2 files.\n"
       "          -m, --merge                           Min: 1 file.\n"
-      "          -n, --not-element-of [bp | percentage] Min: 2 files.\n\n",
+      "          -n, --not-element-of [bp | percentage] Min: 2 files.\n"
+      "          -s, --symmdiff                        Min: 2 files.\n\n",
       f);
 }
 
@@ -207,6 +213,9 @@ int main(int argc, char** argv) {
       case INTERSECTION: op = BK_SETOP_INTERSECT; break;
       case ELEMENTOF: op = BK_SETOP_ELEMENT_OF; break;
       case NOTELEMENTOF: op = BK_SETOP_NOT_ELEMENT_OF; break;
+      case COMPLEMENT: op = BK_SETOP_COMPLEMENT; break;
+      case DIFFERENCE: op = BK_SETOP_DIFFERENCE; break;
+      case SYMMDIFF: op = BK_SETOP_SYMMDIFF; break;
       default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
     if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
@@ -226,7 +235,8 @@ int main(int argc, char** argv) {
       std::vector<bk_bed*> beds;
       for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, ((has_ref && f == 0) ? BK_COL_LINE : 0) | hdr));
       bk_text out;
-      int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), o.subset, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
+      const double thr = op == BK_SETOP_COMPLEMENT ? (o.full_left ? 1.0 : 0.0) : o.subset;
+      int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), thr, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
       if (rc != BK_OK) eng.raise(rc);
       std::string text(out.ptr ? out.ptr : "", out.len);
       bk_free_text(eng.ctx, &out);

@@ -174,7 +174,15 @@ int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len, int ref_fi
                    bk_text* out);
 
 /* ---- bedops set operators ------------------------------------------------------------------- */
-enum { BK_SETOP_MERGE = 1, BK_SETOP_INTERSECT = 2, BK_SETOP_ELEMENT_OF = 3, BK_SETOP_NOT_ELEMENT_OF = 4 };
+enum {
+  BK_SETOP_MERGE = 1,
+  BK_SETOP_INTERSECT = 2,
+  BK_SETOP_ELEMENT_OF = 3,
+  BK_SETOP_NOT_ELEMENT_OF = 4,
+  BK_SETOP_COMPLEMENT = 5, /* --complement; thr != 0 selects -L (Bedops.cpp:475-488, :891-943) */
+  BK_SETOP_DIFFERENCE = 6, /* --difference: files[0] minus the others (:501-525, :948-1018) */
+  BK_SETOP_SYMMDIFF = 7    /* --symmdiff: bases covered by exactly one file (:698-745, :1341-1463) */
+};
 /* thr / thr_is_pct: -e/-n threshold as Input::Threshold()/UsePercentage() deliver it (bedops/src/Input.hpp:344-382):
  * a fraction in (0,1] when thr_is_pct, else a base count.  files[0] is the reference file for -e/-n. */
 int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, double thr, int thr_is_pct,

@@ -374,6 +374,89 @@ def bedops_intersect(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> b
     return b"".join(out)
 
 
+def _subtract(a: List[Tuple[int, int]], b: List[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """pieces of the disjoint sorted list a that no segment of the disjoint sorted list b covers"""
+    res, j = [], 0
+    for s, e in a:
+        while j < len(b) and b[j][1] <= s:
+            j += 1
+        cur, k = s, j
+        while k < len(b) and b[k][0] < e:
+            if b[k][0] > cur:
+                res.append((cur, b[k][0]))
+            cur = max(cur, b[k][1])
+            k += 1
+        if cur < e:
+            res.append((cur, e))
+    return res
+
+
+def bedops_complement(texts: Sequence[bytes], full_left: bool = False, chrom: Optional[bytes] = None) -> bytes:
+    """doComplement / nextComplementLine (Bedops.cpp:475-488, :891-943): the gaps between consecutive segments of the
+    merged union of all files, per chromosome; with -L also [0, first start) when the first segment does not start at 0."""
+    u = merged_union([_sel(parse_bed(t, 3), chrom) for t in texts])
+    out = []
+    for c in sorted(u):
+        segs = u[c]
+        if full_left and segs[0][0] != 0:
+            out.append(c + b"\t0\t%d\n" % segs[0][0])
+        for (s0, e0), (s1, e1) in zip(segs, segs[1:]):
+            out.append(c + b"\t%d\t%d\n" % (e0, s1))
+    return b"".join(out)
+
+
+def bedops_difference(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doDifference / nextDifferenceLine (Bedops.cpp:501-525, :948-1018): the first file merged within itself
+    (getNextFileMergedCoords) minus the merged union of the other files; pieces of positive length."""
+    a = merged_union([_sel(parse_bed(texts[0], 3), chrom)])
+    b = merged_union([_sel(parse_bed(t, 3), chrom) for t in texts[1:]])
+    out = []
+    for c in sorted(a):
+        for s, e in _subtract(a[c], b.get(c, [])):
+            out.append(c + b"\t%d\t%d\n" % (s, e))
+    return b"".join(out)
+
+
+def bedops_symmdiff(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doSymmetricDifference / nextSymmetricDiffLine (Bedops.cpp:698-745, :1341-1463): the bases covered by exactly one
+    file (every file merged within itself), abutting pieces coalesced (mergeOverlap :864-886) =
+    union of all files minus the union of the pairwise intersections."""
+    lists = [merged_union([_sel(parse_bed(t, 3), chrom)]) for t in texts]
+    chroms = sorted(set().union(*[set(l) for l in lists]))
+    out = []
+    for c in chroms:
+        per = [l.get(c, []) for l in lists]
+        cover = sorted(x for l in per for x in l)
+        u: List[Tuple[int, int]] = []
+        for s, e in cover:                      # union, touching coalesced
+            if u and s <= u[-1][1]:
+                u[-1] = (u[-1][0], max(u[-1][1], e))
+            else:
+                u.append((s, e))
+        twice: List[Tuple[int, int]] = []
+        for i in range(len(per)):
+            for j in range(i + 1, len(per)):
+                x, y, a, b = 0, 0, per[i], per[j]
+                while x < len(a) and y < len(b):
+                    lo, hi = max(a[x][0], b[y][0]), min(a[x][1], b[y][1])
+                    if hi > lo:
+                        twice.append((lo, hi))
+                    if a[x][1] < b[y][1]:
+                        x += 1
+                    else:
+                        y += 1
+        twice.sort()
+        t2: List[Tuple[int, int]] = []
+        for s, e in twice:
+            if t2 and s <= t2[-1][1]:
+                t2[-1] = (t2[-1][0], max(t2[-1][1], e))
+            else:
+                t2.append((s, e))
+        for s, e in _subtract(u, t2):
+            out.append(c + b"\t%d\t%d\n" % (s, e))
+    return b"".join(out)
+
+
 def bedops_element_of(texts: Sequence[bytes], thr: float = 1.0, use_pct: bool = True, invert: bool = False,
                       chrom: Optional[bytes] = None) -> bytes:
     """doElementOf / nextElementOfLine (Bedops.cpp:538-566, :1023-1100): overlap bases of each reference row

@@ -30,7 +30,8 @@ REF = os.environ.get("REF", "/root/reference")
 BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 sys.path.insert(0, ROOT)
 
-IN_SCOPE = ("-m", "-i", "-e", "-n", "--merge", "--intersect", "--element-of", "--not-element-of")
+IN_SCOPE = ("-m", "-i", "-e", "-n", "--merge", "--intersect", "--element-of", "--not-element-of",
+            "-c", "-d", "-s", "--complement", "--difference", "--symmdiff")
 
 
 def update_string(s, chrom):
@@ -164,6 +165,9 @@ def synthetic():
             ("bedmap", ["--fraction-both", "0.5", "--count", "r.bed", "m.bed"]),
             ("bedmap", ["--exact", "--count", "m.bed", "m.bed"]),
             ("bedmap", ["--chrom", "chr2", "--skip-unmapped", "--echo", "--count", "r.bed", "m.bed"]),
+            ("bedops", ["-c", "m.bed"]), ("bedops", ["-c", "-L", "m.bed", "r.bed"]), ("bedops", ["-d", "r.bed", "m.bed"]),
+            ("bedops", ["-d", "dm.bed", "dr.bed", "m.bed"]), ("bedops", ["-s", "dr.bed", "dm.bed"]),
+            ("bedops", ["-s", "m.bed", "m2.bed", "r.bed", "m3.bed"]), ("bedops", ["--chrom", "chr21", "-c", "-L", "dm.bed"]),
             ("bedmap", ["--echo", "--echo-map", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map", "--mean", "--echo-map-score", "--prec", "2", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map", "--echo-map-id", "--multidelim", ",", "dr.bed", "dm.bed"]),

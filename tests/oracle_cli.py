@@ -12,7 +12,7 @@ def parse_argv(tool, argv, known_files):
     d = dict(tool=tool, names=[], chrom=None)
     i = 0
     if tool == "bedops":
-        d.update(op=None, thr=1.0, pct=True)
+        d.update(op=None, thr=1.0, pct=True, full_left=False)
         while i < len(argv):
             a = argv[i]
             if a == "--ec":
@@ -24,6 +24,14 @@ def parse_argv(tool, argv, known_files):
                 d["op"] = "merge"
             elif a in ("-i", "--intersect"):
                 d["op"] = "intersect"
+            elif a in ("-c", "--complement"):
+                d["op"] = "complement"
+            elif a == "-L":
+                d["full_left"] = True
+            elif a in ("-d", "--difference"):
+                d["op"] = "difference"
+            elif a in ("-s", "--symmdiff"):
+                d["op"] = "symmdiff"
             elif a in ("-e", "--element-of", "-n", "--not-element-of"):
                 d["op"] = "element-of" if a in ("-e", "--element-of") else "not-element-of"
                 if i + 1 < len(argv) and argv[i + 1] not in known_files:
@@ -110,6 +118,12 @@ def run(tool, argv, files, stdin=None):
             return O.bedops_merge(texts, d["chrom"])
         if d["op"] == "intersect":
             return O.bedops_intersect(texts, d["chrom"])
+        if d["op"] == "complement":
+            return O.bedops_complement(texts, d["full_left"], d["chrom"])
+        if d["op"] == "difference":
+            return O.bedops_difference(texts, d["chrom"])
+        if d["op"] == "symmdiff":
+            return O.bedops_symmdiff(texts, d["chrom"])
         return O.bedops_element_of(texts, d["thr"], d["pct"], d["op"] == "not-element-of", d["chrom"])
     if tool == "bedmap":
         return O.bedmap(texts[0], texts[1] if len(texts) > 1 else None, ops=d["ops"], overlap=d["overlap"],
@@ -126,7 +140,8 @@ def run_kit(kit, tool, argv, files, stdin=None):
     texts = [stdin if n == "-" else files[n] for n in d["names"]]
     if tool == "bedops":
         beds = [kit.load(t, 3, COL_LINE if (k == 0 and d["op"].endswith("element-of")) else 0) for k, t in enumerate(texts)]
-        out = kit.setop(d["op"], beds, d["thr"], d["pct"], d["chrom"])
+        thr = float(d["full_left"]) if d["op"] == "complement" else d["thr"]   # BK_SETOP_COMPLEMENT: thr != 0 is -L
+        out = kit.setop(d["op"], beds, thr, d["pct"], d["chrom"])
         for b in beds:
             b.free()
         return out
