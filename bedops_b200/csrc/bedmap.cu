@@ -362,6 +362,8 @@ struct BedmapRow {
     uint32_t       mn = 0xFFFFFFFFu, mx = 0;   // --echo-map-range
     uint32_t       cs = 0, ce = 0;             // --bases-uniq: the open union run
     uint64_t       uniq = 0;
+    double         vsum = 0.0, vsq = 0.0;      // --variance / --stdev / --cv
+    uint32_t       nhit = 0;
     for (uint64_t k = lo; k < hi; k++) {
       uint32_t       ovl;
       const uint32_t s0 = ms[k], e0 = me[k];
@@ -370,6 +372,13 @@ struct BedmapRow {
         mn = s0 < mn ? s0 : mn;
         mx = e0 > mx ? e0 : mx;
         first = false;
+        continue;
+      }
+      if (op >= BK_OP_VARIANCE) {  // variance family: sum and sum of squares in file order
+        const double v = mscore[k];
+        vsum += v;
+        vsq += v * v;
+        nhit++;
         continue;
       }
       if (op == BK_OP_BASES_UNIQ || op == BK_OP_BASES_UNIQ_F) {
@@ -411,6 +420,24 @@ struct BedmapRow {
       s.put_u32(mn);
       s.put('\t');
       s.put_u32(mx);
+    }
+    if (op >= BK_OP_VARIANCE) {
+      if (nhit <= 1) {
+        s.puts_("NAN", 3);
+        return;
+      }
+      const double n = (double)nhit;
+      const double var = ((n * vsq) - (vsum * vsum)) / (n * (n - 1.0));
+      if (op == BK_OP_VARIANCE) {
+        put_score(s, var, 1, i);
+      } else if (op == BK_OP_STDEV) {
+        put_score(s, sqrt(var), 1, i);
+      } else {
+        const double mean = vsum / n;
+        if (mean == 0.0) s.puts_("NAN", 3);
+        else put_score(s, sqrt(var) / mean, 1, i);
+      }
+      return;
     }
     if (op == BK_OP_BASES_UNIQ || op == BK_OP_BASES_UNIQ_F) {
       if (!first) {
@@ -461,6 +488,7 @@ struct BedmapRow {
         }
         case BK_OP_ECHO_MAP: case BK_OP_ECHO_MAP_SCORE: case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE:
         case BK_OP_ECHO_MAP_RANGE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
+        case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV:
           if (RARE & 4) window_op(s, ops[c], i, row);
           break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
@@ -543,6 +571,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       case BK_OP_ECHO_MAP_RANGE: need |= NEED_IDS; need_refline = true; window_ops = true; break;
       case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
         need |= NEED_IDS; window_ops = true; break;
+      case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }
   }
@@ -555,7 +584,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   if (need_mapline && !map->line_off && map->nrows)
     return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_LINE but --echo-map needs it");
   if (need_mapscore && !map->score && map->nrows)
-    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_SCORE but --echo-map-score needs it");
+    return fail(ctx, BK_ERR_ARG, "map file was loaded without BK_COL_SCORE but a score operation needs it");
 
   OverlapSpec ov{};
   ov.kind = spec->overlap_kind;

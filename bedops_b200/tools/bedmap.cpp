@@ -23,8 +23,8 @@ const OpInfo kOps[] = {
     {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, 0},           {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
     {"indicator", BK_OP_INDICATOR, 3, 0},  {"max", BK_OP_MAX, 5, 0},          {"max-element-rand", 0, 5, 0},
     {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
-    {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", 0, 5, 0},
-    {"stdev", 0, 5, 0},                    {"cv", 0, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
+    {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
+    {"stdev", BK_OP_STDEV, 5, 0},                    {"cv", BK_OP_CV, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
     {"wmean", 0, 5, 0},                    {"median", 0, 5, 0},               {"mad", 0, 5, -1},
     {"kth", 0, 5, 1},                      {"tmean", 0, 5, 2},
 };
@@ -208,7 +208,7 @@ void usage(FILE* f) {
       "     Operations on this build's B200 hot path:\n"
       "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-range\n"
       "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
-      "      --indicator --max --mean --min --sum\n\n",
+      "      --cv --indicator --max --mean --min --stdev --sum --variance\n\n",
       f);
 }
 
@@ -229,7 +229,8 @@ int main(int argc, char** argv) {
     for (int op : o.ops) {
       spec.ops[spec.n_ops++] = op;
       need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
-      need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE;
+      need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE ||
+                    op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV;
       need_id |= op == BK_OP_ECHO_MAP_ID;
       need_mapline |= op == BK_OP_ECHO_MAP;
     }

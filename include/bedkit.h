@@ -134,7 +134,11 @@ enum { /* operations, printed left to right in the order given (MultiVisitor.hpp
   BK_OP_ECHO_OVERLAP_SIZE = 16, /* --echo-overlap-size  EchoMapIntersectLengthVisitor.hpp:64-73 */
   BK_OP_ECHO_MAP_RANGE = 17,    /* --echo-map-range     one chrom<TAB>min start<TAB>max end (ProcessBedVisitorRow.hpp:433-456) */
   BK_OP_BASES_UNIQ = 18,        /* --bases-uniq         OvrUniqueVisitor.hpp:62-77 */
-  BK_OP_BASES_UNIQ_F = 19       /* --bases-uniq-f       OvrUniqueFractionVisitor.hpp:47-50 */
+  BK_OP_BASES_UNIQ_F = 19,      /* --bases-uniq-f       OvrUniqueFractionVisitor.hpp:47-50 */
+  /* (n*sum(x^2) - sum(x)^2) / (n*(n-1)); NAN for fewer than two hits (map needs BK_COL_SCORE) */
+  BK_OP_VARIANCE = 20,          /* --variance           VarianceVisitor.hpp:58-66 */
+  BK_OP_STDEV = 21,             /* --stdev              StdevVisitor.hpp */
+  BK_OP_CV = 22                 /* --cv                 CoeffVariationVisitor.hpp (NAN when the mean is 0) */
 };
 enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */

@@ -15,6 +15,7 @@ Each function cites the reference code it restates (paths relative to the refere
 from __future__ import annotations
 
 import bisect
+import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -192,7 +193,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     identical for exactly representable partial sums, see DESIGN.md parity notes)."""
     need_fields = 3
     for o in ops:
-        if o in ("sum", "mean", "max", "min", "echo-map-score"):
+        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv"):
             need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
         elif o == "echo-map-id":
             need_fields = max(need_fields, 4)
@@ -260,6 +261,24 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                     cols.append(_fmt_score(v, prec, sci))
             elif o == "echo-map-id":     # EchoMapBedVisitor.hpp:39-66 (ties in file order, SURVEY hazard 2)
                 cols.append(multidelim.join(m.id for m in hits))
+            elif o in ("variance", "stdev", "cv"):  # VarianceVisitor.hpp:58-66, StdevVisitor.hpp, CoeffVariationVisitor.hpp
+                sm = sq = 0.0
+                for m in hits:
+                    sm += m.score
+                    sq += m.score * m.score
+                n = float(cnt)
+                if cnt <= 1:
+                    cols.append(b"NAN")
+                else:
+                    var = ((n * sq) - (sm * sm)) / (n * (n - 1.0))
+                    if o == "variance":
+                        cols.append(_fmt_score(var, prec, sci))
+                    elif o == "stdev":
+                        cols.append(_fmt_score(math.sqrt(var), prec, sci))
+                    elif sm / n == 0:
+                        cols.append(b"NAN")
+                    else:
+                        cols.append(_fmt_score(math.sqrt(var) / (sm / n), prec, sci))
             elif o == "echo-map":        # EchoMapBed<PrintRangeDelim<PrintAll>>: the map rows as their record type prints them
                 cols.append(multidelim.join(echo_row(m, need_fields) for m in hits))
             elif o == "echo-map-score":  # PrintRangeDelim<PrintScorePrecision> (ProcessBedVisitorRow.hpp:152-176)

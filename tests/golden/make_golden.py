@@ -179,6 +179,8 @@ def synthetic():
                         "dr.bed", "dm.bed"]),
             ("bedmap", ["--sci", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map-size", "--bases-uniq", "dm.bed"]),
+            ("bedmap", ["--variance", "--stdev", "--cv", "--mean", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--sci", "--prec", "9", "--range", "500", "--stdev", "--cv", "dr.bed", "dm.bed"]),
             ("closest-features", ["--dist", "r.bed", "m.bed"]),
             ("closest-features", ["--closest", "r.bed", "m.bed"]),
             ("closest-features", ["--no-ref", "--dist", "--closest", "r.bed", "m3.bed"]),

@@ -4,7 +4,7 @@ import bed_oracle as O
 
 BEDMAP_OPS = {"echo", "count", "indicator", "bases", "sum", "mean", "max", "min", "echo-map-id", "echo-ref-size",
               "echo-ref-name", "echo-ref-row-id", "echo-map", "echo-map-score", "echo-map-size", "echo-overlap-size",
-              "echo-map-range", "bases-uniq", "bases-uniq-f"}
+              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv"}
 
 
 def parse_argv(tool, argv, known_files):
@@ -147,7 +147,7 @@ def run_kit(kit, tool, argv, files, stdin=None):
         return out
     if tool == "bedmap":
         ops = d["ops"]
-        score = any(o in ("sum", "mean", "max", "min", "echo-map-score") for o in ops)
+        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv") for o in ops)
         ids = "echo-map-id" in ops
         line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)
         mf = 5 if score else (4 if ids else 3)
