@@ -381,4 +381,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
+    try:
+        main()
+    finally:
+        _real_stdout.flush()
