@@ -366,6 +366,7 @@ extern "C" void bk_free_bed(bk_ctx* ctx, bk_bed* bed) {
   dfree(ctx, bed->line_off);
   dfree(ctx, bed->idspan);
   dfree(ctx, bed->pmax_end);
+  dfree(ctx, bed->bmax_end);
   delete bed;
 }
 

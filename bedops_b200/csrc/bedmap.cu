@@ -57,6 +57,7 @@ struct MapStatsParams {
   const uint32_t* ms;
   const uint32_t* me;
   const uint32_t* pm;
+  const uint32_t* bmax;  // max end per 32-row block of the map file (global row index / 32)
   const double*   score;
   const uint32_t* idspan;
   OverlapSpec     ov;
@@ -80,7 +81,7 @@ constexpr int MS_THREADS = 256;
 // loads:  lo = first map row whose running-max end exceeds ref.start (galloped from the previous row's lo, a lower
 // bound because reference rows are sorted by start),  hi = first map row with start >= ref.end (galloped from lo).
 // KIND < 0 selects the generic predicate (runtime overlap kind); FLAGS = NEED_* known at compile time.
-template <int KIND, unsigned FLAGS>
+template <int KIND, unsigned FLAGS, bool SKIP>
 __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
   const int      lane = threadIdx.x & 31;
   const uint64_t warp0 = ((uint64_t)blockIdx.x * MS_THREADS + threadIdx.x) >> 5;
@@ -157,6 +158,55 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
       uint64_t bases = 0;
       double   sum = 0.0, vmax = 0.0, vmin = 0.0;
       bool     have = false;
+      if (SKIP) {
+        // Dense map files (windows of hundreds of rows, most of them short rows that end in front of the reference
+        // row): steps are aligned to the 32-row blocks of the block-max index, and a step whose two blocks hold no end
+        // that reaches the reference row (block max end < key) is skipped without touching its rows.  Rows in front
+        // of lo (alignment) never qualify; a skipped step cannot contain the row that ends the window (start >=
+        // ref.end implies that its end reaches).
+        const uint32_t key = rs >= pad ? rs - pad + 1 : 0;
+        const uint64_t gend = mb + nr;
+#pragma unroll 1
+        for (uint64_t g0 = (mb + lo) & ~31ull; g0 < gend; g0 += 64) {
+          const uint32_t m0 = __ldg(&p.bmax[g0 >> 5]), m1 = g0 + 32 < gend ? __ldg(&p.bmax[(g0 >> 5) + 1]) : 0u;
+          if (m0 < key && m1 < key) continue;
+          const uint64_t ga = g0 + lane, gb = ga + 32;
+          const bool     va = ga >= mb && ga < gend, vb = gb < gend;
+          const uint32_t sa = va ? __ldg(&p.ms[ga]) : 0xFFFFFFFFu, sb = vb ? __ldg(&p.ms[gb]) : 0xFFFFFFFFu;
+          const uint32_t ea = va ? __ldg(&p.me[ga]) : 0u, eb = vb ? __ldg(&p.me[gb]) : 0u;
+          const bool     ina = va && sa < re_pad, inb = vb && sb < re_pad;
+          uint32_t       ova = 0, ovb = 0;
+          const bool     qa = ina && qualifies(ov, rs, re, sa, ea, ova);
+          const bool     qb = inb && qualifies(ov, rs, re, sb, eb, ovb);
+          if (qa) {
+            cnt++;
+            if (FLAGS & NEED_BASES) bases += ova;
+            if (kScore) {
+              const double v = __ldg(&p.score[ga]);
+              sum += v;
+              if (kMinMax) {
+                vmax = have ? (v > vmax ? v : vmax) : v;
+                vmin = have ? (v < vmin ? v : vmin) : v;
+                have = true;
+              }
+            }
+          }
+          if (qb) {
+            cnt++;
+            if (FLAGS & NEED_BASES) bases += ovb;
+            if (kScore) {
+              const double v = __ldg(&p.score[gb]);
+              sum += v;
+              if (kMinMax) {
+                vmax = have ? (v > vmax ? v : vmax) : v;
+                vmin = have ? (v < vmin ? v : vmin) : v;
+                have = true;
+              }
+            }
+          }
+          if (__ballot_sync(0xffffffffu, inb) != 0xffffffffu) break;
+        }
+      } else {
       // Scan 64 map rows per step (two coalesced 32-row chunks whose loads are issued together).  Map starts are
       // sorted, so the window ends in the first step in which some lane of the second chunk sees start >= ref.end.
 #pragma unroll 1
@@ -200,6 +250,7 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
         const unsigned mb_ = __ballot_sync(0xffffffffu, inb);
         if (FLAGS & NEED_IDS) nwin += __popc(__ballot_sync(0xffffffffu, ina)) + __popc(mb_);
         if (mb_ != 0xffffffffu) break;
+      }
       }
       const uint32_t hi = lo + nwin;
       // warp reductions (fixed order: deterministic)
@@ -245,12 +296,15 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
   }
 }
 
-template <int KIND>
+template <int KIND, bool SKIP>
 static void launch_map_stats(unsigned need, unsigned blocks, cudaStream_t st, const MapStatsParams& sp) {
-  switch (need & 31u) {
-#define BK_F(F) case F: k_map_stats<KIND, F><<<blocks, MS_THREADS, 0, st>>>(sp); break;
+  switch (need & (SKIP ? 15u : 31u)) {
+#define BK_F(F) case F: k_map_stats<KIND, F, SKIP><<<blocks, MS_THREADS, 0, st>>>(sp); break;
     BK_F(0) BK_F(1) BK_F(2) BK_F(3) BK_F(4) BK_F(5) BK_F(6) BK_F(7) BK_F(8) BK_F(9) BK_F(10) BK_F(11) BK_F(12) BK_F(13)
-    BK_F(14) BK_F(15) BK_F(16) BK_F(17) BK_F(18) BK_F(19) BK_F(20) BK_F(21) BK_F(22) BK_F(23) BK_F(24) BK_F(25) BK_F(26)
+    BK_F(14) BK_F(15)
+#undef BK_F
+#define BK_F(F) case F: if (!SKIP) k_map_stats<KIND, F, false><<<blocks, MS_THREADS, 0, st>>>(sp); break;
+    BK_F(16) BK_F(17) BK_F(18) BK_F(19) BK_F(20) BK_F(21) BK_F(22) BK_F(23) BK_F(24) BK_F(25) BK_F(26)
     BK_F(27) BK_F(28) BK_F(29) BK_F(30) BK_F(31)
 #undef BK_F
   }
@@ -648,7 +702,8 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   MapStatsParams sp{};
   sp.rs = ref->start; sp.re = ref->end; sp.row0 = row0; sp.n = n;
   sp.run_ref_begin = d_tab; sp.run_map_begin = d_tab + nruns + 1; sp.run_map_end = d_tab + 2 * nruns + 1; sp.nruns = nruns;
-  sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.score = map->score; sp.idspan = map->idspan;
+  sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.bmax = map->bmax_end; sp.score = map->score;
+  sp.idspan = map->idspan;
   sp.ov = ov; sp.need = need; sp.mdelim_len = (uint32_t)strlen(mdelim);
   sp.count = dalloc<uint32_t>(ctx, n);
   if (need & NEED_BASES) sp.bases = dalloc<uint64_t>(ctx, n);
@@ -671,8 +726,12 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     if (blocks > cap) blocks = cap;
     prof_begin(ctx, "k_map_stats");
     // the default criterion (--bp-ovr) gets its own instantiation; the other six share the generic predicate
-    if (ov.kind == BK_OVR_BP) launch_map_stats<BK_OVR_BP>(need, (unsigned)blocks, ctx->stream, sp);
-    else launch_map_stats<-1>(need, (unsigned)blocks, ctx->stream, sp);
+    // dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows) take the variant
+    // that skips dead 32-row blocks; it costs ~20 % on short windows, so it is not the default
+    const bool dense = ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
+    if (dense) launch_map_stats<BK_OVR_BP, true>(need, (unsigned)blocks, ctx->stream, sp);
+    else if (ov.kind == BK_OVR_BP) launch_map_stats<BK_OVR_BP, false>(need, (unsigned)blocks, ctx->stream, sp);
+    else launch_map_stats<-1, false>(need, (unsigned)blocks, ctx->stream, sp);
     prof_end(ctx);
     BK_LAUNCHED(ctx);
   }

@@ -72,6 +72,7 @@ struct bk_bed {
                                    // (bytes up to the NL) when echoing the row is a verbatim copy, else 0xFFFF
   uint32_t*   idspan = nullptr;    // (rel_off << 16) | len  relative to line_off
   uint32_t*   pmax_end = nullptr;  // inclusive running max of end within the chromosome run (lazy)
+  uint32_t*   bmax_end = nullptr;  // max end of every 32-row block (global row index / 32; lazy, with pmax_end)
   std::vector<bk::ChromRun> runs;
 };
 

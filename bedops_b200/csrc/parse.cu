@@ -840,11 +840,35 @@ int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, c
   return BK_OK;
 }
 
+// max end of every block of 32 consecutive rows (blocks on the global row index, chromosome runs ignored: a block that
+// straddles two chromosomes is merely less often skippable).  The window scans skip blocks no row of which reaches the
+// reference row.
+__global__ void __launch_bounds__(256) k_block_max(const uint32_t* __restrict__ end, uint64_t n, uint32_t* __restrict__ bmax) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * 256) >> 5;
+  const uint64_t nblocks = (n + 31) >> 5;
+  for (uint64_t b = w0; b < nblocks; b += nw) {
+    const uint64_t k = (b << 5) + lane;
+    const uint32_t v = __reduce_max_sync(0xffffffffu, k < n ? __ldg(&end[k]) : 0u);
+    if (lane == 0) bmax[b] = v;
+  }
+}
+
 int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
   bk_bed* bed = const_cast<bk_bed*>(cbed);
   if (bed->pmax_end || bed->nrows == 0) return BK_OK;
   bed->pmax_end = dalloc<uint32_t>(ctx, bed->nrows);
-  if (!bed->pmax_end) return BK_ERR_NOMEM;
+  const uint64_t nblocks = (bed->nrows + 31) / 32;
+  bed->bmax_end = dalloc<uint32_t>(ctx, nblocks + 2);
+  if (!bed->pmax_end || !bed->bmax_end) return BK_ERR_NOMEM;
+  if (bed->end) {
+    const uint64_t want = (nblocks + 7) / 8;
+    prof_begin(ctx, "k_block_max");
+    k_block_max<<<grid_for(ctx, (const void*)k_block_max, 256, (uint32_t)std::min<uint64_t>(want, 0xFFFFFFFFu)), 256, 0, ctx->stream>>>(
+        bed->end, bed->nrows, bed->bmax_end);
+    prof_end(ctx);
+    BK_LAUNCHED(ctx);
+  }
   return seg_prefix_max(ctx, bed->end, bed->pmax_end, bed->nrows, bed->runs);
 }
 

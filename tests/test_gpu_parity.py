@@ -165,6 +165,17 @@ def test_synthetic_vs_oracle_bytes(kit, synth_files):
         assert_same(oracle_cli.run_kit(kit, tool, argv, synth_files), oracle_cli.run(tool, argv, synth_files))
 
 
+def test_dense_map_file_takes_the_block_skipping_scan(kit, synth_files):
+    """>= 32 map rows per reference row selects the k_map_stats variant that skips 32-row blocks with no reaching end."""
+    files = dict(synth_files)
+    files["few.bed"] = b"".join(l + b"\n" for l in synth_files["dr.bed"].split(b"\n")[:-1][::12])
+    assert files["dm.bed"].count(b"\n") >= 32 * files["few.bed"].count(b"\n")
+    for argv in (["--echo", "--count", "--mean", "--bases", "few.bed", "dm.bed"],
+                 ["--count", "--sum", "--max", "--min", "--indicator", "few.bed", "dm.bed"],
+                 ["--bp-ovr", "50", "--count", "--bases", "few.bed", "dm.bed"]):
+        assert_same(oracle_cli.run_kit(kit, "bedmap", argv, files), oracle_cli.run("bedmap", argv, files))
+
+
 def test_nested_and_duplicate_intervals(kit):
     # adversarial nesting: one chromosome-long interval, duplicates, touching and abutting intervals
     m = [b"chr1\t0\t1000000\tbig\t5"]
