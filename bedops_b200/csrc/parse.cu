@@ -142,8 +142,12 @@ __device__ __forceinline__ uint32_t ctl_mask4(uint32_t w) {  // bit 8j+7 set iff
 __device__ __forceinline__ uint32_t nl_mask4(uint32_t w, uint32_t ctl) {  // bytes == '\n' (given the ctl mask)
   return ~(((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & ctl;
 }
-__device__ __forceinline__ uint32_t pack4(uint32_t m) {  // bits 7,15,23,31 -> bits 0..3
-  return ((m >> 7) * 0x01020408u) >> 24;
+// Byte flags (bit 7 of each byte) of eight consecutive words -> one bit per byte, bit 4i+j = byte j of word i.
+// One multiply gathers the four flags of a word in its top nibble (7->28, 15->29, 23->30, 31->31: the partial
+// products land on distinct bits, no carries); a funnel shift appends that nibble to the accumulator.  Words are
+// fed last to first so that word 0 ends in the lowest nibble.  Two instructions per word (IMAD + SHF).
+__device__ __forceinline__ uint32_t push_flags4(uint32_t acc, uint32_t m) {
+  return __funnelshift_l(m * 0x00204081u, acc, 4);  // (acc << 4) | (top nibble of the product)
 }
 
 // unaligned 32-bit read of window bytes [x, x+4)
@@ -220,10 +224,10 @@ __device__ __forceinline__ void pack_masks32(const uint32_t (&w8)[8], uint32_t& 
   cm = 0;
   nlp = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 7; i >= 0; i--) {
     const uint32_t ctl = ctl_mask4(w8[i]);
-    cm |= pack4(ctl) << (4 * i);
-    nlp |= pack4(nl_mask4(w8[i], ctl)) << (4 * i);
+    cm = push_flags4(cm, ctl);
+    nlp = push_flags4(nlp, nl_mask4(w8[i], ctl));
   }
 }
 
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         const uint32_t h8[8] = {ha.x, ha.y, ha.z, ha.w, hc.x, hc.y, hc.z, hc.w};
         uint32_t     hm = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) hm |= pack4(nl_mask4(h8[i], ctl_mask4(h8[i]))) << (4 * i);
+        for (int i = 7; i >= 0; i--) hm = push_flags4(hm, nl_mask4(h8[i], ctl_mask4(h8[i])));
         nlw[tid - 32] = hm;
       }
       if (tid < P_POST / 32) {  // tail halo
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         const uint32_t t8[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
         uint32_t     tm = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) tm |= pack4(ctl_mask4(t8[i])) << (4 * i);
+        for (int i = 7; i >= 0; i--) tm = push_flags4(tm, ctl_mask4(t8[i]));
         ctlp[P_TILE / 32 + tid] = tm;
       } else if (tid < P_POST / 32 + 4) {
         ctlp[P_TILE / 32 + tid] = 0;  // padding words read by the 64-bit line windows
