@@ -702,7 +702,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   MapStatsParams sp{};
   sp.rs = ref->start; sp.re = ref->end; sp.row0 = row0; sp.n = n;
   sp.run_ref_begin = d_tab; sp.run_map_begin = d_tab + nruns + 1; sp.run_map_end = d_tab + 2 * nruns + 1; sp.nruns = nruns;
-  sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.bmax = map->bmax_end; sp.score = map->score;
+  sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.score = map->score;
   sp.idspan = map->idspan;
   sp.ov = ov; sp.need = need; sp.mdelim_len = (uint32_t)strlen(mdelim);
   sp.count = dalloc<uint32_t>(ctx, n);
@@ -724,11 +724,15 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     uint64_t       blocks = (batches + per_block - 1) / per_block;
     const uint64_t cap = (uint64_t)kSMs * 8 * 8;  // several resident waves; warps stride over the batches
     if (blocks > cap) blocks = cap;
-    prof_begin(ctx, "k_map_stats");
     // the default criterion (--bp-ovr) gets its own instantiation; the other six share the generic predicate
     // dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows) take the variant
     // that skips dead 32-row blocks; it costs ~20 % on short windows, so it is not the default
     const bool dense = ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
+    if (dense) {
+      BK_TRY(ensure_bmax(ctx, map));
+      sp.bmax = map->bmax_end;
+    }
+    prof_begin(ctx, "k_map_stats");
     if (dense) launch_map_stats<BK_OVR_BP, true>(need, (unsigned)blocks, ctx->stream, sp);
     else if (ov.kind == BK_OVR_BP) launch_map_stats<BK_OVR_BP, false>(need, (unsigned)blocks, ctx->stream, sp);
     else launch_map_stats<-1, false>(need, (unsigned)blocks, ctx->stream, sp);

@@ -862,18 +862,24 @@ int ensure_pmax(bk_ctx* ctx, const bk_bed* cbed) {
   bk_bed* bed = const_cast<bk_bed*>(cbed);
   if (bed->pmax_end || bed->nrows == 0) return BK_OK;
   bed->pmax_end = dalloc<uint32_t>(ctx, bed->nrows);
+  if (!bed->pmax_end) return BK_ERR_NOMEM;
+  return seg_prefix_max(ctx, bed->end, bed->pmax_end, bed->nrows, bed->runs);
+}
+
+// the block-max index is only worth its pass for dense map files (bk_bedmap decides)
+int ensure_bmax(bk_ctx* ctx, const bk_bed* cbed) {
+  bk_bed* bed = const_cast<bk_bed*>(cbed);
+  if (bed->bmax_end || bed->nrows == 0) return BK_OK;
   const uint64_t nblocks = (bed->nrows + 31) / 32;
   bed->bmax_end = dalloc<uint32_t>(ctx, nblocks + 2);
-  if (!bed->pmax_end || !bed->bmax_end) return BK_ERR_NOMEM;
-  if (bed->end) {
-    const uint64_t want = (nblocks + 7) / 8;
-    prof_begin(ctx, "k_block_max");
-    k_block_max<<<grid_for(ctx, (const void*)k_block_max, 256, (uint32_t)std::min<uint64_t>(want, 0xFFFFFFFFu)), 256, 0, ctx->stream>>>(
-        bed->end, bed->nrows, bed->bmax_end);
-    prof_end(ctx);
-    BK_LAUNCHED(ctx);
-  }
-  return seg_prefix_max(ctx, bed->end, bed->pmax_end, bed->nrows, bed->runs);
+  if (!bed->bmax_end) return BK_ERR_NOMEM;
+  const uint64_t want = (nblocks + 7) / 8;
+  prof_begin(ctx, "k_block_max");
+  k_block_max<<<grid_for(ctx, (const void*)k_block_max, 256, (uint32_t)std::min<uint64_t>(want, 0xFFFFFFFFu)), 256, 0, ctx->stream>>>(
+      bed->end, bed->nrows, bed->bmax_end);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  return BK_OK;
 }
 
 }  // namespace bk

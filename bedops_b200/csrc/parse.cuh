@@ -42,6 +42,7 @@ int reset_scratch(bk_ctx* ctx);
 int read_scratch(bk_ctx* ctx);
 int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw);
 int ensure_pmax(bk_ctx* ctx, const bk_bed* bed);
+int ensure_bmax(bk_ctx* ctx, const bk_bed* bed);  // max end per 32-row block (dense-map variant of the window scan)
 int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, const std::vector<ChromRun>& runs);
 
 }  // namespace bk
