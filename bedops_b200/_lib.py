@@ -16,7 +16,7 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4, "complement": 5, "difference": 6,
-          "symmdiff": 7}
+          "symmdiff": 7, "everything": 8}
 COL_LINE, COL_SCORE, COL_ID, LOAD_HEADERS = 1, 2, 4, 8
 
 

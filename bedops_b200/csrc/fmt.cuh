@@ -1,6 +1,6 @@
 // fmt.cuh -- device-side ASCII emission primitives (every field the reference prints with printf).
 //
-// Sinks: a row is formatted twice by the same code, first into a CountSink (byte length for the look-back scan),
+// Sinks: a row is formatted twice by the same code, first into a CountSink (byte length, k_emit_len),
 // then into a MemSink (shared-memory staging or, for oversized tiles, global memory).
 #pragma once
 #include "common.cuh"

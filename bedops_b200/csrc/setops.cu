@@ -687,6 +687,181 @@ static int complement_of(bk_ctx* ctx, const IvList& U, bool full_left, IvList* o
   return BK_OK;
 }
 
+// ---- --everything: multiset union of whole rows (doUnionAll / nextUnionAllLine, Bedops.cpp:761-786, :1468-1516) ----
+// Order: chromosome, start, end, strcmp of the rest of the line, file number.  Every row finds its output slot by
+// ranking itself in every other file (binary searches with that comparator: the inputs are sorted per sort-bed, which
+// orders by the rest of the line too); the emitter then echoes row src[slot].
+constexpr int kMaxEverything = 32;
+struct EverythingFiles {
+  const char*     text[kMaxEverything];
+  const uint64_t* line[kMaxEverything];
+  const uint32_t* s[kMaxEverything];
+  const uint32_t* e[kMaxEverything];
+};
+
+// the rest of a line after its third field (what %[^\n] of B3Rest::readline keeps; strtoul skips blanks and a '+')
+__device__ __forceinline__ const char* rest_of_line(const char* p) {
+  while (is_tok((unsigned char)*p)) p++;
+  for (int f = 0; f < 2; f++) {
+    while (is_ws((unsigned char)*p)) p++;
+    if (*p == '+') p++;
+    while (is_digit((unsigned char)*p)) p++;
+  }
+  return p;
+}
+__device__ __forceinline__ int cmp_rest(const char* a, const char* b) {  // strcmp of two '\n'-terminated strings
+  while (true) {
+    const unsigned char x = *a == '\n' ? 0 : (unsigned char)*a, y = *b == '\n' ? 0 : (unsigned char)*b;
+    if (x != y) return x < y ? -1 : 1;
+    if (x == 0) return 0;
+    a++;
+    b++;
+  }
+}
+
+struct RankRowsParams {
+  EverythingFiles F;
+  int             k, f;
+  const uint64_t* run_begin;   // [nruns] first participating row of each selected run of file f
+  const uint32_t* run_g;       // [nruns] global chromosome index
+  const uint64_t* sel_prefix;  // [nruns+1]
+  int             nruns;
+  uint64_t        nsel;
+  const uint64_t* g_begin;     // [G*k]
+  const uint64_t* g_end;
+  const uint64_t* g_out;       // [G]
+  uint64_t*       src;         // [N] (file << 56) | row
+};
+
+__global__ void __launch_bounds__(256) k_rank_rows(RankRowsParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < p.nsel; t += stride) {
+    int lo = 0, hi = p.nruns;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (p.sel_prefix[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint64_t row = p.run_begin[lo] + (t - p.sel_prefix[lo]);
+    const uint32_t g = p.run_g[lo];
+    const uint32_t ks = p.F.s[p.f][row], ke = p.F.e[p.f][row];
+    const char*    krest = nullptr;  // found lazily: only ties on (start, end) need it
+    uint64_t       pos = p.g_out[g] + (row - p.g_begin[(uint64_t)g * p.k + p.f]);
+    for (int j = 0; j < p.k; j++) {
+      if (j == p.f) continue;
+      uint64_t b = p.g_begin[(uint64_t)g * p.k + j], e = p.g_end[(uint64_t)g * p.k + j];
+      if (b == e) continue;
+      const uint64_t b0 = b;
+      // rows of file j that precede this row: key(j,r) < key for a later file, key(j,r) <= key for an earlier one
+      while (b < e) {
+        const uint64_t mid = b + ((e - b) >> 1);
+        const uint32_t ms = p.F.s[j][mid], me = p.F.e[j][mid];
+        int            c;  // key(j,mid) vs key
+        if (ms != ks) c = ms < ks ? -1 : 1;
+        else if (me != ke) c = me < ke ? -1 : 1;
+        else {
+          if (!krest) krest = rest_of_line(p.F.text[p.f] + (p.F.line[p.f][row] & kLineOffMask));
+          c = cmp_rest(rest_of_line(p.F.text[j] + (p.F.line[j][mid] & kLineOffMask)), krest);
+        }
+        const bool before = j < p.f ? c <= 0 : c < 0;
+        if (before) b = mid + 1; else e = mid;
+      }
+      pos += b - b0;
+    }
+    p.src[pos] = ((uint64_t)p.f << 56) | row;
+  }
+}
+
+struct EverythingRow {
+  EverythingFiles F;
+  const uint64_t* src;
+  template <class Sink>
+  __device__ void operator()(uint64_t i, Sink& sk) const {
+    const uint64_t v = src[i], row = v & ((1ull << 56) - 1);
+    const int      f = (int)(v >> 56);
+    echo_b3rest(sk, F.text[f], F.line[f][row], F.s[f][row], F.e[f][row]);
+    sk.put('\n');
+  }
+};
+
+static int everything(bk_ctx* ctx, const bk_bed* const* files, int k, const char* chrom, int on_device, bk_text* out) {
+  if (k > kMaxEverything) return fail(ctx, BK_ERR_UNSUPPORTED, "--everything over more than %d files", kMaxEverything);
+  EverythingFiles F{};
+  std::vector<IvList> in;
+  for (int f = 0; f < k; f++) {
+    if (!files[f]->line_off && files[f]->nrows) return fail(ctx, BK_ERR_ARG, "--everything needs every file loaded with BK_COL_LINE");
+    F.text[f] = files[f]->d_text; F.line[f] = files[f]->line_off; F.s[f] = files[f]->start; F.e[f] = files[f]->end;
+    in.push_back(view_of(files[f], chrom));
+  }
+  std::vector<std::string> names;
+  for (auto& l : in)
+    for (auto& r : l.runs)
+      if (r.row_end > r.row_begin) names.push_back(r.name);
+  std::sort(names.begin(), names.end(), [](const std::string& a, const std::string& b) { return strcmp(a.c_str(), b.c_str()) < 0; });
+  names.erase(std::unique(names.begin(), names.end()), names.end());
+  const int G = (int)names.size();
+  if (G == 0) return finish_text(ctx, nullptr, 0, 0, on_device, out);
+  std::map<std::string, int> gidx;
+  for (int g = 0; g < G; g++) gidx[names[g]] = g;
+  std::vector<uint64_t> g_begin((size_t)G * k, 0), g_end((size_t)G * k, 0), g_out(G + 1, 0);
+  for (int f = 0; f < k; f++)
+    for (auto& r : in[f].runs) {
+      if (r.row_end == r.row_begin) continue;
+      const int g = gidx[r.name];
+      g_begin[(size_t)g * k + f] = r.row_begin;
+      g_end[(size_t)g * k + f] = r.row_end;
+    }
+  for (int g = 0; g < G; g++) {
+    uint64_t c = 0;
+    for (int f = 0; f < k; f++) c += g_end[(size_t)g * k + f] - g_begin[(size_t)g * k + f];
+    g_out[g + 1] = g_out[g] + c;
+  }
+  const uint64_t N = g_out[G];
+  uint64_t*      src = dalloc<uint64_t>(ctx, N);
+  uint64_t *d_gb = upload(ctx, g_begin), *d_ge = upload(ctx, g_end), *d_go = upload(ctx, g_out);
+  if (!src || !d_gb || !d_ge || !d_go) return BK_ERR_NOMEM;
+  std::vector<void*> tofree{d_gb, d_ge, d_go};
+  std::vector<std::vector<uint64_t>> keep_rb(k), keep_sp(k);
+  std::vector<std::vector<uint32_t>> keep_rg(k);
+  for (int f = 0; f < k; f++) {
+    auto&    rb = keep_rb[f];
+    auto&    sp = keep_sp[f];
+    auto&    rg = keep_rg[f];
+    uint64_t acc = 0;
+    for (auto& r : in[f].runs) {
+      if (r.row_end == r.row_begin) continue;
+      rb.push_back(r.row_begin);
+      rg.push_back((uint32_t)gidx[r.name]);
+      sp.push_back(acc);
+      acc += r.row_end - r.row_begin;
+    }
+    if (acc == 0) continue;
+    sp.push_back(acc);
+    RankRowsParams p{};
+    p.F = F; p.k = k; p.f = f; p.nruns = (int)rg.size(); p.nsel = acc;
+    p.run_begin = upload(ctx, rb); p.run_g = upload(ctx, rg); p.sel_prefix = upload(ctx, sp);
+    if (!p.run_begin || !p.run_g || !p.sel_prefix) return BK_ERR_NOMEM;
+    tofree.push_back((void*)p.run_begin); tofree.push_back((void*)p.run_g); tofree.push_back((void*)p.sel_prefix);
+    p.g_begin = d_gb; p.g_end = d_ge; p.g_out = d_go; p.src = src;
+    const uint64_t blocks = (acc + 255) / 256, cap = (uint64_t)kSMs * 32;
+    prof_begin(ctx, "k_rank_rows");
+    k_rank_rows<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+    prof_end(ctx);
+    BK_LAUNCHED(ctx);
+  }
+  EverythingRow fn{};
+  fn.F = F; fn.src = src;
+  char*    d_out = nullptr;
+  uint64_t bytes = 0, rows = 0;
+  int      rc = run_emit(ctx, fn, N, 0, &d_out, &bytes, &rows);  // run_emit syncs: the uploads are done
+  for (void* q : tofree) dfree(ctx, q);
+  dfree(ctx, src);
+  if (rc != BK_OK) {
+    dfree(ctx, d_out);
+    return rc;
+  }
+  return finish_text(ctx, d_out, bytes, rows, on_device, out);
+}
+
 static int emit_bed3(bk_ctx* ctx, const IvList& l, int on_device, bk_text* out) {
   std::vector<char>     names;
   std::vector<uint32_t> lens;
@@ -762,6 +937,7 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
     free_list(ctx, acc);
     return rc;
   }
+  if (op == BK_SETOP_EVERYTHING) return everything(ctx, files, n_files, chrom, out_on_device, out);
   if (op == BK_SETOP_COMPLEMENT) {
     std::vector<IvList> in;
     for (int i = 0; i < n_files; i++) in.push_back(view_of(files[i], chrom));

@@ -198,7 +198,8 @@ void usage(FILE* f) {
       "          -i, --intersect                       Min: 2 files.\n"
       "          -m, --merge                           Min: 1 file.\n"
       "          -n, --not-element-of [bp | percentage] Min: 2 files.\n"
-      "          -s, --symmdiff                        Min: 2 files.\n\n",
+      "          -s, --symmdiff                        Min: 2 files.\n"
+      "          -u, --everything                      Min: 1 file.\n\n",
       f);
 }
 
@@ -216,6 +217,7 @@ int main(int argc, char** argv) {
       case COMPLEMENT: op = BK_SETOP_COMPLEMENT; break;
       case DIFFERENCE: op = BK_SETOP_DIFFERENCE; break;
       case SYMMDIFF: op = BK_SETOP_SYMMDIFF; break;
+      case UNIONALL: op = BK_SETOP_EVERYTHING; break;
       default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
     if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
@@ -223,17 +225,18 @@ int main(int argc, char** argv) {
     for (size_t f = 0; f < o.files.size(); f++)
       if (!cli::slurp(o.files[f], texts[f])) throw UserError("Cannot find " + o.files[f]);
     const bool has_ref = op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF;
+    const bool all_lines = op == BK_SETOP_EVERYTHING;  // every row of every file is echoed
     const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
     if (o.ec) {  // Bedops.cpp:259-286: BedPadReader over bed_check_iterator; B3Rest for the -e/-n reference, B3NoRest otherwise
       cli::Engine eng;
       for (size_t f = 0; f < texts.size(); f++) {
         cli::ec_prepare(texts[f]);
-        cli::ec_check(eng, texts[f], o.files[f], 3, has_ref && f == 0, false);
+        cli::ec_check(eng, texts[f], o.files[f], 3, (has_ref && f == 0) || all_lines, false);
       }
     }
     auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
       std::vector<bk_bed*> beds;
-      for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, ((has_ref && f == 0) ? BK_COL_LINE : 0) | hdr));
+      for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, (((has_ref && f == 0) || all_lines) ? BK_COL_LINE : 0) | hdr));
       bk_text out;
       const double thr = op == BK_SETOP_COMPLEMENT ? (o.full_left ? 1.0 : 0.0) : o.subset;
       int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), thr, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);

@@ -185,7 +185,8 @@ enum {
   BK_SETOP_NOT_ELEMENT_OF = 4,
   BK_SETOP_COMPLEMENT = 5, /* --complement; thr != 0 selects -L (Bedops.cpp:475-488, :891-943) */
   BK_SETOP_DIFFERENCE = 6, /* --difference: files[0] minus the others (:501-525, :948-1018) */
-  BK_SETOP_SYMMDIFF = 7    /* --symmdiff: bases covered by exactly one file (:698-745, :1341-1463) */
+  BK_SETOP_SYMMDIFF = 7,   /* --symmdiff: bases covered by exactly one file (:698-745, :1341-1463) */
+  BK_SETOP_EVERYTHING = 8  /* --everything: all rows of all files in sort-bed order, every file needs BK_COL_LINE (:761-786, :1468-1516) */
 };
 /* thr / thr_is_pct: -e/-n threshold as Input::Threshold()/UsePercentage() deliver it (bedops/src/Input.hpp:344-382):
  * a fraction in (0,1] when thr_is_pct, else a base count.  files[0] is the reference file for -e/-n. */

@@ -476,6 +476,18 @@ def bedops_symmdiff(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> by
     return b"".join(out)
 
 
+def bedops_everything(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doUnionAll / nextUnionAllLine (Bedops.cpp:761-786, :1468-1516): multiset union of the rows of all files, every row
+    printed as B3Rest (chrom, start, end re-printed, rest verbatim).  Order: chromosome, start, end, then strcmp of the
+    rest of the line; on a full tie the row of the lower-numbered file comes first (the comparisons are strict)."""
+    rows = []
+    for f, t in enumerate(texts):
+        for k, r in enumerate(_sel(parse_bed(t, 3), chrom)):
+            rows.append((r.chrom, r.start, r.end, r.rest3, f, k, r))
+    rows.sort(key=lambda x: x[:6])
+    return b"".join(echo_b3rest(x[6]) + b"\n" for x in rows)
+
+
 def bedops_element_of(texts: Sequence[bytes], thr: float = 1.0, use_pct: bool = True, invert: bool = False,
                       chrom: Optional[bytes] = None) -> bytes:
     """doElementOf / nextElementOfLine (Bedops.cpp:538-566, :1023-1100): overlap bases of each reference row

@@ -168,6 +168,8 @@ def synthetic():
             ("bedops", ["-c", "m.bed"]), ("bedops", ["-c", "-L", "m.bed", "r.bed"]), ("bedops", ["-d", "r.bed", "m.bed"]),
             ("bedops", ["-d", "dm.bed", "dr.bed", "m.bed"]), ("bedops", ["-s", "dr.bed", "dm.bed"]),
             ("bedops", ["-s", "m.bed", "m2.bed", "r.bed", "m3.bed"]), ("bedops", ["--chrom", "chr21", "-c", "-L", "dm.bed"]),
+            ("bedops", ["-u", "m.bed", "m2.bed", "r.bed", "m3.bed"]), ("bedops", ["-u", "dr.bed", "dm.bed"]),
+            ("bedops", ["--chrom", "chr7", "-u", "m.bed", "m3.bed"]),
             ("bedmap", ["--echo", "--echo-map", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map", "--mean", "--echo-map-score", "--prec", "2", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map", "--echo-map-id", "--multidelim", ",", "dr.bed", "dm.bed"]),

@@ -32,6 +32,8 @@ def parse_argv(tool, argv, known_files):
                 d["op"] = "difference"
             elif a in ("-s", "--symmdiff"):
                 d["op"] = "symmdiff"
+            elif a in ("-u", "--everything"):
+                d["op"] = "everything"
             elif a in ("-e", "--element-of", "-n", "--not-element-of"):
                 d["op"] = "element-of" if a in ("-e", "--element-of") else "not-element-of"
                 if i + 1 < len(argv) and argv[i + 1] not in known_files:
@@ -124,6 +126,8 @@ def run(tool, argv, files, stdin=None):
             return O.bedops_difference(texts, d["chrom"])
         if d["op"] == "symmdiff":
             return O.bedops_symmdiff(texts, d["chrom"])
+        if d["op"] == "everything":
+            return O.bedops_everything(texts, d["chrom"])
         return O.bedops_element_of(texts, d["thr"], d["pct"], d["op"] == "not-element-of", d["chrom"])
     if tool == "bedmap":
         return O.bedmap(texts[0], texts[1] if len(texts) > 1 else None, ops=d["ops"], overlap=d["overlap"],
@@ -139,7 +143,8 @@ def run_kit(kit, tool, argv, files, stdin=None):
     d = parse_argv(tool, argv, files)
     texts = [stdin if n == "-" else files[n] for n in d["names"]]
     if tool == "bedops":
-        beds = [kit.load(t, 3, COL_LINE if (k == 0 and d["op"].endswith("element-of")) else 0) for k, t in enumerate(texts)]
+        beds = [kit.load(t, 3, COL_LINE if ((k == 0 and d["op"].endswith("element-of")) or d["op"] == "everything") else 0)
+                for k, t in enumerate(texts)]
         thr = float(d["full_left"]) if d["op"] == "complement" else d["thr"]   # BK_SETOP_COMPLEMENT: thr != 0 is -L
         out = kit.setop(d["op"], beds, thr, d["pct"], d["chrom"])
         for b in beds:

@@ -176,6 +176,19 @@ def test_dense_map_file_takes_the_block_skipping_scan(kit, synth_files):
         assert_same(oracle_cli.run_kit(kit, "bedmap", argv, files), oracle_cli.run("bedmap", argv, files))
 
 
+def test_everything_orders_ties_by_the_rest_of_the_line_then_by_file(kit):
+    """bedops -u: identical coordinates are ordered by strcmp of the rest of the line, full ties by file number
+    (nextUnionAllLine, Bedops.cpp:1468-1516); BED3 and BED5 rows mixed, chromosomes missing from some files."""
+    files = {
+        "t1.bed": b"chr1\t10\t20\tb\t1\nchr1\t10\t20\tb\t1\nchr1\t10\t30\nchr1\t50\t60\tz\nchr2\t5\t9\tq\n",
+        "t2.bed": b"chr1\t10\t20\ta\t9\nchr1\t10\t20\tb\t1\nchr1\t10\t30\tx\nchr1\t50\t60\nchr3\t1\t2\n",
+        "t3.bed": b"chr1\t10\t20\nchr1\t10\t20\tb\nchr1\t50\t60\ty\nchr2\t5\t9\tq\n",
+    }
+    for argv in (["-u", "t1.bed", "t2.bed", "t3.bed"], ["-u", "t3.bed", "t2.bed", "t1.bed"], ["-u", "t2.bed"],
+                 ["--chrom", "chr2", "-u", "t1.bed", "t3.bed"]):
+        assert_same(oracle_cli.run_kit(kit, "bedops", argv, files), oracle_cli.run("bedops", argv, files))
+
+
 def test_nested_and_duplicate_intervals(kit):
     # adversarial nesting: one chromosome-long interval, duplicates, touching and abutting intervals
     m = [b"chr1\t0\t1000000\tbig\t5"]
@@ -291,6 +304,8 @@ def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
             ("bedmap", ["--echo", "--count", "--mean", "--bases", "r.bed", "m.bed"]),
             ("bedmap", ["--faster", "--delim", "\\t", "--sum", "--max", "--echo-map-id", "r.bed", "u.bed"]),
             ("bedmap", ["--count", "m3.bed"]), ("closest-features", ["--dist", "r.bed", "m.bed"]),
+            ("bedops", ["-u", "r.bed", "m3.bed", "m.bed"]), ("bedops", ["-c", "-L", "r.bed", "m3.bed"]),
+            ("bedops", ["-d", "m.bed", "r.bed"]), ("bedops", ["-s", "m.bed", "r.bed", "m2.bed"]),
             ("bedmap", ["--echo", "--echo-map", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
             ("bedmap", ["--range", "200", "--echo-map-range", "--echo-map-size", "--echo-overlap-size", "--bases-uniq", "dr.bed", "dm.bed"]),
             ("closest-features", ["--closest", "--delim", "\\t", "r.bed", "m3.bed"])]
