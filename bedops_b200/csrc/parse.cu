@@ -156,12 +156,15 @@ __device__ __forceinline__ uint32_t ld32u(const unsigned char* sm, int x) {
   return __funnelshift_r(w[0], w[1], (x & 3) * 8);
 }
 
-// four ASCII digits (first digit in the lowest byte) -> 0..9999; bad accumulates a non-zero value on a non-digit
+// four ASCII digits (first digit in the lowest byte) -> 0..9999; bad accumulates a non-zero value on a non-digit.
+// Three multiplies and two masks: the kernel is bound by the ALU pipe (logic/shift/compare), multiplies run on the
+// FMA pipe.  t = digit values d0..d3 in bytes 0..3;  t*0x0A01 puts 10*d0+d1 in byte 1 and 10*d2+d3 in byte 3;
+// the high half of (a<<8 | b<<24) * (100<<24 | 1<<8) is 100*a + b (+ a multiple of 2^16).
 __device__ __forceinline__ uint32_t digits4(uint32_t w, uint32_t& bad) {
   const uint32_t t = w - 0x30303030u;
   bad |= ((w + 0x46464646u) | t) & 0x80808080u;
-  const uint32_t u = t * 10u + (t >> 8);
-  return (u & 0xFFu) * 100u + ((u >> 16) & 0xFFu);
+  const uint32_t y = (t * 0x0A01u) & 0xFF00FF00u;
+  return __umulhi(y, 0x64000100u) & 0xFFFFu;
 }
 
 // decimal field of len digits (1..9) that ENDS at window byte index e (exclusive) -> value
@@ -308,6 +311,13 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
   if (lane == 0) warp_total[wid] = run;
 }
 
+// first row of every tile = base of its warp range + rows of the earlier tiles of the range
+__global__ void k_tile_base(const uint32_t* __restrict__ local_prefix, const uint64_t* __restrict__ warp_base,
+                            uint32_t tiles_per_warp, uint32_t ntiles, uint64_t* __restrict__ tile_base) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntiles) tile_base[t] = warp_base[t / tiles_per_warp] + local_prefix[t];
+}
+
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
 //
 // Per tile (tiles are independent: the first row of each tile comes from pass 1): (1) stage the text, (2) every
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     const uint32_t cnt = __popc(smask);
     const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31) wsum[warp] = incl;
-    if (tid == 0) base_sm = p.warp_base[tile / p.tiles_per_warp] + p.local_prefix[tile];  // first row of this tile (pass 1)
+    if (tid == 0) base_sm = p.tile_base[tile];  // first row of this tile (pass 1)
     __syncthreads();  // [S2] masks, warp totals and the tile's first row visible
     uint32_t ex = incl - cnt;  // rows of this tile that start before this thread's bytes
     {
@@ -718,10 +728,16 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   k_scan_totals<SC_NROWS><<<1, 1024, 0, ctx->stream>>>(d_wtot, d_wbase, nwarps, ctx->d_scratch);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
+  uint64_t* d_tbase = dalloc<uint64_t>(ctx, ntiles);
+  if (!d_tbase) return BK_ERR_NOMEM;
+  k_tile_base<<<(ntiles + 255) / 256, 256, 0, ctx->stream>>>(d_lpre, d_wbase, tiles_per_warp, ntiles, d_tbase);
+  BK_LAUNCHED(ctx);
   BK_TRY(read_scratch(ctx));
   bed->nrows = ctx->h_scratch[SC_NROWS];
   bed->nbytes = ctx->h_scratch[SC_EFFLEN];
   dfree(ctx, d_wtot);
+  dfree(ctx, d_lpre);
+  dfree(ctx, d_wbase);
   const uint64_t cap = bed->nrows;
   {
     bed->start = dalloc<uint32_t>(ctx, cap);
@@ -749,9 +765,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     p.scratch = ctx->d_scratch;
     p.heads = d_heads;
     p.heads_cap = heads_cap;
-    p.local_prefix = d_lpre;
-    p.warp_base = d_wbase;
-    p.tiles_per_warp = tiles_per_warp;
+    p.tile_base = d_tbase;
     prof_begin(ctx, "k_parse");
     {
       const bool sc = (p.cols & BK_COL_SCORE) != 0;
@@ -766,8 +780,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     prof_end(ctx);
     BK_LAUNCHED(ctx);
     BK_TRY(read_scratch(ctx));
-    dfree(ctx, d_lpre);
-    dfree(ctx, d_wbase);
+    dfree(ctx, d_tbase);
     const uint64_t* h = ctx->h_scratch;
     if (h[SC_ERR_CODE]) {
       int code = (int)h[SC_ERR_CODE];

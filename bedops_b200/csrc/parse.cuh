@@ -29,9 +29,7 @@ struct ParseParams {
   uint64_t*   line_off;
   uint32_t*   idspan;
   uint64_t    cap;
-  const uint32_t* local_prefix;  // [ntiles] rows of the earlier tiles of the same pass-1 warp range
-  const uint64_t* warp_base;     // [nwarps+1] first row of each pass-1 warp range
-  uint32_t        tiles_per_warp;
+  const uint64_t* tile_base;     // [ntiles] first row of every tile (pass 1: warp-range base + prefix inside the range)
   uint32_t    ntiles;
   uint64_t*   scratch;
   HeadRec*    heads;
