@@ -348,7 +348,7 @@ def main():
     # from the ncu --set full capture of this very command (profiles/r01_final_ncu_raw.csv); only valid for the default workload
     traffic = None
     if args.ref_rows == 10_000_000 and args.map_rows == 100_000_000:
-        traffic = int((0.376925 + 0.143766 + 3.869676 + 1.611783) * 1e9)
+        traffic = int((0.377873 + 0.143716 + 3.870698 + 1.609264) * 1e9)
     roofline = {"bound": "hbm", "kernel": "k_parse", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
