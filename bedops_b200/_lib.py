@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
         "bk_bedmap_host": (i, [vp, vp, C.c_size_t, i, C.c_uint, vp, C.c_size_t, i, C.c_uint, C.POINTER(_MapSpec),
                                C.POINTER(_Text)]),
         "bk_setop": (i, [vp, i, C.POINTER(vp), i, C.c_double, i, C.c_char_p, i, C.POINTER(_Text)]),
+        "bk_chop": (i, [vp, C.POINTER(vp), i, u64, u64, i, C.c_char_p, i, C.POINTER(_Text)]),
         "bk_cfspec_default": (None, [C.POINTER(_CfSpec)]),
         "bk_closest": (i, [vp, vp, vp, C.POINTER(_CfSpec), C.POINTER(_Text)]),
         "bk_format_bed_device": (i, [vp, C.c_char_p, vp, vp, vp, u64, C.c_int64, C.POINTER(_Text)]),
@@ -110,7 +111,7 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
-           "bk_check_text_device", "bk_release_cached", "bk_bedmap_host"]
+           "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop"]
 
 
 class Bed:
@@ -313,6 +314,14 @@ class BedKit:
         t = _Text()
         self._chk(self.lib.bk_setop(self.ctx, SETOPS[op], arr, len(files), thr, int(use_pct), chrom, int(on_device),
                                     C.byref(t)))
+        return self._take(t, on_device)
+
+    def chop(self, files: Sequence[Bed], chunk: int = 1, stagger: int = 0, exclude_short: bool = False,
+             chrom: Optional[bytes] = None, on_device: bool = False):
+        arr = (C.c_void_p * len(files))(*[f.h for f in files])
+        t = _Text()
+        self._chk(self.lib.bk_chop(self.ctx, arr, len(files), chunk, stagger, int(exclude_short), chrom, int(on_device),
+                                   C.byref(t)))
         return self._take(t, on_device)
 
     def closest(self, ref: Bed, query: Bed, dist=False, closest=False, no_overlaps=False, no_ref=False,

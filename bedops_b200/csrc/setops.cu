@@ -687,6 +687,138 @@ static int complement_of(bk_ctx* ctx, const IvList& U, bool full_left, IvList* o
   return BK_OK;
 }
 
+// ---- --chop: merged segments cut into fixed-size pieces (doChop, Bedops.cpp:438-467) ------------------------------
+// Pieces per segment are a closed form; an exclusive scan over the segments (warp ranges, one-CTA scan of the range
+// totals, no carry chain) gives every segment its first output row, and every OUTPUT row then finds its segment by
+// bisection -- a chromosome-long segment chopped into single bases is still spread over the whole grid.
+struct ChopParams {
+  const uint32_t* us;
+  const uint32_t* ue;
+  uint64_t        nseg;
+  uint32_t        chunk, step;
+  int             exclude_short;
+  uint32_t*       local;       // [nseg] pieces of the earlier segments of the same warp range
+  uint64_t*       range_total; // [nranges]
+  const uint64_t* range_base;  // [nranges+1]
+  uint64_t        nranges;
+  uint64_t        nout;
+  uint32_t*       outS;
+  uint32_t*       outE;
+};
+constexpr int CHOP_RANGE = 1024;  // segments per warp range
+
+__device__ __forceinline__ uint64_t chop_pieces(uint32_t s, uint32_t e, uint32_t chunk, uint32_t step, int exclude_short) {
+  const uint64_t len = (uint64_t)e - s;
+  if (!exclude_short) return (len + step - 1) / step;     // i = s, s+step, ... while i < e
+  return len >= chunk ? (len - chunk) / step + 1 : 0;    // ... while i + chunk <= e
+}
+
+__global__ void __launch_bounds__(256) k_chop_count(ChopParams p) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * 256) >> 5;
+  for (uint64_t r = w0; r < p.nranges; r += nw) {
+    const uint64_t a = r * CHOP_RANGE, b = a + CHOP_RANGE < p.nseg ? a + CHOP_RANGE : p.nseg;
+    uint64_t       run = 0;
+    for (uint64_t k0 = a; k0 < b; k0 += 32) {
+      const uint64_t k = k0 + lane;
+      uint64_t       c = k < b ? chop_pieces(p.us[k], p.ue[k], p.chunk, p.step, p.exclude_short) : 0;
+      uint64_t       incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      // a range holds at most 2^32-1 pieces (checked on the host from the totals): 32-bit local prefixes
+      if (k < b) p.local[k] = (uint32_t)(run + incl - c);
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) p.range_total[r] = run;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_chop_write(ChopParams p) {
+  for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < p.nout; o += (uint64_t)gridDim.x * blockDim.x) {
+    // last range with base <= o, then last segment of it with first-row <= o
+    uint64_t lo = 0, hi = p.nranges;
+    while (hi - lo > 1) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (p.range_base[mid] <= o) lo = mid; else hi = mid;
+    }
+    const uint64_t base = p.range_base[lo];
+    uint64_t       a = lo * CHOP_RANGE, b = a + CHOP_RANGE < p.nseg ? a + CHOP_RANGE : p.nseg;
+    while (b - a > 1) {
+      const uint64_t mid = (a + b) >> 1;
+      if (base + p.local[mid] <= o) a = mid; else b = mid;
+    }
+    const uint64_t j = o - (base + p.local[a]);
+    const uint32_t s = p.us[a], e = p.ue[a];
+    const uint64_t ps = (uint64_t)s + j * p.step, pe = ps + p.chunk;
+    p.outS[o] = (uint32_t)ps;
+    p.outE[o] = pe > e ? e : (uint32_t)pe;
+  }
+}
+
+static int chop_list(bk_ctx* ctx, const IvList& U, uint32_t chunk, uint32_t stagger, bool exclude_short, IvList* out) {
+  out->runs.clear();
+  out->n = 0;
+  out->owned = true;
+  out->s = out->e = nullptr;
+  if (U.n == 0) return BK_OK;
+  ChopParams p{};
+  p.us = U.s; p.ue = U.e; p.nseg = U.n; p.chunk = chunk; p.step = stagger ? stagger : chunk; p.exclude_short = exclude_short;
+  p.nranges = (U.n + CHOP_RANGE - 1) / CHOP_RANGE;
+  if (p.nranges >> 32) return fail(ctx, BK_ERR_UNSUPPORTED, "too many segments to chop");
+  p.local = dalloc<uint32_t>(ctx, U.n);
+  p.range_total = dalloc<uint64_t>(ctx, p.nranges);
+  uint64_t* base = dalloc<uint64_t>(ctx, p.nranges + 1);
+  if (!p.local || !p.range_total || !base) return BK_ERR_NOMEM;
+  p.range_base = base;
+  BK_TRY(reset_scratch(ctx));
+  const uint64_t want = (p.nranges + 7) / 8;
+  prof_begin(ctx, "k_chop_count");
+  k_chop_count<<<grid_for_kernel((const void*)k_chop_count, 256, want), 256, 0, ctx->stream>>>(p);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  k_scan_totals<SC_OUT_ROWS><<<1, 1024, 0, ctx->stream>>>(p.range_total, base, (uint32_t)p.nranges, ctx->d_scratch);
+  BK_LAUNCHED(ctx);
+  // first output row of every chromosome run = first row of its first segment
+  std::vector<uint64_t> h_base(p.nranges + 1);
+  BK_CUDA(ctx, cudaMemcpyAsync(h_base.data(), base, (p.nranges + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BK_TRY(read_scratch(ctx));
+  p.nout = ctx->h_scratch[SC_OUT_ROWS];
+  for (uint64_t r = 0; r < p.nranges; r++)
+    if (h_base[r + 1] - h_base[r] > 0xFFFFFFFFull) {
+      dfree(ctx, p.local); dfree(ctx, p.range_total); dfree(ctx, base);
+      return fail(ctx, BK_ERR_UNSUPPORTED, "--chop output too fine for the device writer (more than 2^32 pieces per 1024 segments)");
+    }
+  std::vector<uint64_t> run_first;
+  std::vector<std::string> names;
+  for (auto& r : U.runs) {
+    if (r.row_end == r.row_begin) continue;
+    uint32_t l = 0;
+    BK_CUDA(ctx, cudaMemcpyAsync(&l, p.local + r.row_begin, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    run_first.push_back(h_base[r.row_begin / CHOP_RANGE] + l);
+    names.push_back(r.name);
+  }
+  if (p.nout) {
+    p.outS = dalloc<uint32_t>(ctx, p.nout);
+    p.outE = dalloc<uint32_t>(ctx, p.nout);
+    if (!p.outS || !p.outE) return BK_ERR_NOMEM;
+    const uint64_t blocks = (p.nout + 255) / 256, cap = (uint64_t)kSMs * 32;
+    prof_begin(ctx, "k_chop_write");
+    k_chop_write<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(p);
+    prof_end(ctx);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  dfree(ctx, p.local); dfree(ctx, p.range_total); dfree(ctx, base);
+  out->s = p.outS; out->e = p.outE; out->n = p.nout;
+  for (size_t g = 0; g < names.size(); g++)
+    out->runs.push_back({names[g], run_first[g], g + 1 < names.size() ? run_first[g + 1] : p.nout});
+  return BK_OK;
+}
+
 // ---- --everything: multiset union of whole rows (doUnionAll / nextUnionAllLine, Bedops.cpp:761-786, :1468-1516) ----
 // Order: chromosome, start, end, strcmp of the rest of the line, file number.  Every row finds its output slot by
 // ranking itself in every other file (binary searches with that comparator: the inputs are sorted per sort-bed, which
@@ -1054,4 +1186,23 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
     return finish_text(ctx, d_out, bytes, rows, out_on_device, out);
   }
   return fail(ctx, BK_ERR_UNSUPPORTED, "bedops operation %d is outside the device hot path", op);
+}
+
+extern "C" int bk_chop(bk_ctx* ctx, const bk_bed* const* files, int n_files, uint64_t chunk, uint64_t stagger,
+                       int exclude_short, const char* chrom, int out_on_device, bk_text* out) {
+  if (!ctx || !files || !out || n_files < 1) return BK_ERR_ARG;
+  ctx->last_error.clear();
+  memset(out, 0, sizeof(*out));
+  for (int i = 0; i < n_files; i++)
+    if (!files[i]) return BK_ERR_ARG;
+  if (chunk == 0 || chunk > 0xFFFFFFFFull || stagger > 0xFFFFFFFFull) return fail(ctx, BK_ERR_ARG, "bp setting for chop must be > 0");
+  std::vector<IvList> in;
+  for (int i = 0; i < n_files; i++) in.push_back(view_of(files[i], chrom));
+  IvList u, c;
+  BK_TRY(union_merge(ctx, in, &u));
+  int rc = chop_list(ctx, u, (uint32_t)chunk, (uint32_t)stagger, exclude_short != 0, &c);
+  free_list(ctx, u);
+  if (rc == BK_OK) rc = emit_bed3(ctx, c, out_on_device, out);
+  free_list(ctx, c);
+  return rc;
 }

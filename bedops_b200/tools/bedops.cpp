@@ -18,6 +18,8 @@ struct Options {
   double subset = 1;  // Input::subsetPerc_
   bool   use_pct = true;
   bool   ec = false, has_range = false, full_left = false;
+  long   chop_bp = 1, chop_stagger = 0;  // Input::chopBP_, chopStaggerBP_
+  bool   chop_cut_short = false;
   std::string chrom = "all";
   std::vector<std::string> files;
 };
@@ -146,6 +148,38 @@ Options parse_args(int argc, char** argv) {
               }
             }
           }
+        } else if (o.mode == CHOP) {  // [chunk] [--stagger nt] [-x], Input.hpp:221-258
+          const char* ints = "1234567890";
+          bool value_set = false, aux_set = false, stagger_set = false;
+          int  cntr = 0;
+          while (i + 1 < argc) {
+            std::string a = argv[i + 1];
+            if (a == "--stagger") {
+              require(!stagger_set, "chop's --stagger suboption specified multiple times.");
+              require(i + 2 < argc, "No #nt value found for --stagger suboption in --chop");
+              std::string v = argv[i + 2];
+              require(cli::only_chars(v, ints), "Invalid --stagger suboption #nt value in --chop.  Expect a +integer.");
+              o.chop_stagger = std::atol(v.c_str());
+              require(o.chop_stagger > 0, "nt setting for chop's --stagger suboption must be > 0");
+              stagger_set = aux_set = true;
+              i += 2;
+            } else if (a == "-x") {
+              require(!o.chop_cut_short, "chop's -x suboption specified multiple times.");
+              o.chop_cut_short = aux_set = true;
+              i += 1;
+            } else if (!a.empty() && cli::only_chars(a, ints)) {
+              require(!value_set, "Stray integer found (invalid argument for --chop?)");
+              require(!aux_set, "Stray integer value found: not valid for --chop");
+              o.chop_bp = std::atol(a.c_str());
+              require(o.chop_bp > 0, "bp setting for chop must be > 0");
+              value_set = true;
+              i += 1;
+            } else {
+              break;
+            }
+            ++cntr;
+          }
+          require(cntr <= 4, "Too many arguments for a --chop operation");
         } else if (o.mode == COMPLEMENT) {
           while (i + 1 < argc && std::string(argv[i + 1]) == "-L") {
             o.full_left = true;
@@ -199,7 +233,8 @@ void usage(FILE* f) {
       "          -m, --merge                           Min: 1 file.\n"
       "          -n, --not-element-of [bp | percentage] Min: 2 files.\n"
       "          -s, --symmdiff                        Min: 2 files.\n"
-      "          -u, --everything                      Min: 1 file.\n\n",
+      "          -u, --everything                      Min: 1 file.\n"
+      "          -w, --chop [bp] [--stagger nt] [-x]   Min: 1 file.\n\n",
       f);
 }
 
@@ -218,6 +253,7 @@ int main(int argc, char** argv) {
       case DIFFERENCE: op = BK_SETOP_DIFFERENCE; break;
       case SYMMDIFF: op = BK_SETOP_SYMMDIFF; break;
       case UNIONALL: op = BK_SETOP_EVERYTHING; break;
+      case CHOP: op = -1; break;  // bk_chop
       default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
     if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
@@ -239,7 +275,9 @@ int main(int argc, char** argv) {
       for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, (((has_ref && f == 0) || all_lines) ? BK_COL_LINE : 0) | hdr));
       bk_text out;
       const double thr = op == BK_SETOP_COMPLEMENT ? (o.full_left ? 1.0 : 0.0) : o.subset;
-      int     rc = bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), thr, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
+      int     rc = op < 0 ? bk_chop(eng.ctx, beds.data(), (int)beds.size(), (uint64_t)o.chop_bp, (uint64_t)o.chop_stagger,
+                                    o.chop_cut_short ? 1 : 0, o.chrom.c_str(), 0, &out)
+                          : bk_setop(eng.ctx, op, beds.data(), (int)beds.size(), thr, o.use_pct ? 1 : 0, o.chrom.c_str(), 0, &out);
       if (rc != BK_OK) eng.raise(rc);
       std::string text(out.ptr ? out.ptr : "", out.len);
       bk_free_text(eng.ctx, &out);

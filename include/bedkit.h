@@ -193,6 +193,12 @@ enum {
 int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, double thr, int thr_is_pct,
              const char* chrom, int out_on_device, bk_text* out);
 
+/* --chop: the merged union of the files cut into pieces of `chunk` bases starting every `stagger` bases (0 = every
+ * chunk bases); a piece passing its segment's end is clipped, or with exclude_short (-x) ends the segment's pieces
+ * (doChop, Bedops.cpp:438-467; option grammar Input.hpp:221-258). */
+int bk_chop(bk_ctx* ctx, const bk_bed* const* files, int n_files, uint64_t chunk, uint64_t stagger, int exclude_short,
+            const char* chrom, int out_on_device, bk_text* out);
+
 /* ---- closest-features ----------------------------------------------------------------------- */
 typedef struct bk_cfspec {
   int         dist;        /* --dist */

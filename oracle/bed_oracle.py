@@ -476,6 +476,28 @@ def bedops_symmdiff(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> by
     return b"".join(out)
 
 
+def bedops_chop(texts: Sequence[bytes], chunk: int = 1, stagger: int = 0, exclude_short: bool = False,
+                chrom: Optional[bytes] = None) -> bytes:
+    """doChop (Bedops.cpp:438-467): every segment of the merged union is cut into pieces of `chunk` bases starting every
+    `stagger` bases (every `chunk` bases when stagger is 0); a piece that would pass the segment end is clipped to it,
+    or, with -x, ends the segment's pieces."""
+    u = merged_union([_sel(parse_bed(t, 3), chrom) for t in texts])
+    step = stagger if stagger else chunk
+    out = []
+    for c in sorted(u):
+        for s, e in u[c]:
+            i = s
+            while i < e:
+                pe = i + chunk
+                if pe > e:
+                    if exclude_short:
+                        break
+                    pe = e
+                out.append(c + b"\t%d\t%d\n" % (i, pe))
+                i += step
+    return b"".join(out)
+
+
 def bedops_everything(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
     """doUnionAll / nextUnionAllLine (Bedops.cpp:761-786, :1468-1516): multiset union of the rows of all files, every row
     printed as B3Rest (chrom, start, end re-printed, rest verbatim).  Order: chromosome, start, end, then strcmp of the

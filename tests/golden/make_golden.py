@@ -31,7 +31,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 sys.path.insert(0, ROOT)
 
 IN_SCOPE = ("-m", "-i", "-e", "-n", "--merge", "--intersect", "--element-of", "--not-element-of",
-            "-c", "-d", "-s", "--complement", "--difference", "--symmdiff")
+            "-c", "-d", "-s", "--complement", "--difference", "--symmdiff", "-w", "--chop")
 
 
 def update_string(s, chrom):
@@ -168,6 +168,8 @@ def synthetic():
             ("bedops", ["-c", "m.bed"]), ("bedops", ["-c", "-L", "m.bed", "r.bed"]), ("bedops", ["-d", "r.bed", "m.bed"]),
             ("bedops", ["-d", "dm.bed", "dr.bed", "m.bed"]), ("bedops", ["-s", "dr.bed", "dm.bed"]),
             ("bedops", ["-s", "m.bed", "m2.bed", "r.bed", "m3.bed"]), ("bedops", ["--chrom", "chr21", "-c", "-L", "dm.bed"]),
+            ("bedops", ["-w", "100", "r.bed", "m.bed"]), ("bedops", ["-w", "250", "--stagger", "100", "-x", "r.bed", "m.bed"]),
+            ("bedops", ["-w", "100", "--stagger", "30", "r.bed"]), ("bedops", ["--chrom", "chr3", "-w", "r.bed"]),
             ("bedops", ["-u", "m.bed", "m2.bed", "r.bed", "m3.bed"]), ("bedops", ["-u", "dr.bed", "dm.bed"]),
             ("bedops", ["--chrom", "chr7", "-u", "m.bed", "m3.bed"]),
             ("bedmap", ["--echo", "--echo-map", "dr.bed", "dm.bed"]),

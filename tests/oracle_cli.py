@@ -34,6 +34,22 @@ def parse_argv(tool, argv, known_files):
                 d["op"] = "symmdiff"
             elif a in ("-u", "--everything"):
                 d["op"] = "everything"
+            elif a in ("-w", "--chop"):
+                d["op"] = "chop"
+                d.update(chunk=1, stagger=0, exclude_short=False)
+                while i + 1 < len(argv):                      # Input.hpp:221-258
+                    n = argv[i + 1]
+                    if n == "--stagger":
+                        d["stagger"] = int(argv[i + 2])
+                        i += 2
+                    elif n == "-x":
+                        d["exclude_short"] = True
+                        i += 1
+                    elif n.isdigit() and n not in known_files:
+                        d["chunk"] = int(n)
+                        i += 1
+                    else:
+                        break
             elif a in ("-e", "--element-of", "-n", "--not-element-of"):
                 d["op"] = "element-of" if a in ("-e", "--element-of") else "not-element-of"
                 if i + 1 < len(argv) and argv[i + 1] not in known_files:
@@ -128,6 +144,8 @@ def run(tool, argv, files, stdin=None):
             return O.bedops_symmdiff(texts, d["chrom"])
         if d["op"] == "everything":
             return O.bedops_everything(texts, d["chrom"])
+        if d["op"] == "chop":
+            return O.bedops_chop(texts, d["chunk"], d["stagger"], d["exclude_short"], d["chrom"])
         return O.bedops_element_of(texts, d["thr"], d["pct"], d["op"] == "not-element-of", d["chrom"])
     if tool == "bedmap":
         return O.bedmap(texts[0], texts[1] if len(texts) > 1 else None, ops=d["ops"], overlap=d["overlap"],
@@ -146,7 +164,10 @@ def run_kit(kit, tool, argv, files, stdin=None):
         beds = [kit.load(t, 3, COL_LINE if ((k == 0 and d["op"].endswith("element-of")) or d["op"] == "everything") else 0)
                 for k, t in enumerate(texts)]
         thr = float(d["full_left"]) if d["op"] == "complement" else d["thr"]   # BK_SETOP_COMPLEMENT: thr != 0 is -L
-        out = kit.setop(d["op"], beds, thr, d["pct"], d["chrom"])
+        if d["op"] == "chop":
+            out = kit.chop(beds, d["chunk"], d["stagger"], d["exclude_short"], d["chrom"])
+        else:
+            out = kit.setop(d["op"], beds, thr, d["pct"], d["chrom"])
         for b in beds:
             b.free()
         return out

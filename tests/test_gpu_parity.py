@@ -305,6 +305,7 @@ def test_cli_tools_byte_identical_to_reference_binaries(tmp_path, synth_files):
             ("bedmap", ["--faster", "--delim", "\\t", "--sum", "--max", "--echo-map-id", "r.bed", "u.bed"]),
             ("bedmap", ["--count", "m3.bed"]), ("closest-features", ["--dist", "r.bed", "m.bed"]),
             ("bedops", ["-u", "r.bed", "m3.bed", "m.bed"]), ("bedops", ["-c", "-L", "r.bed", "m3.bed"]),
+            ("bedops", ["-w", "500", "--stagger", "200", "-x", "r.bed", "m3.bed"]), ("bedops", ["--chop", "r.bed"]),
             ("bedops", ["-d", "m.bed", "r.bed"]), ("bedops", ["-s", "m.bed", "r.bed", "m2.bed"]),
             ("bedmap", ["--echo", "--echo-map", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
             ("bedmap", ["--range", "200", "--echo-map-range", "--echo-map-size", "--echo-overlap-size", "--bases-uniq", "dr.bed", "dm.bed"]),
