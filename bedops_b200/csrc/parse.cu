@@ -172,8 +172,8 @@ __device__ __forceinline__ uint32_t parse_digits_swar(const unsigned char* sm, i
   uint32_t g0 = ld32u(sm, e - 4), g1 = ld32u(sm, e - 8);
   // bytes in front of the field (the lower bytes) are replaced by '0':  keep the top min(len,4) bytes of g0 and
   // the top clamp(len-4,0,4) bytes of g1
-  const uint32_t m0 = len >= 4 ? 0u : (0xFFFFFFFFu >> (8 * len));
-  const uint32_t m1 = len >= 8 ? 0u : (len <= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (8 * (len - 4))));
+  const uint64_t mm = len >= 8 ? 0ull : (~0ull >> (8 * len));  // one 64-bit shift instead of two compare/select chains
+  const uint32_t m1 = (uint32_t)mm, m0 = (uint32_t)(mm >> 32);
   g0 = (g0 & ~m0) | (0x30303030u & m0);
   g1 = (g1 & ~m1) | (0x30303030u & m1);
   uint32_t v = digits4(g1, bad) * 10000u + digits4(g0, bad);
