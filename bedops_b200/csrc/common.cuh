@@ -117,7 +117,7 @@ inline T* dalloc(bk_ctx* ctx, size_t n) {
 enum {
   SC_ERR_CODE = 0,   // first error code seen by any kernel (atomicCAS from 0)
   SC_ERR_ROW = 1,    // row / byte offset attached to it
-  SC_TICKET = 2,     // dynamic tile ticket for look-back kernels
+  SC_SPARE = 2,      // (was the tile ticket of the look-back kernels: no kernel waits on another CTA any more)
   SC_COUNT_A = 3,    // generic counters
   SC_COUNT_B = 4,
   SC_COUNT_C = 5,
@@ -161,15 +161,6 @@ __device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
                : "memory");
 }
 
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 __device__ __forceinline__ bool is_ws(unsigned char c) {  // isspace() minus '\n'
   return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f';
 }
@@ -185,68 +176,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     if (lane >= d) v += t;
   }
   return v;
-}
-
-// Block-wide exclusive scan of one u32 per thread (blockDim.x <= 1024, multiple of 32).
-// smem: at least 33 u32.  Returns the exclusive prefix; *total receives the block total (all threads).
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem, uint32_t* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  uint32_t incl = warp_incl_scan(v);
-  if (lane == 31) smem[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < nwarp ? smem[lane] : 0;
-    uint32_t wi = warp_incl_scan(w);
-    smem[lane] = wi - w;
-    if (lane == 31) smem[32] = wi;
-  }
-  __syncthreads();
-  uint32_t base = smem[warp];
-  *total = smem[32];
-  __syncthreads();
-  return base + incl - v;
-}
-
-// ---- decoupled look-back over self-contained 64-bit tile words --------------------------------------------
-// word = status(2 bits) << 62 | value(62 bits).  status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
-// Tiles are numbered by a dynamic ticket so that every predecessor is already resident (forward progress).
-constexpr uint64_t kTileValMask = (1ull << 62) - 1;
-
-// Sum look-back.  Call with all 32 lanes of one warp; every lane passes the same agg.  Returns the exclusive
-// prefix of this tile (sum of the aggregates of tiles 0..tile-1) in every lane.
-__device__ __forceinline__ uint64_t lookback_sum(uint64_t* state, uint32_t tile, uint64_t agg) {
-  const int lane = threadIdx.x & 31;
-  if (lane == 0) st_relaxed_u64(&state[tile], ((tile == 0 ? 2ull : 1ull) << 62) | agg);
-  if (tile == 0) return 0;
-  uint64_t excl = 0;
-  int64_t  look = (int64_t)tile - 1;
-  while (true) {
-    int64_t  idx = look - lane;
-    uint64_t w = 2ull << 62;  // virtual tiles before 0: inclusive prefix 0
-    if (idx >= 0) {
-      w = ld_relaxed_u64(&state[idx]);
-      while ((w >> 62) == 0) w = ld_relaxed_u64(&state[idx]);
-    }
-    unsigned done = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-    int      first = done ? (__ffs(done) - 1) : 31;
-    uint64_t c = (lane <= first) ? (w & kTileValMask) : 0;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    excl += c;
-    if (done) break;
-    look -= 32;
-  }
-  if (lane == 0) st_relaxed_u64(&state[tile], (2ull << 62) | (excl + agg));
-  return excl;
-}
-
-// dynamic tile ticket: one atomicAdd per tile, broadcast through shared memory
-__device__ __forceinline__ uint32_t next_ticket(uint64_t* scratch, uint32_t* smem_slot) {
-  if (threadIdx.x == 0) *smem_slot = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&scratch[SC_TICKET]), 1ull);
-  __syncthreads();
-  uint32_t t = *smem_slot;
-  __syncthreads();
-  return t;
 }
 
 // ---- binary searches over sorted u32 arrays -----------------------------------------------------------------

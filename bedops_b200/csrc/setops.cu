@@ -173,90 +173,99 @@ struct IsectParams {
   uint32_t*       outS;
   uint32_t*       outE;
   uint64_t*       run_out_begin;  // [nruns]
-  uint64_t*       tile_state;
-  uint32_t        ntiles;
-  uint64_t*       scratch;
-  uint64_t        out_cap;
+  uint32_t*       local;          // [n] pieces of the earlier rows of the same warp range (pass 1)
+  uint64_t*       range_total;    // [nranges]
+  const uint64_t* range_base;     // [nranges+1]
+  uint64_t        nranges;
 };
+constexpr int IS_RANGE = 1024;  // A rows per warp range
 
+// B's segments [lo,hi) that overlap A row `row`, and the number of pieces the row produces.
 // DIFF = false: pieces of A covered by B (intersection).  DIFF = true: pieces of A that B does NOT cover (difference,
-// nextDifferenceLine, Bedops.cpp:948-1018); B's segments [lo,hi) all overlap the A segment, are disjoint and sorted.
+// nextDifferenceLine, Bedops.cpp:948-1018); B's segments are disjoint and sorted.
+template <bool DIFF>
+__device__ __forceinline__ uint32_t isect_row(const IsectParams& p, uint64_t row, int& run, uint32_t& a0, uint32_t& a1,
+                                              uint64_t& lo, uint64_t& hi) {
+  int l = 0, h = p.nruns;
+  while (h - l > 1) {
+    const int mid = (l + h) >> 1;
+    if (p.run_a_begin[mid] <= row) l = mid; else h = mid;
+  }
+  run = l;
+  a0 = p.as[row];
+  a1 = p.ae[row];
+  const uint64_t bb = p.run_b_begin[l], bend = p.run_b_end[l];
+  lo = lower_bound_u32(p.be, bb, bend, (uint64_t)a0 + 1);  // first b.end > a.start
+  hi = lower_bound_u32(p.bs, bb, bend, (uint64_t)a1);      // first b.start >= a.end
+  if (hi < lo) hi = lo;
+  if (!DIFF) return (uint32_t)(hi - lo);
+  uint32_t np = (uint32_t)(hi - lo) + 1;
+  if (hi > lo) {
+    if (p.bs[lo] <= a0) np--;      // no piece in front of the first covering segment
+    if (p.be[hi - 1] >= a1) np--;  // none behind the last
+  }
+  return np;
+}
+
+// pass 1: pieces per row, warp-local prefixes over contiguous ranges of rows (no carry chain between tiles)
+template <bool DIFF>
+__global__ void __launch_bounds__(SEG_THREADS) k_intersect_count(IsectParams p) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * SEG_THREADS + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * SEG_THREADS) >> 5;
+  for (uint64_t r = w0; r < p.nranges; r += nw) {
+    const uint64_t a = r * IS_RANGE, b = a + IS_RANGE < p.n ? a + IS_RANGE : p.n;
+    uint64_t       acc = 0;
+    for (uint64_t k0 = a; k0 < b; k0 += 32) {
+      const uint64_t i = k0 + lane;
+      uint32_t       np = 0;
+      if (i < b) {
+        int      run;
+        uint32_t a0, a1;
+        uint64_t lo, hi;
+        np = isect_row<DIFF>(p, p.row0 + i, run, a0, a1, lo, hi);
+      }
+      const uint32_t incl = warp_incl_scan(np);
+      if (i < b) p.local[i] = (uint32_t)acc + (incl - np);  // a range of 1024 rows of 32-bit counts: < 2^42, host-checked
+      acc += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) p.range_total[r] = acc;
+  }
+}
+
+// pass 2: every row writes its pieces at range_base + local
 template <bool DIFF>
 __global__ void __launch_bounds__(SEG_THREADS) k_intersect(IsectParams p) {
-  __shared__ uint32_t scan_sm[34];
-  __shared__ uint32_t ticket_sm;
-  __shared__ uint64_t base_sm;
-  const int tid = threadIdx.x;
-  while (true) {
-    const uint32_t tile = next_ticket(p.scratch, &ticket_sm);
-    if (tile >= p.ntiles) break;
-    const uint64_t i = (uint64_t)tile * SEG_THREADS + tid;
-    uint64_t       lo = 0, hi = 0;
-    uint32_t       a0 = 0, a1 = 0;
-    int            run = 0;
-    bool           runhead = false;
-    if (i < p.n) {
-      const uint64_t row = p.row0 + i;
-      int l = 0, h = p.nruns;
-      while (h - l > 1) {
-        int mid = (l + h) >> 1;
-        if (p.run_a_begin[mid] <= row) l = mid; else h = mid;
-      }
-      run = l;
-      runhead = p.run_a_begin[l] == row;
-      a0 = p.as[row];
-      a1 = p.ae[row];
-      const uint64_t bb = p.run_b_begin[l], bend = p.run_b_end[l];
-      lo = lower_bound_u32(p.be, bb, bend, (uint64_t)a0 + 1);  // first b.end > a.start
-      hi = lower_bound_u32(p.bs, bb, bend, (uint64_t)a1);      // first b.start >= a.end
-      if (hi < lo) hi = lo;
-    }
-    uint32_t npieces = (uint32_t)(hi - lo);
-    if (DIFF && i < p.n) {
-      npieces = (uint32_t)(hi - lo) + 1;
-      if (hi > lo) {
-        if (p.bs[lo] <= a0) npieces--;       // no piece in front of the first covering segment
-        if (p.be[hi - 1] >= a1) npieces--;   // none behind the last
-      }
-    }
-    uint32_t total;
-    uint32_t ex = block_excl_scan(npieces, scan_sm, &total);
-    if (tid < 32) {
-      uint64_t b = lookback_sum(p.tile_state, tile, total);
-      if (tid == 0) {
-        base_sm = b;
-        if (tile == p.ntiles - 1) p.scratch[SC_OUT_ROWS] = b + total;
-      }
-    }
-    __syncthreads();
-    uint64_t o = base_sm + ex;
-    if (i < p.n) {
-      if (runhead) p.run_out_begin[run] = o;
-      if (DIFF) {
-        uint32_t cur = a0;
-        for (uint64_t k = lo; k < hi; k++) {
-          const uint32_t b0 = p.bs[k], b1 = p.be[k];
-          if (b0 > cur && o < p.out_cap) {
-            p.outS[o] = cur;
-            p.outE[o] = b0;
-            o++;
-          }
-          cur = b1 > cur ? b1 : cur;
-        }
-        if (cur < a1 && o < p.out_cap) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const uint64_t row = p.row0 + i;
+    int            run;
+    uint32_t       a0, a1;
+    uint64_t       lo, hi;
+    isect_row<DIFF>(p, row, run, a0, a1, lo, hi);
+    uint64_t o = p.range_base[i / IS_RANGE] + p.local[i];
+    if (p.run_a_begin[run] == row) p.run_out_begin[run] = o;
+    if (DIFF) {
+      uint32_t cur = a0;
+      for (uint64_t k = lo; k < hi; k++) {
+        const uint32_t b0 = p.bs[k], b1 = p.be[k];
+        if (b0 > cur) {
           p.outS[o] = cur;
-          p.outE[o] = a1;
+          p.outE[o] = b0;
+          o++;
         }
-      } else {
-        for (uint64_t k = lo; k < hi; k++, o++) {
-          if (o >= p.out_cap) break;
-          const uint32_t b0 = p.bs[k], b1 = p.be[k];
-          p.outS[o] = a0 > b0 ? a0 : b0;
-          p.outE[o] = a1 < b1 ? a1 : b1;
-        }
+        cur = b1 > cur ? b1 : cur;
+      }
+      if (cur < a1) {
+        p.outS[o] = cur;
+        p.outE[o] = a1;
+      }
+    } else {
+      for (uint64_t k = lo; k < hi; k++, o++) {
+        const uint32_t b0 = p.bs[k], b1 = p.be[k];
+        p.outS[o] = a0 > b0 ? a0 : b0;
+        p.outE[o] = a1 < b1 ? a1 : b1;
       }
     }
-    __syncthreads();
   }
 }
 
@@ -576,27 +585,41 @@ static int intersect_pair(bk_ctx* ctx, const IvList& A, const IvList& B, IvList*
   p.as = A.s; p.ae = A.e; p.row0 = row0; p.n = n;
   p.run_a_begin = upload(ctx, ab); p.run_b_begin = upload(ctx, bb); p.run_b_end = upload(ctx, be); p.nruns = nruns;
   p.bs = B.s; p.be = B.e;
-  p.out_cap = n + B.n + 1;  // pieces <= |A| + |B|
-  p.outS = dalloc<uint32_t>(ctx, p.out_cap); p.outE = dalloc<uint32_t>(ctx, p.out_cap);
+  p.nranges = (n + IS_RANGE - 1) / IS_RANGE;
+  if (p.nranges >> 32) return fail(ctx, BK_ERR_UNSUPPORTED, "too many rows for one set operation");
   p.run_out_begin = dalloc<uint64_t>(ctx, nruns);
-  p.ntiles = (uint32_t)((n + SEG_THREADS - 1) / SEG_THREADS);
-  p.tile_state = dalloc<uint64_t>(ctx, p.ntiles);
-  p.scratch = ctx->d_scratch;
-  if (!p.run_a_begin || !p.run_b_begin || !p.run_b_end || !p.outS || !p.outE || !p.run_out_begin || !p.tile_state)
+  p.local = dalloc<uint32_t>(ctx, n);
+  p.range_total = dalloc<uint64_t>(ctx, p.nranges);
+  uint64_t* d_base = dalloc<uint64_t>(ctx, p.nranges + 1);
+  if (!p.run_a_begin || !p.run_b_begin || !p.run_b_end || !p.run_out_begin || !p.local || !p.range_total || !d_base)
     return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemsetAsync(p.tile_state, 0, (size_t)p.ntiles * 8, ctx->stream));
+  p.range_base = d_base;
+  BK_CUDA(ctx, cudaMemsetAsync(p.run_out_begin, 0, (size_t)nruns * 8, ctx->stream));
   BK_TRY(reset_scratch(ctx));
+  const uint64_t want = (p.nranges + SEG_THREADS / 32 - 1) / (SEG_THREADS / 32);
+  prof_begin(ctx, diff ? "k_difference_count" : "k_intersect_count");
+  if (diff) k_intersect_count<true><<<grid_for_kernel((const void*)k_intersect_count<true>, SEG_THREADS, want), SEG_THREADS, 0, ctx->stream>>>(p);
+  else k_intersect_count<false><<<grid_for_kernel((const void*)k_intersect_count<false>, SEG_THREADS, want), SEG_THREADS, 0, ctx->stream>>>(p);
+  prof_end(ctx);
+  BK_LAUNCHED(ctx);
+  k_scan_totals<SC_OUT_ROWS><<<1, 1024, 0, ctx->stream>>>(p.range_total, d_base, (uint32_t)p.nranges, ctx->d_scratch);
+  BK_LAUNCHED(ctx);
+  BK_TRY(read_scratch(ctx));  // exact output size (and: the uploaded host vectors have been copied)
+  const uint64_t nout = ctx->h_scratch[SC_OUT_ROWS];
+  p.outS = dalloc<uint32_t>(ctx, nout);
+  p.outE = dalloc<uint32_t>(ctx, nout);
+  if (!p.outS || !p.outE) return BK_ERR_NOMEM;
+  const uint64_t blocks = (n + SEG_THREADS - 1) / SEG_THREADS, cap = (uint64_t)kSMs * 32;
   prof_begin(ctx, diff ? "k_difference" : "k_intersect");
-  if (diff) k_intersect<true><<<grid_for_kernel((const void*)k_intersect<true>, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
-  else k_intersect<false><<<grid_for_kernel((const void*)k_intersect<false>, SEG_THREADS, p.ntiles), SEG_THREADS, 0, ctx->stream>>>(p);
+  if (diff) k_intersect<true><<<(unsigned)(blocks < cap ? blocks : cap), SEG_THREADS, 0, ctx->stream>>>(p);
+  else k_intersect<false><<<(unsigned)(blocks < cap ? blocks : cap), SEG_THREADS, 0, ctx->stream>>>(p);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   std::vector<uint64_t> rob(nruns);
   BK_CUDA(ctx, cudaMemcpyAsync(rob.data(), p.run_out_begin, (size_t)nruns * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  BK_TRY(read_scratch(ctx));
-  const uint64_t nout = ctx->h_scratch[SC_OUT_ROWS];
+  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   dfree(ctx, (void*)p.run_a_begin); dfree(ctx, (void*)p.run_b_begin); dfree(ctx, (void*)p.run_b_end);
-  dfree(ctx, p.run_out_begin); dfree(ctx, p.tile_state);
+  dfree(ctx, p.run_out_begin); dfree(ctx, p.local); dfree(ctx, p.range_total); dfree(ctx, d_base);
   out->s = p.outS; out->e = p.outE; out->n = nout;
   for (int r = 0; r < nruns; r++) out->runs.push_back({names[r], rob[r], r + 1 < nruns ? rob[r + 1] : nout});
   return BK_OK;
