@@ -503,6 +503,46 @@ struct BedmapRow {
     }
   }
 
+  // --echo-map-id-uniq: the distinct ids of the qualifying map rows in strcmp order (std::set<std::string>,
+  // ProcessBedVisitorRow.hpp:361-389).  Selection by repeated minimum: every round emits the smallest id greater than
+  // the one emitted before -- quadratic in the hits, a rare operation on windows of tens of rows.
+  __device__ __forceinline__ int cmp_id(const char* a, uint32_t la, const char* b, uint32_t lb) const {
+    const uint32_t n = la < lb ? la : lb;
+    for (uint32_t k = 0; k < n; k++) {
+      const unsigned char x = (unsigned char)a[k], y = (unsigned char)b[k];
+      if (x != y) return x < y ? -1 : 1;
+    }
+    return la == lb ? 0 : (la < lb ? -1 : 1);
+  }
+  template <class Sink>
+  __device__ __noinline__ void uniq_ids(Sink& s, uint64_t i, uint64_t row) const {
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    const char*    last = nullptr;
+    uint32_t       last_len = 0;
+    while (true) {
+      const char* best = nullptr;
+      uint32_t    best_len = 0;
+      for (uint64_t k = lo; k < hi; k++) {
+        uint32_t ovl;
+        if (!qualifies(ov, a, b, ms[k], me[k], ovl)) continue;
+        const uint32_t sp = midspan[k];
+        const char*    id = mtext + (mline[k] & kLineOffMask) + (sp >> 16);
+        const uint32_t len = sp & 0xFFFFu;
+        if (last && cmp_id(id, len, last, last_len) <= 0) continue;
+        if (!best || cmp_id(id, len, best, best_len) < 0) {
+          best = id;
+          best_len = len;
+        }
+      }
+      if (!best) break;
+      if (last) s.puts_(mdelim, mdelim_len);
+      s.copy(best, best_len);
+      last = best;
+      last_len = best_len;
+    }
+  }
+
   template <class Sink>
   __device__ void operator()(uint64_t i, Sink& s) const {
     const uint32_t cnt = count[i];
@@ -544,6 +584,9 @@ struct BedmapRow {
         case BK_OP_ECHO_MAP_RANGE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
         case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV:
           if (RARE & 4) window_op(s, ops[c], i, row);
+          break;
+        case BK_OP_ECHO_MAP_ID_UNIQ:
+          if (RARE & 4) uniq_ids(s, i, row);
           break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
@@ -625,6 +668,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       case BK_OP_ECHO_MAP_RANGE: need |= NEED_IDS; need_refline = true; window_ops = true; break;
       case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
         need |= NEED_IDS; window_ops = true; break;
+      case BK_OP_ECHO_MAP_ID_UNIQ: need |= NEED_IDS; need_ids = true; window_ops = true; break;
       case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }

@@ -19,7 +19,7 @@ const OpInfo kOps[] = {
     {"echo", BK_OP_ECHO, 3, 0},            {"echo-ref-size", BK_OP_ECHO_REF_SIZE, 3, 0},
     {"echo-ref-name", BK_OP_ECHO_REF_NAME, 3, 0},                             {"echo-ref-row-id", BK_OP_ECHO_REF_ROW_ID, 3, 0},
     {"echo-map", BK_OP_ECHO_MAP, 3, 0},                 {"echo-map-id", BK_OP_ECHO_MAP_ID, 4, 0},
-    {"echo-map-id-uniq", 0, 4, 0},         {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, 0},        {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, 0},
+    {"echo-map-id-uniq", BK_OP_ECHO_MAP_ID_UNIQ, 4, 0},         {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, 0},        {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, 0},
     {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, 0},           {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
     {"indicator", BK_OP_INDICATOR, 3, 0},  {"max", BK_OP_MAX, 5, 0},          {"max-element-rand", 0, 5, 0},
     {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
@@ -206,7 +206,7 @@ void usage(FILE* f) {
       "      --bp-ovr <int>, --exact, --fraction-both <val>, --fraction-either <val>, --fraction-map <val>,\n"
       "      --fraction-ref <val>, --range <int>\n\n"
       "     Operations on this build's B200 hot path:\n"
-      "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-range\n"
+      "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-id-uniq --echo-map-range\n"
       "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
       "      --cv --indicator --max --mean --min --stdev --sum --variance\n\n",
       f);
@@ -231,7 +231,7 @@ int main(int argc, char** argv) {
       need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
       need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE ||
                     op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV;
-      need_id |= op == BK_OP_ECHO_MAP_ID;
+      need_id |= op == BK_OP_ECHO_MAP_ID || op == BK_OP_ECHO_MAP_ID_UNIQ;
       need_mapline |= op == BK_OP_ECHO_MAP;
     }
     spec.overlap_kind = o.overlap_kind;

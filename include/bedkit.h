@@ -138,7 +138,8 @@ enum { /* operations, printed left to right in the order given (MultiVisitor.hpp
   /* (n*sum(x^2) - sum(x)^2) / (n*(n-1)); NAN for fewer than two hits (map needs BK_COL_SCORE) */
   BK_OP_VARIANCE = 20,          /* --variance           VarianceVisitor.hpp:58-66 */
   BK_OP_STDEV = 21,             /* --stdev              StdevVisitor.hpp */
-  BK_OP_CV = 22                 /* --cv                 CoeffVariationVisitor.hpp (NAN when the mean is 0) */
+  BK_OP_CV = 22,                /* --cv                 CoeffVariationVisitor.hpp (NAN when the mean is 0) */
+  BK_OP_ECHO_MAP_ID_UNIQ = 23   /* --echo-map-id-uniq   distinct ids in strcmp order (ProcessBedVisitorRow.hpp:361-389); BK_COL_ID|BK_COL_LINE */
 };
 enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */

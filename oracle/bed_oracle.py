@@ -195,7 +195,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     for o in ops:
         if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv"):
             need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
-        elif o == "echo-map-id":
+        elif o in ("echo-map-id", "echo-map-id-uniq"):
             need_fields = max(need_fields, 4)
     single = map_text is None
     maps = parse_bed(ref_text if single else map_text, need_fields)
@@ -307,6 +307,8 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                     cols.append(str(ovr).encode())
                 else:
                     cols.append(_fmt_score(float(ovr) / float(r.end - r.start), prec, sci))
+            elif o == "echo-map-id-uniq":  # PrintUniqueRangeIDs (ProcessBedVisitorRow.hpp:361-389): std::set<std::string>
+                cols.append(multidelim.join(sorted(set(m.id for m in hits))))
             elif o == "echo-ref-size":
                 cols.append(str(r.end - r.start).encode())
             elif o == "echo-ref-name":

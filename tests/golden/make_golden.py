@@ -183,6 +183,7 @@ def synthetic():
                         "dr.bed", "dm.bed"]),
             ("bedmap", ["--sci", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map-size", "--bases-uniq", "dm.bed"]),
+            ("bedmap", ["--echo-map-id-uniq", "--echo-map-id", "--count", "dr.bed", "dm.bed"]),
             ("bedmap", ["--variance", "--stdev", "--cv", "--mean", "dr.bed", "dm.bed"]),
             ("bedmap", ["--sci", "--prec", "9", "--range", "500", "--stdev", "--cv", "dr.bed", "dm.bed"]),
             ("closest-features", ["--dist", "r.bed", "m.bed"]),

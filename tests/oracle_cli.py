@@ -4,7 +4,7 @@ import bed_oracle as O
 
 BEDMAP_OPS = {"echo", "count", "indicator", "bases", "sum", "mean", "max", "min", "echo-map-id", "echo-ref-size",
               "echo-ref-name", "echo-ref-row-id", "echo-map", "echo-map-score", "echo-map-size", "echo-overlap-size",
-              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv"}
+              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv", "echo-map-id-uniq"}
 
 
 def parse_argv(tool, argv, known_files):
@@ -174,7 +174,7 @@ def run_kit(kit, tool, argv, files, stdin=None):
     if tool == "bedmap":
         ops = d["ops"]
         score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv") for o in ops)
-        ids = "echo-map-id" in ops
+        ids = "echo-map-id" in ops or "echo-map-id-uniq" in ops
         line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)
         mf = 5 if score else (4 if ids else 3)
         mcols = (COL_SCORE if score else 0) | ((COL_ID | COL_LINE) if ids else 0) | (COL_LINE if "echo-map" in ops else 0)

@@ -71,7 +71,7 @@ def rand_bed(rng, n, span, chroms, fields=5, unique=False, disjoint=False, messy
 BEDMAP_SCORE = ["--sum", "--mean", "--max", "--min", "--variance", "--stdev", "--cv"]
 BEDMAP_PLAIN = ["--echo", "--count", "--indicator", "--bases", "--echo-ref-size", "--echo-ref-name", "--bases-uniq",
                 "--bases-uniq-f", "--echo-map-size", "--echo-overlap-size", "--echo-map-range"]
-BEDMAP_LIST = ["--echo-map", "--echo-map-id", "--echo-map-score"]
+BEDMAP_LIST = ["--echo-map", "--echo-map-id", "--echo-map-score", "--echo-map-id-uniq"]
 OVERLAPS = [[], ["--bp-ovr", "3"], ["--range", "5"], ["--fraction-ref", "0.5"], ["--fraction-map", "0.4"],
             ["--fraction-either", "0.6"], ["--fraction-both", "0.3"], ["--exact"]]
 
