@@ -13,7 +13,7 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
        "echo-map-id": 9, "echo-ref-size": 10, "echo-ref-name": 11, "echo-ref-row-id": 12, "echo-map": 13,
        "echo-map-score": 14, "echo-map-size": 15, "echo-overlap-size": 16, "echo-map-range": 17, "bases-uniq": 18,
        "bases-uniq-f": 19, "variance": 20, "stdev": 21, "cv": 22,
-       "echo-map-id-uniq": 23}
+       "echo-map-id-uniq": 23, "median": 24, "kth": 25}
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4, "complement": 5, "difference": 6,
@@ -35,7 +35,7 @@ class _MapSpec(C.Structure):
     _fields_ = [("n_ops", C.c_int), ("ops", C.c_int * BK_MAX_OPS), ("overlap_kind", C.c_int),
                 ("overlap_bp", C.c_uint64), ("overlap_frac", C.c_double), ("precision", C.c_int), ("sci", C.c_int),
                 ("skip_unmapped", C.c_int), ("delim", C.c_char_p), ("multidelim", C.c_char_p),
-                ("chrom", C.c_char_p), ("out_on_device", C.c_int)]
+                ("chrom", C.c_char_p), ("out_on_device", C.c_int), ("op_arg", C.c_double * BK_MAX_OPS)]
 
 
 class _CfSpec(C.Structure):
@@ -296,7 +296,9 @@ class BedKit:
         self.lib.bk_mapspec_default(C.byref(spec))
         spec.n_ops = len(ops)
         for k, o in enumerate(ops):
-            spec.ops[k] = OPS[o]
+            name, _, arg = o.partition(":")          # "kth:0.25"
+            spec.ops[k] = OPS[name]
+            spec.op_arg[k] = float(arg) if arg else 0.0
         kind, val = overlap
         spec.overlap_kind = OVERLAP[kind]
         if kind in ("bp", "range"):

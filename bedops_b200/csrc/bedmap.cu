@@ -343,6 +343,7 @@ struct BedmapRow {
   OverlapSpec     ov;
   int             n_ops;
   unsigned char   ops[BK_MAX_OPS];
+  double          kth_arg[BK_MAX_OPS];  // BK_OP_KTH fraction
   int             prec;
   int             sci;
   int             skip_unmapped;
@@ -543,6 +544,50 @@ struct BedmapRow {
     }
   }
 
+  // --median / --kth: generalised median of the qualifying scores (RollingKthAverageVisitor.hpp:37-68).  The element
+  // at a sorted position is found by rank counting (value, then file order): quadratic in the hits, a rare operation.
+  __device__ __forceinline__ double score_at_rank(uint64_t lo, uint64_t hi, uint32_t a, uint32_t b, uint32_t want) const {
+    for (uint64_t x = lo; x < hi; x++) {
+      uint32_t ovl;
+      if (!qualifies(ov, a, b, ms[x], me[x], ovl)) continue;
+      const double vx = mscore[x];
+      uint32_t     rank = 0;
+      for (uint64_t y = lo; y < hi; y++) {
+        if (!qualifies(ov, a, b, ms[y], me[y], ovl)) continue;
+        const double vy = mscore[y];
+        rank += (vy < vx || (vy == vx && y < x)) ? 1u : 0u;
+      }
+      if (rank == want) return vx;
+    }
+    return 0.0;
+  }
+  template <class Sink>
+  __device__ __noinline__ void kth_op(Sink& s, uint64_t i, uint64_t row, double k) const {
+    const uint32_t n = count[i];
+    if (n == 0) {
+      s.puts_("NAN", 3);
+      return;
+    }
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    if (n == 1) {
+      put_score(s, score_at_rank(lo, hi, a, b, 0), 1, i);
+      return;
+    }
+    const double kn = k * (double)n;
+    const double cl = ceil(kn), fl = floor(kn);
+    uint32_t     up = (uint32_t)cl, down = (uint32_t)fl, pos = (uint32_t)((cl - kn > 0.5) ? fl : cl);  // iround
+    if (up) up--;
+    if (down) down--;
+    if (pos) pos--;
+    if (up == down) {  // "a true integer" (also whenever floor(k*n) is 0): the average of two neighbours
+      const double one = score_at_rank(lo, hi, a, b, pos), two = score_at_rank(lo, hi, a, b, pos + 1);
+      put_score(s, (one + two) / 2.0, 1, i);
+    } else {
+      put_score(s, score_at_rank(lo, hi, a, b, pos == up ? pos : pos + 1), 1, i);
+    }
+  }
+
   template <class Sink>
   __device__ void operator()(uint64_t i, Sink& s) const {
     const uint32_t cnt = count[i];
@@ -587,6 +632,9 @@ struct BedmapRow {
           break;
         case BK_OP_ECHO_MAP_ID_UNIQ:
           if (RARE & 4) uniq_ids(s, i, row);
+          break;
+        case BK_OP_MEDIAN: case BK_OP_KTH:
+          if (RARE & 4) kth_op(s, i, row, ops[c] == BK_OP_MEDIAN ? 0.5 : kth_arg[c]);
           break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
@@ -669,6 +717,11 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       case BK_OP_ECHO_MAP_SIZE: case BK_OP_ECHO_OVERLAP_SIZE: case BK_OP_BASES_UNIQ: case BK_OP_BASES_UNIQ_F:
         need |= NEED_IDS; window_ops = true; break;
       case BK_OP_ECHO_MAP_ID_UNIQ: need |= NEED_IDS; need_ids = true; window_ops = true; break;
+      case BK_OP_KTH:
+        if (!(spec->op_arg[c] > 0.0 && spec->op_arg[c] < 1.0))
+          return fail(ctx, BK_ERR_UNSUPPORTED, "--kth %g: the device path supports 0 < val < 1", spec->op_arg[c]);
+        need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      case BK_OP_MEDIAN: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }
@@ -802,7 +855,10 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
     fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
     fn.ov = ov; fn.n_ops = spec->n_ops;
-    for (int c = 0; c < spec->n_ops; c++) fn.ops[c] = (unsigned char)spec->ops[c];
+    for (int c = 0; c < spec->n_ops; c++) {
+      fn.ops[c] = (unsigned char)spec->ops[c];
+      fn.kth_arg[c] = spec->op_arg[c];
+    }
     fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
     fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
     fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);

@@ -25,13 +25,14 @@ const OpInfo kOps[] = {
     {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
     {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
     {"stdev", BK_OP_STDEV, 5, 0},                    {"cv", BK_OP_CV, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
-    {"wmean", 0, 5, 0},                    {"median", 0, 5, 0},               {"mad", 0, 5, -1},
-    {"kth", 0, 5, 1},                      {"tmean", 0, 5, 2},
+    {"wmean", 0, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", 0, 5, -1},
+    {"kth", BK_OP_KTH, 5, 1},                      {"tmean", 0, 5, 2},
 };
 
 struct Options {
   std::string ref, map;
   std::vector<int> ops;
+  std::vector<double> op_args;  // parallel to ops (--kth <val>)
   std::string unsupported_op;
   int         overlap_kind = -1;
   long        range_bp = 0, overlap_bp = 0;
@@ -147,14 +148,24 @@ Options parse_args(int argc, char** argv) {
       for (const OpInfo& k : kOps)
         if (next == k.name) info = &k;
       if (!info) throw UserError("Unknown option: --" + next);
+      double op_arg = 0;
       if (info->nargs > 0) {
         require(i + info->nargs <= argc, "No arg for --" + next);
+        if (info->op == BK_OP_KTH) {  // Input.hpp:290-302
+          const std::string sval = argv[i];
+          require(cli::only_chars(sval, reals), "Non-numeric argument: " + sval + " for --" + next);
+          op_arg = -1;
+          std::stringstream conv(sval);
+          conv >> op_arg;
+          require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= val <= 1");
+        }
         i += info->nargs;
       } else if (info->nargs < 0 && i < argc && cli::only_chars(argv[i], reals)) {
         i++;  // optional multiplier of --mad
       }
       if (!info->op && o.unsupported_op.empty()) o.unsupported_op = next;
       o.ops.push_back(info->op);
+      o.op_args.push_back(op_arg);
       o.min_map_fields = std::max(o.min_map_fields, info->map_fields);
       o.min_ref_fields = std::max(o.min_ref_fields, 3);
       has_op = true;
@@ -208,7 +219,7 @@ void usage(FILE* f) {
       "     Operations on this build's B200 hot path:\n"
       "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-id-uniq --echo-map-range\n"
       "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
-      "      --cv --indicator --max --mean --min --stdev --sum --variance\n\n",
+      "      --cv --indicator --kth <val> --max --mean --median --min --stdev --sum --variance\n\n",
       f);
 }
 
@@ -226,11 +237,13 @@ int main(int argc, char** argv) {
     bk_mapspec spec;
     bk_mapspec_default(&spec);
     bool need_line = false, need_score = false, need_id = false, need_mapline = false;
-    for (int op : o.ops) {
+    for (size_t k = 0; k < o.ops.size(); k++) {
+      const int op = o.ops[k];
+      spec.op_arg[spec.n_ops] = o.op_args[k];
       spec.ops[spec.n_ops++] = op;
       need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
       need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE ||
-                    op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV;
+                    op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV || op == BK_OP_MEDIAN || op == BK_OP_KTH;
       need_id |= op == BK_OP_ECHO_MAP_ID || op == BK_OP_ECHO_MAP_ID_UNIQ;
       need_mapline |= op == BK_OP_ECHO_MAP;
     }

@@ -193,7 +193,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     identical for exactly representable partial sums, see DESIGN.md parity notes)."""
     need_fields = 3
     for o in ops:
-        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv"):
+        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:"):
             need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
         elif o in ("echo-map-id", "echo-map-id-uniq"):
             need_fields = max(need_fields, 4)
@@ -261,6 +261,29 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                     cols.append(_fmt_score(v, prec, sci))
             elif o == "echo-map-id":     # EchoMapBedVisitor.hpp:39-66 (ties in file order, SURVEY hazard 2)
                 cols.append(multidelim.join(m.id for m in hits))
+            elif o == "median" or o.startswith("kth:"):
+                # RollingKthAverage over RollingKth (RollingKthAverageVisitor.hpp:37-68, RollingKthVisitor.hpp:75-95):
+                # the marker sits at iround(k*n)-1; a "true integer" k*n averages two neighbours -- which also happens
+                # whenever floor(k*n) == 0, because positions are only decremented when they are positive
+                k = 0.5 if o == "median" else float(o[4:])
+                v = sorted(m.score for m in hits)
+                n = len(v)
+                if n == 0:
+                    cols.append(b"NAN")
+                elif n == 1:
+                    cols.append(_fmt_score(v[0], prec, sci))
+                else:
+                    kn = k * n
+                    up, down = math.ceil(kn), math.floor(kn)
+                    d1 = math.ceil(kn)
+                    pos = math.floor(kn) if d1 - kn > 0.5 else d1       # iround, RollingKthVisitor.hpp:117-124
+                    up, down, pos = (x - 1 if x > 0 else x for x in (up, down, pos))
+                    if up == down:
+                        cols.append(_fmt_score((v[pos] + v[pos + 1]) / 2.0, prec, sci))
+                    elif pos == up:
+                        cols.append(_fmt_score(v[pos], prec, sci))
+                    else:
+                        cols.append(_fmt_score(v[pos + 1], prec, sci))
             elif o in ("variance", "stdev", "cv"):  # VarianceVisitor.hpp:58-66, StdevVisitor.hpp, CoeffVariationVisitor.hpp
                 sm = sq = 0.0
                 for m in hits:

@@ -184,6 +184,7 @@ def synthetic():
             ("bedmap", ["--sci", "--echo-map-score", "--bases-uniq-f", "dr.bed", "dm.bed"]),
             ("bedmap", ["--echo-map-size", "--bases-uniq", "dm.bed"]),
             ("bedmap", ["--echo-map-id-uniq", "--echo-map-id", "--count", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--median", "--kth", "0.25", "--kth", "0.9", "--count", "dr.bed", "dm.bed"]),
             ("bedmap", ["--variance", "--stdev", "--cv", "--mean", "dr.bed", "dm.bed"]),
             ("bedmap", ["--sci", "--prec", "9", "--range", "500", "--stdev", "--cv", "dr.bed", "dm.bed"]),
             ("closest-features", ["--dist", "r.bed", "m.bed"]),

@@ -4,7 +4,7 @@ import bed_oracle as O
 
 BEDMAP_OPS = {"echo", "count", "indicator", "bases", "sum", "mean", "max", "min", "echo-map-id", "echo-ref-size",
               "echo-ref-name", "echo-ref-row-id", "echo-map", "echo-map-score", "echo-map-size", "echo-overlap-size",
-              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv", "echo-map-id-uniq"}
+              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv", "echo-map-id-uniq", "median"}
 
 
 def parse_argv(tool, argv, known_files):
@@ -70,6 +70,9 @@ def parse_argv(tool, argv, known_files):
             a = argv[i]
             if a.startswith("--") and a[2:] in BEDMAP_OPS:
                 d["ops"].append(a[2:])
+            elif a == "--kth":
+                i += 1
+                d["ops"].append("kth:" + argv[i])
             elif a == "--prec":
                 i += 1
                 d["prec"] = int(argv[i])
@@ -173,7 +176,8 @@ def run_kit(kit, tool, argv, files, stdin=None):
         return out
     if tool == "bedmap":
         ops = d["ops"]
-        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv") for o in ops)
+        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:")
+                    for o in ops)
         ids = "echo-map-id" in ops or "echo-map-id-uniq" in ops
         line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)
         mf = 5 if score else (4 if ids else 3)

@@ -68,7 +68,7 @@ def rand_bed(rng, n, span, chroms, fields=5, unique=False, disjoint=False, messy
     return text.encode()
 
 
-BEDMAP_SCORE = ["--sum", "--mean", "--max", "--min", "--variance", "--stdev", "--cv"]
+BEDMAP_SCORE = ["--sum", "--mean", "--max", "--min", "--variance", "--stdev", "--cv", "--median", "--kth 0.3", "--kth 0.75"]
 BEDMAP_PLAIN = ["--echo", "--count", "--indicator", "--bases", "--echo-ref-size", "--echo-ref-name", "--bases-uniq",
                 "--bases-uniq-f", "--echo-map-size", "--echo-overlap-size", "--echo-map-range"]
 BEDMAP_LIST = ["--echo-map", "--echo-map-id", "--echo-map-score", "--echo-map-id-uniq"]
@@ -91,6 +91,7 @@ def make_case(seed, for_binary):
         lists = list(rng.choice(BEDMAP_LIST, int(rng.integers(0, 2)), replace=False))
         ops += lists
         rng.shuffle(ops)
+        ops = [t for o in ops for t in o.split(" ")]   # "--kth 0.3" -> two arguments
         argv = list(OVERLAPS[int(rng.integers(0, len(OVERLAPS)))])
         if rng.random() < 0.3:
             argv += ["--prec", str(int(rng.integers(0, 9)))]
