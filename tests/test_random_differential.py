@@ -62,7 +62,8 @@ def rand_bed(rng, n, span, chroms, fields=5, unique=False, disjoint=False, messy
                 rows.append("")                 # blank lines are not records
     if not rows:
         return b""
-    text = "\n".join(rows) + "\n"
+    eol = "\r\n" if messy and rng.random() < 0.15 else "\n"   # DOS line ends: the '\r' stays in the rest of the line
+    text = eol.join(rows) + eol
     if messy and rng.random() < 0.1:
         text = text[:-1]                       # an unterminated last line is not a record either
     return text.encode()
