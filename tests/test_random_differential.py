@@ -171,3 +171,21 @@ def test_device_matches_the_oracle_on_random_inputs():
             assert got == exp, (seed, tool, argv, files, got[:300], exp[:300])
     finally:
         kit.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_command_lines_match_the_reference_binaries_on_random_inputs(tmp_path):
+    """argv -> stdout bytes and exit code, our tools against the reference's, on the same random cases (covers the
+    option grammar of every operation the generator knows, including --kth <val>, -w [bp] --stagger nt -x, -c -L)."""
+    from bedops_b200._lib import tool_path
+    for seed in range(5000, 5040):
+        tool, argv, files = make_case(seed, for_binary=True)
+        if tool == "closest-features" and any(len(v) == 0 for v in files.values()):
+            continue
+        for name, data in files.items():
+            (tmp_path / name).write_bytes(data)
+        exp = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
+        got = subprocess.run([tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
+        assert got.returncode == exp.returncode, (seed, tool, argv, got.stderr[:300], exp.stderr[:300])
+        assert got.stdout == exp.stdout, (seed, tool, argv, files, got.stdout[:300], exp.stdout[:300])
