@@ -295,10 +295,10 @@ int main(int argc, char** argv) {
     if (gpus > 1 && o.chrom == "all" && !row_ids) {
       std::vector<const std::vector<char>*> files{&rtext};
       if (o.num_files == 2) files.push_back(&mtext);
-      auto slices = cli::plan_slices(files, gpus);
+      auto slices = cli::plan_slices(files, gpus * 4);
       cli::run_sharded(slices, [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
         return run_one(eng, sl[0].ptr, sl[0].len, o.num_files == 2 ? sl[1].ptr : nullptr, o.num_files == 2 ? sl[1].len : 0);
-      });
+      }, gpus);
     } else {
       cli::Engine eng;
       std::string text = run_one(eng, rtext.data(), rtext.size(), mtext.data(), mtext.size());

@@ -289,7 +289,7 @@ int main(int argc, char** argv) {
     if (gpus > 1 && o.chrom == "all" && !(has_ref && !o.use_pct && o.subset <= 0)) {
       std::vector<const std::vector<char>*> files;
       for (auto& t : texts) files.push_back(&t);
-      cli::run_sharded(cli::plan_slices(files, gpus), run_one);
+      cli::run_sharded(cli::plan_slices(files, gpus * 4), run_one, gpus);
     } else {
       cli::Engine eng;
       std::vector<cli::Slice> sl;

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <algorithm>
 #include <stdexcept>
+#include <atomic>
 #include <thread>
 #include <string>
 #include <vector>
@@ -164,18 +165,22 @@ inline std::vector<std::vector<Slice>> plan_slices(const std::vector<const std::
 
 // run fn(engine, slices_of_this_shard) -> result text on n_shards GPUs concurrently; write the outputs in shard order
 template <class Fn>
-inline void run_sharded(const std::vector<std::vector<Slice>>& slices, Fn fn) {
+inline void run_sharded(const std::vector<std::vector<Slice>>& slices, Fn fn, int n_gpus) {
+  // more shards than GPUs (plan_slices is asked for 4 per GPU): every GPU thread pulls the next shard, which evens
+  // out chromosomes of very different sizes; the outputs are written in shard (= chromosome) order
   const int                n = (int)slices.size();
-  std::vector<std::string> outs(n), errs(n);
+  std::vector<std::string> outs(n), errs(n_gpus);
+  std::atomic<int>         next{0};
   std::vector<std::thread> th;
-  for (int s = 0; s < n; s++)
-    th.emplace_back([&, s]() {
+  for (int g = 0; g < n_gpus; g++)
+    th.emplace_back([&, g]() {
       try {
-        Engine eng(s);
-        outs[s] = fn(eng, slices[s]);
+        Engine eng(g);
+        for (int s = next.fetch_add(1); s < n; s = next.fetch_add(1)) outs[s] = fn(eng, slices[s]);
       } catch (const std::exception& e) {
-        errs[s] = e.what();
-        if (errs[s].empty()) errs[s] = "unknown error";
+        errs[g] = e.what();
+        if (errs[g].empty()) errs[g] = "unknown error";
+        next.store(n);  // the other threads stop at their next pull
       }
     });
   for (auto& t : th) t.join();

@@ -107,7 +107,7 @@ int main(int argc, char** argv) {
     };
     const int gpus = cli::gpus_requested();
     if (gpus > 1 && o.chrom == "all") {
-      cli::run_sharded(cli::plan_slices({&rtext, &qtext}, gpus), run_one);
+      cli::run_sharded(cli::plan_slices({&rtext, &qtext}, gpus * 4), run_one, gpus);
     } else {
       cli::Engine eng;
       std::string text = run_one(eng, {cli::Slice{rtext.data(), rtext.size()}, cli::Slice{qtext.data(), qtext.size()}});
