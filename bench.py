@@ -94,7 +94,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines = index, None, []   # lines: (monotonic time, text)
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
@@ -107,15 +114,21 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        # nvidia-smi needs 0.1-0.5 s to produce its first line (longer on an 8-GPU box), so it is started before the
+        # warm-up; only the samples taken between mark_begin() and mark_end() -- the timed region -- are used
+        lines = [l for t, l in self.lines if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        if not lines and self.lines:   # region shorter than the polling period: the sample closest to it
+            mid = ((self.t0 or 0) + (self.t1 or 0)) / 2
+            lines = [min(self.lines, key=lambda tl: abs(tl[0] - mid))[1]]
         sm, mx, reasons = [], None, set()
-        for l in self.lines:
+        for l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -265,13 +278,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 1)):  # the first pass also sizes the memory pool
         out_bytes, out_rows = step_device()
     assert out_rows == nref, (out_rows, nref)
     kit.profile(True)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     l0 = kit.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -279,6 +293,7 @@ def main():
         step_device()
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = kit.launches - l0
     ms = ev0.elapsed_time(ev1)
