@@ -88,6 +88,31 @@ def gen_device_bed(kit, torch, n_total, seed, mu, sigma, device):
     return buf, nbytes, k
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of the e2e leg are
+    placed there (eight ranks sharing one node's memory controller cost the N=8 e2e a third of its rate).  Best effort:
+    returns the node number or None."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                    # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -254,6 +279,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)      # host buffers of the e2e leg: first touch on the GPU's own node
     kit = bedops_b200.BedKit(local)          # raises without a B200: there is no CPU fallback
     stream = torch.cuda.current_stream(device)
     kit.set_stream(stream.cuda_stream)
@@ -381,7 +407,8 @@ def main():
                    "ref_rows": nref, "map_rows": nmap, "ref_text_bytes": ref_bytes, "map_text_bytes": map_bytes,
                    "out_text_bytes": int(out_bytes), "per_gpu": True,
                    "l2": "inputs (%.2f GB text per step) are larger than the 126 MB L2; no explicit flush" % ((ref_bytes + map_bytes) / 1e9),
-                   "sharding": "one independent genomic shard of this shape per GPU, no data-path collective"},
+                   "sharding": "one independent genomic shard of this shape per GPU, no data-path collective",
+                   "numa_node": numa},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
     }
     if e2e:
