@@ -175,6 +175,16 @@ def test_config2_bedmap_every_row_against_closed_forms(env, tmp_path):
     r1, m1 = kit.load(rt, 3, COL_LINE), kit.load(mt, 5, COL_SCORE)
     part = kit.bedmap(r1, m1, ["echo", "count", "mean", "bases"])
     assert full.endswith(part) and full.count(b"\n") == ref.rows
+    # the pipelined host-buffer call (chromosome groups, transfers overlapped with the kernels) gives the same bytes
+    rh = torch.empty(ref.nbytes, dtype=torch.uint8, pin_memory=True)
+    mh = torch.empty(mp.nbytes, dtype=torch.uint8, pin_memory=True)
+    rh.copy_(ref.buf[:ref.nbytes])
+    mh.copy_(mp.buf[:mp.nbytes])
+    torch.cuda.synchronize()
+    piped = kit.bedmap_host(rh.data_ptr(), ref.nbytes, 3, COL_LINE, mh.data_ptr(), mp.nbytes, 5, COL_SCORE,
+                            ["echo", "count", "mean", "bases"])
+    assert piped == full
+    del rh, mh, piped
     if have_ref():
         assert part == run_ref("bedmap", ["--echo", "--count", "--mean", "--bases"], [rt, mt], tmp_path)
     for b in (rb, mb, r1, m1):
