@@ -17,7 +17,8 @@ import pytest
 from conftest import REFBIN, have_ref
 import oracle_cli
 
-N_CPU, N_GPU = 500, 600
+N_CPU = int(os.environ.get("BEDKIT_FUZZ_CPU", "500"))   # raise for a one-off fuzzing session
+N_GPU = int(os.environ.get("BEDKIT_FUZZ_GPU", "600"))
 
 
 def rand_bed(rng, n, span, chroms, fields=5, unique=False, disjoint=False, messy=False):
