@@ -71,28 +71,56 @@ __global__ void __launch_bounds__(CF_THREADS) k_closest(ClosestParams p) {
         if (p.run_ref_begin[mid] <= row) my_run = mid; else hi_r = mid;
       }
     }
+    // Candidate windows of the whole batch at once (same scheme as k_map_stats): lo = first query row whose running-max
+    // end exceeds ref.start, hi = first query row with start >= ref.end.  Two warp-cooperative searches bracket the
+    // batch's lo values (reference rows are sorted by start), one bounds every hi, then each lane bisects its own.
+    const int nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
+    uint32_t  my_lo, my_hi;
+    {
+      const int run_a = __shfl_sync(0xffffffffu, my_run, 0);
+      if (__all_sync(0xffffffffu, my_run == run_a)) {
+        const uint64_t  qb0 = p.run_q_begin[run_a];
+        const uint32_t  nr0 = (uint32_t)(p.run_q_end[run_a] - qb0);
+        const uint32_t* pm0 = p.pm + qb0;
+        const uint32_t* qs0 = p.qs + qb0;
+        const uint32_t  key_a = __shfl_sync(0xffffffffu, my_rs, 0) + 1u, key_b = __shfl_sync(0xffffffffu, my_rs, nj - 1) + 1u;
+        uint32_t        a = warp_search32(pm0, nr0, key_a, lane);
+        uint32_t        b = warp_gallop(pm0, a, nr0, key_b, lane, true);
+        while (a < b) {
+          const uint32_t mid = a + ((b - a) >> 1);
+          if (__ldg(&pm0[mid]) < my_rs + 1u) a = mid + 1; else b = mid;
+        }
+        my_lo = a;
+        const uint32_t hmax = warp_search32(qs0, nr0, __reduce_max_sync(0xffffffffu, my_re), lane);
+        uint32_t       h0 = my_lo, h1 = hmax > my_lo ? hmax : my_lo;
+        while (h0 < h1) {
+          const uint32_t mid = h0 + ((h1 - h0) >> 1);
+          if (__ldg(&qs0[mid]) < my_re) h0 = mid + 1; else h1 = mid;
+        }
+        my_hi = h0;
+      } else {  // the batch straddles a chromosome boundary: every lane searches its own chromosome
+        const uint64_t qbl = p.run_q_begin[my_run];
+        const uint64_t nrl = p.run_q_end[my_run] - qbl;
+        my_lo = (uint32_t)lower_bound_u32(p.pm + qbl, 0, nrl, (uint64_t)my_rs + 1);
+        my_hi = (uint32_t)lower_bound_u32(p.qs + qbl, my_lo, nrl, my_re);
+      }
+    }
     uint64_t out_left = ~0ull, out_right = ~0ull;
     int      hint_run = -1;
-    uint32_t hint = 0, nr = 0;
+    uint32_t nr = 0;
     uint64_t qb = 0;
     const uint32_t *qs = nullptr, *qe = nullptr, *pm = nullptr, *pmi = nullptr;
-    const int nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
 #pragma unroll 1
     for (int j = 0; j < nj; j++) {
       const uint32_t rs = __shfl_sync(0xffffffffu, my_rs, j), re = __shfl_sync(0xffffffffu, my_re, j);
       const int      run = __shfl_sync(0xffffffffu, my_run, j);
-      const bool     fresh = run != hint_run;
-      if (fresh) {
+      const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, j), hi = __shfl_sync(0xffffffffu, my_hi, j);
+      if (run != hint_run) {
         qb = p.run_q_begin[run];
         nr = (uint32_t)(p.run_q_end[run] - qb);
         qs = p.qs + qb; qe = p.qe + qb; pm = p.pm + qb; pmi = p.pmi + qb;
         hint_run = run;
-        hint = 0;
       }
-      // lo = first row whose running-max end exceeds ref.start; hi = first row with start >= ref.end
-      const uint32_t lo = warp_gallop(pm, hint, nr, rs + 1u, lane, !fresh);
-      hint = lo;
-      const uint32_t hi = warp_gallop(qs, lo, nr, re, lane, false);
       // non-overlapping left candidate from the prefix [0,lo): (max end, last row attaining it)
       unsigned long long bestL = 0;  // (end + 1) << 32 | (row-in-run + 1); 0 = none
       if (lo > 0) bestL = ((unsigned long long)(__ldg(&pm[lo - 1]) + 1ull) << 32) | __ldg(&pmi[lo - 1]);
