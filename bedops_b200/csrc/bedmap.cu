@@ -212,10 +212,16 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
 #pragma unroll 1
       for (uint32_t k0 = lo; k0 < nr; k0 += 64) {
         const uint32_t ka = k0 + lane, kb = ka + 32;
-        const bool     va = ka < nr, vb = kb < nr;
-        const uint32_t sa = va ? __ldg(&ms[ka]) : 0xFFFFFFFFu, sb = vb ? __ldg(&ms[kb]) : 0xFFFFFFFFu;
-        const uint32_t ea = va ? __ldg(&me[ka]) : 0u, eb = vb ? __ldg(&me[kb]) : 0u;
-        const bool     ina = va && sa < re_pad, inb = vb && sb < re_pad;
+        uint32_t       sa, sb, ea, eb;
+        if (k0 + 64 <= nr) {  // interior step (warp-uniform): no bounds checks on the 64 rows
+          sa = __ldg(&ms[ka]); sb = __ldg(&ms[kb]);
+          ea = __ldg(&me[ka]); eb = __ldg(&me[kb]);
+        } else {              // last step of the chromosome: rows past its end read as "starts at infinity"
+          const bool va = ka < nr, vb = kb < nr;
+          sa = va ? __ldg(&ms[ka]) : 0xFFFFFFFFu; sb = vb ? __ldg(&ms[kb]) : 0xFFFFFFFFu;
+          ea = va ? __ldg(&me[ka]) : 0u; eb = vb ? __ldg(&me[kb]) : 0u;
+        }
+        const bool ina = sa < re_pad, inb = sb < re_pad;  // re_pad <= 0xFFFFFFFF: the sentinel is never in range
         uint32_t       ova = 0, ovb = 0;
         const bool     qa = ina && qualifies(ov, rs, re, sa, ea, ova);
         const bool     qb = inb && qualifies(ov, rs, re, sb, eb, ovb);
