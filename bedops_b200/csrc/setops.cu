@@ -1,16 +1,22 @@
-// setops.cu -- bedops --merge / --intersect / --element-of / --not-element-of as scans and binary searches
-// (SURVEY A14).  Replaces the streaming k-way state machines nextMergeAllLines (Bedops.cpp:1186-1243),
-// getNextFileMergedCoords/mergeOverlap (:791-814, :864-886), nextIntersectLine (:1105-1181) and
-// nextElementOfLine (:1023-1100).
+// setops.cu -- the bedops set operators as scans and binary searches: --merge, --intersect,
+// --element-of / --not-element-of, --complement, --difference, --symmdiff, --everything, --chop.
+// Replaces the streaming k-way state machines nextMergeAllLines (Bedops.cpp:1186-1243),
+// getNextFileMergedCoords/mergeOverlap (:791-814, :864-886), nextIntersectLine (:1105-1181), nextElementOfLine
+// (:1023-1100), nextComplementLine (:891-943), nextDifferenceLine (:948-1018), nextSymmetricDiffLine (:1341-1463),
+// nextUnionAllLine (:1468-1516) and doChop (:438-467).
 //
-//   union-merge of k sorted files:  rank-merge (each row's output slot = its own rank + lower/upper_bound ranks in
-//       the other files, per chromosome) -> segmented prefix-max of end -> a row opens a segment iff
-//       start > running max end (touching intervals coalesce: "bt->start() <= toRtn->end()", Bedops.cpp:1233) ->
-//       stream compaction of (segment start, segment max end) with a look-back scan.
-//   intersect: every file is self-merged, then folded pairwise; for a segment a of A the overlapping pieces of the
-//       disjoint sorted list B are the index range [lower_bound(B.end, a.start+1), lower_bound(B.start, a.end)).
+//   union-merge of k sorted files:  every file is merged within itself, the segment lists are rank-merged (each row's
+//       output slot = its own rank + lower/upper_bound ranks in the other lists, per chromosome) -> segmented
+//       prefix-max of end -> a row opens a segment iff start > running max end (touching intervals coalesce:
+//       "bt->start() <= toRtn->end()", Bedops.cpp:1233) -> compaction in two passes (heads per warp range, scan, write).
+//   intersect / difference: every file is self-merged, then folded pairwise; for a segment a of A the overlapping
+//       segments of the disjoint sorted list B are the index range [lower_bound(B.end, a.start+1),
+//       lower_bound(B.start, a.end)); the pieces are the overlaps (-i) or what lies between them (-d).
+//   symmdiff: union of all files minus the union of the pairwise intersections.  complement: gaps of the union.
 //   element-of: overlap bases of each reference row with the union-merge of the other files, compared with the
 //       threshold exactly as Bedops.cpp:1094-1099 does (double arithmetic), then the kept rows are echoed.
+//   everything: rows ranked across files by (start, end, rest of line, file).  chop: closed-form piece counts.
+// No kernel here waits on another CTA: every compaction is count -> scan -> write over warp-owned ranges.
 #include <algorithm>
 #include <map>
 #include "common.cuh"

@@ -306,7 +306,7 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 1)):  # the first pass also sizes the memory pool
+    for _ in range(max(args.warmup, 1)):  # the first pass also fills the library's block cache
         out_bytes, out_rows = step_device()
     assert out_rows == nref, (out_rows, nref)
     kit.profile(True)

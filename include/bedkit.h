@@ -31,7 +31,7 @@ extern "C" {
 
 #define BEDKIT_ABI_VERSION 1
 
-typedef struct bk_ctx bk_ctx; /* one per GPU: stream, memory pool, pinned staging, last error text */
+typedef struct bk_ctx bk_ctx; /* one per GPU: stream, cached device blocks, pinned staging, last error text */
 typedef struct bk_bed bk_bed; /* a parsed, device-resident sorted BED file: SoA columns + chromosome runs */
 
 /* result text; ptr is pinned host memory (on_device == 0) or device memory (on_device == 1) */
