@@ -13,7 +13,7 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
        "echo-map-id": 9, "echo-ref-size": 10, "echo-ref-name": 11, "echo-ref-row-id": 12, "echo-map": 13,
        "echo-map-score": 14, "echo-map-size": 15, "echo-overlap-size": 16, "echo-map-range": 17, "bases-uniq": 18,
        "bases-uniq-f": 19, "variance": 20, "stdev": 21, "cv": 22,
-       "echo-map-id-uniq": 23, "median": 24, "kth": 25}
+       "echo-map-id-uniq": 23, "median": 24, "kth": 25, "mad": 26}
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4, "complement": 5, "difference": 6,

@@ -567,6 +567,43 @@ struct BedmapRow {
     }
     return 0.0;
   }
+  // |score - centre| at sorted position `want` among the qualifying rows (rank counting as above)
+  __device__ __forceinline__ double dev_at_rank(uint64_t lo, uint64_t hi, uint32_t a, uint32_t b, uint32_t want, double centre) const {
+    for (uint64_t x = lo; x < hi; x++) {
+      uint32_t ovl;
+      if (!qualifies(ov, a, b, ms[x], me[x], ovl)) continue;
+      const double vx = fabs(mscore[x] - centre);
+      uint32_t     rank = 0;
+      for (uint64_t y = lo; y < hi; y++) {
+        if (!qualifies(ov, a, b, ms[y], me[y], ovl)) continue;
+        const double vy = fabs(mscore[y] - centre);
+        rank += (vy < vx || (vy == vx && y < x)) ? 1u : 0u;
+      }
+      if (rank == want) return vx;
+    }
+    return 0.0;
+  }
+  // --mad [mult]: median of |x - median| times mult; NAN for fewer than two hits (MedianAbsoluteDeviationVisitor.hpp:57-93)
+  template <class Sink>
+  __device__ __noinline__ void mad_op(Sink& s, uint64_t i, uint64_t row, double mult) const {
+    const uint32_t n = count[i];
+    if (n <= 1) {
+      s.puts_("NAN", 3);
+      return;
+    }
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    double         med, mad;
+    if (n % 2 == 0) {
+      med = (score_at_rank(lo, hi, a, b, n / 2 - 1) + score_at_rank(lo, hi, a, b, n / 2)) / 2.0;
+      mad = (dev_at_rank(lo, hi, a, b, n / 2 - 1, med) + dev_at_rank(lo, hi, a, b, n / 2, med)) / 2.0;
+    } else {
+      med = score_at_rank(lo, hi, a, b, (n - 1) / 2);
+      mad = dev_at_rank(lo, hi, a, b, n / 2, med);
+    }
+    put_score(s, mad * mult, 1, i);
+  }
+
   template <class Sink>
   __device__ __noinline__ void kth_op(Sink& s, uint64_t i, uint64_t row, double k) const {
     const uint32_t n = count[i];
@@ -641,6 +678,9 @@ struct BedmapRow {
           break;
         case BK_OP_MEDIAN: case BK_OP_KTH:
           if (RARE & 4) kth_op(s, i, row, ops[c] == BK_OP_MEDIAN ? 0.5 : kth_arg[c]);
+          break;
+        case BK_OP_MAD:
+          if (RARE & 4) mad_op(s, i, row, kth_arg[c] > 0.0 ? kth_arg[c] : 1.0);
           break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
@@ -728,6 +768,9 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
           return fail(ctx, BK_ERR_UNSUPPORTED, "--kth %g: the device path supports 0 < val < 1", spec->op_arg[c]);
         need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       case BK_OP_MEDIAN: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      case BK_OP_MAD:
+        if (spec->op_arg[c] < 0.0) return fail(ctx, BK_ERR_ARG, "--mad Expect 0 < val");
+        need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }

@@ -25,7 +25,7 @@ const OpInfo kOps[] = {
     {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
     {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
     {"stdev", BK_OP_STDEV, 5, 0},                    {"cv", BK_OP_CV, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
-    {"wmean", 0, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", 0, 5, -1},
+    {"wmean", 0, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", BK_OP_MAD, 5, -1},
     {"kth", BK_OP_KTH, 5, 1},                      {"tmean", 0, 5, 2},
 };
 
@@ -160,8 +160,12 @@ Options parse_args(int argc, char** argv) {
           require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= val <= 1");
         }
         i += info->nargs;
-      } else if (info->nargs < 0 && i < argc && cli::only_chars(argv[i], reals)) {
-        i++;  // optional multiplier of --mad
+      } else if (info->nargs < 0 && i < argc && cli::only_chars(argv[i], reals)) {  // optional multiplier of --mad
+        op_arg = -1;
+        std::stringstream conv(std::string(argv[i]));
+        conv >> op_arg;
+        require(op_arg > 0, "--" + next + " Expect 0 < val");  // Input.hpp:275-288
+        i++;
       }
       if (!info->op && o.unsupported_op.empty()) o.unsupported_op = next;
       o.ops.push_back(info->op);
@@ -219,7 +223,7 @@ void usage(FILE* f) {
       "     Operations on this build's B200 hot path:\n"
       "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-id-uniq --echo-map-range\n"
       "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
-      "      --cv --indicator --kth <val> --max --mean --median --min --stdev --sum --variance\n\n",
+      "      --cv --indicator --kth <val> --mad [mult] --max --mean --median --min --stdev --sum --variance\n\n",
       f);
 }
 
@@ -243,7 +247,8 @@ int main(int argc, char** argv) {
       spec.ops[spec.n_ops++] = op;
       need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
       need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE ||
-                    op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV || op == BK_OP_MEDIAN || op == BK_OP_KTH;
+                    op == BK_OP_VARIANCE || op == BK_OP_STDEV || op == BK_OP_CV || op == BK_OP_MEDIAN || op == BK_OP_KTH ||
+                    op == BK_OP_MAD;
       need_id |= op == BK_OP_ECHO_MAP_ID || op == BK_OP_ECHO_MAP_ID_UNIQ;
       need_mapline |= op == BK_OP_ECHO_MAP;
     }

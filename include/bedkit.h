@@ -142,7 +142,8 @@ enum { /* operations, printed left to right in the order given (MultiVisitor.hpp
   BK_OP_ECHO_MAP_ID_UNIQ = 23,  /* --echo-map-id-uniq   distinct ids in strcmp order (ProcessBedVisitorRow.hpp:361-389); BK_COL_ID|BK_COL_LINE */
   /* generalised median of the scores (RollingKthAverageVisitor.hpp:37-68 over RollingKthVisitor.hpp:75-95) */
   BK_OP_MEDIAN = 24,            /* --median             = --kth 0.5 */
-  BK_OP_KTH = 25                /* --kth <val>          0 < val < 1 in bk_mapspec.op_arg[] of the same slot */
+  BK_OP_KTH = 25,               /* --kth <val>          0 < val < 1 in bk_mapspec.op_arg[] of the same slot */
+  BK_OP_MAD = 26                /* --mad [mult]         median absolute deviation * mult (op_arg[], 0 = default 1); MedianAbsoluteDeviationVisitor.hpp:57-93 */
 };
 enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */
@@ -167,7 +168,7 @@ typedef struct bk_mapspec {
   const char* multidelim;    /* --multidelim, default ";" */
   const char* chrom;         /* --chrom, NULL or "all" = every chromosome */
   int         out_on_device; /* leave result text in HBM (bench: device-resident timing) */
-  double      op_arg[BK_MAX_OPS]; /* per-operation argument (BK_OP_KTH: the fraction); 0 otherwise */
+  double      op_arg[BK_MAX_OPS]; /* per-operation argument (BK_OP_KTH: the fraction, BK_OP_MAD: the multiplier); 0 otherwise */
 } bk_mapspec;
 void bk_mapspec_default(bk_mapspec* spec);
 /* map == NULL: single-file mode, ref is mapped onto itself (Input.hpp:359-364) */

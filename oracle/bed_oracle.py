@@ -193,7 +193,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     identical for exactly representable partial sums, see DESIGN.md parity notes)."""
     need_fields = 3
     for o in ops:
-        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:"):
+        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:") or o.startswith("mad"):
             need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
         elif o in ("echo-map-id", "echo-map-id-uniq"):
             need_fields = max(need_fields, 4)
@@ -284,6 +284,19 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                         cols.append(_fmt_score(v[pos], prec, sci))
                     else:
                         cols.append(_fmt_score(v[pos + 1], prec, sci))
+            elif o.startswith("mad"):
+                # MedianAbsoluteDeviationVisitor.hpp:57-93: NAN for fewer than two hits; the median (as --median gives
+                # it), then the plain median of |x - median| (mean of the two middle values for an even count) * mult
+                mult = float(o[4:]) if o.startswith("mad:") else 1.0
+                v = sorted(m.score for m in hits)
+                n = len(v)
+                if n <= 1:
+                    cols.append(b"NAN")
+                else:
+                    med = (v[n // 2 - 1] + v[n // 2]) / 2.0 if n % 2 == 0 else v[(n - 1) // 2]
+                    dv = sorted(abs(x - med) for x in v)
+                    mad = (dv[n // 2 - 1] + dv[n // 2]) / 2.0 if n % 2 == 0 else dv[n // 2]
+                    cols.append(_fmt_score(mad * mult, prec, sci))
             elif o in ("variance", "stdev", "cv"):  # VarianceVisitor.hpp:58-66, StdevVisitor.hpp, CoeffVariationVisitor.hpp
                 sm = sq = 0.0
                 for m in hits:

@@ -185,6 +185,7 @@ def synthetic():
             ("bedmap", ["--echo-map-size", "--bases-uniq", "dm.bed"]),
             ("bedmap", ["--echo-map-id-uniq", "--echo-map-id", "--count", "dr.bed", "dm.bed"]),
             ("bedmap", ["--median", "--kth", "0.25", "--kth", "0.9", "--count", "dr.bed", "dm.bed"]),
+            ("bedmap", ["--mad", "--mad", "1.4826", "--median", "dr.bed", "dm.bed"]),
             ("bedmap", ["--variance", "--stdev", "--cv", "--mean", "dr.bed", "dm.bed"]),
             ("bedmap", ["--sci", "--prec", "9", "--range", "500", "--stdev", "--cv", "dr.bed", "dm.bed"]),
             ("closest-features", ["--dist", "r.bed", "m.bed"]),

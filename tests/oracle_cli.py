@@ -73,6 +73,12 @@ def parse_argv(tool, argv, known_files):
             elif a == "--kth":
                 i += 1
                 d["ops"].append("kth:" + argv[i])
+            elif a == "--mad":   # optional multiplier (Input.hpp:275-288): a following all-numeric argument
+                if i + 1 < len(argv) and argv[i + 1] and all(c in ".-0123456789" for c in argv[i + 1]):
+                    i += 1
+                    d["ops"].append("mad:" + argv[i])
+                else:
+                    d["ops"].append("mad")
             elif a == "--prec":
                 i += 1
                 d["prec"] = int(argv[i])
@@ -176,7 +182,7 @@ def run_kit(kit, tool, argv, files, stdin=None):
         return out
     if tool == "bedmap":
         ops = d["ops"]
-        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:")
+        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:") or o.startswith("mad")
                     for o in ops)
         ids = "echo-map-id" in ops or "echo-map-id-uniq" in ops
         line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)

@@ -70,7 +70,7 @@ def rand_bed(rng, n, span, chroms, fields=5, unique=False, disjoint=False, messy
     return text.encode()
 
 
-BEDMAP_SCORE = ["--sum", "--mean", "--max", "--min", "--variance", "--stdev", "--cv", "--median", "--kth 0.3", "--kth 0.75"]
+BEDMAP_SCORE = ["--sum", "--mean", "--max", "--min", "--variance", "--stdev", "--cv", "--median", "--kth 0.3", "--kth 0.75", "--mad", "--mad 2.5"]
 BEDMAP_PLAIN = ["--echo", "--count", "--indicator", "--bases", "--echo-ref-size", "--echo-ref-name", "--bases-uniq",
                 "--bases-uniq-f", "--echo-map-size", "--echo-overlap-size", "--echo-map-range"]
 BEDMAP_LIST = ["--echo-map", "--echo-map-id", "--echo-map-score", "--echo-map-id-uniq"]
