@@ -7,7 +7,7 @@ import os
 from typing import List, Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-BK_MAX_OPS = 32
+BK_MAX_OPS = 64
 
 OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "max": 7, "min": 8,
        "echo-map-id": 9, "echo-ref-size": 10, "echo-ref-name": 11, "echo-ref-row-id": 12, "echo-map": 13,
@@ -35,7 +35,8 @@ class _MapSpec(C.Structure):
     _fields_ = [("n_ops", C.c_int), ("ops", C.c_int * BK_MAX_OPS), ("overlap_kind", C.c_int),
                 ("overlap_bp", C.c_uint64), ("overlap_frac", C.c_double), ("precision", C.c_int), ("sci", C.c_int),
                 ("skip_unmapped", C.c_int), ("delim", C.c_char_p), ("multidelim", C.c_char_p),
-                ("chrom", C.c_char_p), ("out_on_device", C.c_int), ("op_arg", C.c_double * BK_MAX_OPS)]
+                ("chrom", C.c_char_p), ("out_on_device", C.c_int), ("op_arg", C.c_double * BK_MAX_OPS),
+                ("row_id_base", C.c_uint64)]
 
 
 class _CfSpec(C.Structure):

@@ -346,6 +346,9 @@ struct BedmapRow {
   const uint64_t* win_lo;
   const uint32_t* win_n;
   const uint32_t* idbytes;
+  const uint64_t* rank;        // --echo-ref-row-id with --skip-unmapped: printed rows before row i (else null: i)
+  uint64_t        rowid_base;  // ids issued by earlier calls of the same command
+  int             rowid_ops;   // how many --echo-ref-row-id columns a row prints (each one bumps the counter)
   OverlapSpec     ov;
   int             n_ops;
   unsigned char   ops[BK_MAX_OPS];
@@ -636,6 +639,7 @@ struct BedmapRow {
     const uint32_t cnt = count[i];
     if (skip_unmapped && cnt == 0) return;  // MultiVisitor.hpp:84-85
     const uint64_t row = row0 + i;
+    int            rowid_seen = 0;
     for (int c = 0; c < n_ops; c++) {
       if (c) s.puts_(delim, delim_len);
       switch (ops[c]) {
@@ -695,14 +699,44 @@ struct BedmapRow {
           break;
         }
         case BK_OP_ECHO_REF_ROW_ID:
+          // PrintRowID: a static counter bumped once per printed id (ProcessBedVisitorRow.hpp:347-354) -- rows the
+          // command does not print (--skip-unmapped, other chromosomes under --chrom) do not count
           s.puts_("id-", 3);
-          s.put_u64(row + 1);
+          s.put_u64(rowid_base + (rank ? rank[i] : i) * (uint64_t)rowid_ops + (uint64_t)(++rowid_seen));
           break;
       }
     }
     s.put('\n');
   }
 };
+
+// rank[i] = number of rows j < i with count[j] > 0 (the rows --skip-unmapped prints): warp ranges of 2048 rows,
+// range totals -> k_scan_totals -> ranks
+constexpr int RK_RANGE = 2048;
+__global__ void __launch_bounds__(256) k_rank_totals(const uint32_t* __restrict__ count, uint64_t n, uint64_t* __restrict__ tot) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const uint64_t a = w * RK_RANGE, b = a + RK_RANGE < n ? a + RK_RANGE : n;
+  if (a >= n) return;
+  uint32_t c = 0;
+  for (uint64_t k = a + lane; k < b; k += 32) c += count[k] ? 1u : 0u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if (lane == 0) tot[w] = c;
+}
+__global__ void __launch_bounds__(256) k_rank_write(const uint32_t* __restrict__ count, uint64_t n, const uint64_t* __restrict__ base,
+                                                    uint64_t* __restrict__ rank) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const uint64_t a = w * RK_RANGE, b = a + RK_RANGE < n ? a + RK_RANGE : n;
+  if (a >= n) return;
+  uint64_t run = base[w];
+  for (uint64_t k0 = a; k0 < b; k0 += 32) {
+    const uint64_t k = k0 + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, k < b && count[k] != 0);
+    if (k < b) rank[k] = run + __popc(m & ((1u << lane) - 1u));
+    run += __popc(m);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 int finish_text(bk_ctx* ctx, char* d_out, uint64_t bytes, uint64_t rows, int on_device, bk_text* out);
@@ -745,13 +779,15 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   if (strlen(delim) > 23 || strlen(mdelim) > 23) return fail(ctx, BK_ERR_UNSUPPORTED, "delimiter longer than 23 bytes");
 
   unsigned need = 0;
+  int      rowid_ops = 0;
   bool     need_echo = false, need_refline = false, need_ids = false, need_mapline = false, need_mapscore = false;
   bool     window_ops = false;
   for (int c = 0; c < spec->n_ops; c++) {
     switch (spec->ops[c]) {
       case BK_OP_ECHO: need_echo = true; need_refline = true; break;
       case BK_OP_ECHO_REF_NAME: need_refline = true; break;
-      case BK_OP_COUNT: case BK_OP_INDICATOR: case BK_OP_ECHO_REF_SIZE: case BK_OP_ECHO_REF_ROW_ID: break;
+      case BK_OP_COUNT: case BK_OP_INDICATOR: case BK_OP_ECHO_REF_SIZE: break;
+      case BK_OP_ECHO_REF_ROW_ID: rowid_ops++; break;
       case BK_OP_BASES: need |= NEED_BASES; break;
       case BK_OP_SUM: case BK_OP_MEAN: need |= NEED_SUM; break;
       case BK_OP_MAX: need |= NEED_MAX; break;
@@ -890,6 +926,23 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
 
   const uint64_t dl = strlen(delim);
   const uint64_t cap = 0;  // the emitter sizes the result itself (length pass)
+  uint64_t*      d_rank = nullptr;
+  if (rowid_ops && spec->skip_unmapped) {
+    const uint64_t nranges = (n + RK_RANGE - 1) / RK_RANGE;
+    d_rank = dalloc<uint64_t>(ctx, n);
+    uint64_t* d_tot = dalloc<uint64_t>(ctx, nranges);
+    uint64_t* d_base = dalloc<uint64_t>(ctx, nranges + 1);
+    if (!d_rank || !d_tot || !d_base) return BK_ERR_NOMEM;
+    const unsigned blocks = (unsigned)((nranges + 7) / 8);
+    k_rank_totals<<<blocks, 256, 0, ctx->stream>>>(sp.count, n, d_tot);
+    BK_LAUNCHED(ctx);
+    k_scan_totals<SC_COUNT_D><<<1, 1024, 0, ctx->stream>>>(d_tot, d_base, (uint32_t)nranges, ctx->d_scratch);
+    BK_LAUNCHED(ctx);
+    k_rank_write<<<blocks, 256, 0, ctx->stream>>>(sp.count, n, d_base, d_rank);
+    BK_LAUNCHED(ctx);
+    dfree(ctx, d_tot);
+    dfree(ctx, d_base);
+  }
 
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
@@ -903,6 +956,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     fn.map_fields = (map->min_fields >= 5 && !map->score) ? 4 : map->min_fields;
     fn.count = sp.count; fn.bases = sp.bases; fn.sum = sp.sum; fn.vmax = sp.vmax; fn.vmin = sp.vmin;
     fn.win_lo = sp.win_lo; fn.win_n = sp.win_n; fn.idbytes = sp.idbytes;
+    fn.rank = d_rank; fn.rowid_base = spec->row_id_base; fn.rowid_ops = rowid_ops;
     fn.ov = ov; fn.n_ops = spec->n_ops;
     for (int c = 0; c < spec->n_ops; c++) {
       fn.ops[c] = (unsigned char)spec->ops[c];
@@ -921,7 +975,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   else if (!spec->sci) emit(BedmapRow<2>{});
   else emit(BedmapRow<3>{});
   dfree(ctx, sp.count); dfree(ctx, sp.bases); dfree(ctx, sp.sum); dfree(ctx, sp.vmax); dfree(ctx, sp.vmin);
-  dfree(ctx, sp.win_lo); dfree(ctx, sp.win_n); dfree(ctx, sp.idbytes);
+  dfree(ctx, sp.win_lo); dfree(ctx, sp.win_n); dfree(ctx, sp.idbytes); dfree(ctx, d_rank);
   if (rc != BK_OK) {
     dfree(ctx, d_out);
     return rc;

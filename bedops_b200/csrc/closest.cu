@@ -1,16 +1,22 @@
 // closest.cu -- closest-features: nearest left / right query element per reference row.
 //
-// Replaces the streaming two-pointer state machine findDistances (applications/bed/closestfeats/src/
-// ClosestFeature.cpp:260-413) by its declarative rule, evaluated per reference row by one warp over the
-// candidate window of the sorted query columns (the same [lo,hi) window the bedmap kernel scans):
-//   non-overlapping left  = the query row with the largest end <= ref.start, the LATER row on ties (":300  >=")
-//                           = max over { prefix [0,lo): running-max end with its last index;  window rows with end <= ref.start }
-//   non-overlapping right = the first query row with start >= ref.end (= row hi)
-//   overlapping rows take precedence, in file order (:326-388):  start <= ref.start -> left (last one wins);
-//       else end >= ref.end -> right; else (contained) by the centroid proportion: >= 0.5 -> left if no overlapping left
-//       yet, < 0.5 -> right; the last row assigned to the right wins.
-// The reference's streaming push-back list loses candidates when reference rows are nested (SURVEY 8c hazard 3);
-// this implementation always answers the declarative rule (parity notes).
+// Replaces findDistances (applications/bed/closestfeats/src/ClosestFeature.cpp:260-413).  The reference's answer is
+// a function of its streaming state, not only of the two files: query elements it drops are gone for every later
+// reference row, and elements held as left/right re-enter the stream behind the ones pushed back while they were held
+// (BedReader::PushBack, BedReader.hpp:64-66), so with nested or overlapping reference rows the stream is neither
+// complete nor in file order.  Byte parity therefore needs the state machine itself.  It is sequential per chromosome,
+// so it is run speculatively in parallel:
+//   k_cf_sim    one thread per chunk of CF_CHUNK consecutive reference rows of one chromosome.  A chunk that does not
+//               begin its chromosome warms up over the CF_WARM rows in front of it from a guessed state (the best
+//               non-overlapping left of the warm-up row + the unread file from the row's candidate window), records
+//               the stream it ASSUMED at its first row, simulates its rows, records the stream it LEFT behind.
+//   k_cf_check  chunk k is consistent iff the stream it assumed equals, element by element, the stream chunk k-1 left.
+//   k_cf_sim    (rerun mode) every inconsistent chunk starts again from the stream chunk k-1 left; check; repeat.
+// The first chunk of a chromosome starts from the exact state (empty push-back, file at the chromosome's first row), so
+// by induction round r makes the first r chunks of every chromosome exact; states converge within a chunk in practice
+// (two rounds).  After CF_MAX_ROUNDS a last kernel walks each chromosome's remaining rows with one thread.
+// No approximation anywhere: when the loop ends every chunk ran from the true stream.
+#include <algorithm>
 #include "common.cuh"
 #include "emit.cuh"
 #include "fmt.cuh"
@@ -19,23 +25,11 @@
 namespace bk {
 
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
-
-struct ClosestParams {
-  const uint32_t* rs;
-  const uint32_t* re;
-  uint64_t        row0, n;
-  const uint64_t* run_ref_begin;  // [nruns+1]
-  const uint64_t* run_q_begin;    // [nruns]
-  const uint64_t* run_q_end;
-  int             nruns;
-  const uint32_t* qs;
-  const uint32_t* qe;
-  const uint32_t* pm;   // running max of end within the run
-  const uint32_t* pmi;  // 1 + (index within the run) of the last row attaining pm, same scan
-  int             allow_overlaps;
-  uint64_t*       left;   // global query row or UINT64_MAX
-  uint64_t*       right;
-};
+constexpr int      CF_THREADS = 128;
+constexpr int      CF_CHUNK = 256;      // reference rows per chunk
+constexpr int      CF_WARM = 96;        // warm-up rows in front of a speculative chunk
+constexpr int      CF_MAX_ROUNDS = 6;
+constexpr uint64_t kExactState = ~0ull;  // "assumed" marker of a chunk that begins its chromosome
 
 // pmi source: v[k] = (end[k] == pm[k]) ? k - run_begin + 1 : 0
 __global__ void k_argmark(const uint32_t* __restrict__ end, const uint32_t* __restrict__ pm, uint32_t* __restrict__ v,
@@ -51,125 +45,239 @@ __global__ void k_argmark(const uint32_t* __restrict__ end, const uint32_t* __re
   }
 }
 
-constexpr int CF_THREADS = 256;
+struct CfRun {
+  uint64_t ref_begin, ref_end;  // reference rows of the chromosome
+  uint64_t q_begin, q_end;      // query rows of the same chromosome (empty if absent)
+  uint64_t first_chunk;
+};
 
-__global__ void __launch_bounds__(CF_THREADS) k_closest(ClosestParams p) {
-  const int      lane = threadIdx.x & 31;
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * CF_THREADS + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * CF_THREADS) >> 5;
-  const uint64_t nbatch = (p.n + 31) >> 5;
-  for (uint64_t batch = warp0; batch < nbatch; batch += nwarps) {
-    const uint64_t i = (batch << 5) + lane;
-    const bool     valid = i < p.n;
-    const uint64_t row = p.row0 + (valid ? i : p.n - 1);
-    const uint32_t my_rs = p.rs[row], my_re = p.re[row];
-    int my_run = 0;
-    {
-      int hi_r = p.nruns;
-      while (hi_r - my_run > 1) {
-        int mid = (my_run + hi_r) >> 1;
-        if (p.run_ref_begin[mid] <= row) my_run = mid; else hi_r = mid;
-      }
+struct CfParams {
+  const uint32_t* rs;
+  const uint32_t* re;
+  const CfRun*    runs;
+  int             nruns;
+  uint64_t        nchunks;
+  uint64_t        row0;  // first reference row of the call (left/right are indexed by row - row0)
+  const uint32_t* qs;
+  const uint32_t* qe;
+  const uint32_t* pm;   // running max of end within the run
+  const uint32_t* pmi;  // 1 + (index within the run) of the last row attaining pm
+  int             allow_overlaps;
+  uint64_t*       left;  // global query row or UINT64_MAX
+  uint64_t*       right;
+  // per-thread stream buffers: two of `cap` entries each
+  uint32_t*       bufs;
+  uint32_t        cap;
+  // recorded streams: arena[off] = file position, arena[off+1] = n, then n query rows (relative to the run)
+  uint32_t*       arena;
+  uint64_t        arena_cap;
+  uint64_t*       arena_top;
+  uint64_t*       assumed;   // [nchunks] arena offset of the stream the chunk started from (kExactState: exact)
+  uint64_t*       fin_cur;   // [nchunks] arena offset of the stream the chunk left (read by rerun mode: chunk k-1)
+  uint64_t*       fin_next;  // [nchunks] written by this launch
+  const uint32_t* todo;      // rerun mode: chunks to run
+  uint32_t        ntodo;
+  uint64_t*       scratch;
+};
+
+__device__ __forceinline__ void cf_locate(const CfRun* __restrict__ runs, int nruns, uint64_t c, int& run, uint64_t& a, uint64_t& b) {
+  int lo = 0, hi = nruns;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (runs[mid].first_chunk <= c) lo = mid; else hi = mid;
+  }
+  run = lo;
+  a = runs[lo].ref_begin + (c - runs[lo].first_chunk) * CF_CHUNK;
+  b = a + CF_CHUNK < runs[lo].ref_end ? a + CF_CHUNK : runs[lo].ref_end;
+}
+
+// the stream of one simulation: pushed-back elements A[r..n) in read order, then the file from row `pos`
+struct CfStream {
+  uint32_t* A;
+  uint32_t* B;  // the push-back list being built for the current reference row (`read`, ClosestFeature.cpp:275)
+  uint32_t  r, n, pos;
+  bool      overflow;
+};
+
+// one reference row of findDistances (:277-411); returns left/right as query rows relative to the run
+__device__ __forceinline__ void cf_row(CfStream& st, uint32_t cap, const uint32_t* __restrict__ qs,
+                                       const uint32_t* __restrict__ qe, uint32_t nq, uint32_t rs, uint32_t re, bool allow,
+                                       uint32_t& out_left, uint32_t& out_right) {
+  uint32_t left = kNoRow, right = kNoRow, left_end = 0, m = 0;
+  bool     left_ov = false, left_cached = false, drained = true;
+  uint32_t* const B = st.B;
+  const long long c2 = (long long)re - 1 + (long long)rs;  // 2 * getCentroid(b), :236-239
+  // every branch appends at most three entries: one bound check per element
+  while (true) {
+    uint32_t c;
+    if (st.r < st.n) c = st.A[st.r++];
+    else if (st.pos < nq) c = st.pos++;
+    else break;
+    if (m + 3 > cap) {
+      st.overflow = true;
+      break;
     }
-    // Candidate windows of the whole batch at once (same scheme as k_map_stats): lo = first query row whose running-max
-    // end exceeds ref.start, hi = first query row with start >= ref.end.  Two warp-cooperative searches bracket the
-    // batch's lo values (reference rows are sorted by start), one bounds every hi, then each lane bisects its own.
-    const int nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
-    uint32_t  my_lo, my_hi;
-    {
-      const int run_a = __shfl_sync(0xffffffffu, my_run, 0);
-      if (__all_sync(0xffffffffu, my_run == run_a)) {
-        const uint64_t  qb0 = p.run_q_begin[run_a];
-        const uint32_t  nr0 = (uint32_t)(p.run_q_end[run_a] - qb0);
-        const uint32_t* pm0 = p.pm + qb0;
-        const uint32_t* qs0 = p.qs + qb0;
-        const uint32_t  key_a = __shfl_sync(0xffffffffu, my_rs, 0) + 1u, key_b = __shfl_sync(0xffffffffu, my_rs, nj - 1) + 1u;
-        uint32_t        a = warp_search32(pm0, nr0, key_a, lane);
-        uint32_t        b = warp_gallop(pm0, a, nr0, key_b, lane, true);
-        while (a < b) {
-          const uint32_t mid = a + ((b - a) >> 1);
-          if (__ldg(&pm0[mid]) < my_rs + 1u) a = mid + 1; else b = mid;
-        }
-        my_lo = a;
-        const uint32_t hmax = warp_search32(qs0, nr0, __reduce_max_sync(0xffffffffu, my_re), lane);
-        uint32_t       h0 = my_lo, h1 = hmax > my_lo ? hmax : my_lo;
-        while (h0 < h1) {
-          const uint32_t mid = h0 + ((h1 - h0) >> 1);
-          if (__ldg(&qs0[mid]) < my_re) h0 = mid + 1; else h1 = mid;
-        }
-        my_hi = h0;
-      } else {  // the batch straddles a chromosome boundary: every lane searches its own chromosome
-        const uint64_t qbl = p.run_q_begin[my_run];
-        const uint64_t nrl = p.run_q_end[my_run] - qbl;
-        my_lo = (uint32_t)lower_bound_u32(p.pm + qbl, 0, nrl, (uint64_t)my_rs + 1);
-        my_hi = (uint32_t)lower_bound_u32(p.qs + qbl, my_lo, nrl, my_re);
+    const uint32_t s = __ldg(&qs[c]), e = __ldg(&qe[c]);
+    if (e <= rs) {  // left of the reference row (dist < 0)
+      if (left == kNoRow || (!left_ov && e >= left_end)) {  // :300-309 new best left: the list so far is dropped
+        m = 0;
+        left = c; left_end = e; left_ov = false; left_cached = false;
+      } else {  // :310-314 (c is dropped)
+        if (!left_cached) B[m++] = left;
+        left_cached = true;
       }
+    } else if (s >= re) {  // right of the reference row (dist > 0): :315-331
+      if (left != kNoRow && !left_cached) B[m++] = left;
+      left_cached = left != kNoRow;
+      if (right == kNoRow) right = c; else B[m++] = right;
+      B[m++] = c;
+      drained = false;
+      break;
+    } else if (allow) {  // overlap, :332-388
+      if (s <= rs) {  // hangs over the left edge
+        if (left != kNoRow && !left_cached && left_end > e) B[m++] = left;  // else dropped (:336-339)
+        left = c; left_end = e; left_ov = true; left_cached = false;
+      } else {
+        // proportionOverlapLeft(c, centroid) >= 0.5 (:226-231) in exact integers: centroid >= s and
+        // 2 * (centroid + 1 - s) >= e - s  (the correctly rounded double quotient compares the same way: 2x and the
+        // length are integers below 2^53)
+        const bool contained = e < re;
+        const bool more_left = contained && c2 >= 2ll * s && c2 + 2 >= (long long)e + (long long)s;
+        if (contained && left_ov && more_left) {  // :362-368 left stays; c may be needed later
+          if (!left_cached) B[m++] = left;
+          left_cached = true;
+          B[m++] = c;
+        } else if (contained && !left_ov && more_left) {  // :369-378 new left: the list so far is dropped
+          m = 0;
+          left = c; left_end = e; left_ov = true; left_cached = false;
+        } else {  // hangs over the right edge (:343-350) or contained nearer the right edge (:354-361, :379-387)
+          if (left != kNoRow && !left_cached) B[m++] = left;
+          left_cached = left != kNoRow;
+          if (right != kNoRow) B[m++] = right;
+          right = c;
+        }
+      }
+    } else {  // :389-397 --no-overlaps: kept for later reference rows
+      if (left != kNoRow && !left_cached) {
+        B[m++] = left;
+        left_cached = true;
+      }
+      B[m++] = c;
     }
-    uint64_t out_left = ~0ull, out_right = ~0ull;
-    int      hint_run = -1;
-    uint32_t nr = 0;
-    uint64_t qb = 0;
-    const uint32_t *qs = nullptr, *qe = nullptr, *pm = nullptr, *pmi = nullptr;
-#pragma unroll 1
-    for (int j = 0; j < nj; j++) {
-      const uint32_t rs = __shfl_sync(0xffffffffu, my_rs, j), re = __shfl_sync(0xffffffffu, my_re, j);
-      const int      run = __shfl_sync(0xffffffffu, my_run, j);
-      const uint32_t lo = __shfl_sync(0xffffffffu, my_lo, j), hi = __shfl_sync(0xffffffffu, my_hi, j);
-      if (run != hint_run) {
-        qb = p.run_q_begin[run];
-        nr = (uint32_t)(p.run_q_end[run] - qb);
-        qs = p.qs + qb; qe = p.qe + qb; pm = p.pm + qb; pmi = p.pmi + qb;
-        hint_run = run;
-      }
-      // non-overlapping left candidate from the prefix [0,lo): (max end, last row attaining it)
-      unsigned long long bestL = 0;  // (end + 1) << 32 | (row-in-run + 1); 0 = none
-      if (lo > 0) bestL = ((unsigned long long)(__ldg(&pm[lo - 1]) + 1ull) << 32) | __ldg(&pmi[lo - 1]);
-      uint32_t lastL = 0, firstC = 0xFFFFFFFFu, lastR = 0;  // row-in-run + 1 (0 / ~0 = none)
-      const double centroid = ((double)re - 1.0 + (double)rs) / 2.0;  // getCentroid, :236-239
-#pragma unroll 1
-      for (uint32_t k = lo + lane; k < hi; k += 32) {
-        const uint32_t s = __ldg(&qs[k]), e = __ldg(&qe[k]);
-        if (e <= rs) {  // left of the reference (start < end <= ref.start)
-          const unsigned long long key = ((unsigned long long)(e + 1ull) << 32) | (k + 1u);
-          bestL = key > bestL ? key : bestL;
-        } else if (p.allow_overlaps) {  // overlaps: start < ref.end (k < hi) and end > ref.start
-          if (s <= rs) {
-            lastL = k + 1u;
-          } else if (e >= re) {
-            lastR = k + 1u;
-          } else {
-            // proportionOverlapLeft(c, centroid), :226-231
-            const double prop = centroid < (double)s ? 0.0 : (centroid + 1.0 - (double)s) / ((double)e - (double)s);
-            if (prop >= 0.5) firstC = firstC < k + 1u ? firstC : k + 1u;
-            else lastR = k + 1u;
-          }
+  }
+  if (drained && !st.overflow) {  // :403-406 the stream ran dry
+    if (left != kNoRow && !left_cached) B[m++] = left;
+    if (right != kNoRow) B[m++] = right;
+  }
+  // PushBack(read): the list is read first, then whatever of the old push-back was not reached (:407)
+  const uint32_t rem = st.n - st.r;
+  if (m + rem > cap) st.overflow = true;
+  if (!st.overflow) {
+    for (uint32_t k = 0; k < rem; k++) B[m + k] = st.A[st.r + k];
+    st.B = st.A;
+    st.A = B;
+    st.r = 0;
+    st.n = m + rem;
+  }
+  out_left = left;
+  out_right = right;
+}
+
+__device__ __forceinline__ uint64_t cf_record(const CfParams& p, const CfStream& st) {
+  const uint32_t len = st.n - st.r;
+  const uint64_t off = atomicAdd(reinterpret_cast<unsigned long long*>(p.arena_top), (unsigned long long)len + 2ull);
+  if (off + len + 2 > p.arena_cap) {
+    dev_set_error(p.scratch, BK_ERR_NOMEM, 1);
+    return 0;
+  }
+  p.arena[off] = st.pos;
+  p.arena[off + 1] = len;
+  for (uint32_t k = 0; k < len; k++) p.arena[off + 2 + k] = st.A[st.r + k];
+  return off;
+}
+
+// MODE 0: speculative pass over every chunk.  MODE 1: rerun of the chunks in todo[] from the stream their predecessor
+// left.  MODE 2: one thread per todo[] chunk walks on to the end of its chromosome (termination guarantee).
+template <int MODE>
+__global__ void __launch_bounds__(CF_THREADS) k_cf_sim(CfParams p) {
+  const uint64_t t = (uint64_t)blockIdx.x * CF_THREADS + threadIdx.x;
+  const uint64_t nthreads = (uint64_t)gridDim.x * CF_THREADS;
+  const uint64_t nwork = MODE == 0 ? p.nchunks : p.ntodo;
+  CfStream       st;
+  uint32_t* const buf0 = p.bufs + t * 2ull * p.cap;
+  for (uint64_t wk = t; wk < nwork; wk += nthreads) {
+    const uint64_t c = MODE == 0 ? wk : p.todo[wk];
+    int      run;
+    uint64_t a, b;
+    cf_locate(p.runs, p.nruns, c, run, a, b);
+    const CfRun     R = p.runs[run];
+    const uint32_t  nq = (uint32_t)(R.q_end - R.q_begin);
+    const uint32_t* qs = p.qs + R.q_begin;
+    const uint32_t* qe = p.qe + R.q_begin;
+    st.A = buf0; st.B = buf0 + p.cap; st.r = 0; st.n = 0; st.pos = 0; st.overflow = false;
+    uint32_t l, r;
+    if (MODE == 0) {
+      uint64_t assumed = kExactState;
+      if (a != R.ref_begin) {
+        const uint64_t w = a - R.ref_begin > (uint64_t)CF_WARM ? a - CF_WARM : R.ref_begin;
+        if (w != R.ref_begin && nq) {
+          // guessed state at the warm-up row: its best non-overlapping left, then the file from its candidate window
+          const uint32_t lo = (uint32_t)lower_bound_u32(p.pm + R.q_begin, 0, nq, (uint64_t)p.rs[w] + 1);
+          if (lo > 0) st.A[st.n++] = __ldg(&p.pmi[R.q_begin + lo - 1]) - 1u;
+          st.pos = lo;
         }
+        for (uint64_t row = w; row < a && !st.overflow; row++) cf_row(st, p.cap, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
+        if (w != R.ref_begin) assumed = cf_record(p, st);
       }
-      // warp reductions
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, bestL, d);
-        bestL = o > bestL ? o : bestL;
-      }
-      lastL = __reduce_max_sync(0xffffffffu, lastL);
-      lastR = __reduce_max_sync(0xffffffffu, lastR);
-      firstC = __reduce_min_sync(0xffffffffu, firstC);
-      uint32_t l = kNoRow, r = kNoRow;  // row-in-run
-      if (lastL) l = lastL - 1;
-      else if (firstC != 0xFFFFFFFFu) l = firstC - 1;
-      else if (bestL) l = (uint32_t)(bestL & 0xFFFFFFFFull) - 1;
-      // a contained row with proportion < 0.5 that precedes the first ">= 0.5" row goes right either way; rows after
-      // it with proportion >= 0.5 are ignored once an overlapping left exists (:356-368) -- both covered by lastR
-      if (lastR) r = lastR - 1;
-      else if (hi < nr) r = hi;
-      if (lane == j) {
-        out_left = l == kNoRow ? ~0ull : qb + l;
-        out_right = r == kNoRow ? ~0ull : qb + r;
-      }
+      p.assumed[c] = assumed;
+    } else {
+      const uint64_t off = p.fin_cur[c - 1];  // chunk c-1 is in the same chromosome (first chunks are never inconsistent)
+      const uint32_t len = p.arena[off + 1];
+      st.pos = p.arena[off];
+      if (len > p.cap) st.overflow = true;
+      else
+        for (uint32_t k = 0; k < len; k++) st.A[k] = p.arena[off + 2 + k];
+      st.n = len;
+      p.assumed[c] = off;
     }
-    if (valid) {
-      p.left[i] = out_left;
-      p.right[i] = out_right;
+    const uint64_t stop = MODE == 2 ? R.ref_end : b;
+    for (uint64_t row = a; row < stop && !st.overflow; row++) {
+      cf_row(st, p.cap, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
+      p.left[row - p.row0] = l == kNoRow ? ~0ull : R.q_begin + l;
+      p.right[row - p.row0] = r == kNoRow ? ~0ull : R.q_begin + r;
+    }
+    if (st.overflow) {
+      dev_set_error(p.scratch, BK_ERR_NOMEM, 2);
+      continue;
+    }
+    if (MODE != 2) p.fin_next[c] = cf_record(p, st);
+  }
+}
+
+// consistent(k) = the stream chunk k assumed == the stream chunk k-1 left.  Inconsistent chunks are appended to todo[]
+// (MODE 2 wants only the first one of each chromosome: first_only).
+__global__ void k_cf_check(CfParams p, uint32_t* __restrict__ todo, int first_only) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += stride) {
+    const uint64_t as = p.assumed[c];
+    if (as == kExactState) continue;
+    const uint64_t fo = p.fin_cur[c - 1];
+    bool same = as == fo;
+    if (!same) {
+      const uint32_t n = p.arena[as + 1];
+      same = p.arena[as] == p.arena[fo] && n == p.arena[fo + 1];
+      for (uint32_t k = 0; same && k < n; k++) same = p.arena[as + 2 + k] == p.arena[fo + 2 + k];
+    }
+    if (same) continue;
+    if (first_only) {  // keep the smallest inconsistent chunk of every chromosome: slot = run index
+      int      run;
+      uint64_t a, b;
+      cf_locate(p.runs, p.nruns, c, run, a, b);
+      atomicMin(&todo[run], (uint32_t)c);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_COUNT_A]), 1ull);
+    } else {
+      const uint64_t slot = atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_COUNT_A]), 1ull);
+      todo[slot] = (uint32_t)c;
     }
   }
 }
@@ -267,25 +375,23 @@ extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, c
   if (strlen(delim) > 23) return fail(ctx, BK_ERR_UNSUPPORTED, "delimiter longer than 23 bytes");
 
   const bool all = !spec->chrom || !*spec->chrom || strcmp(spec->chrom, "all") == 0;
-  std::vector<uint64_t> rrb, qb, qe;
-  uint64_t row0 = 0, row1 = 0;
-  bool     first = true;
+  std::vector<CfRun> runs;
+  uint64_t row0 = 0, row1 = 0, nchunks = 0;
   for (auto& r : ref->runs) {
     if (!all && r.name != spec->chrom) continue;
     if (r.row_end == r.row_begin) continue;
-    if (first) { row0 = r.row_begin; first = false; }
+    if (runs.empty()) row0 = r.row_begin;
     row1 = r.row_end;
-    rrb.push_back(r.row_begin);
-    uint64_t b = 0, e = 0;
+    CfRun c{r.row_begin, r.row_end, 0, 0, nchunks};
     for (auto& q : query->runs)
-      if (q.name == r.name) { b = q.row_begin; e = q.row_end; }
-    qb.push_back(b);
-    qe.push_back(e);
+      if (q.name == r.name) { c.q_begin = q.row_begin; c.q_end = q.row_end; }
+    nchunks += (r.row_end - r.row_begin + CF_CHUNK - 1) / CF_CHUNK;
+    runs.push_back(c);
   }
   const uint64_t n = row1 - row0;
   if (n == 0) return finish_text(ctx, nullptr, 0, 0, spec->out_on_device, out);
-  rrb.push_back(row1);
-  const int nruns = (int)qb.size();
+  if (nchunks >= 0xFFFFFFFEull) return fail(ctx, BK_ERR_UNSUPPORTED, "reference file too large for the chunk index");
+  const int nruns = (int)runs.size();
 
   BK_TRY(ensure_pmax(ctx, query));
   // last row attaining the running max (ties: the later row wins, ClosestFeature.cpp:300)
@@ -308,37 +414,114 @@ extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, c
     int rc = seg_prefix_max(ctx, d_mark, d_pmi, query->nrows, query->runs);
     dfree(ctx, d_qrb);
     dfree(ctx, d_mark);
-    if (rc != BK_OK) return rc;
+    if (rc != BK_OK) { dfree(ctx, d_pmi); return rc; }
   }
 
-  std::vector<uint64_t> tab;
-  tab.insert(tab.end(), rrb.begin(), rrb.end());
-  tab.insert(tab.end(), qb.begin(), qb.end());
-  tab.insert(tab.end(), qe.begin(), qe.end());
-  uint64_t* d_tab = dalloc<uint64_t>(ctx, tab.size());
-  if (!d_tab) return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  ClosestParams p{};
-  p.rs = ref->start; p.re = ref->end; p.row0 = row0; p.n = n;
-  p.run_ref_begin = d_tab; p.run_q_begin = d_tab + nruns + 1; p.run_q_end = d_tab + 2 * nruns + 1; p.nruns = nruns;
+  CfParams p{};
+  p.rs = ref->start; p.re = ref->end; p.nruns = nruns; p.nchunks = nchunks; p.row0 = row0;
   p.qs = query->start; p.qe = query->end; p.pm = query->pmax_end; p.pmi = d_pmi;
   p.allow_overlaps = !spec->no_overlaps;
+  p.scratch = ctx->d_scratch;
+  CfRun*    d_runs = dalloc<CfRun>(ctx, runs.size());
+  uint64_t* d_chunk = dalloc<uint64_t>(ctx, 3 * nchunks + 1);  // assumed | fin A | fin B | arena top
+  uint32_t* d_todo = dalloc<uint32_t>(ctx, nchunks + nruns);
   p.left = dalloc<uint64_t>(ctx, n);
   p.right = dalloc<uint64_t>(ctx, n);
-  if (!p.left || !p.right) return BK_ERR_NOMEM;
-  {
-    const uint64_t batches = (n + 31) / 32, per_block = CF_THREADS / 32;
-    uint64_t       blocks = (batches + per_block - 1) / per_block;
-    const uint64_t cap = (uint64_t)ctx->sms * 8 * 8;
-    if (blocks > cap) blocks = cap;
-    prof_begin(ctx, "k_closest");
-    k_closest<<<(unsigned)blocks, CF_THREADS, 0, ctx->stream>>>(p);
-    prof_end(ctx);
-    BK_LAUNCHED(ctx);
+  std::vector<void*> temps{d_pmi, d_runs, d_chunk, d_todo};
+  auto drop = [&](bool results) {
+    for (void* t : temps) dfree(ctx, t);
+    temps.clear();
+    if (results) { dfree(ctx, p.left); dfree(ctx, p.right); }
+  };
+  if (!d_runs || !d_chunk || !d_todo || !p.left || !p.right) { drop(true); return BK_ERR_NOMEM; }
+  BK_CUDA(ctx, cudaMemcpyAsync(d_runs, runs.data(), runs.size() * sizeof(CfRun), cudaMemcpyHostToDevice, ctx->stream));
+  p.runs = d_runs;
+  p.assumed = d_chunk;
+  p.arena_top = d_chunk + 3 * nchunks;
+
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_cf_sim<0>, CF_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t resident = (uint64_t)ctx->sms * per_sm * CF_THREADS;
+  uint32_t       cap = 1024;
+  uint64_t       arena_cap = 16 * n + (4ull << 20);  // u32 entries
+  int            rc = BK_OK;
+  uint64_t       rounds = 0, reruns = 0;
+  while (true) {  // retried with larger buffers when a stream outgrows them (loud, exact)
+    uint64_t threads = std::min<uint64_t>(resident, (nchunks + CF_THREADS - 1) / CF_THREADS * CF_THREADS);
+    while (threads > CF_THREADS && threads * 2ull * cap * 4ull > (16ull << 30)) threads /= 2;
+    threads = threads / CF_THREADS * CF_THREADS;
+    p.cap = cap;
+    p.arena_cap = arena_cap;
+    p.bufs = dalloc<uint32_t>(ctx, threads * 2ull * cap);
+    p.arena = dalloc<uint32_t>(ctx, arena_cap);
+    if (!p.bufs || !p.arena) { dfree(ctx, p.bufs); dfree(ctx, p.arena); rc = BK_ERR_NOMEM; break; }
+    uint64_t* fin[2] = {d_chunk + nchunks, d_chunk + 2 * nchunks};
+    int       cur = 0;
+    auto run = [&]() -> int {
+      BK_TRY(reset_scratch(ctx));
+      BK_CUDA(ctx, cudaMemsetAsync(p.arena_top, 0, 8, ctx->stream));
+      p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
+      prof_begin(ctx, "k_cf_sim");
+      k_cf_sim<0><<<(unsigned)(threads / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
+      prof_end(ctx);
+      BK_LAUNCHED(ctx);
+      cur ^= 1;
+      for (int round = 0;; round++) {
+        const bool last = round >= CF_MAX_ROUNDS;
+        p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
+        if (last) BK_CUDA(ctx, cudaMemsetAsync(d_todo + nchunks, 0xFF, (size_t)nruns * 4, ctx->stream));
+        const uint64_t cb = std::min<uint64_t>((nchunks + 255) / 256, (uint64_t)ctx->sms * 8);
+        k_cf_check<<<(unsigned)cb, 256, 0, ctx->stream>>>(p, last ? d_todo + nchunks : d_todo, last ? 1 : 0);
+        BK_LAUNCHED(ctx);
+        BK_TRY(read_scratch(ctx));
+        if (ctx->h_scratch[SC_ERR_CODE]) return BK_ERR_NOMEM;
+        uint64_t bad = ctx->h_scratch[SC_COUNT_A];
+        if (bad == 0) return BK_OK;
+        rounds++;
+        reruns += bad;
+        BK_CUDA(ctx, cudaMemsetAsync(&ctx->d_scratch[SC_COUNT_A], 0, 8, ctx->stream));
+        if (last) {  // one thread per chromosome from its first inconsistent chunk to its end
+          std::vector<uint32_t> firsts(nruns);
+          BK_CUDA(ctx, cudaMemcpyAsync(firsts.data(), d_todo + nchunks, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+          BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+          firsts.erase(std::remove(firsts.begin(), firsts.end(), 0xFFFFFFFFu), firsts.end());
+          BK_CUDA(ctx, cudaMemcpyAsync(d_todo, firsts.data(), firsts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+          p.todo = d_todo; p.ntodo = (uint32_t)firsts.size();
+          prof_begin(ctx, "k_cf_sim");
+          k_cf_sim<2><<<(unsigned)((firsts.size() + CF_THREADS - 1) / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
+          prof_end(ctx);
+          BK_LAUNCHED(ctx);
+          BK_TRY(read_scratch(ctx));
+          return ctx->h_scratch[SC_ERR_CODE] ? BK_ERR_NOMEM : BK_OK;
+        }
+        BK_CUDA(ctx, cudaMemcpyAsync(p.fin_next, p.fin_cur, nchunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        p.todo = d_todo; p.ntodo = (uint32_t)bad;
+        const uint64_t tb = std::min<uint64_t>((bad + CF_THREADS - 1) / CF_THREADS, threads / CF_THREADS);
+        prof_begin(ctx, "k_cf_sim");
+        k_cf_sim<1><<<(unsigned)tb, CF_THREADS, 0, ctx->stream>>>(p);
+        prof_end(ctx);
+        BK_LAUNCHED(ctx);
+        cur ^= 1;
+      }
+    };
+    rc = run();
+    const uint64_t where = ctx->h_scratch[SC_ERR_ROW];
+    const bool     grow = rc == BK_ERR_NOMEM && ctx->h_scratch[SC_ERR_CODE] == BK_ERR_NOMEM;
+    dfree(ctx, p.bufs);
+    dfree(ctx, p.arena);
+    if (!grow) break;
+    if (where == 1) arena_cap *= 4; else cap *= 8;
+    if (cap > (1u << 28) || arena_cap > (1ull << 36)) {
+      rc = fail(ctx, BK_ERR_NOMEM, "closest-features: push-back state exceeds the device buffers");
+      break;
+    }
   }
+  if (getenv("BEDKIT_TRACE")) fprintf(stderr, "[bedkit] closest: %llu chunks, %llu repair rounds, %llu chunk reruns, cap %u\n",
+                                      (unsigned long long)nchunks, (unsigned long long)rounds, (unsigned long long)reruns, cap);
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  dfree(ctx, d_tab);
-  dfree(ctx, d_pmi);
+  drop(false);
+  if (rc != BK_OK) { dfree(ctx, p.left); dfree(ctx, p.right); return rc; }
 
   ClosestRow fn{};
   fn.rtext = ref->d_text; fn.rline = ref->line_off; fn.rs = ref->start; fn.re = ref->end; fn.row0 = row0;
@@ -347,17 +530,9 @@ extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, c
   fn.dist = spec->dist; fn.closest = spec->closest; fn.no_ref = spec->no_ref;
   fn.delim_len = (int)strlen(delim);
   memcpy(fn.delim, delim, fn.delim_len);
-  // bound: the reference line + two query lines (each at most the longest query line) + distances
-  // the longest query line is not known cheaply; bound it by the whole query text when the file is tiny, otherwise
-  // by a generous per-row constant and let the emitter report an overflow
-  uint64_t per_row = 3 * (uint64_t)fn.delim_len + 2 * 24 + 4 + 2 * 22;
-  uint64_t cap = ref->nbytes + n * per_row + 64;
-  uint64_t qavg = query->nrows ? (query->nbytes / query->nrows + 1) : 0;
-  cap += n * 2 * (qavg * 4 + 64);
-  if (query->nbytes < (1u << 20)) cap += n * 2 * query->nbytes;
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
-  int rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
+  rc = run_emit(ctx, fn, n, 0, &d_out, &bytes, &rows);
   dfree(ctx, p.left);
   dfree(ctx, p.right);
   if (rc != BK_OK) {

@@ -140,7 +140,9 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
   bk_mapspec dspec = *spec;
   dspec.out_on_device = 1;
   char*    h_out = nullptr;
-  uint64_t h_cap = 0, h_off = 0, rows = 0;
+  uint64_t h_cap = 0, h_off = 0, rows = 0, rowids = 0;
+  int      rowid_ops = 0;
+  for (int c = 0; c < spec->n_ops; c++) rowid_ops += spec->ops[c] == BK_OP_ECHO_REF_ROW_ID;
   size_t   flushed = 0;  // parts [0, flushed) have their D2H queued
   uint64_t ref_done = 0, out_done = 0;
   auto     flush = [&](size_t upto) {
@@ -161,7 +163,9 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
     bk_bed *ref = nullptr, *map = nullptr;
     if (rc == BK_OK) rc = bk_load_bed_device(ctx, d_stage + G.d_ref, G.re - G.rb, ref_fields, ref_cols, &ref);
     if (rc == BK_OK) rc = bk_load_bed_device(ctx, d_stage + G.d_map, G.me - G.mb, map_fields, map_cols, &map);
+    dspec.row_id_base = spec->row_id_base + rowids;  // ids already issued by the earlier groups (each printed id bumps the counter)
     if (rc == BK_OK) rc = bk_bedmap(ctx, ref, map, &dspec, &parts[g]);
+    if (rc == BK_OK) rowids += parts[g].rows * (uint64_t)rowid_ops;
     if (rc == BK_OK) cuda_ok(cudaEventRecord(ev_done[g], ctx->stream), "cudaEventRecord");
     bk_free_bed(ctx, ref);
     bk_free_bed(ctx, map);

@@ -241,6 +241,8 @@ int main(int argc, char** argv) {
     bk_mapspec spec;
     bk_mapspec_default(&spec);
     bool need_line = false, need_score = false, need_id = false, need_mapline = false;
+    if (o.ops.size() > (size_t)BK_MAX_OPS)  // bk_mapspec carries a fixed table (the reference chains any number of visitors)
+      throw UserError("More than " + std::to_string(BK_MAX_OPS) + " operations given; this build prints at most that many columns.");
     for (size_t k = 0; k < o.ops.size(); k++) {
       const int op = o.ops[k];
       spec.op_arg[spec.n_ops] = o.op_args[k];

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BEDKIT_ABI_VERSION 1
+#define BEDKIT_ABI_VERSION 2
 
 typedef struct bk_ctx bk_ctx; /* one per GPU: stream, cached device blocks, pinned staging, last error text */
 typedef struct bk_bed bk_bed; /* a parsed, device-resident sorted BED file: SoA columns + chromosome runs */
@@ -154,7 +154,7 @@ enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_FRAC_BOTH = 5,   /* --fraction-both F */
   BK_OVR_EXACT = 6        /* --exact */
 };
-#define BK_MAX_OPS 32
+#define BK_MAX_OPS 64
 typedef struct bk_mapspec {
   int         n_ops;
   int         ops[BK_MAX_OPS];
@@ -169,6 +169,8 @@ typedef struct bk_mapspec {
   const char* chrom;         /* --chrom, NULL or "all" = every chromosome */
   int         out_on_device; /* leave result text in HBM (bench: device-resident timing) */
   double      op_arg[BK_MAX_OPS]; /* per-operation argument (BK_OP_KTH: the fraction, BK_OP_MAD: the multiplier); 0 otherwise */
+  uint64_t    row_id_base;   /* --echo-ref-row-id: rows already printed by earlier calls of the same command (the reference
+                                counts printed rows, ProcessBedVisitorRow.hpp:347-354); 0 for a whole-file call */
 } bk_mapspec;
 void bk_mapspec_default(bk_mapspec* spec);
 /* map == NULL: single-file mode, ref is mapped onto itself (Input.hpp:359-364) */

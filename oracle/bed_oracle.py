@@ -205,6 +205,7 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     pad = val if kind == "range" else 0
     out: List[bytes] = []
     cache = {}
+    rowid = 0
     for ri, r in enumerate(refs):
         if chrom is not None and chrom != b"all" and r.chrom != chrom:
             continue
@@ -350,7 +351,8 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
             elif o == "echo-ref-name":
                 cols.append(r.chrom + b":" + str(r.start).encode() + b"-" + str(r.end).encode())
             elif o == "echo-ref-row-id":
-                cols.append(b"id-" + str(ri + 1).encode())
+                rowid += 1   # PrintRowID: a static counter bumped by every printed id (ProcessBedVisitorRow.hpp:347-354)
+                cols.append(b"id-" + str(rowid).encode())
             else:
                 raise ValueError(o)
         out.append(delim.join(cols) + b"\n")
@@ -579,50 +581,147 @@ def bedops_element_of(texts: Sequence[bytes], thr: float = 1.0, use_pct: bool = 
 # --------------------------------------------------------------------------------------------------
 # closest-features (declarative rule; see SURVEY.md 8c hazard 3 for where the streaming reference differs)
 # --------------------------------------------------------------------------------------------------
+def _cf_distance(c: Row, b: Row):
+    """getDistance(c, b) (ClosestFeature.cpp:244-255): -inf / +inf across chromosomes (strcmp order), negative when c
+    lies left of b, positive when right, 0 on overlap."""
+    if c.chrom != b.chrom:
+        return float("-inf") if c.chrom < b.chrom else float("inf")
+    if c.end <= b.start:
+        return -(b.start - c.end + 1)
+    if b.end <= c.start:
+        return c.start - b.end + 1
+    return 0
+
+
+def closest_pairs(refs: Sequence[Row], qrys: Sequence[Row], allow_overlaps: bool = True):
+    """findDistances (ClosestFeature.cpp:260-413) restated statement by statement, including the push-back list
+    (`read`, handed to BedReader::PushBack, BedReader.hpp:64-66: the list is re-read front first, ahead of whatever was
+    pushed back earlier) -- the reference's answer is a function of this streaming state, not only of the two files:
+    elements dropped ("delete") are gone for every later reference row, and elements held as left/right re-enter the
+    stream after the ones pushed while they were held.  Returns [(left, right)] per reference row (Row or None)."""
+    NEG, POS = float("-inf"), float("inf")
+    cache: List[Row] = []          # BedReader::cache_: a stack, the back is read next
+    pos = 0                        # next unread row of the query file
+
+    def read_line():
+        nonlocal pos
+        if cache:
+            return cache.pop()
+        if pos < len(qrys):
+            pos += 1
+            return qrys[pos - 1]
+        return None
+
+    out = []
+    for b in refs:
+        left_dist, right_dist = NEG, POS
+        left = right = None
+        left_cached = False
+        read: List[Row] = []
+        c = None
+        while True:
+            c = read_line()
+            if c is None:
+                break
+            dist = _cf_distance(c, b)
+            if dist == NEG:                                   # :286-288 query is on an earlier chromosome: drop
+                continue
+            if dist == POS:                                   # :289-296 query is on a later chromosome
+                if left is not None and not left_cached:
+                    read.append(left)
+                left_cached = left is not None
+                if right is not None:
+                    read.append(right)
+                read.append(c)
+                break
+            if dist < 0 and dist >= left_dist:                # :300-309 new best left: everything pushed so far is dropped
+                read.clear()
+                left_dist, left, left_cached = dist, c, False
+            elif dist < 0:                                    # :310-314
+                if not left_cached:
+                    read.append(left)
+                left_cached = True
+            elif dist > 0 and dist < right_dist:              # :315-323
+                if left is not None and not left_cached:
+                    read.append(left)
+                left_cached = left is not None
+                right_dist, right = dist, c
+                read.append(c)
+                break
+            elif dist > 0:                                    # :324-331 read one too many
+                if left is not None and not left_cached:
+                    read.append(left)
+                left_cached = left is not None
+                if right is not None:
+                    read.append(right)
+                read.append(c)
+                break
+            elif allow_overlaps:                              # :332-388
+                if c.start <= b.start:                        # hangs over the left edge
+                    if left is not None and left.end <= c.end and not left_cached:
+                        pass                                  # delete left
+                    elif left is not None and not left_cached:
+                        read.append(left)
+                    left, left_dist, left_cached = c, 0, False
+                elif b.end <= c.end:                          # hangs over the right edge
+                    if left is not None and not left_cached:
+                        read.append(left)
+                    left_cached = left is not None
+                    if right is not None:
+                        read.append(right)
+                    right, right_dist = c, 0
+                else:                                         # contained in the reference row
+                    centroid = (b.end - 1.0 + b.start) / 2.0  # getCentroid :236-239
+                    prop = 0.0 if centroid < c.start else (centroid + 1 - c.start) / (c.end - c.start)  # :226-231
+                    if left_dist == 0:
+                        if prop < 0.5:
+                            if not left_cached:
+                                read.append(left)
+                            left_cached = True
+                            if right is not None:
+                                read.append(right)
+                            right, right_dist = c, 0
+                        else:
+                            if not left_cached:
+                                read.append(left)
+                            left_cached = True
+                            read.append(c)
+                    elif prop >= 0.5:                         # :369-378 new left: the push-back list is dropped
+                        read.clear()
+                        left_cached = False
+                        left, left_dist = c, 0
+                    else:
+                        if left is not None and not left_cached:
+                            read.append(left)
+                        left_cached = left is not None
+                        if right is not None:
+                            read.append(right)
+                        right, right_dist = c, 0
+            else:                                             # :389-397 --no-overlaps: keep for later reference rows
+                if left is not None and not left_cached:
+                    read.append(left)
+                    left_cached = True
+                read.append(c)
+        if c is None and left is not None and not left_cached:    # :403-406
+            read.append(left)
+        if c is None and right is not None:
+            read.append(right)
+        cache.extend(reversed(read))                          # PushBack(list): front of `read` is read first
+        out.append((left, right))
+    return out
+
+
 def closest_features(ref_text: bytes, qry_text: bytes, dist: bool = False, closest: bool = False,
                      no_overlaps: bool = False, no_ref: bool = False, delim: bytes = b"|",
                      chrom: Optional[bytes] = None) -> bytes:
     """findDistances (applications/bed/closestfeats/src/ClosestFeature.cpp:260-413) + PrintAll/PrintShortest
     (Printers.hpp:46-205)."""
     refs = _sel(parse_bed(ref_text, 3), chrom)
-    qc = by_chrom(_sel(parse_bed(qry_text, 3), chrom))
+    qrys = _sel(parse_bed(qry_text, 3), chrom)
     out = []
-    for b in refs:
-        ql = qc.get(b.chrom, [])
-        left = right = None
-        ldist = rdist = None
-        # nearest non-overlapping neighbours
-        for c in ql:
-            if c.end <= b.start:
-                d = -(b.start - c.end + 1)          # getDistance :244-255
-                if ldist is None or d >= ldist:     # ">=": later row wins ties (:300)
-                    left, ldist = c, d
-            elif c.start >= b.end:
-                d = c.start - b.end + 1
-                if rdist is None or d < rdist:
-                    right, rdist = c, d
-                break
-        if not no_overlaps:
-            lov = False
-            for c in ql:
-                if c.start >= b.end:
-                    break
-                if c.end <= b.start:
-                    continue
-                if c.start <= b.start:              # hangs over the left edge (:335-342)
-                    left, ldist, lov = c, 0, True
-                elif b.end <= c.end:                # hangs over the right edge (:343-350)
-                    right, rdist = c, 0
-                else:                               # contained: centroid rule (:351-388)
-                    centroid = (b.end - 1.0 + b.start) / 2.0
-                    prop = 0.0 if centroid < c.start else (centroid + 1 - c.start) / (c.end - c.start)
-                    if lov:
-                        if prop < 0.5:
-                            right, rdist = c, 0
-                    elif prop >= 0.5:
-                        left, ldist, lov = c, 0, True
-                    else:
-                        right, rdist = c, 0
+    for b, (left, right) in zip(refs, closest_pairs(refs, qrys, not no_overlaps)):
+        ldist = _cf_distance(left, b) if left is not None else None
+        rdist = _cf_distance(right, b) if right is not None else None
         parts: List[bytes] = []
 
         def show(x, d):

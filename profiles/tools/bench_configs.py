@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 KERNELS = ["k_efflen", "k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_rank_merge", "k_segments",
-           "k_intersect", "k_element_of", "k_argmark", "k_closest", "k_map_stats", "k_emit_len", "k_emit"]
+           "k_intersect", "k_element_of", "k_argmark", "k_cf_sim", "k_map_stats", "k_emit_len", "k_emit"]
 
 
 def main():
@@ -45,6 +45,17 @@ def main():
         print(json.dumps({"op": name, "input_rows": units, "ms": round(ms, 3), "rows_per_s": units / (ms * 1e-3),
                           "kernel_ms": split}), flush=True)
 
+    only = os.environ.get("BEDKIT_CONFIGS", "3,4,5").split(",")
+    if "3" in only:
+      run_config3(kit, torch, timed, scale, SynthFile, MAP_SHAPE, COL_LINE)
+    if "4" in only:
+      run_config4(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE, COL_LINE)
+    if "5" in only:
+      run_config5(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE, COL_LINE, COL_SCORE)
+    kit.close()
+
+
+def run_config3(kit, torch, timed, scale, SynthFile, MAP_SHAPE, COL_LINE):
     # configuration 3: bedops over 4 files of 250 M rows (load + operation, as the tools do)
     files = [SynthFile(kit, torch, int(250_000_000 * scale), s, MAP_SHAPE) for s in (1, 3, 4, 5)]
     rows = sum(f.rows for f in files)
@@ -65,6 +76,9 @@ def main():
     kit.release_cached()
     torch.cuda.empty_cache()
 
+
+
+def run_config4(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE, COL_LINE):
     # configuration 4: closest-features 50 M x 200 M
     ref = SynthFile(kit, torch, int(50_000_000 * scale), 2, REF_SHAPE)
     qry = SynthFile(kit, torch, int(200_000_000 * scale), 1, MAP_SHAPE)
@@ -76,10 +90,21 @@ def main():
         rb.free()
         qb.free()
     timed("closest-features --dist, 50M x 200M", ref.rows + qry.rows, closest)
+
+    def closest_no():
+        rb, qb = ref.load(kit, 3, COL_LINE), qry.load(kit, 3, COL_LINE)
+        out = kit.closest(rb, qb, dist=True, no_overlaps=True, on_device=True)
+        out.free()
+        rb.free()
+        qb.free()
+    timed("closest-features --dist --no-overlaps, 50M x 200M", ref.rows + qry.rows, closest_no)
     del ref, qry
     kit.release_cached()
     torch.cuda.empty_cache()
 
+
+
+def run_config5(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE, COL_LINE, COL_SCORE):
     # configuration 5: bedmap --mean over 1 B map rows on one GPU
     ref = SynthFile(kit, torch, int(10_000_000 * scale), 2, REF_SHAPE)
     mp = SynthFile(kit, torch, int(1_000_000_000 * scale), 1, MAP_SHAPE)
@@ -91,7 +116,6 @@ def main():
         rb.free()
         mb.free()
     timed("bedmap --echo --mean, 10M x 1B", ref.rows + mp.rows, bedmap)
-    kit.close()
 
 
 if __name__ == "__main__":

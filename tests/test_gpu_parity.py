@@ -387,3 +387,42 @@ def test_ec_validation_matches_reference_messages(tmp_path):
         assert ours.returncode == ref.returncode, (tool, argv, ours.stderr, ref.stderr)
         assert ours.stdout == ref.stdout, (tool, argv, ours.stdout, ref.stdout)
         assert ours.stderr == ref.stderr, (tool, argv, ours.stderr, ref.stderr)
+
+
+def test_closest_features_streaming_state_across_chunks(kit, tmp_path):
+    from bedops_b200._lib import COL_LINE
+    """Dense nesting on both sides with thousands of reference rows per chromosome: the device runs findDistances
+    speculatively in chunks of 256 reference rows (closest.cu) and must reproduce the reference's streaming push-back
+    state exactly -- against the oracle's statement-by-statement restatement and, where it travelled, the binary."""
+    import numpy as np
+    from conftest import have_ref, REFBIN
+    import subprocess
+    for seed, (nr, nq, span, mu_r, mu_q) in enumerate([(3000, 6000, 40000, 4.0, 3.0), (5000, 20000, 60000, 5.0, 2.5),
+                                                       (2500, 2500, 3000, 3.0, 3.0), (4000, 1000, 200000, 6.0, 5.0),
+                                                       (6000, 30000, 30000, 2.0, 4.5)]):
+        rng = np.random.default_rng(100 + seed)
+
+        def make(n, mu):
+            rows = []
+            for c in ("chr1", "chr2"):
+                s = rng.integers(0, span, n)
+                e = s + np.maximum(1, rng.lognormal(mu, 1.2, n).astype(np.int64))
+                o = np.lexsort((e, s))
+                rows += ["%s\t%d\t%d" % (c, a, b) for a, b in zip(s[o].tolist(), e[o].tolist())]
+            return ("\n".join(rows) + "\n").encode()
+        rt, qt = make(nr, mu_r), make(nq, mu_q)
+        ref, qry = kit.load(rt, 3, COL_LINE), kit.load(qt, 3, COL_LINE)
+        for kw in (dict(dist=True), dict(no_overlaps=True, dist=True), dict(closest=True, no_ref=True)):
+            got = kit.closest(ref, qry, **kw)
+            exp = O.closest_features(rt, qt, **kw)
+            if got != exp:
+                ge, gg = exp.split(b"\n"), got.split(b"\n")
+                bad = [i for i, (x, y) in enumerate(zip(ge, gg)) if x != y]
+                raise AssertionError("seed %d %s: %d of %d rows differ, first %d: %r vs %r" % (seed, kw, len(bad), len(ge), bad[0], ge[bad[0]], gg[bad[0]]))
+        if have_ref():
+            (tmp_path / "r.bed").write_bytes(rt)
+            (tmp_path / "q.bed").write_bytes(qt)
+            r = subprocess.run([os.path.join(REFBIN, "closest-features"), "--dist", "r.bed", "q.bed"], cwd=tmp_path, capture_output=True)
+            assert r.stdout == kit.closest(ref, qry, dist=True)
+        ref.free()
+        qry.free()

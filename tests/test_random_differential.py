@@ -5,9 +5,9 @@ chromosomes missing from one side, empty files.
     absent) -- keeps the oracle pinned on inputs no golden vector covers;
   * GPU (-m gpu):        the CUDA path through the C ABI against the oracle, byte-identical.
 
-Where the reference's output depends on heap addresses or on its streaming state (SURVEY 8c hazards 2 and 3) the
-generator avoids the trigger: per-hit list operations get files without duplicate coordinates, closest-features gets
-pairwise disjoint reference rows when compared with the binary."""
+Where the reference's output depends on heap addresses (SURVEY 8c hazard 2) the generator avoids the trigger: per-hit
+list operations get files without duplicate coordinates.  closest-features is compared on nested / overlapping /
+duplicate reference and query rows, with and without --no-overlaps: its streaming state is emulated exactly."""
 import os
 import subprocess
 
@@ -140,9 +140,15 @@ def make_case(seed, for_binary):
             argv = ["--chrom", chroms[0]] + argv
         return "bedops", argv + names, files
     # closest-features
-    files["r.bed"] = rand_bed(rng, n, span, sub(), disjoint=for_binary, messy=messy)
+    # nested / overlapping / duplicate rows on both sides: the streaming push-back state of findDistances is part of
+    # the contract (oracle: closest_pairs)
+    files["r.bed"] = rand_bed(rng, n, span, sub(), messy=messy)
     files["q.bed"] = rand_bed(rng, 2 * n, span, sub(), messy=messy)
     argv = [a for a in ("--dist", "--closest", "--no-ref") if rng.random() < 0.5]
+    if rng.random() < 0.35:
+        argv.append("--no-overlaps")
+    if rng.random() < 0.1:
+        argv += ["--chrom", chroms[0]]
     return "closest-features", argv + ["r.bed", "q.bed"], files
 
 
