@@ -100,6 +100,13 @@ def load_library() -> C.CDLL:
         "bk_free_text": (None, [vp, C.POINTER(_Text)]),
         "bk_check_text": (i, [vp, C.c_char_p, C.c_size_t, i, i, i]),
         "bk_check_text_device": (i, [vp, vp, C.c_size_t, i, i, i]),
+        "bk_find_start": (u64, [vp, u64, u64, u64]),
+        "bk_bed_reach_start": (i, [vp, vp, C.c_char_p, u64, C.POINTER(u64)]),
+        "bk_bed_chrom_max_end": (i, [vp, vp, C.c_char_p, C.POINTER(u64)]),
+        "bk_bed_concat": (i, [vp, vp, vp, C.POINTER(vp)]),
+        "bk_shard_free": (None, [vp, vp]),
+        "bk_shard_bytes_in": (u64, [vp]),
+        "bk_bedmap_shard_finish": (i, [vp, vp, C.POINTER(u64), C.POINTER(_Text)]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
@@ -113,7 +120,9 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_launch_count", "bk_profile", "bk_profile_query", "bk_copy", "bk_load_bed", "bk_load_bed_device", "bk_free_bed", "bk_bed_rows", "bk_bed_nchrom",
            "bk_bed_chrom_name", "bk_bed_chrom_rows", "bk_bed_copy_columns", "bk_mapspec_default", "bk_bedmap",
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
-           "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop"]
+           "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop", "bk_find_start", "bk_plan_cuts",
+           "bk_cut_offset", "bk_bed_reach_start", "bk_bed_chrom_max_end", "bk_bed_concat", "bk_shard_plan_make",
+           "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in"]
 
 
 class Bed:

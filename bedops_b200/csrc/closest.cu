@@ -13,9 +13,9 @@
 //   k_cf_check  chunk k is consistent iff the stream it assumed equals, element by element, the stream chunk k-1 left.
 //   k_cf_sim    (rerun mode) every inconsistent chunk starts again from the stream chunk k-1 left; check; repeat.
 // The first chunk of a chromosome starts from the exact state (empty push-back, file at the chromosome's first row), so
-// by induction round r makes the first r chunks of every chromosome exact; states converge within a chunk in practice
-// (two rounds).  After CF_MAX_ROUNDS a last kernel walks each chromosome's remaining rows with one thread.
-// No approximation anywhere: when the loop ends every chunk ran from the true stream.
+// by induction round r makes the first r chunks of every chromosome exact, and the loop ends when every chunk ran from
+// the true stream: no approximation anywhere.  In practice streams converge within a chunk or two (measured on the
+// 50 M x 200 M configuration: a third of the chunks rerun once, then a handful for 3-6 more rounds).
 #include <algorithm>
 #include "common.cuh"
 #include "emit.cuh"
@@ -28,7 +28,6 @@ constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 constexpr int      CF_THREADS = 128;
 constexpr int      CF_CHUNK = 256;      // reference rows per chunk
 constexpr int      CF_WARM = 96;        // warm-up rows in front of a speculative chunk
-constexpr int      CF_MAX_ROUNDS = 6;
 constexpr uint64_t kExactState = ~0ull;  // "assumed" marker of a chunk that begins its chromosome
 
 // pmi source: v[k] = (end[k] == pm[k]) ? k - run_begin + 1 : 0
@@ -66,7 +65,7 @@ struct CfParams {
   uint64_t*       left;  // global query row or UINT64_MAX
   uint64_t*       right;
   // per-thread stream buffers: two of `cap` entries each
-  uint32_t*       bufs;
+  uint4*          bufs;
   uint32_t        cap;
   // recorded streams: arena[off] = file position, arena[off+1] = n, then n query rows (relative to the run)
   uint32_t*       arena;
@@ -75,8 +74,10 @@ struct CfParams {
   uint64_t*       assumed;   // [nchunks] arena offset of the stream the chunk started from (kExactState: exact)
   uint64_t*       fin_cur;   // [nchunks] arena offset of the stream the chunk left (read by rerun mode: chunk k-1)
   uint64_t*       fin_next;  // [nchunks] written by this launch
-  const uint32_t* todo;      // rerun mode: chunks to run
+  const uint32_t* todo;      // chunks to run (null in the first speculative pass: all of them)
   uint32_t        ntodo;
+  uint32_t*       ovf;       // chunks whose stream outgrew the buffers of this launch: run again with larger ones
+  uint64_t*       ovf_count;
   uint64_t*       scratch;
 };
 
@@ -91,122 +92,143 @@ __device__ __forceinline__ void cf_locate(const CfRun* __restrict__ runs, int nr
   b = a + CF_CHUNK < runs[lo].ref_end ? a + CF_CHUNK : runs[lo].ref_end;
 }
 
-// the stream of one simulation: pushed-back elements A[r..n) in read order, then the file from row `pos`
+// The stream of one simulation: the push-back stack S[0..top) (BedReader::cache_, BedReader.hpp:76-84: the back is
+// read next), then the file from row `pos`.  Entries carry the row's coordinates so that a step is one 16-byte load.
 struct CfStream {
-  uint32_t* A;
-  uint32_t* B;  // the push-back list being built for the current reference row (`read`, ClosestFeature.cpp:275)
-  uint32_t  r, n, pos;
-  bool      overflow;
+  uint4*   S;   // x = query row (relative to the run), y = start, z = end
+  uint4*   RD;  // the push-back list of the current reference row (`read`, ClosestFeature.cpp:275), filled downwards
+  uint32_t top, pos, cap;
+  bool     overflow;
 };
 
+// Rows at the bottom of the stack that are exactly the file rows in front of `pos`, in file order, are the same stream
+// as not having read them: how many can be handed back (the canonical form used to compare and to record states, and
+// to keep the stack short behind a long reference row)
+__device__ __forceinline__ uint32_t cf_strippable(const CfStream& st) {
+  uint32_t b = 0;
+  while (b < st.top && st.S[b].x + 1u + b == st.pos) b++;
+  return b;
+}
+
 // one reference row of findDistances (:277-411); returns left/right as query rows relative to the run
-__device__ __forceinline__ void cf_row(CfStream& st, uint32_t cap, const uint32_t* __restrict__ qs,
-                                       const uint32_t* __restrict__ qe, uint32_t nq, uint32_t rs, uint32_t re, bool allow,
-                                       uint32_t& out_left, uint32_t& out_right) {
-  uint32_t left = kNoRow, right = kNoRow, left_end = 0, m = 0;
+__device__ __forceinline__ void cf_row(CfStream& st, const uint32_t* __restrict__ qs, const uint32_t* __restrict__ qe,
+                                       uint32_t nq, uint32_t rs, uint32_t re, bool allow, uint32_t& out_left,
+                                       uint32_t& out_right) {
+  uint4    left = make_uint4(kNoRow, 0, 0, 0), right = make_uint4(kNoRow, 0, 0, 0);
   bool     left_ov = false, left_cached = false, drained = true;
-  uint32_t* const B = st.B;
+  uint4* const   RD = st.RD;
+  const uint32_t cap = st.cap;
+  uint32_t       m = 0;  // RD[cap-1], RD[cap-2], ... RD[cap-m]: the list in push order
   const long long c2 = (long long)re - 1 + (long long)rs;  // 2 * getCentroid(b), :236-239
-  // every branch appends at most three entries: one bound check per element
+  auto push = [&](const uint4& v) { RD[cap - 1 - m++] = v; };
   while (true) {
-    uint32_t c;
-    if (st.r < st.n) c = st.A[st.r++];
-    else if (st.pos < nq) c = st.pos++;
-    else break;
-    if (m + 3 > cap) {
+    uint4 c;
+    if (st.top) c = st.S[--st.top];
+    else if (st.pos < nq) {
+      c = make_uint4(st.pos, __ldg(&qs[st.pos]), __ldg(&qe[st.pos]), 0);
+      st.pos++;
+    } else break;
+    if (m + 3 > cap) {  // every branch appends at most three entries
       st.overflow = true;
-      break;
+      return;
     }
-    const uint32_t s = __ldg(&qs[c]), e = __ldg(&qe[c]);
+    const uint32_t s = c.y, e = c.z;
     if (e <= rs) {  // left of the reference row (dist < 0)
-      if (left == kNoRow || (!left_ov && e >= left_end)) {  // :300-309 new best left: the list so far is dropped
+      if (left.x == kNoRow || (!left_ov && e >= left.z)) {  // :300-309 new best left: the list so far is dropped
         m = 0;
-        left = c; left_end = e; left_ov = false; left_cached = false;
+        left = c; left_ov = false; left_cached = false;
       } else {  // :310-314 (c is dropped)
-        if (!left_cached) B[m++] = left;
+        if (!left_cached) push(left);
         left_cached = true;
       }
     } else if (s >= re) {  // right of the reference row (dist > 0): :315-331
-      if (left != kNoRow && !left_cached) B[m++] = left;
-      left_cached = left != kNoRow;
-      if (right == kNoRow) right = c; else B[m++] = right;
-      B[m++] = c;
+      if (left.x != kNoRow && !left_cached) push(left);
+      left_cached = left.x != kNoRow;
+      if (right.x == kNoRow) right = c; else push(right);
+      push(c);
       drained = false;
       break;
     } else if (allow) {  // overlap, :332-388
       if (s <= rs) {  // hangs over the left edge
-        if (left != kNoRow && !left_cached && left_end > e) B[m++] = left;  // else dropped (:336-339)
-        left = c; left_end = e; left_ov = true; left_cached = false;
+        if (left.x != kNoRow && !left_cached && left.z > e) push(left);  // else dropped (:336-339)
+        left = c; left_ov = true; left_cached = false;
       } else {
         // proportionOverlapLeft(c, centroid) >= 0.5 (:226-231) in exact integers: centroid >= s and
         // 2 * (centroid + 1 - s) >= e - s  (the correctly rounded double quotient compares the same way: 2x and the
         // length are integers below 2^53)
         const bool contained = e < re;
         const bool more_left = contained && c2 >= 2ll * s && c2 + 2 >= (long long)e + (long long)s;
-        if (contained && left_ov && more_left) {  // :362-368 left stays; c may be needed later
-          if (!left_cached) B[m++] = left;
+        if (more_left && left_ov) {  // :362-368 left stays; c may be needed later
+          if (!left_cached) push(left);
           left_cached = true;
-          B[m++] = c;
-        } else if (contained && !left_ov && more_left) {  // :369-378 new left: the list so far is dropped
+          push(c);
+        } else if (more_left) {  // :369-378 new left: the list so far is dropped
           m = 0;
-          left = c; left_end = e; left_ov = true; left_cached = false;
+          left = c; left_ov = true; left_cached = false;
         } else {  // hangs over the right edge (:343-350) or contained nearer the right edge (:354-361, :379-387)
-          if (left != kNoRow && !left_cached) B[m++] = left;
-          left_cached = left != kNoRow;
-          if (right != kNoRow) B[m++] = right;
+          if (left.x != kNoRow && !left_cached) push(left);
+          left_cached = left.x != kNoRow;
+          if (right.x != kNoRow) push(right);
           right = c;
         }
       }
     } else {  // :389-397 --no-overlaps: kept for later reference rows
-      if (left != kNoRow && !left_cached) {
-        B[m++] = left;
+      if (left.x != kNoRow && !left_cached) {
+        push(left);
         left_cached = true;
       }
-      B[m++] = c;
+      push(c);
     }
   }
-  if (drained && !st.overflow) {  // :403-406 the stream ran dry
-    if (left != kNoRow && !left_cached) B[m++] = left;
-    if (right != kNoRow) B[m++] = right;
+  if (drained) {  // :403-406 the stream ran dry
+    if (left.x != kNoRow && !left_cached) push(left);
+    if (right.x != kNoRow) push(right);
   }
-  // PushBack(read): the list is read first, then whatever of the old push-back was not reached (:407)
-  const uint32_t rem = st.n - st.r;
-  if (m + rem > cap) st.overflow = true;
-  if (!st.overflow) {
-    for (uint32_t k = 0; k < rem; k++) B[m + k] = st.A[st.r + k];
-    st.B = st.A;
-    st.A = B;
-    st.r = 0;
-    st.n = m + rem;
+  // PushBack(read) (:407): the front of the list is read first = ends on top of the stack.  RD[cap-m .. cap) in address
+  // order is the list reversed: a straight copy.
+  if (st.top + m > cap) {  // make room: hand the file-order tail back to the file
+    const uint32_t b = cf_strippable(st);
+    if (b == 0 || st.top - b + m > cap) {
+      st.overflow = true;
+      return;
+    }
+    for (uint32_t k = b; k < st.top; k++) st.S[k - b] = st.S[k];
+    st.top -= b;
+    st.pos -= b;
   }
-  out_left = left;
-  out_right = right;
+  for (uint32_t k = 0; k < m; k++) st.S[st.top + k] = RD[cap - m + k];
+  st.top += m;
+  out_left = left.x;
+  out_right = right.x;
 }
 
+// recorded state (canonical form): arena[off] = file position, arena[off+1] = n, then the n stack rows, bottom first
 __device__ __forceinline__ uint64_t cf_record(const CfParams& p, const CfStream& st) {
-  const uint32_t len = st.n - st.r;
+  const uint32_t b = cf_strippable(st), len = st.top - b;
   const uint64_t off = atomicAdd(reinterpret_cast<unsigned long long*>(p.arena_top), (unsigned long long)len + 2ull);
   if (off + len + 2 > p.arena_cap) {
     dev_set_error(p.scratch, BK_ERR_NOMEM, 1);
     return 0;
   }
-  p.arena[off] = st.pos;
+  p.arena[off] = st.pos - b;
   p.arena[off + 1] = len;
-  for (uint32_t k = 0; k < len; k++) p.arena[off + 2 + k] = st.A[st.r + k];
+  for (uint32_t k = 0; k < len; k++) p.arena[off + 2 + k] = st.S[b + k].x;
   return off;
 }
 
-// MODE 0: speculative pass over every chunk.  MODE 1: rerun of the chunks in todo[] from the stream their predecessor
-// left.  MODE 2: one thread per todo[] chunk walks on to the end of its chromosome (termination guarantee).
+// MODE 0: speculative run (warm-up from a guessed state).  MODE 1: run from the stream the predecessor left.
+// Either over every chunk (todo == null) or over the chunks listed in todo[].
 template <int MODE>
 __global__ void __launch_bounds__(CF_THREADS) k_cf_sim(CfParams p) {
   const uint64_t t = (uint64_t)blockIdx.x * CF_THREADS + threadIdx.x;
   const uint64_t nthreads = (uint64_t)gridDim.x * CF_THREADS;
-  const uint64_t nwork = MODE == 0 ? p.nchunks : p.ntodo;
+  const uint64_t nwork = p.todo ? p.ntodo : p.nchunks;
   CfStream       st;
-  uint32_t* const buf0 = p.bufs + t * 2ull * p.cap;
+  st.cap = p.cap;
+  st.S = p.bufs + t * 2ull * p.cap;
+  st.RD = st.S + p.cap;
   for (uint64_t wk = t; wk < nwork; wk += nthreads) {
-    const uint64_t c = MODE == 0 ? wk : p.todo[wk];
+    const uint64_t c = p.todo ? p.todo[wk] : wk;
     int      run;
     uint64_t a, b;
     cf_locate(p.runs, p.nruns, c, run, a, b);
@@ -214,8 +236,8 @@ __global__ void __launch_bounds__(CF_THREADS) k_cf_sim(CfParams p) {
     const uint32_t  nq = (uint32_t)(R.q_end - R.q_begin);
     const uint32_t* qs = p.qs + R.q_begin;
     const uint32_t* qe = p.qe + R.q_begin;
-    st.A = buf0; st.B = buf0 + p.cap; st.r = 0; st.n = 0; st.pos = 0; st.overflow = false;
-    uint32_t l, r;
+    st.top = 0; st.pos = 0; st.overflow = false;
+    uint32_t l = kNoRow, r = kNoRow;
     if (MODE == 0) {
       uint64_t assumed = kExactState;
       if (a != R.ref_begin) {
@@ -223,11 +245,14 @@ __global__ void __launch_bounds__(CF_THREADS) k_cf_sim(CfParams p) {
         if (w != R.ref_begin && nq) {
           // guessed state at the warm-up row: its best non-overlapping left, then the file from its candidate window
           const uint32_t lo = (uint32_t)lower_bound_u32(p.pm + R.q_begin, 0, nq, (uint64_t)p.rs[w] + 1);
-          if (lo > 0) st.A[st.n++] = __ldg(&p.pmi[R.q_begin + lo - 1]) - 1u;
+          if (lo > 0) {
+            const uint32_t k = __ldg(&p.pmi[R.q_begin + lo - 1]) - 1u;
+            st.S[st.top++] = make_uint4(k, qs[k], qe[k], 0);
+          }
           st.pos = lo;
         }
-        for (uint64_t row = w; row < a && !st.overflow; row++) cf_row(st, p.cap, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
-        if (w != R.ref_begin) assumed = cf_record(p, st);
+        for (uint64_t row = w; row < a && !st.overflow; row++) cf_row(st, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
+        if (w != R.ref_begin && !st.overflow) assumed = cf_record(p, st);
       }
       p.assumed[c] = assumed;
     } else {
@@ -236,27 +261,29 @@ __global__ void __launch_bounds__(CF_THREADS) k_cf_sim(CfParams p) {
       st.pos = p.arena[off];
       if (len > p.cap) st.overflow = true;
       else
-        for (uint32_t k = 0; k < len; k++) st.A[k] = p.arena[off + 2 + k];
-      st.n = len;
+        for (uint32_t k = 0; k < len; k++) {
+          const uint32_t q = p.arena[off + 2 + k];
+          st.S[k] = make_uint4(q, qs[q], qe[q], 0);
+        }
+      st.top = len;
       p.assumed[c] = off;
     }
-    const uint64_t stop = MODE == 2 ? R.ref_end : b;
-    for (uint64_t row = a; row < stop && !st.overflow; row++) {
-      cf_row(st, p.cap, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
+    for (uint64_t row = a; row < b && !st.overflow; row++) {
+      cf_row(st, qs, qe, nq, p.rs[row], p.re[row], p.allow_overlaps, l, r);
       p.left[row - p.row0] = l == kNoRow ? ~0ull : R.q_begin + l;
       p.right[row - p.row0] = r == kNoRow ? ~0ull : R.q_begin + r;
     }
     if (st.overflow) {
-      dev_set_error(p.scratch, BK_ERR_NOMEM, 2);
+      p.ovf[atomicAdd(reinterpret_cast<unsigned long long*>(p.ovf_count), 1ull)] = (uint32_t)c;
       continue;
     }
-    if (MODE != 2) p.fin_next[c] = cf_record(p, st);
+    p.fin_next[c] = cf_record(p, st);
   }
 }
 
-// consistent(k) = the stream chunk k assumed == the stream chunk k-1 left.  Inconsistent chunks are appended to todo[]
-// (MODE 2 wants only the first one of each chromosome: first_only).
-__global__ void k_cf_check(CfParams p, uint32_t* __restrict__ todo, int first_only) {
+// consistent(k) = the stream chunk k assumed == the stream chunk k-1 left (canonical forms, element by element).
+// Inconsistent chunks are appended to todo[].
+__global__ void k_cf_check(CfParams p, uint32_t* __restrict__ todo) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += stride) {
     const uint64_t as = p.assumed[c];
@@ -269,16 +296,8 @@ __global__ void k_cf_check(CfParams p, uint32_t* __restrict__ todo, int first_on
       for (uint32_t k = 0; same && k < n; k++) same = p.arena[as + 2 + k] == p.arena[fo + 2 + k];
     }
     if (same) continue;
-    if (first_only) {  // keep the smallest inconsistent chunk of every chromosome: slot = run index
-      int      run;
-      uint64_t a, b;
-      cf_locate(p.runs, p.nruns, c, run, a, b);
-      atomicMin(&todo[run], (uint32_t)c);
-      atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_COUNT_A]), 1ull);
-    } else {
-      const uint64_t slot = atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_COUNT_A]), 1ull);
-      todo[slot] = (uint32_t)c;
-    }
+    const uint64_t slot = atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_COUNT_A]), 1ull);
+    todo[slot] = (uint32_t)c;
   }
 }
 
@@ -424,7 +443,7 @@ extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, c
   p.scratch = ctx->d_scratch;
   CfRun*    d_runs = dalloc<CfRun>(ctx, runs.size());
   uint64_t* d_chunk = dalloc<uint64_t>(ctx, 3 * nchunks + 1);  // assumed | fin A | fin B | arena top
-  uint32_t* d_todo = dalloc<uint32_t>(ctx, nchunks + nruns);
+  uint32_t* d_todo = dalloc<uint32_t>(ctx, nchunks + 1);
   p.left = dalloc<uint64_t>(ctx, n);
   p.right = dalloc<uint64_t>(ctx, n);
   std::vector<void*> temps{d_pmi, d_runs, d_chunk, d_todo};
@@ -443,82 +462,98 @@ extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, c
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_cf_sim<0>, CF_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
   const uint64_t resident = (uint64_t)ctx->sms * per_sm * CF_THREADS;
-  uint32_t       cap = 1024;
-  uint64_t       arena_cap = 16 * n + (4ull << 20);  // u32 entries
+  const uint64_t buf_budget = 24ull << 30;  // bytes of stream buffers per launch
+  uint64_t       arena_cap = 24 * n + (4ull << 20);  // u32 entries
   int            rc = BK_OK;
-  uint64_t       rounds = 0, reruns = 0;
-  while (true) {  // retried with larger buffers when a stream outgrows them (loud, exact)
-    uint64_t threads = std::min<uint64_t>(resident, (nchunks + CF_THREADS - 1) / CF_THREADS * CF_THREADS);
-    while (threads > CF_THREADS && threads * 2ull * cap * 4ull > (16ull << 30)) threads /= 2;
-    threads = threads / CF_THREADS * CF_THREADS;
-    p.cap = cap;
-    p.arena_cap = arena_cap;
-    p.bufs = dalloc<uint32_t>(ctx, threads * 2ull * cap);
-    p.arena = dalloc<uint32_t>(ctx, arena_cap);
-    if (!p.bufs || !p.arena) { dfree(ctx, p.bufs); dfree(ctx, p.arena); rc = BK_ERR_NOMEM; break; }
-    uint64_t* fin[2] = {d_chunk + nchunks, d_chunk + 2 * nchunks};
-    int       cur = 0;
-    auto run = [&]() -> int {
-      BK_TRY(reset_scratch(ctx));
-      BK_CUDA(ctx, cudaMemsetAsync(p.arena_top, 0, 8, ctx->stream));
-      p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
+  uint64_t       rounds = 0, reruns = 0, big_runs = 0;
+  uint32_t       cap_used = 0;
+  uint32_t*      d_ovf = dalloc<uint32_t>(ctx, nchunks + 4);  // the list, then its counter (u64, 8-byte aligned)
+  if (!d_ovf) { drop(true); return BK_ERR_NOMEM; }
+  temps.push_back(d_ovf);
+  std::vector<uint32_t> h_list;
+  // One launch over `count` chunks (list == null: all) with stacks of `cap` entries; chunks whose stream outgrows them
+  // come back in d_ovf and run again, alone, with stacks four times as deep -- as often as it takes (loud failure at
+  // the memory budget).  The results of a chunk do not depend on the buffers it ran in.
+  auto launch = [&](int mode, const uint32_t* d_list, uint64_t count) -> int {
+    uint32_t cap = 4096;
+    while (count) {
+      uint64_t threads = std::min<uint64_t>(resident, (count + CF_THREADS - 1) / CF_THREADS * CF_THREADS);
+      while (threads > CF_THREADS && threads * 2ull * cap * sizeof(uint4) > buf_budget) threads /= 2;
+      threads = std::max<uint64_t>(CF_THREADS, threads / CF_THREADS * CF_THREADS);
+      if (threads * 2ull * cap * sizeof(uint4) > buf_budget)
+        return fail(ctx, BK_ERR_NOMEM, "closest-features: a push-back stream exceeds %u entries", cap / 4);
+      p.cap = cap;
+      cap_used = std::max(cap_used, cap);
+      p.bufs = dalloc<uint4>(ctx, threads * 2ull * cap);
+      if (!p.bufs) return BK_ERR_NOMEM;
+      p.todo = d_list; p.ntodo = (uint32_t)count;
+      p.ovf = d_ovf; p.ovf_count = reinterpret_cast<uint64_t*>(d_ovf + ((nchunks + 1) & ~1ull));
+      BK_CUDA(ctx, cudaMemsetAsync(p.ovf_count, 0, 8, ctx->stream));
       prof_begin(ctx, "k_cf_sim");
-      k_cf_sim<0><<<(unsigned)(threads / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
+      if (mode == 0) k_cf_sim<0><<<(unsigned)(threads / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
+      else k_cf_sim<1><<<(unsigned)(threads / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
       prof_end(ctx);
       BK_LAUNCHED(ctx);
+      uint64_t novf = 0;
+      BK_CUDA(ctx, cudaMemcpyAsync(&novf, p.ovf_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      dfree(ctx, p.bufs);
+      p.bufs = nullptr;
+      if (novf == 0) break;
+      // the overflowed chunks become the work list of the next, deeper launch (d_todo is free to reuse: its content was
+      // consumed by the launch that just ended)
+      BK_CUDA(ctx, cudaMemcpyAsync(d_todo, d_ovf, novf * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      d_list = d_todo;
+      count = novf;
+      cap *= 4;
+      big_runs++;
+    }
+    return BK_OK;
+  };
+  uint64_t* fin[2] = {d_chunk + nchunks, d_chunk + 2 * nchunks};
+  int       cur = 0;
+  auto run = [&]() -> int {
+    BK_TRY(reset_scratch(ctx));
+    BK_CUDA(ctx, cudaMemsetAsync(p.arena_top, 0, 8, ctx->stream));
+    p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
+    BK_TRY(launch(0, nullptr, nchunks));
+    cur ^= 1;
+    while (true) {  // at most (chunks of the longest chromosome) rounds: round r makes chunk r of every chromosome exact
+      p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
+      const uint64_t cb = std::min<uint64_t>((nchunks + 255) / 256, (uint64_t)ctx->sms * 8);
+      k_cf_check<<<(unsigned)cb, 256, 0, ctx->stream>>>(p, d_todo);
+      BK_LAUNCHED(ctx);
+      BK_TRY(read_scratch(ctx));
+      if (ctx->h_scratch[SC_ERR_CODE]) return BK_ERR_NOMEM;
+      const uint64_t bad = ctx->h_scratch[SC_COUNT_A];
+      if (bad == 0) return BK_OK;
+      rounds++;
+      reruns += bad;
+      BK_CUDA(ctx, cudaMemsetAsync(&ctx->d_scratch[SC_COUNT_A], 0, 8, ctx->stream));
+      BK_CUDA(ctx, cudaMemcpyAsync(p.fin_next, p.fin_cur, nchunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      BK_TRY(launch(1, d_todo, bad));
       cur ^= 1;
-      for (int round = 0;; round++) {
-        const bool last = round >= CF_MAX_ROUNDS;
-        p.fin_cur = fin[cur]; p.fin_next = fin[cur ^ 1];
-        if (last) BK_CUDA(ctx, cudaMemsetAsync(d_todo + nchunks, 0xFF, (size_t)nruns * 4, ctx->stream));
-        const uint64_t cb = std::min<uint64_t>((nchunks + 255) / 256, (uint64_t)ctx->sms * 8);
-        k_cf_check<<<(unsigned)cb, 256, 0, ctx->stream>>>(p, last ? d_todo + nchunks : d_todo, last ? 1 : 0);
-        BK_LAUNCHED(ctx);
-        BK_TRY(read_scratch(ctx));
-        if (ctx->h_scratch[SC_ERR_CODE]) return BK_ERR_NOMEM;
-        uint64_t bad = ctx->h_scratch[SC_COUNT_A];
-        if (bad == 0) return BK_OK;
-        rounds++;
-        reruns += bad;
-        BK_CUDA(ctx, cudaMemsetAsync(&ctx->d_scratch[SC_COUNT_A], 0, 8, ctx->stream));
-        if (last) {  // one thread per chromosome from its first inconsistent chunk to its end
-          std::vector<uint32_t> firsts(nruns);
-          BK_CUDA(ctx, cudaMemcpyAsync(firsts.data(), d_todo + nchunks, (size_t)nruns * 4, cudaMemcpyDeviceToHost, ctx->stream));
-          BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-          firsts.erase(std::remove(firsts.begin(), firsts.end(), 0xFFFFFFFFu), firsts.end());
-          BK_CUDA(ctx, cudaMemcpyAsync(d_todo, firsts.data(), firsts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-          p.todo = d_todo; p.ntodo = (uint32_t)firsts.size();
-          prof_begin(ctx, "k_cf_sim");
-          k_cf_sim<2><<<(unsigned)((firsts.size() + CF_THREADS - 1) / CF_THREADS), CF_THREADS, 0, ctx->stream>>>(p);
-          prof_end(ctx);
-          BK_LAUNCHED(ctx);
-          BK_TRY(read_scratch(ctx));
-          return ctx->h_scratch[SC_ERR_CODE] ? BK_ERR_NOMEM : BK_OK;
-        }
-        BK_CUDA(ctx, cudaMemcpyAsync(p.fin_next, p.fin_cur, nchunks * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        p.todo = d_todo; p.ntodo = (uint32_t)bad;
-        const uint64_t tb = std::min<uint64_t>((bad + CF_THREADS - 1) / CF_THREADS, threads / CF_THREADS);
-        prof_begin(ctx, "k_cf_sim");
-        k_cf_sim<1><<<(unsigned)tb, CF_THREADS, 0, ctx->stream>>>(p);
-        prof_end(ctx);
-        BK_LAUNCHED(ctx);
-        cur ^= 1;
-      }
-    };
+    }
+  };
+  while (true) {  // the arena of recorded states grows on demand (a full rerun: rare, sized generously)
+    p.arena_cap = arena_cap;
+    p.arena = dalloc<uint32_t>(ctx, arena_cap);
+    if (!p.arena) { rc = BK_ERR_NOMEM; break; }
     rc = run();
-    const uint64_t where = ctx->h_scratch[SC_ERR_ROW];
-    const bool     grow = rc == BK_ERR_NOMEM && ctx->h_scratch[SC_ERR_CODE] == BK_ERR_NOMEM;
-    dfree(ctx, p.bufs);
+    const bool grow = rc == BK_ERR_NOMEM && ctx->h_scratch[SC_ERR_CODE] == BK_ERR_NOMEM && ctx->h_scratch[SC_ERR_ROW] == 1;
     dfree(ctx, p.arena);
+    dfree(ctx, p.bufs);
+    p.bufs = nullptr;
     if (!grow) break;
-    if (where == 1) arena_cap *= 4; else cap *= 8;
-    if (cap > (1u << 28) || arena_cap > (1ull << 36)) {
-      rc = fail(ctx, BK_ERR_NOMEM, "closest-features: push-back state exceeds the device buffers");
+    arena_cap *= 4;
+    if (arena_cap > (1ull << 36)) {
+      rc = fail(ctx, BK_ERR_NOMEM, "closest-features: recorded push-back states exceed the device arena");
       break;
     }
   }
-  if (getenv("BEDKIT_TRACE")) fprintf(stderr, "[bedkit] closest: %llu chunks, %llu repair rounds, %llu chunk reruns, cap %u\n",
-                                      (unsigned long long)nchunks, (unsigned long long)rounds, (unsigned long long)reruns, cap);
+  if (getenv("BEDKIT_TRACE"))
+    fprintf(stderr, "[bedkit] closest: %llu chunks, %llu repair rounds, %llu chunk reruns, %llu deep launches, deepest stack %u\n",
+            (unsigned long long)nchunks, (unsigned long long)rounds, (unsigned long long)reruns, (unsigned long long)big_runs, cap_used);
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   drop(false);
   if (rc != BK_OK) { dfree(ctx, p.left); dfree(ctx, p.right); return rc; }

@@ -134,3 +134,93 @@ extern "C" int bk_plan_shards(const uint64_t* load, int n_items, int n_shards, i
   first_item[n_shards] = n_items;
   return BK_OK;
 }
+
+// ---- cuts inside a chromosome (balanced genomic ranges with boundary halos) ------------------------------
+namespace {
+
+// start coordinate of the record that begins at line start `pos` (second token, strtoul-like); false if malformed
+bool start_at(const char* t, size_t n, size_t pos, uint64_t* out) {
+  while (pos < n && is_ws((unsigned char)t[pos])) pos++;
+  while (pos < n && !is_ws((unsigned char)t[pos]) && t[pos] != '\n') pos++;  // chromosome token
+  while (pos < n && is_ws((unsigned char)t[pos])) pos++;
+  if (pos < n && t[pos] == '+') pos++;
+  if (pos >= n || t[pos] < '0' || t[pos] > '9') return false;
+  uint64_t v = 0;
+  while (pos < n && t[pos] >= '0' && t[pos] <= '9') v = v * 10 + (uint64_t)(t[pos++] - '0');
+  *out = v;
+  return true;
+}
+
+int cmp_name(const char* a, const char* b) { return strcmp(a, b); }
+
+}  // namespace
+
+// First record of [begin,end) -- the lines of ONE chromosome, sorted by start -- whose start >= coord: bisection on
+// line-aligned probes, O(log bytes) lines touched.  Returns `end` if there is none.
+extern "C" uint64_t bk_find_start(const char* text, uint64_t begin, uint64_t end, uint64_t coord) {
+  if (!text || begin >= end) return end;
+  // invariant: every record that begins before lo has start < coord; the record at hi (or hi == end) has start >= coord
+  uint64_t lo = next_record(text, end, begin, true), hi = end;
+  if (lo >= end) return end;
+  {
+    uint64_t s0;
+    if (!start_at(text, end, lo, &s0) || s0 >= coord) return lo;
+  }
+  // now: the record at lo has start < coord
+  while (true) {
+    const uint64_t after_lo = next_record(text, end, lo, false);
+    if (after_lo >= hi) return hi;
+    uint64_t mid = lo + (hi - lo) / 2;
+    uint64_t r = next_record(text, end, mid, false);
+    if (r >= hi) r = after_lo;
+    uint64_t s;
+    if (start_at(text, end, r, &s) && s < coord) lo = r; else hi = r;
+  }
+}
+
+// n_shards - 1 cut points that balance the BYTES of a sorted BED text: cut k is the (chromosome, start) of the first
+// record at or after byte k * nbytes / n_shards.  Cuts are non-decreasing; equal cuts make empty shards.
+extern "C" int bk_plan_cuts(const char* text, size_t nbytes, const bk_chrom_span* idx, int n_idx, int n_shards, bk_cut* cuts) {
+  if ((!text && nbytes) || (n_idx > 0 && !idx) || n_shards < 1 || (n_shards > 1 && !cuts)) return BK_ERR_ARG;
+  const uint64_t lo_all = n_idx ? idx[0].begin : 0, hi_all = n_idx ? idx[n_idx - 1].end : 0;
+  for (int k = 1; k < n_shards; k++) {
+    bk_cut& c = cuts[k - 1];
+    memset(&c, 0, sizeof(c));
+    const uint64_t target = lo_all + (hi_all - lo_all) / (uint64_t)n_shards * (uint64_t)k;
+    int j = 0;
+    while (j < n_idx && idx[j].end <= target) j++;
+    if (j >= n_idx) {  // beyond the last record: an empty tail shard
+      c.at_end = 1;
+      continue;
+    }
+    uint64_t pos = target <= idx[j].begin ? idx[j].begin : next_record(text, idx[j].end, target, false);
+    if (pos >= idx[j].end) {  // the target fell into the chromosome's last line: cut at the next chromosome
+      j++;
+      if (j >= n_idx) {
+        c.at_end = 1;
+        continue;
+      }
+      pos = idx[j].begin;
+    }
+    memcpy(c.chrom, idx[j].name, sizeof(c.chrom));
+    uint64_t s = 0;
+    if (pos > idx[j].begin && start_at(text, idx[j].end, pos, &s)) c.coord = s;  // at a chromosome's first line the cut is (chrom, 0)
+  }
+  return BK_OK;
+}
+
+// Byte offset at which a cut falls in another sorted BED text of the same genome: the first record whose
+// (chromosome, start) >= (cut.chrom, cut.coord) in sort-bed order.
+extern "C" uint64_t bk_cut_offset(const char* text, size_t nbytes, const bk_chrom_span* idx, int n_idx, const bk_cut* cut) {
+  size_t n = nbytes;
+  while (n > 0 && text[n - 1] != '\n') n--;
+  const uint64_t end_all = n_idx ? idx[n_idx - 1].end : n;
+  if (!cut || cut->at_end) return end_all;
+  for (int j = 0; j < n_idx; j++) {
+    const int c = cmp_name(idx[j].name, cut->chrom);
+    if (c < 0) continue;
+    if (c > 0) return idx[j].begin;
+    return cut->coord == 0 ? idx[j].begin : bk_find_start(text, idx[j].begin, idx[j].end, cut->coord);
+  }
+  return end_all;
+}

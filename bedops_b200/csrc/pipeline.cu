@@ -222,3 +222,175 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
     return plain(ctx, ref_text, ref_len, map_text, map_len, ref_fields, ref_cols, map_fields, map_cols, spec, out);
   return rc;
 }
+
+// ---- range-sharded bedmap (protocol: include/bedkit.h) ---------------------------------------------------------------
+struct bk_shard {
+  bk_shard_plan plan;
+  int           rank = 0;
+  const char *  map_text = nullptr, *map_src = nullptr;
+  int           map_fields = 5;
+  unsigned      map_cols = 0;
+  bk_mapspec    spec;
+  std::string   delim, mdelim;
+  bk_bed *      ref = nullptr, *map = nullptr;
+  uint64_t      bytes_in = 0;
+};
+
+namespace {
+
+// copy [off, off+len) of src (host, pinned host or device memory) into a fresh device block and parse it
+int load_slice(bk_ctx* ctx, const char* src, uint64_t off, uint64_t len, int fields, unsigned cols, bk_bed** out) {
+  *out = nullptr;
+  char* d = reinterpret_cast<char*>(dmalloc(ctx, len + 64));
+  if (!d) return BK_ERR_NOMEM;
+  if (len) {
+    cudaError_t e = cudaMemcpyAsync(d, src + off, len, cudaMemcpyDefault, ctx->stream);
+    if (e != cudaSuccess) {
+      dfree(ctx, d);
+      return cuda_fail(ctx, e, "copy of a BED slice", __FILE__, __LINE__);
+    }
+  }
+  int rc = bk_load_bed_device(ctx, d, len, fields, cols, out);
+  if (rc != BK_OK) {
+    dfree(ctx, d);
+    return rc;
+  }
+  (*out)->owns_text = true;  // the slice belongs to the bed from here on
+  return BK_OK;
+}
+
+uint64_t range_pad(const bk_mapspec& s) { return s.overlap_kind == BK_OVR_RANGE ? s.overlap_bp : 0; }
+
+}  // namespace
+
+extern "C" int bk_shard_plan_make(const char* ref_text, size_t ref_len, const char* map_text, size_t map_len, int n_shards,
+                                  bk_shard_plan* plan) {
+  if (!plan || n_shards < 1 || n_shards > BK_MAX_SHARDS || (!ref_text && ref_len) || (!map_text && map_len)) return BK_ERR_ARG;
+  memset(plan, 0, sizeof(*plan));
+  plan->n_shards = n_shards;
+  std::vector<bk_chrom_span> rix, mix;
+  int rc = index_of(ref_text, ref_len, &rix);
+  if (rc == BK_OK) rc = index_of(map_text, map_len, &mix);
+  if (rc != BK_OK) return rc;
+  if (!strictly_sorted(rix) || !strictly_sorted(mix)) return BK_ERR_UNSORTED;
+  const bool by_map = map_len >= ref_len;  // cut where the bytes are
+  if (n_shards > 1) {
+    rc = by_map ? bk_plan_cuts(map_text, map_len, mix.data(), (int)mix.size(), n_shards, plan->cuts)
+                : bk_plan_cuts(ref_text, ref_len, rix.data(), (int)rix.size(), n_shards, plan->cuts);
+    if (rc != BK_OK) return rc;
+  }
+  plan->ref_off[0] = rix.empty() ? 0 : rix.front().begin;
+  plan->map_off[0] = mix.empty() ? 0 : mix.front().begin;
+  for (int k = 0; k + 1 < n_shards; k++) {
+    plan->ref_off[k + 1] = bk_cut_offset(ref_text, ref_len, rix.data(), (int)rix.size(), &plan->cuts[k]);
+    plan->map_off[k + 1] = bk_cut_offset(map_text, map_len, mix.data(), (int)mix.size(), &plan->cuts[k]);
+    plan->map_chrom_begin[k] = plan->map_chrom_end[k] = plan->map_off[k + 1];
+    for (auto& sp : mix)
+      if (!plan->cuts[k].at_end && strcmp(sp.name, plan->cuts[k].chrom) == 0) {
+        plan->map_chrom_begin[k] = sp.begin;
+        plan->map_chrom_end[k] = sp.end;
+      }
+  }
+  plan->ref_off[n_shards] = rix.empty() ? 0 : rix.back().end;
+  plan->map_off[n_shards] = mix.empty() ? 0 : mix.back().end;
+  return BK_OK;
+}
+
+extern "C" void bk_shard_free(bk_ctx* ctx, bk_shard* sh) {
+  if (!sh) return;
+  bk_free_bed(ctx, sh->ref);
+  bk_free_bed(ctx, sh->map);
+  delete sh;
+}
+
+extern "C" uint64_t bk_shard_bytes_in(const bk_shard* sh) { return sh ? sh->bytes_in : 0; }
+
+extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int rank, const char* ref_text, size_t ref_len,
+                                     int ref_fields, unsigned ref_cols, const char* map_text, size_t map_len, int map_fields,
+                                     unsigned map_cols, const char* ref_src, const char* map_src, const bk_mapspec* spec,
+                                     bk_shard** out, uint64_t* reach) {
+  if (!ctx || !plan || !spec || !out || !reach || rank < 0 || rank >= plan->n_shards) return BK_ERR_ARG;
+  (void)ref_len;
+  (void)map_len;
+  *out = nullptr;
+  ctx->last_error.clear();
+  const int n = plan->n_shards;
+  for (int j = 0; j < n; j++) reach[j] = ~0ull;
+  if (spec->chrom && strcmp(spec->chrom, "all") != 0) return fail(ctx, BK_ERR_ARG, "range sharding and --chrom exclude each other");
+  bk_shard* sh = new bk_shard();
+  sh->plan = *plan;
+  sh->rank = rank;
+  sh->map_text = map_text;
+  sh->map_src = map_src ? map_src : map_text;
+  sh->map_fields = map_fields;
+  sh->map_cols = map_cols;
+  sh->spec = *spec;
+  sh->delim = spec->delim ? spec->delim : "|";
+  sh->mdelim = spec->multidelim ? spec->multidelim : ";";
+  sh->spec.delim = sh->delim.c_str();
+  sh->spec.multidelim = sh->mdelim.c_str();
+  sh->spec.chrom = nullptr;
+  const uint64_t pad = range_pad(*spec);
+  // this rank's reference rows: the records whose start lies in its range
+  const uint64_t r0 = plan->ref_off[rank], r1 = plan->ref_off[rank + 1];
+  int rc = load_slice(ctx, ref_src ? ref_src : ref_text, r0, r1 - r0, ref_fields, ref_cols, &sh->ref);
+  sh->bytes_in += r1 - r0;
+  // right halo: map records behind the right cut that start before the largest reference end of the shard
+  uint64_t m0 = plan->map_off[rank], m1 = plan->map_off[rank + 1];
+  if (rc == BK_OK && rank + 1 < n && !plan->cuts[rank].at_end && plan->cuts[rank].coord > 0) {
+    uint64_t maxend = 0;
+    rc = bk_bed_chrom_max_end(ctx, sh->ref, plan->cuts[rank].chrom, &maxend);
+    if (rc == BK_OK && maxend + pad > plan->cuts[rank].coord)
+      m1 = bk_find_start(map_text, m1, plan->map_chrom_end[rank], maxend + pad);
+  }
+  if (rc == BK_OK) rc = load_slice(ctx, sh->map_src, m0, m1 - m0, map_fields, map_cols, &sh->map);
+  sh->bytes_in += m1 - m0;
+  // what the later shards need from this one: where, among these records, their left halo would begin
+  for (int j = rank + 1; j < n && rc == BK_OK; j++) {
+    const bk_cut& c = plan->cuts[j - 1];
+    if (c.at_end || c.coord == 0) continue;
+    uint64_t s = ~0ull;
+    rc = bk_bed_reach_start(ctx, sh->map, c.chrom, c.coord > pad ? c.coord - pad : 0, &s);
+    if (s < c.coord) reach[j] = s;
+  }
+  if (rc != BK_OK) {
+    bk_shard_free(ctx, sh);
+    return rc;
+  }
+  *out = sh;
+  return BK_OK;
+}
+
+extern "C" int bk_bedmap_shard_finish(bk_ctx* ctx, bk_shard* sh, const uint64_t* all_reach, bk_text* out) {
+  if (!ctx || !sh || !out || (!all_reach && sh->rank > 0)) return BK_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  const int n = sh->plan.n_shards, rank = sh->rank;
+  int       rc = BK_OK;
+  if (rank > 0) {
+    const bk_cut& c = sh->plan.cuts[rank - 1];
+    uint64_t      s = ~0ull;
+    for (int i = 0; i < rank; i++) s = std::min(s, all_reach[(size_t)i * n + rank]);
+    if (!c.at_end && c.coord > 0 && s < c.coord) {
+      // left halo: from the first record that starts at s to the cut.  Records in between that do not reach the cut
+      // are carried along: they are map rows like any other and simply overlap nothing here.
+      const uint64_t cut_off = sh->plan.map_off[rank];
+      const uint64_t h0 = bk_find_start(sh->map_text, sh->plan.map_chrom_begin[rank - 1], cut_off, s);
+      if (h0 < cut_off) {
+        bk_bed *halo = nullptr, *both = nullptr;
+        rc = load_slice(ctx, sh->map_src, h0, cut_off - h0, sh->map_fields, sh->map_cols, &halo);
+        sh->bytes_in += cut_off - h0;
+        if (rc == BK_OK) rc = bk_bed_concat(ctx, halo, sh->map, &both);
+        bk_free_bed(ctx, halo);
+        if (rc == BK_OK) {
+          bk_free_bed(ctx, sh->map);
+          sh->map = both;
+        }
+      }
+    }
+  }
+  if (rc == BK_OK) rc = bk_bedmap(ctx, sh->ref, sh->map, &sh->spec, out);
+  bk_free_bed(ctx, sh->ref);  // the columns go back to the cache now; the handle itself lives until bk_shard_free
+  bk_free_bed(ctx, sh->map);
+  sh->ref = sh->map = nullptr;
+  return rc;
+}

@@ -246,6 +246,67 @@ int bk_chrom_index(const char* host_text, size_t nbytes, bk_chrom_span* out, int
  * first_item[0..n_shards] receives the group boundaries */
 int bk_plan_shards(const uint64_t* load, int n_items, int n_shards, int* first_item);
 
+
+/* ---- cuts INSIDE chromosomes: one dataset over N GPUs by balanced genomic ranges with boundary halos --------------
+ * A cut is a genomic position (chromosome, start coordinate); shard k owns the records whose (chromosome, start) lies in
+ * [cut k-1, cut k).  Reference rows go to the shard that owns their start.  A shard's map rows are its own records plus
+ *   a right halo: records after its right cut that start before the largest reference end of the shard
+ *                 (bk_bed_chrom_max_end of the parsed reference slice, then bk_find_start on the host text), and
+ *   a left halo:  records before its left cut whose end passes the cut.  Where it begins is known only to the shards
+ *                 that parsed those records: every shard reports, for each later cut in a chromosome it holds,
+ *                 bk_bed_reach_start = the smallest start among its records that end beyond the cut (the prefix-max-end
+ *                 index), the shards exchange these few numbers (the path's only collective: an allgather of
+ *                 n_shards^2 u64), and the minimum over the earlier shards, bisected in the host text with bk_find_start,
+ *                 is the halo's first byte.  bk_bed_concat puts halo and own records into one bk_bed.
+ * Replaces the reference's seek to a chromosome by bisection over byte offsets (AllocateIterator_BED_starch.hpp:113-160
+ * -> FindBedRange.hpp:68) with a seek to any genomic position. */
+typedef struct bk_cut {
+  char     chrom[128];
+  uint64_t coord;  /* records with start >= coord (in chrom) belong to the right of the cut; 0 = the chromosome's first record */
+  int      at_end; /* the cut lies behind the last record (empty shards to its right) */
+} bk_cut;
+uint64_t bk_find_start(const char* host_text, uint64_t begin, uint64_t end, uint64_t coord);
+int      bk_plan_cuts(const char* host_text, size_t nbytes, const bk_chrom_span* idx, int n_idx, int n_shards, bk_cut* cuts);
+uint64_t bk_cut_offset(const char* host_text, size_t nbytes, const bk_chrom_span* idx, int n_idx, const bk_cut* cut);
+/* smallest start among the records of `chrom` whose end > pos; UINT64_MAX if none (or the chromosome is absent) */
+int bk_bed_reach_start(bk_ctx* ctx, const bk_bed* bed, const char* chrom, uint64_t pos, uint64_t* start_out);
+/* largest end among the records of `chrom`; 0 if none */
+int bk_bed_chrom_max_end(bk_ctx* ctx, const bk_bed* bed, const char* chrom, uint64_t* end_out);
+/* head ++ tail as one bk_bed (every record of head sorts before every record of tail; same min_fields and columns).
+ * The result owns copies of the columns (and of the text when lines are kept); head and tail stay valid. */
+int bk_bed_concat(bk_ctx* ctx, const bk_bed* head, const bk_bed* tail, bk_bed** out);
+
+/* ---- range-sharded bedmap: ONE dataset over N GPUs (one rank = one bk_ctx = one GPU) ----------------------------------
+ * bk_shard_plan_make (host only, deterministic: every rank computes the same plan from the same text) cuts the larger
+ * file into n_shards byte-balanced genomic ranges and locates the cuts in the other file.
+ * bk_bedmap_shard_begin uploads and parses this rank's reference slice and its map slice (own records + right halo)
+ * and fills reach[j] (j > rank; UINT64_MAX = none) for the exchange; the caller allgathers the n_shards vectors
+ * (row i = rank i's) -- NCCL across processes, shared memory across threads -- and bk_bedmap_shard_finish adds the left
+ * halo, maps, and returns this rank's part of the output.  The parts in rank order are byte-identical to the unsharded
+ * call.  *_src: where the bytes are copied from -- NULL (the host text itself) or a mirror with identical offsets
+ * (pinned host or device memory); the host text is always needed for the bisections. */
+#define BK_MAX_SHARDS 64
+typedef struct bk_shard_plan {
+  int      n_shards;
+  bk_cut   cuts[BK_MAX_SHARDS];            /* cuts[k] separates shard k from shard k+1 (n_shards - 1 used) */
+  uint64_t ref_off[BK_MAX_SHARDS + 1];     /* shard k owns ref bytes [ref_off[k], ref_off[k+1]) */
+  uint64_t map_off[BK_MAX_SHARDS + 1];     /* ... and map bytes [map_off[k], map_off[k+1]) */
+  uint64_t map_chrom_begin[BK_MAX_SHARDS]; /* byte span, in the map file, of the chromosome cut k falls into */
+  uint64_t map_chrom_end[BK_MAX_SHARDS];
+} bk_shard_plan;
+typedef struct bk_shard bk_shard;
+/* BK_ERR_UNSORTED when the chromosomes of a file are not in strictly ascending strcmp order (run unsharded then) */
+int bk_shard_plan_make(const char* ref_text, size_t ref_len, const char* map_text, size_t map_len, int n_shards,
+                       bk_shard_plan* plan);
+int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int rank, const char* ref_text, size_t ref_len,
+                          int ref_fields, unsigned ref_cols, const char* map_text, size_t map_len, int map_fields,
+                          unsigned map_cols, const char* ref_src, const char* map_src, const bk_mapspec* spec,
+                          bk_shard** out, uint64_t* reach);
+int bk_bedmap_shard_finish(bk_ctx* ctx, bk_shard* shard, const uint64_t* all_reach, bk_text* out);
+void bk_shard_free(bk_ctx* ctx, bk_shard* shard); /* after finish, or to abandon a call after begin */
+/* bytes this rank copied from *_src so far (own slices + halos): bench.py's h2d_bytes_per_step */
+uint64_t bk_shard_bytes_in(const bk_shard* shard);
+
 #ifdef __cplusplus
 }
 #endif
