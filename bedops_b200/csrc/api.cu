@@ -1,5 +1,6 @@
 // api.cu -- context, memory and the load/free half of the C ABI (include/bedkit.h).
 #include <chrono>
+#include <thread>
 #include <stdarg.h>
 #include "common.cuh"
 #include "emit.cuh"
@@ -123,6 +124,49 @@ void pinned_put(bk_ctx* ctx, char* p) {
     if (b.ptr == p) b.busy = false;
 }
 
+int upload(bk_ctx* ctx, char* d_dst, const char* src, size_t n, cudaStream_t st) {
+  if (n == 0) return BK_OK;
+  constexpr size_t kChunk = 32u << 20;
+  cudaPointerAttributes at;
+  bool direct = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  if (direct || n < (4u << 20)) {
+    BK_CUDA(ctx, cudaMemcpyAsync(d_dst, src, n, cudaMemcpyDefault, st));
+    return BK_OK;
+  }
+  for (int k = 0; k < 3; k++)
+    if (!ctx->stage[k]) {
+      BK_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->stage[k]), kChunk, cudaHostAllocDefault));
+      BK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    }
+  unsigned nt = std::thread::hardware_concurrency() / 2;
+  nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+  size_t off = 0;
+  for (int i = 0; off < n; i++) {
+    const int    k = i % 3;
+    const size_t len = n - off < kChunk ? n - off : kChunk;
+    if (i >= 3) BK_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[k]));  // the DMA that last read this buffer is done
+    {  // fill the staging buffer with nt threads (page faults and memcpy of the mapped file in parallel)
+      std::vector<std::thread> th;
+      const size_t per = ((len + nt - 1) / nt + 4095) & ~(size_t)4095;
+      for (unsigned t = 1; t < nt; t++) {
+        const size_t a = (size_t)t * per;
+        if (a >= len) break;
+        const size_t m = len - a < per ? len - a : per;
+        th.emplace_back([=]() { memcpy(ctx->stage[k] + a, src + off + a, m); });
+      }
+      memcpy(ctx->stage[k], src + off, len < per ? len : per);
+      for (auto& t : th) t.join();
+    }
+    BK_CUDA(ctx, cudaMemcpyAsync(d_dst + off, ctx->stage[k], len, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx, cudaEventRecord(ctx->stage_ev[k], st));
+    off += len;
+  }
+  // the staging ring is reused by the next upload of this ctx: wait for the last chunks here
+  for (int k = 0; k < 3; k++) BK_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[k]));
+  return BK_OK;
+}
+
 static cudaEvent_t prof_event(bk_ctx* ctx) {
   if (!ctx->prof_free.empty()) {
     cudaEvent_t e = ctx->prof_free.back();
@@ -232,6 +276,10 @@ extern "C" void bk_destroy(bk_ctx* ctx) {
     cudaEventDestroy(r.b);
   }
   for (auto e : ctx->prof_free) cudaEventDestroy(e);
+  for (int k = 0; k < 3; k++) {
+    if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+    if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+  }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -336,11 +384,11 @@ extern "C" int bk_load_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, in
   }
   bed->d_text = d;
   bed->owns_text = true;
-  if (nbytes) {
-    cudaError_t e = cudaMemcpyAsync(d, host_text, nbytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) {
+  {
+    const int rc = upload(ctx, d, host_text, nbytes, ctx->stream);
+    if (rc != BK_OK) {
       bk_free_bed(ctx, bed);
-      return cuda_fail(ctx, e, "H2D copy of BED text", __FILE__, __LINE__);
+      return rc;
     }
   }
   return load_common(ctx, bed, nbytes, min_fields, cols, out);

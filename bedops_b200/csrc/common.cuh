@@ -43,6 +43,9 @@ struct bk_ctx {
     bool   busy;
   };
   std::vector<Pinned> pinned;
+  // staging ring for uploads from pageable host memory (api.cu: upload)
+  char*       stage[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
   // device block cache (api.cu): freed blocks by size class, live blocks by address
   std::multimap<size_t, void*>      dev_free;
   std::unordered_map<void*, size_t> dev_live;
@@ -83,6 +86,11 @@ int  cuda_fail(bk_ctx* ctx, cudaError_t e, const char* what, const char* file, i
 void  release_cached(bk_ctx* ctx);         // give every cached device block back to the driver
 void* dmalloc(bk_ctx* ctx, size_t bytes);  // stream-ordered; returns nullptr and sets last_error on failure
 void  dfree(bk_ctx* ctx, void* p);
+// host -> device copy of n bytes on `st`.  Pinned / registered / device sources go down as one asynchronous copy; pageable
+// memory (a tool's mmap of its input file) is moved through a ring of pinned staging buffers filled by several host
+// threads, so that the copy runs at PCIe speed rather than at one core's page-fault-and-memcpy speed.  Returns after
+// the last chunk has been QUEUED (the source may be reused once the stream reaches that point -- callers sync).
+int   upload(bk_ctx* ctx, char* d_dst, const char* src, size_t n, cudaStream_t st);
 char* pinned_get(bk_ctx* ctx, size_t bytes);
 void  pinned_put(bk_ctx* ctx, char* p);
 

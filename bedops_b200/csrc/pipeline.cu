@@ -8,6 +8,8 @@
 // Output = the groups' outputs in chromosome order = the output of one unsplit call (same contract as the reference's
 // per-chromosome scale-out, bedmap/src/Input.hpp:117-122).  Inputs should be pinned for the overlap to happen.
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include "common.cuh"
 
 using namespace bk;
@@ -128,13 +130,31 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
     cuda_ok(cudaStreamWaitEvent(copy_s, ev_start, 0), "cudaStreamWaitEvent");
   }
   for (size_t g = 0; g < groups.size() && rc == BK_OK; g++) {
-    const Group& G = groups[g];
     cuda_ok(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming), "cudaEventCreate");
     cuda_ok(cudaEventCreateWithFlags(&ev_done[g], cudaEventDisableTiming), "cudaEventCreate");
-    if (G.re > G.rb) cuda_ok(cudaMemcpyAsync(d_stage + G.d_ref, ref_text + G.rb, G.re - G.rb, cudaMemcpyHostToDevice, copy_s), "H2D");
-    if (G.me > G.mb) cuda_ok(cudaMemcpyAsync(d_stage + G.d_map, map_text + G.mb, G.me - G.mb, cudaMemcpyHostToDevice, copy_s), "H2D");
-    cuda_ok(cudaEventRecord(ev_in[g], copy_s), "cudaEventRecord");
   }
+  // The uploads run on their own host thread: from pinned memory they are plain asynchronous copies, from pageable memory
+  // (the tools' mmap of the input files) they are staged through pinned buffers by upload(), which keeps a host thread
+  // busy -- either way the calling thread is free to queue the kernels of the groups that have arrived.
+  std::vector<std::atomic<int>> arrived(groups.size());
+  for (auto& a : arrived) a.store(0);
+  std::atomic<int> up_rc{BK_OK};
+  std::thread      uploader;
+  if (rc == BK_OK)
+    uploader = std::thread([&]() {
+      cudaSetDevice(ctx->device);
+      for (size_t g = 0; g < groups.size(); g++) {
+        const Group& G = groups[g];
+        int          r = BK_OK;
+        if (up_rc.load() == BK_OK) {
+          r = upload(ctx, d_stage + G.d_ref, ref_text + G.rb, G.re - G.rb, copy_s);
+          if (r == BK_OK) r = upload(ctx, d_stage + G.d_map, map_text + G.mb, G.me - G.mb, copy_s);
+          if (r == BK_OK && cudaEventRecord(ev_in[g], copy_s) != cudaSuccess) r = BK_ERR_CUDA;
+          if (r != BK_OK) up_rc.store(r);
+        }
+        arrived[g].store(1, std::memory_order_release);
+      }
+    });
 
   // compute, group by group; results stay in HBM until their D2H has been queued with a known offset
   bk_mapspec dspec = *spec;
@@ -159,6 +179,11 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
   };
   for (size_t g = 0; g < groups.size() && rc == BK_OK; g++) {
     const Group& G = groups[g];
+    while (!arrived[g].load(std::memory_order_acquire)) std::this_thread::yield();  // its copies and event are queued
+    if (up_rc.load() != BK_OK) {
+      rc = up_rc.load();
+      break;
+    }
     cuda_ok(cudaStreamWaitEvent(ctx->stream, ev_in[g], 0), "cudaStreamWaitEvent");
     bk_bed *ref = nullptr, *map = nullptr;
     if (rc == BK_OK) rc = bk_load_bed_device(ctx, d_stage + G.d_ref, G.re - G.rb, ref_fields, ref_cols, &ref);
@@ -205,6 +230,7 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
     }
   }
   // teardown: nothing may be reused while a stream still reads it
+  if (uploader.joinable()) uploader.join();
   if (copy_s) cudaStreamSynchronize(copy_s);
   if (out_s) cudaStreamSynchronize(out_s);
   cudaStreamSynchronize(ctx->stream);
@@ -243,11 +269,11 @@ int load_slice(bk_ctx* ctx, const char* src, uint64_t off, uint64_t len, int fie
   *out = nullptr;
   char* d = reinterpret_cast<char*>(dmalloc(ctx, len + 64));
   if (!d) return BK_ERR_NOMEM;
-  if (len) {
-    cudaError_t e = cudaMemcpyAsync(d, src + off, len, cudaMemcpyDefault, ctx->stream);
-    if (e != cudaSuccess) {
+  {
+    const int rc = upload(ctx, d, src + off, len, ctx->stream);
+    if (rc != BK_OK) {
       dfree(ctx, d);
-      return cuda_fail(ctx, e, "copy of a BED slice", __FILE__, __LINE__);
+      return rc;
     }
   }
   int rc = bk_load_bed_device(ctx, d, len, fields, cols, out);

@@ -3,6 +3,7 @@
 // WindowSweep::sweep call (Bedmap.cpp:288) with bk_bedmap().
 #include <sstream>
 #include "cli_common.hpp"
+#include "help_text.hpp"
 
 namespace {
 
@@ -207,25 +208,7 @@ std::string unescape_delim(const std::string& d) {  // PrintDelim, ProcessVisito
   return d;
 }
 
-void usage(FILE* f) {
-  std::fputs(
-      "\n USAGE: bedmap [process-flags] [overlap-option] <operation(s)...> <ref-file> [map-file]\n"
-      "     Any input file must be sorted per the sort-bed utility.\n"
-      "     You may use '-' for a BED file to indicate the input comes from stdin.\n\n"
-      "     Traverse <ref-file>, while applying <operation(s)> on qualified, overlapping elements from\n"
-      "       <map-file>.  Output is one line for each line in <ref-file>, sent to standard output.\n\n"
-      "     Process Flags:\n"
-      "      --chrom <chromosome>, --delim <delim>, --ec, --faster, --header, --help, --multidelim <delim>,\n"
-      "      --prec <int>, --sci, --skip-unmapped, --sweep-all, --version\n\n"
-      "     Overlap Options (one):\n"
-      "      --bp-ovr <int>, --exact, --fraction-both <val>, --fraction-either <val>, --fraction-map <val>,\n"
-      "      --fraction-ref <val>, --range <int>\n\n"
-      "     Operations on this build's B200 hot path:\n"
-      "      --bases --bases-uniq --bases-uniq-f --count --echo --echo-map --echo-map-id --echo-map-id-uniq --echo-map-range\n"
-      "      --echo-map-score --echo-map-size --echo-overlap-size --echo-ref-name --echo-ref-row-id --echo-ref-size\n"
-      "      --cv --indicator --kth <val> --mad [mult] --max --mean --median --min --stdev --sum --variance\n\n",
-      f);
-}
+void usage(FILE* f) { std::fputs(kUsageBedmap, f); }  // byte for byte the reference's text (help_text.hpp)
 
 }  // namespace
 
@@ -234,9 +217,9 @@ int main(int argc, char** argv) {
     Options o = parse_args(argc, argv);
     if (!o.unsupported_op.empty())
       throw UserError("--" + o.unsupported_op + " is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
-    std::vector<char> rtext, mtext;
-    if (!cli::slurp(o.ref, rtext)) throw UserError("Unable to find file: " + o.ref);
-    if (o.num_files == 2 && !cli::slurp(o.map, mtext)) throw UserError("Unable to find file: " + o.map);
+    cli::Input rtext, mtext;
+    if (!rtext.open(o.ref)) throw UserError("Unable to find file: " + o.ref);
+    if (o.num_files == 2 && !mtext.open(o.map)) throw UserError("Unable to find file: " + o.map);
 
     bk_mapspec spec;
     bk_mapspec_default(&spec);
@@ -279,38 +262,29 @@ int main(int argc, char** argv) {
         cli::ec_check(eng, rtext, o.ref, o.min_ref_fields, true, o.fast);
       }
     }
-    auto run_one = [&](cli::Engine& eng, const char* rp, size_t rn, const char* mp, size_t mn) {
-      bk_bed *ref = nullptr, *map = nullptr;
-      if (o.num_files == 2) {
-        ref = eng.load(rp, rn, 3, (need_line ? BK_COL_LINE : 0) | hdr);
-        map = eng.load(mp, mn, o.min_map_fields, map_cols);
-      } else {
-        ref = eng.load(rp, rn, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));
-      }
-      bk_text out;
-      int     rc = bk_bedmap(eng.ctx, ref, map, &spec, &out);
-      if (rc != BK_OK) eng.raise(rc);
-      std::string text(out.ptr ? out.ptr : "", out.len);
-      bk_free_text(eng.ctx, &out);
-      bk_free_bed(eng.ctx, ref);
-      bk_free_bed(eng.ctx, map);
-      return text;
-    };
+    const unsigned ref_cols = (need_line ? BK_COL_LINE : 0) | hdr;
     bool row_ids = false;
     for (int op : o.ops) row_ids |= op == BK_OP_ECHO_REF_ROW_ID;
     const int gpus = cli::gpus_requested();
-    if (gpus > 1 && o.chrom == "all" && !row_ids) {
-      std::vector<const std::vector<char>*> files{&rtext};
-      if (o.num_files == 2) files.push_back(&mtext);
-      auto slices = cli::plan_slices(files, gpus * 4);
-      cli::run_sharded(slices, [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
-        return run_one(eng, sl[0].ptr, sl[0].len, o.num_files == 2 ? sl[1].ptr : nullptr, o.num_files == 2 ? sl[1].len : 0);
-      }, gpus);
+    // N GPUs: ONE dataset cut into genomic ranges with boundary halos (include/bedkit.h); the printed-row counter of
+    // --echo-ref-row-id runs across shards, so that operation stays on one GPU
+    if (gpus > 1 && o.num_files == 2 && o.chrom == "all" && !row_ids &&
+        cli::run_range_sharded_bedmap(rtext, mtext, 3, ref_cols, o.min_map_fields, map_cols, spec, gpus))
+      return EXIT_SUCCESS;
+    cli::Engine eng;
+    bk_text     out;
+    int         rc;
+    if (o.num_files == 2) {
+      // the whole call over the (mapped) host text: chromosome groups uploaded, parsed, mapped and downloaded in a pipeline
+      rc = bk_bedmap_host(eng.ctx, rtext.data, rtext.size, 3, ref_cols, mtext.data, mtext.size, o.min_map_fields, map_cols, &spec, &out);
     } else {
-      cli::Engine eng;
-      std::string text = run_one(eng, rtext.data(), rtext.size(), mtext.data(), mtext.size());
-      cli::write_all(text.data(), text.size());
+      bk_bed* ref = eng.load(rtext, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));
+      rc = bk_bedmap(eng.ctx, ref, nullptr, &spec, &out);
+      bk_free_bed(eng.ctx, ref);
     }
+    if (rc != BK_OK) eng.raise(rc);
+    cli::write_all(out.ptr, out.len);  // pinned result buffer -> stdout, no intermediate copy
+    bk_free_text(eng.ctx, &out);
     return EXIT_SUCCESS;
   } catch (const Help&) {
     cli::banner(stdout, "bedmap");

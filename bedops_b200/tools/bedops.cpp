@@ -5,6 +5,7 @@
 #include <fstream>
 #include <map>
 #include "cli_common.hpp"
+#include "help_text.hpp"
 
 namespace {
 
@@ -28,7 +29,9 @@ void require(bool ok, const std::string& msg) {
   if (!ok) throw UserError(msg);
 }
 
-struct Help {};
+struct Help {
+  std::string which;  // "--help" or "--help-<operation>"
+};
 struct Version {};
 struct NoInput {};
 
@@ -110,9 +113,9 @@ Options parse_args(int argc, char** argv) {
         require(++i < argc, "No value for --range given.");
         o.has_range = true;
       } else if (next == "--help") {
-        throw Help();
+        throw Help{next};
       } else if (next.find("--help-") == 0) {
-        throw Help();
+        throw Help{next};
       } else if (next == "--version") {
         throw Version();
       } else if (next.find("-") != 0) {
@@ -215,28 +218,7 @@ Options parse_args(int argc, char** argv) {
   return o;
 }
 
-void usage(FILE* f) {
-  std::fputs(
-      "\n      USAGE: bedops [process-flags] <operation> <File(s)>*\n\n"
-      "          Every input file must be sorted per the sort-bed utility.\n"
-      "          Each operation requires a minimum number of files as shown below.\n"
-      "            There is no fixed maximum number of files that may be used.\n"
-      "          Input files must have at least the first 3 columns of the BED specification.\n"
-      "          '-' may be used to indicate data should be read from standard input.\n\n"
-      "      Process Flags:\n"
-      "          --chrom <chromosome>, --ec, --header, --help, --version\n\n"
-      "      Operations on this build's B200 hot path (choose one):\n"
-      "          -c, --complement [-L]                 Min: 1 file.\n"
-      "          -d, --difference                      Min: 2 files.\n"
-      "          -e, --element-of [bp | percentage]    Min: 2 files.\n"
-      "          -i, --intersect                       Min: 2 files.\n"
-      "          -m, --merge                           Min: 1 file.\n"
-      "          -n, --not-element-of [bp | percentage] Min: 2 files.\n"
-      "          -s, --symmdiff                        Min: 2 files.\n"
-      "          -u, --everything                      Min: 1 file.\n"
-      "          -w, --chop [bp] [--stagger nt] [-x]   Min: 1 file.\n\n",
-      f);
-}
+void usage(FILE* f) { std::fputs(kUsageBedops, f); }  // byte for byte the reference's text (help_text.hpp)
 
 }  // namespace
 
@@ -257,9 +239,9 @@ int main(int argc, char** argv) {
       default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
     if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
-    std::vector<std::vector<char>> texts(o.files.size());
+    std::vector<cli::Input> texts(o.files.size());
     for (size_t f = 0; f < o.files.size(); f++)
-      if (!cli::slurp(o.files[f], texts[f])) throw UserError("Cannot find " + o.files[f]);
+      if (!texts[f].open(o.files[f])) throw UserError("Cannot find " + o.files[f]);
     const bool has_ref = op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF;
     const bool all_lines = op == BK_SETOP_EVERYTHING;  // every row of every file is echoed
     const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;
@@ -286,27 +268,35 @@ int main(int argc, char** argv) {
     };
     const int gpus = cli::gpus_requested();
     // "-e 0" / "-n 0" look at later chromosomes (Bedops.cpp:1044-1049): keep those runs on one GPU
+    std::vector<std::vector<cli::Slice>> slices;
     if (gpus > 1 && o.chrom == "all" && !(has_ref && !o.use_pct && o.subset <= 0)) {
-      std::vector<const std::vector<char>*> files;
+      std::vector<const cli::Input*> files;
       for (auto& t : texts) files.push_back(&t);
-      cli::run_sharded(cli::plan_slices(files, gpus * 4), run_one, gpus);
+      slices = cli::plan_slices(files, gpus * 4);
+    }
+    if (!slices.empty()) {
+      cli::run_sharded(slices, run_one, gpus);
     } else {
       cli::Engine eng;
       std::vector<cli::Slice> sl;
-      for (auto& t : texts) sl.push_back(cli::Slice{t.data(), t.size()});
+      for (auto& t : texts) sl.push_back(cli::Slice{t.data, t.size});
       std::string text = run_one(eng, sl);
       cli::write_all(text.data(), text.size());
     }
     return EXIT_SUCCESS;
-  } catch (const Help&) {
+  } catch (const Help& h) {
     cli::banner(stdout, "bedops");
-    usage(stdout);
+    const char* text = kUsageBedops;
+    for (const BedopsHelp* e = kBedopsHelp; e->op; e++)
+      if (h.which == e->op) text = e->text;
+    std::fputs(text, stdout);
     return EXIT_SUCCESS;
   } catch (const Version&) {
     cli::banner(stdout, "bedops");
     return EXIT_SUCCESS;
   } catch (const NoInput&) {
-    cli::banner(stderr, "bedops");
+    cli::banner(stdout, "bedops");  // the reference sends the banner to stdout and the usage text to stderr
+    std::fflush(stdout);
     usage(stderr);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "May use bedops --help for more help.\n\nError: %s\n", e.what());

@@ -12,9 +12,14 @@
 #include <thread>
 #include <string>
 #include <vector>
+#include <memory>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <cerrno>
+#include <sys/mman.h>
+#include <condition_variable>
+#include <mutex>
 #include "bedkit.h"
 
 namespace cli {
@@ -33,39 +38,75 @@ inline void banner(FILE* f, const char* prog) {
 
 inline bool only_chars(const std::string& s, const char* set) { return s.find_first_not_of(set) == std::string::npos; }
 
-// whole-file read ("-" = stdin).  Returns false if the file cannot be opened.
-inline bool slurp(const std::string& name, std::vector<char>& buf) {
-  int fd = name == "-" ? 0 : ::open(name.c_str(), O_RDONLY);
-  if (fd < 0) return false;
-  struct stat st;
-  size_t      hint = 0;
-  if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) hint = (size_t)st.st_size;
-  buf.clear();
-  buf.resize(hint ? hint : (1u << 20));
-  size_t n = 0;
-  while (true) {
-    if (n == buf.size()) buf.resize(buf.size() * 2);
-    ssize_t r = ::read(fd, buf.data() + n, buf.size() - n);
-    if (r < 0) {
-      if (fd) ::close(fd);
-      return false;
+// A whole input: a regular file is mapped (the library stages it to the GPU in parallel chunks, no intermediate copy in
+// the tool), stdin ("-") and pipes are read into memory.
+struct Input {
+  const char*       data = nullptr;
+  size_t            size = 0;
+  std::vector<char> owned;
+  void*             map = nullptr;
+  size_t            map_len = 0;
+  Input() = default;
+  Input(const Input&) = delete;
+  Input& operator=(const Input&) = delete;
+  ~Input() {
+    if (map) ::munmap(map, map_len);
+  }
+  bool open(const std::string& name) {  // false if the file cannot be opened
+    int fd = name == "-" ? 0 : ::open(name.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fd && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void* p = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (p != MAP_FAILED) {
+        ::madvise(p, (size_t)st.st_size, MADV_WILLNEED);
+        map = p;
+        map_len = (size_t)st.st_size;
+        data = static_cast<const char*>(p);
+        size = map_len;
+        ::close(fd);
+        return true;
+      }
     }
-    if (r == 0) break;
-    n += (size_t)r;
+    owned.resize(1u << 20);
+    size_t n = 0;
+    while (true) {
+      if (n == owned.size()) owned.resize(owned.size() * 2);
+      ssize_t r = ::read(fd, owned.data() + n, owned.size() - n);
+      if (r < 0) {
+        if (fd) ::close(fd);
+        return false;
+      }
+      if (r == 0) break;
+      n += (size_t)r;
+    }
+    owned.resize(n);
+    if (fd) ::close(fd);
+    data = owned.data();
+    size = n;
+    return true;
   }
-  buf.resize(n);
-  if (fd) ::close(fd);
-  return true;
-}
+  // the checking iterator of the reference also reads an unterminated last line: give the text its final NL
+  void ensure_final_newline() {
+    if (size == 0 || data[size - 1] == '\n') return;
+    if (owned.empty() || data != owned.data()) owned.assign(data, data + size);
+    owned.push_back('\n');
+    data = owned.data();
+    size = owned.size();
+  }
+};
 
-inline void write_all(const char* p, size_t n) {
-  while (n) {
-    size_t w = std::fwrite(p, 1, n, stdout);
-    if (w == 0) break;
-    p += w;
-    n -= w;
-  }
+inline void write_all(const char* p, size_t n) {  // straight to fd 1: the result text is not copied again
   std::fflush(stdout);
+  while (n) {
+    ssize_t w = ::write(1, p, n > (1u << 30) ? (1u << 30) : n);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    p += w;
+    n -= (size_t)w;
+  }
 }
 
 struct Engine {
@@ -81,9 +122,7 @@ struct Engine {
     const char* detail = bk_last_error(ctx);
     throw std::runtime_error(detail && *detail ? std::string(detail) : std::string(bk_strerror(rc)));
   }
-  bk_bed* load(const std::vector<char>& text, int min_fields, unsigned cols) const {
-    return load(text.data(), text.size(), min_fields, cols);
-  }
+  bk_bed* load(const Input& text, int min_fields, unsigned cols) const { return load(text.data, text.size, min_fields, cols); }
   bk_bed* load(const char* p, size_t n, int min_fields, unsigned cols) const {
     bk_bed* b = nullptr;
     int     rc = bk_load_bed(ctx, p, n, min_fields, cols, &b);
@@ -92,14 +131,11 @@ struct Engine {
   }
 };
 
-// --ec / --header: the checking iterator also reads an unterminated last line, so give the text its final NL, then run
-// the device validation (bk_check_text); failures are reported the way BedCheckIterator.hpp:589-593 words them.
-inline void ec_prepare(std::vector<char>& text) {
-  if (!text.empty() && text.back() != '\n') text.push_back('\n');
-}
-inline void ec_check(const Engine& eng, const std::vector<char>& text, const std::string& name, int n_fields, bool has_rest,
-                     bool nest_check) {
-  int rc = bk_check_text(eng.ctx, text.data(), text.size(), n_fields, has_rest ? 1 : 0, nest_check ? 1 : 0);
+// --ec / --header: run the device validation (bk_check_text) on a text that ends with NL (Input::ensure_final_newline);
+// failures are reported the way BedCheckIterator.hpp:589-593 words them.
+inline void ec_prepare(Input& text) { text.ensure_final_newline(); }
+inline void ec_check(const Engine& eng, const Input& text, const std::string& name, int n_fields, bool has_rest, bool nest_check) {
+  int rc = bk_check_text(eng.ctx, text.data, text.size, n_fields, has_rest ? 1 : 0, nest_check ? 1 : 0);
   if (rc == BK_ERR_CHECK) throw std::runtime_error("in " + name + "\n" + bk_last_error(eng.ctx));
   if (rc != BK_OK) eng.raise(rc);
 }
@@ -118,19 +154,24 @@ inline int gpus_requested() {
 }
 
 // slices[shard][file]
-inline std::vector<std::vector<Slice>> plan_slices(const std::vector<const std::vector<char>*>& files, int n_shards) {
+// Whole-chromosome shards (bedops, closest-features).  Returns an empty plan when a file's chromosomes are not in strictly
+// ascending strcmp order (a UCSC header line read as a chromosome, or unsorted input): the caller then runs unsharded and
+// the single-GPU path reports what is wrong.
+inline std::vector<std::vector<Slice>> plan_slices(const std::vector<const Input*>& files, int n_shards) {
   std::vector<std::vector<bk_chrom_span>> idx(files.size());
   std::vector<std::string>                names;
   for (size_t f = 0; f < files.size(); f++) {
     int n = 0, cap = 64;
     while (true) {
       idx[f].resize(cap);
-      int rc = bk_chrom_index(files[f]->data(), files[f]->size(), idx[f].data(), cap, &n);
+      int rc = bk_chrom_index(files[f]->data, files[f]->size, idx[f].data(), cap, &n);
       if (rc == BK_OK) break;
       if (rc != BK_ERR_NOMEM) throw std::runtime_error("chromosome index failed");
       cap = n + 8;
     }
     idx[f].resize(n);
+    for (int k = 1; k < n; k++)
+      if (std::strcmp(idx[f][k - 1].name, idx[f][k].name) >= 0) return {};
     for (auto& s : idx[f]) names.push_back(s.name);
   }
   std::sort(names.begin(), names.end(), [](const std::string& a, const std::string& b) { return std::strcmp(a.c_str(), b.c_str()) < 0; });
@@ -158,7 +199,7 @@ inline std::vector<std::vector<Slice>> plan_slices(const std::vector<const std::
           any = true;
         }
       }
-      out[s][f] = Slice{files[f]->data() + b, (size_t)(e - b)};
+      out[s][f] = Slice{files[f]->data + b, (size_t)(e - b)};
     }
   return out;
 }
@@ -187,6 +228,61 @@ inline void run_sharded(const std::vector<std::vector<Slice>>& slices, Fn fn, in
   for (auto& e : errs)
     if (!e.empty()) throw std::runtime_error(e);
   for (auto& o : outs) write_all(o.data(), o.size());
+}
+
+// ---- bedmap over N GPUs by genomic RANGES (cuts inside chromosomes, boundary halos; include/bedkit.h) -----------------
+// One host thread + one bk_ctx per GPU.  begin (upload + parse own slices, report halo coordinates) -> all threads meet ->
+// finish (left halo, map) -> outputs written in rank order straight from the pinned result buffers.
+// Returns false when the inputs cannot be range-sharded (chromosomes not strictly ascending): run unsharded.
+inline bool run_range_sharded_bedmap(const Input& ref, const Input& map, int ref_fields, unsigned ref_cols, int map_fields,
+                                     unsigned map_cols, const bk_mapspec& spec, int n_gpus) {
+  bk_shard_plan plan;
+  if (n_gpus > BK_MAX_SHARDS || bk_shard_plan_make(ref.data, ref.size, map.data, map.size, n_gpus, &plan) != BK_OK) return false;
+  std::vector<uint64_t>    reach((size_t)n_gpus * n_gpus, ~0ull);
+  std::vector<std::string> errs(n_gpus);
+  std::vector<bk_text>     outs(n_gpus);
+  std::vector<std::unique_ptr<Engine>> engines(n_gpus);
+  std::mutex              mu;
+  std::condition_variable cv;
+  int                     arrived = 0;
+  bool                    failed = false;
+  std::vector<std::thread> th;
+  for (int g = 0; g < n_gpus; g++)
+    th.emplace_back([&, g]() {
+      bk_shard* sh = nullptr;
+      std::memset(&outs[g], 0, sizeof(bk_text));
+      try {
+        engines[g].reset(new Engine(g));
+        int rc = bk_bedmap_shard_begin(engines[g]->ctx, &plan, g, ref.data, ref.size, ref_fields, ref_cols, map.data, map.size,
+                                       map_fields, map_cols, nullptr, nullptr, &spec, &sh, &reach[(size_t)g * n_gpus]);
+        if (rc != BK_OK) engines[g]->raise(rc);
+      } catch (const std::exception& e) {
+        errs[g] = *e.what() ? e.what() : "unknown error";
+      }
+      {  // everyone meets here, failed or not: the reach matrix is complete behind this point
+        std::unique_lock<std::mutex> lk(mu);
+        failed = failed || !errs[g].empty();
+        if (++arrived == n_gpus) cv.notify_all();
+        else cv.wait(lk, [&] { return arrived == n_gpus; });
+      }
+      if (!failed && sh) {
+        try {
+          int rc = bk_bedmap_shard_finish(engines[g]->ctx, sh, reach.data(), &outs[g]);
+          if (rc != BK_OK) engines[g]->raise(rc);
+        } catch (const std::exception& e) {
+          errs[g] = *e.what() ? e.what() : "unknown error";
+        }
+      }
+      if (sh && engines[g]) bk_shard_free(engines[g]->ctx, sh);
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : errs)
+    if (!e.empty()) throw std::runtime_error(e);
+  for (int g = 0; g < n_gpus; g++) {
+    write_all(outs[g].ptr, outs[g].len);
+    bk_free_text(engines[g]->ctx, &outs[g]);
+  }
+  return true;
 }
 
 }  // namespace cli

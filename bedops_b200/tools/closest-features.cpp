@@ -2,6 +2,7 @@
 // applications/bed/closestfeats/src/Input.hpp:58-102 and replaces findDistances()
 // (ClosestFeature.cpp:260-413) with bk_closest().
 #include "cli_common.hpp"
+#include "help_text.hpp"
 
 namespace {
 using cli::UserError;
@@ -55,26 +56,15 @@ Options parse_args(int argc, char** argv) {
   return o;
 }
 
-void usage(FILE* f) {
-  std::fputs(
-      "\nUSAGE: closest-features [Process-Flags] <input-file> <query-file>\n"
-      "   All input files must be sorted per sort-bed.\n"
-      "   For every element in <input-file>, determine the two elements from <query-file> falling\n"
-      "     nearest to its left and right edges.  By default, output consists of the <input-file> element,\n"
-      "     followed by results from <query-file>.\n\n"
-      "  Process Flags:\n"
-      "    --chrom <chromosome>, --closest, --delim <delim>, --dist, --ec, --header, --help, --no-overlaps,\n"
-      "    --no-ref, --version\n\n",
-      f);
-}
+void usage(FILE* f) { std::fputs(kUsageClosest, f); }  // byte for byte the reference's text (help_text.hpp)
 }  // namespace
 
 int main(int argc, char** argv) {
   try {
     Options           o = parse_args(argc, argv);
-    std::vector<char> rtext, qtext;
-    if (!cli::slurp(o.ref, rtext)) throw UserError("Unable to find file: " + o.ref);
-    if (!cli::slurp(o.query, qtext)) throw UserError("Unable to find file: " + o.query);
+    cli::Input rtext, qtext;
+    if (!rtext.open(o.ref)) throw UserError("Unable to find file: " + o.ref);
+    if (!qtext.open(o.query)) throw UserError("Unable to find file: " + o.query);
     bk_cfspec spec;
     bk_cfspec_default(&spec);
     spec.dist = o.dist;
@@ -106,11 +96,13 @@ int main(int argc, char** argv) {
       return text;
     };
     const int gpus = cli::gpus_requested();
-    if (gpus > 1 && o.chrom == "all") {
-      cli::run_sharded(cli::plan_slices({&rtext, &qtext}, gpus * 4), run_one, gpus);
+    std::vector<std::vector<cli::Slice>> slices;
+    if (gpus > 1 && o.chrom == "all") slices = cli::plan_slices({&rtext, &qtext}, gpus * 4);
+    if (!slices.empty()) {
+      cli::run_sharded(slices, run_one, gpus);
     } else {
       cli::Engine eng;
-      std::string text = run_one(eng, {cli::Slice{rtext.data(), rtext.size()}, cli::Slice{qtext.data(), qtext.size()}});
+      std::string text = run_one(eng, {cli::Slice{rtext.data, rtext.size}, cli::Slice{qtext.data, qtext.size}});
       cli::write_all(text.data(), text.size());
     }
     return EXIT_SUCCESS;

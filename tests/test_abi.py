@@ -6,7 +6,7 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, REFBIN, have_ref
 
 
 def header_symbols():
@@ -92,3 +92,28 @@ def test_cli_banners_and_errors_match_reference_shape():
     assert p.stderr == "May use bedmap --help for more help.\n\nError: Unable to find file: /nonexistent.bed\n"
     p = subprocess.run([bedops_b200.tool_path("bedmap"), "--bogus", "a", "b"], capture_output=True, text=True)
     assert p.stderr == "May use bedmap --help for more help.\n\nError: Unknown option: --bogus\n"
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_help_and_usage_texts_are_the_reference_s_byte_for_byte():
+    """--help (stdout, exit 0), no arguments (stderr, exit 1), bedops --help-<operation>: part of the process-boundary
+    contract.  Needs no GPU: the tools print them before touching the library."""
+    import bedops_b200
+    for tool in ("bedmap", "bedops", "closest-features"):
+        for argv in (["--help"], []):
+            exp = subprocess.run([os.path.join(REFBIN, tool)] + argv, capture_output=True)
+            got = subprocess.run([bedops_b200.tool_path(tool)] + argv, capture_output=True)
+            assert (got.returncode, got.stdout, got.stderr) == (exp.returncode, exp.stdout, exp.stderr), (tool, argv)
+    for op in ("merge", "intersect", "element-of", "not-element-of", "complement", "difference", "symmdiff", "chop",
+               "everything", "partition"):
+        exp = subprocess.run([os.path.join(REFBIN, "bedops"), "--help-" + op], capture_output=True)
+        got = subprocess.run([bedops_b200.tool_path("bedops"), "--help-" + op], capture_output=True)
+        assert (got.returncode, got.stdout) == (exp.returncode, exp.stdout), op
+
+
+def test_more_operations_than_the_spec_table_holds_is_a_clean_error(tmp_path):
+    """200 x --count used to smash the stack of the tool (bk_mapspec.ops is a fixed table)."""
+    import bedops_b200
+    (tmp_path / "a.bed").write_bytes(b"chr1\t1\t2\n")
+    p = subprocess.run([bedops_b200.tool_path("bedmap")] + ["--count"] * 200 + ["a.bed", "a.bed"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and "operations given" in p.stderr and "stack smashing" not in p.stderr

@@ -426,3 +426,74 @@ def test_closest_features_streaming_state_across_chunks(kit, tmp_path):
             assert r.stdout == kit.closest(ref, qry, dist=True)
         ref.free()
         qry.free()
+
+
+def test_range_shards_with_halos_equal_the_unsharded_call(kit, synth_files, tmp_path):
+    """ONE dataset cut at genomic positions inside chromosomes (bk_shard_plan_make), boundary halos found with the
+    prefix-max-end index (bk_bed_reach_start / bk_bed_chrom_max_end), halo ++ own records by bk_bed_concat: the parts in
+    rank order are the unsharded output, byte for byte.  Ranks run one after the other on this GPU (the exchange is a
+    Python list here; bench.py does it with an NCCL allgather, the tools with threads).  Cases: the hg38-shaped pair, a
+    single chromosome with an interval spanning every cut, --range padding, list operations that need the map text."""
+    from bedops_b200._lib import COL_ID, COL_LINE, COL_SCORE
+    from bedops_b200.shard import make_plan, RangeShard
+    from test_shard import halo_cases
+    for ci, (ref, mp_, ops, overlap) in enumerate(halo_cases(synth_files)):
+        ids = any(o.startswith("echo-map") for o in ops)
+        fields = 5 if any(o in ("sum", "mean") for o in ops) else (4 if ids else 3)
+        mcols = (COL_SCORE if fields == 5 else 0) | ((COL_ID | COL_LINE) if ids else 0)
+        rcols = COL_LINE if "echo" in ops else 0
+        r0, m0 = kit.load(ref, 3, rcols), kit.load(mp_, fields, mcols)
+        whole = kit.bedmap(r0, m0, ops, overlap=overlap)
+        r0.free()
+        m0.free()
+        assert_same(whole, O.bedmap(ref, mp_, ops, overlap=overlap))
+        for world in (2, 3, 7):
+            plan = make_plan(ref, mp_, world)
+            shards = [RangeShard(kit, plan, k, ref, mp_, ops, ref_fields=3, ref_cols=rcols, map_fields=fields, map_cols=mcols,
+                                 overlap=overlap) for k in range(world)]
+            allr = [s.reach_list() for s in shards]
+            parts = [s.finish(allr) for s in shards]
+            assert_same(b"".join(parts), whole)
+            assert sum(s.bytes_in for s in shards) >= len(ref) + len(mp_)   # every byte is uploaded at least once
+    # the tools: BEDKIT_GPUS=N on a single-chromosome input (the whole-chromosome planner could not split it)
+    if have_ref():
+        import bedops_b200
+        import torch
+        ref, mp_, ops, overlap = halo_cases(synth_files)[2]
+        (tmp_path / "r.bed").write_bytes(ref)
+        (tmp_path / "m.bed").write_bytes(mp_)
+        env = dict(os.environ, BEDKIT_GPUS="4")
+        if torch.cuda.device_count() < 4:
+            env["BEDKIT_SHARE_DEVICE"] = "1"
+        argv = ["--echo", "--count", "--sum", "--bases", "--echo-map-id", "r.bed", "m.bed"]
+        ours = subprocess.run([bedops_b200.tool_path("bedmap")] + argv, cwd=tmp_path, capture_output=True, env=env)
+        exp = subprocess.run([os.path.join(REFBIN, "bedmap")] + argv, cwd=tmp_path, capture_output=True)
+        assert ours.returncode == 0, ours.stderr
+        assert_same(ours.stdout, exp.stdout)
+        # a UCSC header under --ec makes "track" a chromosome name that sorts last: the planner must refuse, not duplicate rows
+        (tmp_path / "h.bed").write_bytes(b"track name=x\n" + synth_files["r.bed"])
+        for tool, argv in (("bedmap", ["--ec", "--count", "h.bed", "h.bed"]), ("bedops", ["--ec", "-m", "h.bed"])):
+            ours = subprocess.run([bedops_b200.tool_path(tool)] + argv, cwd=tmp_path, capture_output=True, env=env)
+            exp = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
+            assert ours.returncode == exp.returncode, ours.stderr
+            assert_same(ours.stdout, exp.stdout)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/bin not built")
+def test_row_ids_count_printed_rows(kit, tmp_path):
+    """--echo-ref-row-id: the reference's static counter is bumped by every printed id (ProcessBedVisitorRow.hpp:347-354):
+    rows dropped by --skip-unmapped or outside --chrom do not count, two id columns take two numbers per row."""
+    import bedops_b200
+    r = b"chr1\t1\t5\nchr1\t50\t60\nchr1\t100\t110\nchr2\t1\t5\nchr2\t70\t80\nchr3\t5\t9\n"
+    m = b"chr1\t2\t3\tx\t1\nchr1\t101\t102\ty\t2\nchr2\t72\t75\tz\t3\n"
+    (tmp_path / "r.bed").write_bytes(r)
+    (tmp_path / "m.bed").write_bytes(m)
+    for argv in (["--echo-ref-row-id", "--count"], ["--skip-unmapped", "--echo-ref-row-id", "--echo"],
+                 ["--chrom", "chr2", "--echo-ref-row-id"], ["--skip-unmapped", "--echo-ref-row-id", "--count", "--echo-ref-row-id"],
+                 ["--chrom", "chr2", "--skip-unmapped", "--echo-ref-row-id"]):
+        full = argv + ["r.bed", "m.bed"]
+        exp = subprocess.run([os.path.join(REFBIN, "bedmap")] + full, cwd=tmp_path, capture_output=True)
+        got = subprocess.run([bedops_b200.tool_path("bedmap")] + full, cwd=tmp_path, capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert_same(got.stdout, exp.stdout)
+        assert_same(oracle_cli.run("bedmap", full, {"r.bed": r, "m.bed": m}), exp.stdout)
