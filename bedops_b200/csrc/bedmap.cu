@@ -7,6 +7,7 @@
 //     lo = lower_bound(map.pmax_end, ref.start - pad + 1)   first map row whose running max end reaches the reference
 // Every row in [lo,hi) is tested with the exact overlap predicate (Bed::Overlapping / RangedDist / PercentOverlap* /
 // Exact, BedDistances.hpp:41-317) and reduced; the prefix-max index makes the range tight under nesting.
+#include <algorithm>
 #include "common.cuh"
 #include "emit.cuh"
 #include "fmt.cuh"
@@ -923,6 +924,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   }
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host table `tab` must outlive its copy
   dfree(ctx, d_tab);
+
 
   const uint64_t dl = strlen(delim);
   const uint64_t cap = 0;  // the emitter sizes the result itself (length pass)

@@ -497,3 +497,26 @@ def test_row_ids_count_printed_rows(kit, tmp_path):
         assert got.returncode == 0, got.stderr
         assert_same(got.stdout, exp.stdout)
         assert_same(oracle_cli.run("bedmap", full, {"r.bed": r, "m.bed": m}), exp.stdout)
+
+
+def test_tile_kernel_streams_long_ranges_in_chunks(kit):
+    """k_map_tile (sparse maps, --bp-ovr): reference rows whose windows are far longer than the shared-memory range
+    (a row spanning the chromosome among short ones) stream through it in chunks; piece lengths grow when every row of a
+    tile has a long window.  Every aggregate against the oracle, float scores within 1e-12 (the summation order differs)."""
+    import numpy as np
+    from bedops_b200._lib import COL_LINE, COL_SCORE
+    rng = np.random.default_rng(5)
+    for n_ref, n_map, span, giant in ((2000, 20000, 400000, 3), (600, 9000, 60000, 600)):
+        ms = np.sort(rng.integers(0, span, n_map))
+        me = ms + np.maximum(1, rng.lognormal(3.0, 1.0, n_map).astype(np.int64))
+        mp_ = "".join("chrQ\t%d\t%d\tm%d\t%d\n" % (a, b, k, k % 1000) for k, (a, b) in enumerate(zip(ms.tolist(), me.tolist()))).encode()
+        rs = rng.integers(0, span, n_ref)
+        rl = np.maximum(1, rng.lognormal(4.0, 1.0, n_ref).astype(np.int64))
+        rl[rng.choice(n_ref, giant, replace=False)] = span   # rows that overlap (nearly) every map row
+        order = np.lexsort((rs + rl, rs))
+        ref = "".join("chrQ\t%d\t%d\n" % (a, a + l) for a, l in zip(rs[order].tolist(), rl[order].tolist())).encode()
+        rb, mb = kit.load(ref, 3, COL_LINE), kit.load(mp_, 5, COL_SCORE)
+        for ops in (["echo", "count", "sum", "bases"], ["count", "max", "min", "mean"], ["indicator", "bases"]):
+            assert_same(kit.bedmap(rb, mb, ops), O.bedmap(ref, mp_, ops))
+        rb.free()
+        mb.free()
