@@ -9,6 +9,7 @@
 // per-chromosome scale-out, bedmap/src/Input.hpp:117-122).  Inputs should be pinned for the overlap to happen.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include "common.cuh"
 
@@ -287,6 +288,19 @@ int load_slice(bk_ctx* ctx, const char* src, uint64_t off, uint64_t len, int fie
 
 uint64_t range_pad(const bk_mapspec& s) { return s.overlap_kind == BK_OVR_RANGE ? s.overlap_bp : 0; }
 
+struct Lap {  // BEDKIT_TRACE: host wall clock of the sub-steps of a call, to stderr
+  const char* what;
+  bool        on = getenv("BEDKIT_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  explicit Lap(const char* w) : what(w) {}
+  void operator()(const char* step) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bedkit] %s: %s %.3f ms\n", what, step, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 }  // namespace
 
 extern "C" int bk_shard_plan_make(const char* ref_text, size_t ref_len, const char* map_text, size_t map_len, int n_shards,
@@ -357,10 +371,12 @@ extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int
   sh->spec.multidelim = sh->mdelim.c_str();
   sh->spec.chrom = nullptr;
   const uint64_t pad = range_pad(*spec);
+  Lap            lap("shard_begin");
   // this rank's reference rows: the records whose start lies in its range
   const uint64_t r0 = plan->ref_off[rank], r1 = plan->ref_off[rank + 1];
   int rc = load_slice(ctx, ref_src ? ref_src : ref_text, r0, r1 - r0, ref_fields, ref_cols, &sh->ref);
   sh->bytes_in += r1 - r0;
+  lap("ref slice");
   // right halo: map records behind the right cut that start before the largest reference end of the shard
   uint64_t m0 = plan->map_off[rank], m1 = plan->map_off[rank + 1];
   if (rc == BK_OK && rank + 1 < n && !plan->cuts[rank].at_end && plan->cuts[rank].coord > 0) {
@@ -369,8 +385,10 @@ extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int
     if (rc == BK_OK && maxend + pad > plan->cuts[rank].coord)
       m1 = bk_find_start(map_text, m1, plan->map_chrom_end[rank], maxend + pad);
   }
+  lap("right halo bound");
   if (rc == BK_OK) rc = load_slice(ctx, sh->map_src, m0, m1 - m0, map_fields, map_cols, &sh->map);
   sh->bytes_in += m1 - m0;
+  lap("map slice");
   // what the later shards need from this one: where, among these records, their left halo would begin
   for (int j = rank + 1; j < n && rc == BK_OK; j++) {
     const bk_cut& c = plan->cuts[j - 1];
@@ -379,6 +397,7 @@ extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int
     rc = bk_bed_reach_start(ctx, sh->map, c.chrom, c.coord > pad ? c.coord - pad : 0, &s);
     if (s < c.coord) reach[j] = s;
   }
+  lap("reach");
   if (rc != BK_OK) {
     bk_shard_free(ctx, sh);
     return rc;
@@ -392,6 +411,7 @@ extern "C" int bk_bedmap_shard_finish(bk_ctx* ctx, bk_shard* sh, const uint64_t*
   memset(out, 0, sizeof(*out));
   const int n = sh->plan.n_shards, rank = sh->rank;
   int       rc = BK_OK;
+  Lap       lap("shard_finish");
   if (rank > 0) {
     const bk_cut& c = sh->plan.cuts[rank - 1];
     uint64_t      s = ~0ull;
@@ -414,7 +434,9 @@ extern "C" int bk_bedmap_shard_finish(bk_ctx* ctx, bk_shard* sh, const uint64_t*
       }
     }
   }
+  lap("left halo");
   if (rc == BK_OK) rc = bk_bedmap(ctx, sh->ref, sh->map, &sh->spec, out);
+  lap("bedmap");
   bk_free_bed(ctx, sh->ref);  // the columns go back to the cache now; the handle itself lives until bk_shard_free
   bk_free_bed(ctx, sh->map);
   sh->ref = sh->map = nullptr;

@@ -115,7 +115,7 @@ class RangeShard:
     """One rank's half-finished range-sharded bedmap call: begin() -> exchange reach vectors -> finish()."""
 
     def __init__(self, kit, plan: ShardPlan, rank: int, ref_text, map_text, ops, ref_fields=3, ref_cols=0, map_fields=5,
-                 map_cols=0, ref_src=None, map_src=None, **spec_kw):
+                 map_cols=0, ref_src=None, map_src=None, on_device=False, **spec_kw):
         from ._lib import _Text  # noqa: F401
         self.kit, self.plan, self.rank = kit, plan, rank
         lib = kit.lib
@@ -125,8 +125,9 @@ class RangeShard:
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         self._keep = (ref_text, map_text, ref_src, map_src)
         (rp, rn), (mp, mn) = _addr(ref_text), _addr(map_text)
-        spec = kit._mapspec(ops, **spec_kw)
+        spec = kit._mapspec(ops, on_device=on_device, **spec_kw)   # where the result text is left: HBM or pinned host
         self._spec = spec
+        self.on_device = on_device
         self.h = C.c_void_p()
         self.reach = (C.c_uint64 * plan.n_shards)()
         kit._chk(lib.bk_bedmap_shard_begin(kit.ctx, C.byref(plan), rank, rp, rn, ref_fields, ref_cols, mp, mn, map_fields, map_cols,
@@ -137,8 +138,9 @@ class RangeShard:
     def reach_list(self):
         return [int(x) for x in self.reach]
 
-    def finish(self, all_reach, on_device=False):
-        """all_reach: n_shards x n_shards (row i = rank i's reach list).  Returns this rank's output text."""
+    def finish(self, all_reach, _raw=False):
+        """all_reach: n_shards x n_shards (row i = rank i's reach list).  Returns this rank's output text (_raw: the
+        library's own pinned bk_text, not copied into a Python object; release with kit.free_text)."""
         from ._lib import _Text
         n = self.plan.n_shards
         flat = (C.c_uint64 * (n * n))(*[int(v) for row in all_reach for v in row])
@@ -149,7 +151,7 @@ class RangeShard:
             self.bytes_in = self.kit.lib.bk_shard_bytes_in(h)   # own slices + halos copied from the source
         finally:
             self.kit.lib.bk_shard_free(self.kit.ctx, h)
-        return self.kit._take(t, on_device)
+        return self.kit._take(t, self.on_device, _raw)
 
     def __del__(self):
         try:

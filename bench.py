@@ -566,6 +566,8 @@ def run_sharded(args, kit, torch, dist, device, stream, numa, world, rank):
                 err = rt.cudaHostRegister(arr.ctypes.data + lo, hi - lo, 0)
                 if int(err) == 0:
                     pinned.append(arr.ctypes.data + lo)
+                else:
+                    print("[bench] rank %d: cudaHostRegister(%d bytes) failed: %s" % (rank, hi - lo, err), file=sys.stderr)
 
         gather_buf = [torch.empty(world, dtype=torch.int64, device=device) for _ in range(world)]
 
@@ -576,29 +578,43 @@ def run_sharded(args, kit, torch, dist, device, stream, numa, world, rank):
             rows = torch.stack(gather_buf).cpu().tolist()
             return [[INF if v >= (1 << 62) else v for v in r] for r in rows]
 
-        def step(from_device, on_device):
+        phases = {"begin": 0.0, "exchange": 0.0, "finish": 0.0, "n": 0}
+
+        def step(from_device, on_device, raw=False):
+            t0 = time.perf_counter()
             sh = RangeShard(kit, plan, rank, ref_host, map_host, OPS, ref_fields=3, ref_cols=COL_LINE, map_fields=5,
                             map_cols=COL_SCORE, ref_src=(ref_buf.data_ptr(), ref_bytes) if from_device else None,
-                            map_src=(map_buf.data_ptr(), map_bytes) if from_device else None)
+                            map_src=(map_buf.data_ptr(), map_bytes) if from_device else None, on_device=on_device)
+            t1 = time.perf_counter()
             allr = exchange(sh.reach_list())
-            out = sh.finish(allr, on_device=on_device)
+            t2 = time.perf_counter()
+            out = sh.finish(allr, _raw=raw)
+            t3 = time.perf_counter()
+            phases["begin"] += t1 - t0; phases["exchange"] += t2 - t1; phases["finish"] += t3 - t2; phases["n"] += 1
             return sh, out
 
         def timed(from_device, on_device, steps, warmup):
             for _ in range(warmup):
-                sh, out = step(from_device, on_device)
+                sh, out = step(from_device, on_device, raw=not on_device)
                 if on_device:
                     out.free()
+                else:
+                    kit.free_text(out)
             barrier()
+            if steps == 0:
+                return 0.0, 0, 0
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             t0 = time.perf_counter()
             last = None
             for _ in range(steps):
-                sh, out = step(from_device, on_device)
-                last = (sh.bytes_in, out.nbytes if on_device else len(out))
+                # e2e: the result text lands in the library's pinned host buffer (the tools write it to stdout from there)
+                sh, out = step(from_device, on_device, raw=not on_device)
+                last = (sh.bytes_in, out.nbytes if on_device else out.len)
                 if on_device:
                     out.free()
+                else:
+                    kit.free_text(out)
             e1.record(stream)
             torch.cuda.synchronize()
             wall = (time.perf_counter() - t0) * 1e3
@@ -617,7 +633,9 @@ def run_sharded(args, kit, torch, dist, device, stream, numa, world, rank):
         kit.profile(True)
         l0 = kit.launches
         sampler.mark_begin()
+        phases.update(begin=0.0, exchange=0.0, finish=0.0, n=0)
         ms, bytes_in, out_bytes = timed(True, True, args.steps, 0)
+        host_phases_ms = {k: 1e3 * phases[k] / max(1, phases["n"]) for k in ("begin", "exchange", "finish")}
         sampler.mark_end()
         clocks = sampler.stop()
         launches = kit.launches - l0
@@ -628,9 +646,11 @@ def run_sharded(args, kit, torch, dist, device, stream, numa, world, rank):
         e2e = None
         if not args.no_e2e:
             k = max(1, min(args.steps, 5))
+            phases.update(begin=0.0, exchange=0.0, finish=0.0, n=0)
             te, h2d, d2h = timed(False, False, k, max(1, min(args.warmup, 2)))
+            e2e_phases_ms = {k_: 1e3 * phases[k_] / max(1, phases["n"]) for k_ in ("begin", "exchange", "finish")}
             e2e = {"value": units * k / (te * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "steps": k, "ms_per_step": te / k,
+                   "steps": k, "ms_per_step": te / k, "rank0_host_phases_ms": e2e_phases_ms,
                    "note": "bytes summed over ranks: every rank uploads only its own slice of the shared text (+ halos)"}
 
         # ---- the sharded output is the unsharded output: rank 0 maps the whole dataset alone and compares part by part
@@ -701,7 +721,7 @@ def run_sharded(args, kit, torch, dist, device, stream, numa, world, rank):
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                          "note": "rank 0's launches", "kernel_ms_per_step": split},
-            "same_workload_one_gpu": single,
+            "same_workload_one_gpu": single, "rank0_host_phases_ms": host_phases_ms,
         }
         if e2e:
             line["e2e"] = e2e

@@ -499,10 +499,10 @@ def test_row_ids_count_printed_rows(kit, tmp_path):
         assert_same(oracle_cli.run("bedmap", full, {"r.bed": r, "m.bed": m}), exp.stdout)
 
 
-def test_tile_kernel_streams_long_ranges_in_chunks(kit):
-    """k_map_tile (sparse maps, --bp-ovr): reference rows whose windows are far longer than the shared-memory range
-    (a row spanning the chromosome among short ones) stream through it in chunks; piece lengths grow when every row of a
-    tile has a long window.  Every aggregate against the oracle, float scores within 1e-12 (the summation order differs)."""
+def test_windows_far_longer_than_a_warp_step(kit):
+    """Reference rows whose windows are thousands of map rows long among short ones
+    (a row spanning the chromosome; a tile in which every row has a long window): the window scan must not depend on
+    the window length.  Every aggregate against the oracle."""
     import numpy as np
     from bedops_b200._lib import COL_LINE, COL_SCORE
     rng = np.random.default_rng(5)
