@@ -256,7 +256,7 @@ extern "C" int bk_init(bk_ctx** out, int device) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->dev_cache_limit = total_b / 4;
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_scratch), SC_N * sizeof(uint64_t)) != cudaSuccess ||
-      cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_scratch), SC_N * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
+      cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_scratch), SC_N * sizeof(uint64_t) + kHostScratchExtra, cudaHostAllocDefault) != cudaSuccess) {
     bk_destroy(ctx);
     return BK_ERR_NOMEM;
   }

@@ -137,6 +137,7 @@ enum {
   SC_OUT_ROWS = 11,  // emitters: total rows written
   SC_N = 64
 };
+constexpr size_t kHostScratchExtra = 16384;  // pinned bytes behind the SC_N words of h_scratch (parser: first chromosome heads)
 
 // ---------------------------------------------------------------------------------------------------------
 // device side
@@ -155,6 +156,36 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- bulk asynchronous copy global -> shared (cp.async.bulk, SASS UBLKCP) completed on an mbarrier -------------------
+// One elected thread arms the barrier with the byte count and issues ONE instruction for the whole window; the copy
+// engine moves the bytes, no thread spends issue slots on them.  Addresses 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst), b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc),
+               "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(b),
+      "r"(parity)
+      : "memory");
+}
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // streaming 16-byte load, no L1 allocation
   uint4 r;

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
                                                            const uint64_t* __restrict__ scratch,
                                                            uint32_t* __restrict__ local_prefix, uint64_t* __restrict__ warp_total,
                                                            uint32_t ntiles, uint32_t tiles_per_warp, uint32_t nwarps,
-                                                           int skip_headers) {
+                                                           int skip_headers, int strict_blank) {
   const int      lane = threadIdx.x & 31;
   const uint32_t wid = (blockIdx.x * CR_THREADS + threadIdx.x) >> 5;
   if (wid >= nwarps) return;
@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
       for (uint32_t m = smask & cm; m; m &= m - 1) {  // a line that begins with a control byte may be blank
         const int j = __ffs(m) - 1;
         uint64_t  q = p0 + j;
-        while (q < eff && is_ws(text[q])) q++;
+        if (!strict_blank)  // sort-bed skips only empty lines (SortDetails.cpp:625-629); fscanf skips any whitespace
+          while (q < eff && is_ws(text[q])) q++;
         if (q >= eff || text[q] == '\n') smask &= ~(1u << j);
       }
       if (skip_headers) {
@@ -318,58 +319,95 @@ __global__ void k_tile_base(const uint32_t* __restrict__ local_prefix, const uin
   if (t < ntiles) tile_base[t] = warp_base[t / tiles_per_warp] + local_prefix[t];
 }
 
+// decimal field of len digits (1..4) that ENDS at window byte index e (exclusive) -> value (scores of a few digits)
+__device__ __forceinline__ uint32_t parse_digits_short(const unsigned char* sm, int e, int len, uint32_t& bad) {
+  uint32_t       g0 = ld32u(sm, e - 4);
+  const uint32_t m0 = len >= 4 ? 0u : (0xFFFFFFFFu >> (8 * len));  // the bytes in front of the field become '0'
+  g0 = (g0 & ~m0) | (0x30303030u & m0);
+  return digits4(g0, bad);
+}
+
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
 //
-// Per tile (tiles are independent: the first row of each tile comes from pass 1): (1) stage the text, (2) every
-// thread builds the control-byte / NL bitmasks of its 32 bytes and counts the lines that START there, (3) block scan
-// -> row index, (4) every thread parses ITS lines and writes the SoA columns directly (the lanes of a warp hold
-// consecutive rows, so the stores coalesce).  Two block barriers per tile; the text of the next tile is copied
-// into the other window buffer (cp.async) while this one is parsed.
+// Per tile (tiles are independent: the first row of each tile comes from pass 1):
+//  [A] the text window (tile + halos) arrives by ONE bulk asynchronous copy (cp.async.bulk, completes on an mbarrier),
+//      issued by one thread a whole tile ahead into the other buffer -- staging costs the other 255 threads nothing;
+//  [B] every thread builds the control-byte / NL bitmasks of its 32 bytes and counts the lines that START there;
+//  [C] block scan -> every line start is written to a compact list (lstart[i] = window index of the i-th line);
+//  [D] thread i parses line i and writes row base+i of the SoA columns: full warps (the last one excepted) whatever the
+//      line length, perfectly coalesced stores, and the previous row -- needed for the chromosome-head test -- is simply
+//      lstart[i-1].
+// Two block barriers per tile.  The mask arrays are double-buffered so that a warp may start [B] of the next tile while
+// others still parse; lstart is written only after barrier [S2], when every thread has left [D] of the previous tile.
 template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p) {
-  __shared__ __align__(16) unsigned char smbuf[2][P_BUF + 16];  // double-buffered text window
-  __shared__ uint32_t                    ctlp[P_NW + 4];
-  __shared__ uint32_t                    nlw[P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
-  __shared__ uint32_t                    wsum[P_THREADS / 32];
-  __shared__ uint64_t                    base_sm;
+  __shared__ __align__(128) unsigned char smbuf[2][P_BUF + 16];  // double-buffered text window
+  __shared__ uint32_t                     ctlp2[2][P_NW + 4];
+  __shared__ uint32_t                     nlw2[2][P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
+  __shared__ uint32_t                     wsum2[2][P_THREADS / 32];
+  __shared__ uint64_t                     base2[2];
+  __shared__ uint16_t                     lstart[P_MAXROWS];
+  __shared__ __align__(8) uint64_t        mbar[2];
   const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t eff = p.scratch[SC_EFFLEN];  // bytes up to and including the last '\n'
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
 
-  // stage [ts-PRE, ts+TILE+POST) of a tile into a window buffer: 16-byte asynchronous copies (global -> shared
-  // without passing through registers), issued one tile ahead so that the copy of tile t+1 overlaps the parse of t
-  auto stage = [&](uint32_t tile, unsigned char* dst) {
+  // a tile whose whole window lies inside the text is moved by the copy engine; the first and the last tiles of a file
+  // are staged by the threads themselves (zero-filled outside the text)
+  auto bulkable = [&](uint32_t tile) {
+    const int64_t g0 = (int64_t)tile * P_TILE - P_PRE;
+    return g0 >= 0 && (uint64_t)g0 + P_BUF <= p.nbytes_raw;
+  };
+  auto issue = [&](uint32_t tile, int b) {  // one thread
+    fence_proxy_async();                    // the buffer's earlier generic-proxy accesses are ordered before the async write
+    bulk_g2s(smbuf[b], text + ((int64_t)tile * P_TILE - P_PRE), P_BUF, &mbar[b]);
+  };
+  auto stage_edge = [&](uint32_t tile, unsigned char* dst) {
     const int64_t g0 = (int64_t)tile * P_TILE - P_PRE;
     for (int v = tid; v < P_BUF / 16; v += P_THREADS) {
       const int64_t g = g0 + (int64_t)v * 16;
+      uint32_t      w[4] = {0, 0, 0, 0};
       if (g >= 0 && (uint64_t)g + 16 <= p.nbytes_raw) {
-        cp_async16(dst + v * 16, text + g);
-      } else {  // window edge: before the text, or across its end -- zero-filled, byte by byte
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < p.nbytes_raw) {
+        const uint4 q = *reinterpret_cast<const uint4*>(text + g);
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+      } else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < p.nbytes_raw) {
 #pragma unroll 1
-          for (int i = 0; i < 16; i++) {
-            const int64_t gi = g + i;
-            if (gi >= 0 && (uint64_t)gi < p.nbytes_raw) w[i >> 2] |= (uint32_t)text[gi] << (8 * (i & 3));
-          }
+        for (int i = 0; i < 16; i++) {
+          const int64_t gi = g + i;
+          if (gi >= 0 && (uint64_t)gi < p.nbytes_raw) w[i >> 2] |= (uint32_t)text[gi] << (8 * (i & 3));
         }
-        reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      reinterpret_cast<uint4*>(dst)[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    cp_async_commit();
   };
 
-  int buf = 0;
-  if (blockIdx.x < p.ntiles) stage(blockIdx.x, smbuf[0]);
-  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, buf ^= 1) {
-    const int64_t ts = (int64_t)tile * P_TILE;
-    const int64_t g0 = ts - P_PRE;
-    unsigned char* const sm = smbuf[buf];
-    cp_async_wait_all();
-    __syncthreads();  // [S1] this tile's text staged (the other buffer is free: everyone passed [S3] of the previous tile)
-    if (tile + gridDim.x < p.ntiles) stage(tile + gridDim.x, smbuf[buf ^ 1]);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_init_fence();
+    if (p.line_off && blockIdx.x == 0) p.line_off[p.cap] = eff;  // sentinel: end of the last row's line
+  }
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < p.ntiles && bulkable(blockIdx.x)) issue(blockIdx.x, 0);
 
-    // ---- control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' -----------
+  uint32_t phase = 0;  // bit b = parity of the next completion of mbar[b]
+  int      buf = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t        ts = (int64_t)tile * P_TILE;
+    const int64_t        g0 = ts - P_PRE;
+    unsigned char* const sm = smbuf[buf];
+    uint32_t* const      ctlp = ctlp2[buf];
+    uint32_t* const      nlw = nlw2[buf];
+    // ---- [A] this tile's text -----------------------------------------------------------------------------------
+    if (bulkable(tile)) {
+      mbar_wait(&mbar[buf], (phase >> buf) & 1u);
+      phase ^= 1u << buf;
+    } else {
+      stage_edge(tile, sm);  // the buffer is free: every thread passed [S2] of the previous tile after leaving tile-2
+      __syncthreads();
+    }
+
+    // ---- [B] control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' ---------
     Cursor        cur{sm, g0, text, eff};
     const int     off = P_PRE + tid * 32;
     const int64_t p0 = ts + tid * 32;  // global offset of this thread's first byte
@@ -393,16 +431,16 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         for (int i = 7; i >= 0; i--) hm = push_flags4(hm, nl_mask4(h8[i], ctl_mask4(h8[i])));
         nlw[tid - 32] = hm;
       }
-      if (tid < P_POST / 32) {  // tail halo
-        const uint4* t4 = reinterpret_cast<const uint4*>(sm + P_PRE + P_TILE + tid * 32);
+      if (tid >= 64 && tid < 64 + P_POST / 32) {  // tail halo
+        const uint4* t4 = reinterpret_cast<const uint4*>(sm + P_PRE + P_TILE + (tid - 64) * 32);
         const uint4  ta = t4[0], tc = t4[1];
         const uint32_t t8[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
         uint32_t     tm = 0;
 #pragma unroll
         for (int i = 7; i >= 0; i--) tm = push_flags4(tm, ctl_mask4(t8[i]));
-        ctlp[P_TILE / 32 + tid] = tm;
-      } else if (tid < P_POST / 32 + 4) {
-        ctlp[P_TILE / 32 + tid] = 0;  // padding words read by the 64-bit line windows
+        ctlp[P_TILE / 32 + tid - 64] = tm;
+      } else if (tid >= 96 && tid < 100) {
+        ctlp[P_TILE / 32 + P_POST / 32 + tid - 96] = 0;  // padding words read by the 64-bit line windows
       }
     }
     if ((uint64_t)p0 + 32 > eff)  // clip to the effective text length (last tile only)
@@ -412,7 +450,8 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     for (uint32_t m = smask & cm; m; m &= m - 1) {
       const int j = __ffs(m) - 1;
       int64_t   q = off + j;
-      while (is_ws(cur.at(q))) q++;
+      if (!(p.cols & BK_LOAD_SORTBED))
+        while (is_ws(cur.at(q))) q++;
       if (cur.at(q) == '\n') smask &= ~(1u << j);
     }
     if (p.cols & BK_LOAD_HEADERS)
@@ -422,35 +461,31 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       }
     const uint32_t cnt = __popc(smask);
     const uint32_t incl = warp_incl_scan(cnt);
-    if (lane == 31) wsum[warp] = incl;
-    if (tid == 0) base_sm = p.tile_base[tile];  // first row of this tile (pass 1)
-    __syncthreads();  // [S2] masks, warp totals and the tile's first row visible
-    uint32_t ex = incl - cnt;  // rows of this tile that start before this thread's bytes
+    if (lane == 31) wsum2[buf][warp] = incl;
+    if (tid == 0) base2[buf] = p.tile_base[tile];  // first row of this tile (pass 1)
+    __syncthreads();  // [S2] masks, warp totals and the tile's first row visible; everyone has left [D] of the previous tile
+    if (tid == 0 && tile + gridDim.x < p.ntiles && bulkable(tile + gridDim.x)) issue(tile + gridDim.x, buf ^ 1);
+
+    // ---- [C] compact the line starts --------------------------------------------------------------------------
+    uint32_t nl;
     {
-      const uint32_t t = (lane < warp && lane < P_THREADS / 32) ? wsum[lane] : 0u;
-      ex += __reduce_add_sync(0xffffffffu, t);
+      const uint32_t v = lane < P_THREADS / 32 ? wsum2[buf][lane] : 0u;
+      uint32_t       ex = incl - cnt + __reduce_add_sync(0xffffffffu, lane < warp ? v : 0u);
+      nl = __reduce_add_sync(0xffffffffu, v);
+      for (uint32_t m = smask; m; m &= m - 1) lstart[ex++] = (uint16_t)(off + __ffs(m) - 1);
     }
+    __syncthreads();  // [S3]
+    const uint64_t base = base2[buf];
 
-    const uint64_t base = base_sm;
-
-    // ---- every thread parses the lines that START in its 32 bytes ---------------------------------------------
-    // The loop is warp-uniform: lanes without a (further) line idle.
-    uint32_t m = smask;
+    // ---- [D] thread i parses line i ---------------------------------------------------------------------------
 #pragma unroll 1
-    for (int round = 0; round == 0 || __any_sync(0xffffffffu, m != 0); round++) {
-      const bool     has = m != 0;
-      const uint32_t k = ex;
-      const int      q0 = has ? off + __ffs(m) - 1 : off;
-      if (has) {
-        ex++;
-        m &= m - 1;
-      }
-      uint32_t v_start = 0, v_end = 0, v_id = 0;
-      double   v_score = 0.0;
-      int      tok0 = q0, toklen = 0, err = 0;
-      uint32_t linelen = 0xFFFFu;  // bytes up to the NL when the line is canonical (echo = verbatim copy), else 0xFFFF
-      bool     head = false;
-      if (has) {
+    for (uint32_t i = tid; i < nl; i += P_THREADS) {
+      const int q0 = lstart[i];
+      uint32_t  v_start = 0, v_end = 0, v_id = 0;
+      double    v_score = 0.0;
+      int       tok0 = q0, toklen = 0, err = 0;
+      uint32_t  linelen = 0xFFFFu;  // bytes up to the NL when the line is canonical (echo = verbatim copy), else 0xFFFF
+      bool      head = false;
       // 64 line bytes of control-byte mask, starting at the line start
       const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
       const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
@@ -468,7 +503,6 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           Whi &= Whi - 1;
         }
       }
-      unsigned long long W = ((unsigned long long)Whi << 32) | Wlo;  // the remaining control bytes
       uint32_t bad = 0;
       if (fast) {
         // every separator but the last must be a TAB, the last a TAB or the NL
@@ -495,7 +529,8 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           bad |= l4 < 1 ? 1u : 0u;
           if (WANT_SCORE && !bad) {
             uint32_t sbad = l4 > 9 ? 1u : 0u;
-            if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
+            if (l4 <= 4) v_score = (double)parse_digits_short(sm, q0 + s4, l4, sbad);
+            else if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
             if (sbad) bad |= parse_score_slow(sm, q0 + s3 + 1, v_score) ? 1u : 0u;  // exact strtod on the field
           }
         }
@@ -505,12 +540,15 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           // input bytes, so the whole line can be copied.  Find the NL among the remaining control bytes.
           int nlpos = -1;
           if (sm[q0 + sp[NSEP - 1]] == '\n') nlpos = sp[NSEP - 1];
-          for (int it = 0; nlpos < 0 && W != 0 && it < 8; it++) {
-            const int r = __ffsll((long long)W) - 1;
-            if (sm[q0 + r] == '\n') nlpos = r;
-            W &= W - 1;
+          else {
+            unsigned long long W = ((unsigned long long)Whi << 32) | Wlo;  // the remaining control bytes
+            for (int it = 0; nlpos < 0 && W != 0 && it < 8; it++) {
+              const int r = __ffsll((long long)W) - 1;
+              if (sm[q0 + r] == '\n') nlpos = r;
+              W &= W - 1;
+            }
           }
-          const bool lz = (sm[q0 + sp[0] + 1] == '0' && sp[1] - sp[0] > 2) || (sm[q0 + sp[1] + 1] == '0' && sp[2] - sp[1] > 2);
+          const bool lz = (sm[q0 + sp[0] + 1] == '0' && l1 > 1) || (sm[q0 + sp[1] + 1] == '0' && l2 > 1);
           if (nlpos >= 0 && !lz) linelen = (uint32_t)nlpos;
         }
       }
@@ -525,52 +563,47 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         tok0 = (int)r.tok0;
         toklen = r.toklen;
       }
-      }  // has
-      // chromosome run head?  Compare the token with the previous row's.  Shortcut: the previous row is usually the one
-      // the nearest lower lane with a line parsed in this very round (each lane owns 32 bytes, a line is longer),
-      // so its token arrives by shuffle.
-      {
-        const bool     cand = has && !err && toklen <= 8 && tok0 == q0;
-        const uint2    t8 = cand ? token8(sm, tok0, toklen) : make_uint2(0u, 0u);
-        const unsigned act = __ballot_sync(0xffffffffu, has);
-        const unsigned below = act & ((1u << lane) - 1u);
-        const int      src = below ? 31 - __clz(below) : lane;
-        const uint32_t pk = __shfl_sync(0xffffffffu, k, src);
-        const uint32_t px = __shfl_sync(0xffffffffu, t8.x, src), py = __shfl_sync(0xffffffffu, t8.y, src);
-        const int      plen = __shfl_sync(0xffffffffu, cand ? toklen : -1, src);
-        bool           done = false;
-        if (cand && below && pk + 1 == k && plen >= 0) {
-          head = plen != toklen || px != t8.x || py != t8.y;
-          done = true;
+      const uint64_t row = base + i;
+      if (p.cols & BK_LOAD_SORTBED) {
+        // sort-bed reading: any chromosome order (no run heads), and a row this tokeniser does not take is left to the
+        // sorter's own validation (k_sort_validate re-reads every non-canonical row by sort-bed's grammar)
+        if (row < p.cap) {
+          const bool plain = fast && err == 0;
+          p.start[row] = plain ? v_start : 0u;
+          p.end[row] = plain ? v_end : 0u;
+          p.line_off[row] = ((uint64_t)(plain ? linelen : 0xFFFFu) << 48) | (uint64_t)(g0 + q0);
         }
-        if (has && !err && !done) {
-          // the previous line ends at the NL just before this line's start; the NL before that one (found in the
-          // window's NL mask) is where the previous line starts
-          if (cand && q0 >= 2 && g0 + q0 >= 2) {
+        continue;
+      }
+      if (err) {
+        dev_set_error(p.scratch, err, row);
+        continue;
+      }
+      // chromosome run head?  Compare the token with the previous row's: row i-1 of this tile starts at lstart[i-1];
+      // the row before the tile's first one starts after the last NL but one before q0 (NL mask of the head halo).
+      {
+        bool done = false;
+        if (toklen <= 8 && tok0 == q0) {
+          int ps = -1;
+          if (i > 0) ps = lstart[i - 1];
+          else if (q0 >= 2 && g0 + q0 >= 2) {
             const int x = q0 - 2;
             int       w = x >> 5;
             uint32_t  pm = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
             while (!pm && w > 0) pm = nlw[--w];
-            int ps = -1;
             if (pm) ps = 32 * w + 32 - __clz(pm);   // first byte after that NL
             else if (g0 <= 0) ps = (int)(-g0);      // the previous line is the first line of the file
-            if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
-              const uint2 c = token8(sm, ps, toklen);
-              head = t8.x != c.x || t8.y != c.y || sm[ps + toklen] > 0x20;
-              done = true;
-            }
           }
-          if (!done) {
-            int64_t pt = prev_line_token(cur, q0);
-            head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
+          if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
+            const uint2 t8 = token8(sm, q0, toklen), c = token8(sm, ps, toklen);
+            head = t8.x != c.x || t8.y != c.y || sm[ps + toklen] > 0x20;
+            done = true;
           }
         }
-      }
-      if (!has) continue;
-      const uint64_t row = base + k;
-      if (err) {
-        dev_set_error(p.scratch, err, row);
-        continue;
+        if (!done) {
+          int64_t pt = prev_line_token(cur, q0);
+          head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
+        }
       }
       if (head) {
         uint32_t h = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_NHEADS]), 1ull);
@@ -578,7 +611,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           HeadRec* hr = &p.heads[h];
           hr->row = row;
           hr->len = toklen;
-          for (int i = 0; i < toklen; i++) hr->name[i] = cur.at(tok0 + i);
+          for (int k = 0; k < toklen; k++) hr->name[k] = cur.at(tok0 + k);
           hr->name[toklen] = 0;
         }
       }
@@ -590,8 +623,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
       }
     }
-    // no barrier here: nothing in shared memory is written again before [S1] of the next tile, which every thread
-    // reaches only after it has finished this tile's lines
+    // no barrier here: [S2] of the next tile is the point where every thread has left this tile's [D]
   }
 }
 
@@ -705,6 +737,8 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   }
   const uint32_t ntiles = (uint32_t)((nbytes_raw + P_TILE - 1) / P_TILE);
   const uint32_t heads_cap = 1u << 16;
+  constexpr size_t kHeadsInline = 64;
+  HeadRec* const heads_pre = reinterpret_cast<HeadRec*>(ctx->h_scratch + SC_N);  // pinned
   HeadRec*       d_heads = dalloc<HeadRec>(ctx, heads_cap);
   // pass 1 geometry: one warp per contiguous range of tiles
   const uint32_t max_warps = (uint32_t)ctx->sms * 8 * (CR_THREADS / 32);
@@ -721,7 +755,8 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_count_rows");
   k_count_rows<<<(nwarps * 32 + CR_THREADS - 1) / CR_THREADS, CR_THREADS, 0, ctx->stream>>>(
-      text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps, (bed->cols & BK_LOAD_HEADERS) ? 1 : 0);
+      text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps, (bed->cols & BK_LOAD_HEADERS) ? 1 : 0,
+      (bed->cols & BK_LOAD_SORTBED) ? 1 : 0);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_scan_warps");
@@ -779,6 +814,9 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     }
     prof_end(ctx);
     BK_LAUNCHED(ctx);
+    // one host round trip: the first heads travel with the scratch words (a genome has a few dozen chromosome runs)
+    static_assert(kHeadsInline * sizeof(HeadRec) <= kHostScratchExtra, "inline heads must fit the pinned scratch tail");
+    BK_CUDA(ctx, cudaMemcpyAsync(heads_pre, d_heads, kHeadsInline * sizeof(HeadRec), cudaMemcpyDeviceToHost, ctx->stream));
     BK_TRY(read_scratch(ctx));
     dfree(ctx, d_tbase);
     const uint64_t* h = ctx->h_scratch;
@@ -791,11 +829,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
       return fail(ctx, code, "BED parse error at row %llu: %s", (unsigned long long)h[SC_ERR_ROW] + 1, what);
     }
   }
-  if (bed->line_off && bed->nrows) {
-    uint64_t endoff = bed->nbytes;
-    BK_CUDA(ctx, cudaMemcpyAsync(bed->line_off + bed->nrows, &endoff, 8, cudaMemcpyHostToDevice, ctx->stream));
-    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  }
+  // (line_off[nrows] = effective length is written by k_parse itself)
   // chromosome runs
   uint64_t nheads = ctx->h_scratch[SC_NHEADS];
   if (nheads > heads_cap) {
@@ -803,7 +837,9 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     return fail(ctx, BK_ERR_UNSUPPORTED, "more than %u chromosome runs in one file", heads_cap);
   }
   std::vector<HeadRec> heads(nheads);
-  if (nheads) {
+  if (nheads <= kHeadsInline) {
+    std::copy(heads_pre, heads_pre + nheads, heads.begin());
+  } else {
     BK_CUDA(ctx, cudaMemcpyAsync(heads.data(), d_heads, nheads * sizeof(HeadRec), cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }

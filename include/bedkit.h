@@ -87,8 +87,10 @@ enum {
   BK_COL_LINE = 1,  /* byte offset of each line (needed to echo a row or copy its id) */
   BK_COL_SCORE = 2, /* column 5 as double (strtod-exact); requires min_fields == 5 */
   BK_COL_ID = 4,    /* (offset,len) of column 4; requires min_fields >= 4 and BK_COL_LINE */
-  BK_LOAD_HEADERS = 8 /* --ec/--header: UCSC browser/track lines and lines starting with '@' or '#' are not records
+  BK_LOAD_HEADERS = 8, /* --ec/--header: UCSC browser/track lines and lines starting with '@' or '#' are not records
                          (BedCheckIterator.hpp:315-360) */
+  BK_LOAD_SORTBED = 16 /* sort-bed's reader (SortDetails.cpp:617-629): rows in any order, only empty lines are skipped, rows
+                          the tokeniser does not take are kept for bk_sort_bed's own validation; used by bk_sort_bed only */
 };
 /* min_fields = 3|4|5 selects the reference record type B3Rest / B4Rest / B5Rest (bedmap/src/Bedmap.cpp:623-654).
  * host text: copied to the device (pinned staging, async), then parsed.  The text must stay valid until return. */
