@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
         "bk_shard_free": (None, [vp, vp]),
         "bk_shard_bytes_in": (u64, [vp]),
         "bk_bedmap_shard_finish": (i, [vp, vp, C.POINTER(u64), C.POINTER(_Text)]),
+        "bk_sort_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
+        "bk_sort_bed_device": (i, [vp, vp, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
@@ -122,7 +124,8 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_setop", "bk_cfspec_default", "bk_closest", "bk_format_bed_device", "bk_free_text", "bk_chrom_index", "bk_plan_shards", "bk_check_text",
            "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop", "bk_find_start", "bk_plan_cuts",
            "bk_cut_offset", "bk_bed_reach_start", "bk_bed_chrom_max_end", "bk_bed_concat", "bk_shard_plan_make",
-           "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in"]
+           "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in", "bk_sort_bed",
+           "bk_sort_bed_device"]
 
 
 class Bed:
@@ -335,6 +338,23 @@ class BedKit:
         t = _Text()
         self._chk(self.lib.bk_chop(self.ctx, arr, len(files), chunk, stagger, int(exclude_short), chrom, int(on_device),
                                    C.byref(t)))
+        return self._take(t, on_device)
+
+    def sort_bed(self, text: bytes, on_device: bool = False):
+        """sort-bed over one text (files concatenated, leading headers removed, final NL present).  A row sort-bed
+        rejects raises BedKitError with .bad_offset = byte offset of the offending line."""
+        t = _Text()
+        bad = C.c_uint64(0xFFFFFFFFFFFFFFFF)
+        rc = self.lib.bk_sort_bed(self.ctx, text, len(text), int(on_device), C.byref(t), C.byref(bad))
+        if rc != 0:
+            err = BedKitError(rc, self.lib.bk_last_error(self.ctx).decode() or self.lib.bk_strerror(rc).decode())
+            err.bad_offset = bad.value
+            raise err
+        return self._take(t, on_device)
+
+    def sort_bed_device(self, dev_ptr: int, nbytes: int, on_device: bool = True):
+        t = _Text()
+        self._chk(self.lib.bk_sort_bed_device(self.ctx, dev_ptr, nbytes, int(on_device), C.byref(t), None))
         return self._take(t, on_device)
 
     def closest(self, ref: Bed, query: Bed, dist=False, closest=False, no_overlaps=False, no_ref=False,

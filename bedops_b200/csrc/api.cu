@@ -348,7 +348,11 @@ static int load_common(bk_ctx* ctx, bk_bed* bed, size_t nbytes, int min_fields, 
     return fail(ctx, BK_ERR_ARG, "min_fields must be 3, 4 or 5");
   }
   if ((cols & BK_COL_SCORE) && min_fields < 5) cols &= ~BK_COL_SCORE;
-  if ((cols & BK_COL_ID) && min_fields < 4) cols &= ~BK_COL_ID;
+  if ((cols & BK_COL_ID) && min_fields < 4 && !(cols & BK_LOAD_SORTBED)) cols &= ~BK_COL_ID;
+  if ((cols & BK_LOAD_SORTBED) && (min_fields != 3 || !(cols & BK_COL_LINE))) {
+    delete bed;
+    return fail(ctx, BK_ERR_ARG, "BK_LOAD_SORTBED needs min_fields == 3 and BK_COL_LINE");
+  }
   if (cols & BK_COL_ID) cols |= BK_COL_LINE;
   bed->min_fields = min_fields;
   bed->cols = cols;

@@ -354,10 +354,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
 
   // a tile whose whole window lies inside the text is moved by the copy engine; the first and the last tiles of a file
   // are staged by the threads themselves (zero-filled outside the text)
-  auto bulkable = [&](uint32_t tile) {
-    const int64_t g0 = (int64_t)tile * P_TILE - P_PRE;
-    return g0 >= 0 && (uint64_t)g0 + P_BUF <= p.nbytes_raw;
-  };
+  auto bulkable = [&](uint32_t tile) { return tile - 1u < p.bulk_tiles; };  // tiles 1 .. bulk_tiles (host: parse_bed)
   auto issue = [&](uint32_t tile, int b) {  // one thread
     fence_proxy_async();                    // the buffer's earlier generic-proxy accesses are ordered before the async write
     bulk_g2s(smbuf[b], text + ((int64_t)tile * P_TILE - P_PRE), P_BUF, &mbar[b]);
@@ -443,7 +440,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         ctlp[P_TILE / 32 + P_POST / 32 + tid - 96] = 0;  // padding words read by the 64-bit line windows
       }
     }
-    if ((uint64_t)p0 + 32 > eff)  // clip to the effective text length (last tile only)
+    if ((uint64_t)ts + P_TILE > eff && (uint64_t)p0 + 32 > eff)  // clip to the effective text length (last tile only)
       smask = (uint64_t)p0 >= eff ? 0u : (smask & ((1u << (int)(eff - (uint64_t)p0)) - 1u));
     // drop blank lines (fscanf's %s skips them: whitespace, including '\n', is not a record); only a line that
     // begins with a control byte can be blank
@@ -572,6 +569,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
           p.start[row] = plain ? v_start : 0u;
           p.end[row] = plain ? v_end : 0u;
           p.line_off[row] = ((uint64_t)(plain ? linelen : 0xFFFFu) << 48) | (uint64_t)(g0 + q0);
+          if (p.idspan) p.idspan[row] = plain ? (uint32_t)sp[2] : 0u;  // offset of the separator after the end coordinate
         }
         continue;
       }
@@ -801,6 +799,8 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     p.heads = d_heads;
     p.heads_cap = heads_cap;
     p.tile_base = d_tbase;
+    // tiles whose whole window [tile*P_TILE - P_PRE, +P_BUF) lies inside the text travel by bulk copy: tiles 1 .. bulk_tiles
+    p.bulk_tiles = nbytes_raw >= (uint64_t)(P_TILE + P_POST) ? (uint32_t)((nbytes_raw - P_TILE - P_POST) / P_TILE) : 0u;
     prof_begin(ctx, "k_parse");
     {
       const bool sc = (p.cols & BK_COL_SCORE) != 0;

@@ -31,6 +31,7 @@ struct ParseParams {
   uint64_t    cap;
   const uint64_t* tile_base;     // [ntiles] first row of every tile (pass 1: warp-range base + prefix inside the range)
   uint32_t    ntiles;
+  uint32_t    bulk_tiles;        // tiles 1..bulk_tiles have their whole window inside the text (staged by cp.async.bulk)
   uint64_t*   scratch;
   HeadRec*    heads;
   uint32_t    heads_cap;

@@ -21,6 +21,7 @@
 #include <map>
 #include "common.cuh"
 #include "emit.cuh"
+#include "sort.cuh"
 #include "fmt.cuh"
 #include "parse.cuh"
 
@@ -1054,6 +1055,146 @@ static int emit_bed3(bk_ctx* ctx, const IvList& l, int on_device, bk_text* out) 
   return finish_text(ctx, d_out, bytes, rows, on_device, out);
 }
 
+// ---- --partition ------------------------------------------------------------------------------------------
+// doPartitions / nextPartitionGroup (Bedops.cpp:615-653, :1249-1335): every start and every end of every input row is a
+// break point; the output is the pieces between consecutive distinct break points of a chromosome that at least one
+// input row covers (touching rows stay apart: their common coordinate is a break point; duplicates give one piece).
+// Device form: the ends are not sorted in the input (nesting), so all 2N coordinates are radix-sorted as
+// (chromosome rank << 32 | coordinate); a piece [key j, key j+1) is printed when the two keys differ, share the
+// chromosome, and key j lies inside a segment of the merged union of all files (whose borders are break points too).
+struct PartKeyParams {
+  const uint32_t* s;
+  const uint32_t* e;
+  const uint64_t* run_begin;  // [nruns+1] rows of the participating runs of this file (contiguous, ascending)
+  const uint32_t* run_rank;   // [nruns] rank of the run's chromosome among all names
+  int             nruns;
+  uint64_t        row0, n;    // participating rows [row0, row0+n)
+};
+__global__ void __launch_bounds__(256) k_part_keys(PartKeyParams p, uint64_t* __restrict__ keys) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.n) return;
+  const uint64_t row = p.row0 + i;
+  int            l = 0, h = p.nruns;
+  while (h - l > 1) {
+    const int mid = (l + h) >> 1;
+    if (p.run_begin[mid] <= row) l = mid; else h = mid;
+  }
+  const uint64_t r = (uint64_t)p.run_rank[l] << 32;
+  keys[2 * i] = r | p.s[row];
+  keys[2 * i + 1] = r | p.e[row];
+}
+
+struct PartRow {
+  const uint64_t* keys;
+  uint64_t        n;
+  const uint32_t* us;        // merged union of all files
+  const uint32_t* ue;
+  const uint64_t* u_begin;   // [nranks] rows of the union per chromosome rank
+  const uint64_t* u_end;
+  const char*     names;     // [nranks][128]
+  const uint32_t* name_len;
+  template <class Sink>
+  __device__ void operator()(uint64_t j, Sink& sk) const {
+    if (j + 1 >= n) return;
+    const uint64_t a = keys[j], b = keys[j + 1];
+    if (a == b || (a >> 32) != (b >> 32)) return;
+    const uint32_t r = (uint32_t)(a >> 32), x = (uint32_t)a;
+    const uint64_t ub = u_begin[r], uend = u_end[r];
+    const uint64_t hi = upper_bound_u32(us, ub, uend, x);  // first segment that starts after x
+    if (hi == ub || x >= ue[hi - 1]) return;              // x lies in no segment: a gap between rows
+    sk.puts_(names + (size_t)r * 128, (int)name_len[r]);
+    sk.put('\t');
+    sk.put_u32(x);
+    sk.put('\t');
+    sk.put_u32((uint32_t)b);
+    sk.put('\n');
+  }
+};
+
+static int partition(bk_ctx* ctx, const bk_bed* const* files, int k, const char* chrom, int on_device, bk_text* out) {
+  std::vector<IvList> in;
+  for (int i = 0; i < k; i++) in.push_back(view_of(files[i], chrom));
+  std::vector<std::string> names;
+  uint64_t                 total = 0;
+  for (auto& l : in)
+    for (auto& r : l.runs)
+      if (r.row_end > r.row_begin) {
+        names.push_back(r.name);
+        total += r.row_end - r.row_begin;
+      }
+  if (total == 0) return finish_text(ctx, nullptr, 0, 0, on_device, out);
+  auto less = [](const std::string& a, const std::string& b) { return strcmp(a.c_str(), b.c_str()) < 0; };
+  std::sort(names.begin(), names.end(), less);
+  names.erase(std::unique(names.begin(), names.end()), names.end());
+  auto rank_of = [&](const std::string& nm) { return (uint32_t)(std::lower_bound(names.begin(), names.end(), nm, less) - names.begin()); };
+  const uint64_t n2 = 2 * total;
+  uint64_t*      keys = dalloc<uint64_t>(ctx, n2);
+  uint64_t*      keys2 = dalloc<uint64_t>(ctx, n2);
+  if (!keys || !keys2) return BK_ERR_NOMEM;
+  std::vector<void*> tmp;
+  uint64_t           at = 0;
+  for (int i = 0; i < k; i++) {
+    std::vector<uint64_t> rb;
+    std::vector<uint32_t> rr;
+    for (auto& r : in[i].runs)
+      if (r.row_end > r.row_begin) {
+        rb.push_back(r.row_begin);
+        rr.push_back(rank_of(r.name));
+      }
+    if (rb.empty()) continue;
+    uint64_t row1 = 0;
+    for (auto& r : in[i].runs)
+      if (r.row_end > r.row_begin) row1 = r.row_end;
+    rb.push_back(row1);
+    PartKeyParams p{};
+    p.s = in[i].s; p.e = in[i].e; p.nruns = (int)rr.size(); p.row0 = rb[0]; p.n = row1 - rb[0];
+    p.run_begin = upload(ctx, rb); p.run_rank = upload(ctx, rr);
+    if (!p.run_begin || !p.run_rank) return BK_ERR_NOMEM;
+    tmp.push_back((void*)p.run_begin); tmp.push_back((void*)p.run_rank);
+    prof_begin(ctx, "k_part_keys");
+    k_part_keys<<<(unsigned)((p.n + 255) / 256), 256, 0, ctx->stream>>>(p, keys + at);
+    prof_end(ctx);
+    BK_LAUNCHED(ctx);
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // rb / rr (host vectors) must outlive their copies
+    at += 2 * p.n;
+  }
+  int rank_bits = 1;
+  while ((names.size() - 1) >> rank_bits) rank_bits++;
+  int rc = radix_sort_pairs(ctx, &keys, nullptr, &keys2, nullptr, n2, 32 + rank_bits);
+  IvList u;
+  if (rc == BK_OK) rc = union_merge(ctx, in, &u);
+  if (rc == BK_OK) {
+    std::vector<uint64_t> ub(names.size(), 0), ue(names.size(), 0);
+    for (auto& r : u.runs) {
+      if (r.row_end == r.row_begin) continue;
+      const uint32_t q = rank_of(r.name);
+      ub[q] = r.row_begin;
+      ue[q] = r.row_end;
+    }
+    std::vector<char>     nm(names.size() * 128, 0);
+    std::vector<uint32_t> nl(names.size());
+    for (size_t q = 0; q < names.size(); q++) {
+      memcpy(&nm[q * 128], names[q].c_str(), names[q].size());
+      nl[q] = (uint32_t)names[q].size();
+    }
+    PartRow fn{};
+    fn.keys = keys; fn.n = n2; fn.us = u.s; fn.ue = u.e;
+    fn.u_begin = upload(ctx, ub); fn.u_end = upload(ctx, ue); fn.names = upload(ctx, nm); fn.name_len = upload(ctx, nl);
+    if (!fn.u_begin || !fn.u_end || !fn.names || !fn.name_len) rc = BK_ERR_NOMEM;
+    char*    d_out = nullptr;
+    uint64_t bytes = 0, rows = 0;
+    if (rc == BK_OK) rc = run_emit(ctx, fn, n2, 0, &d_out, &bytes, &rows);  // run_emit syncs: the uploads are done
+    dfree(ctx, (void*)fn.u_begin); dfree(ctx, (void*)fn.u_end); dfree(ctx, (void*)fn.names); dfree(ctx, (void*)fn.name_len);
+    if (rc == BK_OK) rc = finish_text(ctx, d_out, bytes, rows, on_device, out);
+    else dfree(ctx, d_out);
+  }
+  free_list(ctx, u);
+  for (void* q : tmp) dfree(ctx, q);
+  dfree(ctx, keys);
+  dfree(ctx, keys2);
+  return rc;
+}
+
 }  // namespace bk
 
 using namespace bk;
@@ -1099,6 +1240,7 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
     return rc;
   }
   if (op == BK_SETOP_EVERYTHING) return everything(ctx, files, n_files, chrom, out_on_device, out);
+  if (op == BK_SETOP_PARTITION) return partition(ctx, files, n_files, chrom, out_on_device, out);
   if (op == BK_SETOP_COMPLEMENT) {
     std::vector<IvList> in;
     for (int i = 0; i < n_files; i++) in.push_back(view_of(files[i], chrom));

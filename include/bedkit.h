@@ -196,7 +196,8 @@ enum {
   BK_SETOP_COMPLEMENT = 5, /* --complement; thr != 0 selects -L (Bedops.cpp:475-488, :891-943) */
   BK_SETOP_DIFFERENCE = 6, /* --difference: files[0] minus the others (:501-525, :948-1018) */
   BK_SETOP_SYMMDIFF = 7,   /* --symmdiff: bases covered by exactly one file (:698-745, :1341-1463) */
-  BK_SETOP_EVERYTHING = 8  /* --everything: all rows of all files in sort-bed order, every file needs BK_COL_LINE (:761-786, :1468-1516) */
+  BK_SETOP_EVERYTHING = 8, /* --everything: all rows of all files in sort-bed order, every file needs BK_COL_LINE (:761-786, :1468-1516) */
+  BK_SETOP_PARTITION = 9   /* --partition: the covered pieces between consecutive break points of all files (:615-653, :1249-1335) */
 };
 /* thr / thr_is_pct: -e/-n threshold as Input::Threshold()/UsePercentage() deliver it (bedops/src/Input.hpp:344-382):
  * a fraction in (0,1] when thr_is_pct, else a base count.  files[0] is the reference file for -e/-n. */
@@ -223,6 +224,18 @@ typedef struct bk_cfspec {
 } bk_cfspec;
 void bk_cfspec_default(bk_cfspec* spec);
 int  bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, const bk_cfspec* spec, bk_text* out);
+
+/* ---- sort-bed ------------------------------------------------------------------------------ */
+/* Replaces processData / lexSortBedData / printBed (applications/bed/sort-bed/src/SortDetails.cpp:530-1208): BED rows in
+ * any order -> rows ordered by chromosome (strcmp), start, end, rest of the line (strcmp; a row without a rest first,
+ * Structures.hpp:47-76), printed "chrom\tstart\tend[\trest]\n".  The text is the concatenation of the input files
+ * with each file's leading header lines removed (the tool does that, SortDetails.cpp:645-653) and must end with '\n'.
+ * A row sort-bed rejects (SortDetails.cpp:638-779, :833-853) gives BK_ERR_PARSE, a coordinate >= 2^32-1
+ * BK_ERR_COORD_RANGE; *bad_offset (may be NULL) receives the byte offset of that row's line so that the caller can
+ * name the file, the line and the reference's message for it. */
+int bk_sort_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, int out_on_device, bk_text* out, uint64_t* bad_offset);
+int bk_sort_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int out_on_device, bk_text* out,
+                       uint64_t* bad_offset);
 
 /* ---- BED writer used by the synthetic-input generator and tests -------------------------------------------- */
 /* format n rows "chrom\tstart\tend[\tid<k>\tscore]\n" from device SoA arrays (one chromosome name per call);

@@ -743,3 +743,101 @@ def closest_features(ref_text: bytes, qry_text: bytes, dist: bool = False, close
             show(right, rdist)
         out.append(delim.join(parts) + b"\n")
     return b"".join(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sort-bed (applications/bed/sort-bed/src/SortDetails.cpp:530-1208, Structures.hpp:47-76)
+# ---------------------------------------------------------------------------------------------------------
+class SortBedError(ValueError):
+    """A line sort-bed rejects; .message is the text it prints on stderr (SortDetails.cpp:631-779, :833-853)."""
+
+    def __init__(self, message: str):
+        super().__init__(message)
+        self.message = message
+
+
+_SB_WS = b" \t\r\v\f\n"
+
+
+def _sortbed_line(line: bytes, has_nl: bool, lineno: int, fname: str):
+    """One data line (without its NL) -> (chrom, start, end, rest-or-None), as processData reads it."""
+    def at(fmt):
+        return SortBedError(fmt % (lineno, fname))
+    if line[:1] in (b" ", b"\t"):
+        raise at("Row begins with a tab or space at line %d in %s.\n")
+    def find_sep(pos):
+        k = pos
+        while k < len(line) and line[k:k + 1] not in (b"\t", b" "):
+            k += 1
+        return k
+    c = find_sep(0)
+    if c == len(line):
+        raise at("No tabs/spaces found at line %d in %s.\n")                                    # :657-663
+    if c > 127:
+        raise at("Chromosome name too long at line %d in %s.\n"
+                 "Check that you have unix newlines (cat -A) or increase TOKEN_CHR_MAX_LENGTH in BEDOPS.Constants.hpp "
+                 "and recompile BEDOPS.\n")
+    d = find_sep(c + 1)
+    if d == len(line):
+        raise at("No tabs/spaces found after the start coordinate (or no start coordinate at all) at line %d in %s.\n")
+    if d - (c + 1) > 12:
+        raise at("Start coordinate is too large.  Max decimal digits allowed is 12 in BEDOPS.Constants.hpp.  See line %d in %s.\n")
+    if d == c + 1:
+        raise at("Consecutive tabs and/or spaces between chromosome and start coordinate.  See line %d in %s.\n")
+    if not line[c + 1:d].isdigit():
+        raise at("Non-numeric start coordinate.  See line %d in %s.\n(remember that chromosome names should not contain spaces.)\n")
+    e = find_sep(d + 1)
+    if e == len(line) and not has_nl:                                                           # :719-730
+        raise at("No end of line found at %d in %s.\nMay need to increase BED_LINE_LEN and recompile.\n"
+                 "First check that you have unix newlines (cat -A).")
+    if e - (d + 1) > 12:
+        raise at("End coordinate is too large.  Max decimal digits allowed is 12 in BEDOPS.Constants.hpp.  See line %d in %s.\n")
+    if e == d + 1:
+        raise at("Extra tab and/or space found in between start and end coordinates.  See line %d in %s.\n")
+    if not line[d + 1:e].isdigit():
+        raise at("Non-numeric end coordinate.  See line %d in %s.\n")
+    start, end = int(line[c + 1:d]), int(line[d + 1:e])
+    if end <= start:
+        raise at("Error on line %d in %s. Genomic end coordinate is less than (or equal to) start coordinate.\n")
+    q = e                                                                                       # sscanf "\t%[^\n]s\n", :764
+    while q < len(line) and line[q:q + 1] in (b" ", b"\t", b"\r", b"\v", b"\f"):
+        q += 1
+    rest = line[q:] if q < len(line) else None
+    if rest is not None:
+        k = 0
+        while k < len(rest) and rest[k:k + 1] not in (b"\t", b" "):
+            k += 1
+        if k > 16383:
+            raise at("ID field too long at line %d in %s.\nCheck that you have unix newlines (cat -A) or increase "
+                     "TOKEN_ID_MAX_LENGTH in BEDOPS.Constants.hpp and recompile BEDOPS.\nYou may instead choose to put a "
+                     "dummy id column (like 'id') in as the 4th field to fix this.\n")
+    return line[:c], start, end, rest
+
+
+def sort_bed(texts: Sequence[bytes], names: Optional[Sequence[str]] = None) -> bytes:
+    """sort-bed file1 file2 ...: rows of all files ordered by chromosome (strcmp), start, end, rest (strcmp; no rest
+    first, bcd_cmp Structures.hpp:47-76), printed "%s\\t%ld\\t%ld[\\t%s]\\n" (printBed :1120-1140).  Empty lines are
+    skipped (:625-629); browser/track/#/@ lines are skipped until the first data row of each file (:645-653)."""
+    rows = []
+    for fi, text in enumerate(texts):
+        fname = names[fi] if names else "file%d" % fi
+        head = True
+        lines = text.split(b"\n")
+        terminated = text.endswith(b"\n")
+        if terminated:
+            lines.pop()
+        for li, line in enumerate(lines):
+            if line == b"":
+                continue
+            has_nl = terminated or li + 1 < len(lines)
+            if line[:1] not in (b" ", b"\t") and head and (line.startswith(b"browser") or line.startswith(b"track")
+                                                            or line.startswith(b"#") or line.startswith(b"@")):
+                continue
+            rows.append(_sortbed_line(line, has_nl, li + 1, fname))
+            head = False
+    # bytes compare like strcmp (unsigned bytes); None (no rest) sorts first
+    rows.sort(key=lambda r: (r[0], r[1], r[2], (0, b"") if r[3] is None else (1, r[3])))
+    out = []
+    for chrom, s, e, rest in rows:
+        out.append(chrom + b"\t%d\t%d" % (s, e) + (b"\t" + rest if rest is not None else b"") + b"\n")
+    return b"".join(out)
