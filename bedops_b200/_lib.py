@@ -17,7 +17,7 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4, "complement": 5, "difference": 6,
-          "symmdiff": 7, "everything": 8}
+          "symmdiff": 7, "everything": 8, "partition": 9}
 COL_LINE, COL_SCORE, COL_ID, LOAD_HEADERS = 1, 2, 4, 8
 
 
@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
         "bk_shard_free": (None, [vp, vp]),
         "bk_shard_bytes_in": (u64, [vp]),
         "bk_bedmap_shard_finish": (i, [vp, vp, C.POINTER(u64), C.POINTER(_Text)]),
+        "bk_bed_pad": (i, [vp, vp, C.c_longlong, C.c_longlong, C.POINTER(vp)]),
         "bk_sort_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
         "bk_sort_bed_device": (i, [vp, vp, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
     }
@@ -125,7 +126,7 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop", "bk_find_start", "bk_plan_cuts",
            "bk_cut_offset", "bk_bed_reach_start", "bk_bed_chrom_max_end", "bk_bed_concat", "bk_shard_plan_make",
            "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in", "bk_sort_bed",
-           "bk_sort_bed_device"]
+           "bk_sort_bed_device", "bk_bed_pad"]
 
 
 class Bed:
@@ -339,6 +340,12 @@ class BedKit:
         self._chk(self.lib.bk_chop(self.ctx, arr, len(files), chunk, stagger, int(exclude_short), chrom, int(on_device),
                                    C.byref(t)))
         return self._take(t, on_device)
+
+    def pad(self, bed: "Bed", lpad: int, rpad: int) -> "Bed":
+        """bedops --range L:R view of a loaded file (keeps `bed` alive: the view borrows its text)."""
+        h = C.c_void_p()
+        self._chk(self.lib.bk_bed_pad(self.ctx, bed.h, lpad, rpad, C.byref(h)))
+        return Bed(self, h, keep=bed)
 
     def sort_bed(self, text: bytes, on_device: bool = False):
         """sort-bed over one text (files concatenated, leading headers removed, final NL present).  A row sort-bed

@@ -77,6 +77,7 @@ struct bk_bed {
   uint32_t*   pmax_end = nullptr;  // inclusive running max of end within the chromosome run (lazy)
   uint32_t*   bmax_end = nullptr;  // max end of every 32-row block (global row index / 32; lazy, with pmax_end)
   std::vector<bk::ChromRun> runs;
+  bool        pad_tie_disorder = false;  // bk_bed_pad: rows clamped to start 0 with equal ends are not in rest order (--everything over several files refuses)
 };
 
 namespace bk {

@@ -951,6 +951,10 @@ static int everything(bk_ctx* ctx, const bk_bed* const* files, int k, const char
   std::vector<IvList> in;
   for (int f = 0; f < k; f++) {
     if (!files[f]->line_off && files[f]->nrows) return fail(ctx, BK_ERR_ARG, "--everything needs every file loaded with BK_COL_LINE");
+    if (k > 1 && files[f]->pad_tie_disorder)
+      return fail(ctx, BK_ERR_UNSUPPORTED,
+                  "--range clamped rows of different starts onto equal coordinates in file %d; the order in which the reference merges "
+                  "such rows across files depends on its reader state and is not reproduced", f + 1);
     F.text[f] = files[f]->d_text; F.line[f] = files[f]->line_off; F.s[f] = files[f]->start; F.e[f] = files[f]->end;
     in.push_back(view_of(files[f], chrom));
   }

@@ -4,6 +4,7 @@
 // with bk_setop().
 #include <fstream>
 #include <map>
+#include <sstream>
 #include "cli_common.hpp"
 #include "help_text.hpp"
 
@@ -21,12 +22,20 @@ struct Options {
   bool   ec = false, has_range = false, full_left = false;
   long   chop_bp = 1, chop_stagger = 0;  // Input::chopBP_, chopStaggerBP_
   bool   chop_cut_short = false;
+  int    lpad = 0, rpad = 0;  // Input::lpad_, rpad_
   std::string chrom = "all";
   std::vector<std::string> files;
 };
 
 void require(bool ok, const std::string& msg) {
   if (!ok) throw UserError(msg);
+}
+
+int stream_int(const std::string& t) {  // what "std::stringstream(t) >> int" leaves in an int initialised to 0
+  std::stringstream conv(t);
+  int               v = 0;
+  conv >> v;
+  return v;
 }
 
 struct Help {
@@ -111,6 +120,26 @@ Options parse_args(int argc, char** argv) {
       } else if (next == "--range") {
         require(!o.has_range, "--range specified multiple times.");
         require(++i < argc, "No value for --range given.");
+        const std::string v = argv[i];  // Input.hpp:89-126
+        const std::string ok = std::string("-") + plusints;
+        auto one_minus = [](const std::string& t) { return t.find_first_of("-") == t.find_last_of("-"); };
+        if (v.find(":") != std::string::npos) {
+          const std::string l = v.substr(0, v.find(":")), r = v.substr(v.find(":") + 1);
+          require(!l.empty(), "integer expected for the 'L' value of --range L:R.");
+          require(!r.empty(), "integer expected for the 'R' value of --range L:R.");
+          require(l.find_first_not_of(ok) == std::string::npos, "integer expected for the 'L' value of --range L:R.");
+          require(r.find_first_not_of(ok) == std::string::npos, "integer expected for the 'R' value of --range L:R.");
+          require(one_minus(l), "multiple '-' signs detected for 'L' value of --range option");
+          require(one_minus(r), "multiple '-' signs detected for 'R' value of --range option");
+          o.lpad = stream_int(l);
+          o.rpad = stream_int(r);
+        } else {
+          require(v.find_first_not_of(ok) == std::string::npos, "integer value expected for --range");
+          require(one_minus(v), "multiple '-' signs detected in <val> for --range option");
+          const int range = stream_int(v);
+          o.lpad = -range;
+          o.rpad = range;
+        }
         o.has_range = true;
       } else if (next == "--help") {
         throw Help{next};
@@ -235,10 +264,9 @@ int main(int argc, char** argv) {
       case DIFFERENCE: op = BK_SETOP_DIFFERENCE; break;
       case SYMMDIFF: op = BK_SETOP_SYMMDIFF; break;
       case UNIONALL: op = BK_SETOP_EVERYTHING; break;
+      case PARTITION: op = BK_SETOP_PARTITION; break;
       case CHOP: op = -1; break;  // bk_chop
-      default: throw UserError("this bedops operation is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     }
-    if (o.has_range) throw UserError("--range padding is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     std::vector<cli::Input> texts(o.files.size());
     for (size_t f = 0; f < o.files.size(); f++)
       if (!texts[f].open(o.files[f])) throw UserError("Cannot find " + o.files[f]);
@@ -255,6 +283,16 @@ int main(int argc, char** argv) {
     auto run_one = [&](cli::Engine& eng, const std::vector<cli::Slice>& sl) {
       std::vector<bk_bed*> beds;
       for (size_t f = 0; f < sl.size(); f++) beds.push_back(eng.load(sl[f].ptr, sl[f].len, 3, (((has_ref && f == 0) || all_lines) ? BK_COL_LINE : 0) | hdr));
+      std::vector<bk_bed*> plain;  // --range: the operators see the padded view; -e/-n leave the reference file alone (Bedops.cpp:220-236)
+      if (o.has_range && (o.lpad != 0 || o.rpad != 0))
+        for (size_t f = 0; f < beds.size(); f++) {
+          if (has_ref && f == 0) continue;
+          bk_bed* padded = nullptr;
+          int     prc = bk_bed_pad(eng.ctx, beds[f], o.lpad, o.rpad, &padded);
+          if (prc != BK_OK) eng.raise(prc);
+          plain.push_back(beds[f]);
+          beds[f] = padded;
+        }
       bk_text out;
       const double thr = op == BK_SETOP_COMPLEMENT ? (o.full_left ? 1.0 : 0.0) : o.subset;
       int     rc = op < 0 ? bk_chop(eng.ctx, beds.data(), (int)beds.size(), (uint64_t)o.chop_bp, (uint64_t)o.chop_stagger,
@@ -264,12 +302,14 @@ int main(int argc, char** argv) {
       std::string text(out.ptr ? out.ptr : "", out.len);
       bk_free_text(eng.ctx, &out);
       for (bk_bed* b : beds) bk_free_bed(eng.ctx, b);
+      for (bk_bed* b : plain) bk_free_bed(eng.ctx, b);
       return text;
     };
     const int gpus = cli::gpus_requested();
     // "-e 0" / "-n 0" look at later chromosomes (Bedops.cpp:1044-1049): keep those runs on one GPU
     std::vector<std::vector<cli::Slice>> slices;
-    if (gpus > 1 && o.chrom == "all" && !(has_ref && !o.use_pct && o.subset <= 0)) {
+    // --range: what the reader does around zero depends on the position in the FILE (BedPadReader's constructor): one GPU
+    if (gpus > 1 && o.chrom == "all" && !o.has_range && !(has_ref && !o.use_pct && o.subset <= 0)) {
       std::vector<const cli::Input*> files;
       for (auto& t : texts) files.push_back(&t);
       slices = cli::plan_slices(files, gpus * 4);

@@ -210,6 +210,13 @@ int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, doubl
 int bk_chop(bk_ctx* ctx, const bk_bed* const* files, int n_files, uint64_t chunk, uint64_t stagger, int exclude_short,
             const char* chrom, int out_on_device, bk_text* out);
 
+/* --range L:R: the padded view of a parsed file as the set operators read it (BedPadReader.hpp:116-277): start += lpad,
+ * end += rpad; rows that stop being intervals vaporise; with lpad < 0 the starts that would pass zero are clamped to 0 and
+ * those rows re-ordered by their end (input order on ties).  The result borrows the text of `src` (which must outlive it)
+ * and owns its columns.  BK_ERR_COORD_RANGE when a padded coordinate leaves the 32-bit layout (the reference wraps an
+ * end below |rpad| to 2^64 - x there). */
+int bk_bed_pad(bk_ctx* ctx, const bk_bed* src, long long lpad, long long rpad, bk_bed** out);
+
 /* ---- closest-features ----------------------------------------------------------------------- */
 typedef struct bk_cfspec {
   int         dist;        /* --dist */

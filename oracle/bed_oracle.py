@@ -841,3 +841,139 @@ def sort_bed(texts: Sequence[bytes], names: Optional[Sequence[str]] = None) -> b
     for chrom, s, e, rest in rows:
         out.append(chrom + b"\t%d\t%d" % (s, e) + (b"\t" + rest if rest is not None else b"") + b"\n")
     return b"".join(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bedops --range L:R (BedPadReader.hpp:116-277) and --partition (Bedops.cpp:615-653, :1249-1335)
+# ---------------------------------------------------------------------------------------------------------
+U64 = 1 << 64
+
+
+def pad_rows(rows: Sequence[Row], lpad: int, rpad: int) -> List[Row]:
+    """BedPadReader::ReadLine over one file: start += lpad, end += rpad.
+    * rpad < 0 or lpad > 0 (:133-141): a row whose padded end does not pass its padded start vaporises; the start is an
+      unsigned 64-bit value, so start + lpad < 0 wraps to a huge number and the row vaporises too -- except in the zone
+      the constructor's getFirst() (:194-277) consumed when lpad < 0: from the first row of the file up to the first
+      surviving row with start > |lpad|, where starts are clamped to 0 instead.
+    * lpad < 0 otherwise (:142-155): at every chromosome getFirst() clamps the starts <= |lpad| to 0 and re-sorts those
+      rows by their end (input order on ties); the others shift.
+    * rpad > 0 (:156-160): ends shift."""
+    import copy
+    out: List[Row] = []
+    if lpad == 0 and rpad == 0:
+        return list(rows)
+    lpd = abs(lpad)
+
+    def clamp_group(group):          # rows whose start became 0: ordered by end, stable (multiset + tie list, :203-275)
+        return sorted(group, key=lambda r: (r.chrom, r.start, r.end))
+
+    def mk(r, s, e):
+        q = copy.copy(r)
+        q.start, q.end = s, e
+        return q
+
+    if rpad < 0 or lpad > 0:
+        k = 0
+        if lpad < 0:                 # the constructor's getFirst()
+            zone = []
+            while k < len(rows):
+                r = rows[k]
+                k += 1
+                if r.start > lpd:
+                    s = r.start - lpd
+                    if (r.end + rpad) % U64 > s:      # unsigned arithmetic here (:209): an end below |rpad| wraps and is kept
+                        zone.append(mk(r, s, (r.end + rpad) % U64))
+                        break
+                    continue
+                if r.end + rpad <= 0:
+                    continue
+                zone.append(mk(r, 0, r.end + rpad))
+            out.extend(clamp_group(zone))
+        for r in rows[k:]:
+            s = (r.start + lpad) % U64
+            if float(r.end) + rpad > s:
+                out.append(mk(r, s, r.end + rpad))
+        return out
+    if lpad < 0:
+        k = 0
+        last = None
+        while k < len(rows):
+            r = rows[k]
+            if r.chrom != last:
+                zone = []
+                while k < len(rows):
+                    r = rows[k]
+                    k += 1
+                    if r.start > lpd:
+                        zone.append(mk(r, r.start - lpd, r.end + rpad))
+                        break
+                    zone.append(mk(r, 0, r.end + rpad))
+                zone = clamp_group(zone)
+                out.extend(zone)
+                last = zone[-1].chrom
+                # rows handed out of the cache set lastChr_ as they go (:125-127): the last one names the chromosome
+            else:
+                out.append(mk(r, r.start - lpd, r.end + rpad))
+                k += 1
+        return out
+    return [mk(r, r.start, r.end + rpad) for r in rows]
+
+
+def merge_everything(files: Sequence[Sequence[Row]]) -> bytes:
+    """nextUnionAllLine (Bedops.cpp:1468-1516) as the k-way merge it is: the smallest head by (chromosome, start, end,
+    rest), strict comparisons, so the lower-numbered file wins ties.  On sort-bed-sorted files this equals a full sort; on
+    padded files, where rows clamped to start 0 keep their input order, it does not."""
+    heads = [0] * len(files)
+    out = []
+    while True:
+        best = -1
+        for i, f in enumerate(files):
+            if heads[i] >= len(f):
+                continue
+            if best < 0:
+                best = i
+                continue
+            a, b = f[heads[i]], files[best][heads[best]]
+            if (a.chrom, a.start, a.end, a.rest3) < (b.chrom, b.start, b.end, b.rest3):
+                best = i
+        if best < 0:
+            break
+        out.append(echo_b3rest(files[best][heads[best]]) + b"\n")
+        heads[best] += 1
+    return b"".join(out)
+
+
+def _rows_to_text(rows: Sequence[Row]) -> bytes:
+    return b"".join(echo_b3rest(r) + b"\n" for r in rows)
+
+
+def pad_text(text: bytes, lpad: int, rpad: int) -> bytes:
+    """a file as the set operators see it under --range L:R"""
+    return _rows_to_text(pad_rows(parse_bed(text, 3), lpad, rpad))
+
+
+def bedops_partition(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> bytes:
+    """doPartitions: the pieces between consecutive break points (all starts and ends of all files) of a chromosome that
+    some row covers; touching rows are not joined, duplicate rows give one piece."""
+    per: Dict[bytes, List[Tuple[int, int]]] = {}
+    for t in texts:
+        for r in _sel(parse_bed(t, 3), chrom):
+            per.setdefault(r.chrom, []).append((r.start, r.end))
+    out = []
+    for c in sorted(per):
+        iv = per[c]
+        pts = sorted({p for s, e in iv for p in (s, e)})
+        iv.sort()
+        # coverage by a sweep over the break points
+        import heapq
+        ends: List[int] = []
+        k = 0
+        for a, b in zip(pts, pts[1:]):
+            while k < len(iv) and iv[k][0] <= a:
+                heapq.heappush(ends, iv[k][1])
+                k += 1
+            while ends and ends[0] <= a:
+                heapq.heappop(ends)
+            if ends:
+                out.append(c + b"\t%d\t%d\n" % (a, b))
+    return b"".join(out)

@@ -12,7 +12,7 @@ def parse_argv(tool, argv, known_files):
     d = dict(tool=tool, names=[], chrom=None)
     i = 0
     if tool == "bedops":
-        d.update(op=None, thr=1.0, pct=True, full_left=False)
+        d.update(op=None, thr=1.0, pct=True, full_left=False, pad=(0, 0))
         while i < len(argv):
             a = argv[i]
             if a == "--ec":
@@ -20,6 +20,12 @@ def parse_argv(tool, argv, known_files):
             elif a == "--chrom":
                 i += 1
                 d["chrom"] = argv[i].encode()
+            elif a == "--range":                                  # Input.hpp:86-126
+                i += 1
+                v = argv[i]
+                d["pad"] = tuple(int(x) for x in v.split(":")) if ":" in v else (-int(v), int(v))
+            elif a in ("-p", "--partition"):
+                d["op"] = "partition"
             elif a in ("-m", "--merge"):
                 d["op"] = "merge"
             elif a in ("-i", "--intersect"):
@@ -141,6 +147,14 @@ def run(tool, argv, files, stdin=None):
     d = parse_argv(tool, argv, files)
     texts = [stdin if n == "-" else files[n] for n in d["names"]]
     if tool == "bedops":
+        if d["pad"] != (0, 0):   # the operators read the padded view; -e/-n leave the reference file alone
+            first = 1 if d["op"].endswith("element-of") else 0
+            padded = [O.pad_rows(O.parse_bed(t, 3), *d["pad"]) for t in texts[first:]]
+            if d["op"] == "everything":
+                return O.merge_everything([O._sel(f, d["chrom"]) for f in padded])
+            texts = texts[:first] + [O._rows_to_text(f) for f in padded]
+        if d["op"] == "partition":
+            return O.bedops_partition(texts, d["chrom"])
         if d["op"] == "merge":
             return O.bedops_merge(texts, d["chrom"])
         if d["op"] == "intersect":
@@ -173,6 +187,9 @@ def run_kit(kit, tool, argv, files, stdin=None):
         beds = [kit.load(t, 3, COL_LINE if ((k == 0 and d["op"].endswith("element-of")) or d["op"] == "everything") else 0)
                 for k, t in enumerate(texts)]
         thr = float(d["full_left"]) if d["op"] == "complement" else d["thr"]   # BK_SETOP_COMPLEMENT: thr != 0 is -L
+        if d["pad"] != (0, 0):
+            first = 1 if d["op"].endswith("element-of") else 0
+            beds = beds[:first] + [kit.pad(b, *d["pad"]) for b in beds[first:]]
         if d["op"] == "chop":
             out = kit.chop(beds, d["chunk"], d["stagger"], d["exclude_short"], d["chrom"])
         else:
