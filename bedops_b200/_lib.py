@@ -13,7 +13,8 @@ OPS = {"echo": 1, "count": 2, "indicator": 3, "bases": 4, "sum": 5, "mean": 6, "
        "echo-map-id": 9, "echo-ref-size": 10, "echo-ref-name": 11, "echo-ref-row-id": 12, "echo-map": 13,
        "echo-map-score": 14, "echo-map-size": 15, "echo-overlap-size": 16, "echo-map-range": 17, "bases-uniq": 18,
        "bases-uniq-f": 19, "variance": 20, "stdev": 21, "cv": 22,
-       "echo-map-id-uniq": 23, "median": 24, "kth": 25, "mad": 26}
+       "echo-map-id-uniq": 23, "median": 24, "kth": 25, "mad": 26, "wmean": 27, "tmean": 28, "max-element": 29,
+       "min-element": 30}
 OVERLAP = {"bp": 0, "range": 1, "fraction-ref": 2, "fraction-map": 3, "fraction-either": 4, "fraction-both": 5,
            "exact": 6}
 SETOPS = {"merge": 1, "intersect": 2, "element-of": 3, "not-element-of": 4, "complement": 5, "difference": 6,
@@ -36,7 +37,7 @@ class _MapSpec(C.Structure):
                 ("overlap_bp", C.c_uint64), ("overlap_frac", C.c_double), ("precision", C.c_int), ("sci", C.c_int),
                 ("skip_unmapped", C.c_int), ("delim", C.c_char_p), ("multidelim", C.c_char_p),
                 ("chrom", C.c_char_p), ("out_on_device", C.c_int), ("op_arg", C.c_double * BK_MAX_OPS),
-                ("row_id_base", C.c_uint64)]
+                ("row_id_base", C.c_uint64), ("op_arg2", C.c_double * BK_MAX_OPS)]
 
 
 class _CfSpec(C.Structure):
@@ -107,6 +108,10 @@ def load_library() -> C.CDLL:
         "bk_shard_free": (None, [vp, vp]),
         "bk_shard_bytes_in": (u64, [vp]),
         "bk_bedmap_shard_finish": (i, [vp, vp, C.POINTER(u64), C.POINTER(_Text)]),
+        "bk_is_starch": (i, [C.c_char_p, C.c_size_t]),
+        "bk_unstarch": (i, [vp, C.c_char_p, C.c_size_t, C.c_char_p, i, C.POINTER(_Text)]),
+        "bk_starch_inflate_host": (i, [C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+        "bk_host_free": (None, [vp]),
         "bk_bed_pad": (i, [vp, vp, C.c_longlong, C.c_longlong, C.POINTER(vp)]),
         "bk_sort_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
         "bk_sort_bed_device": (i, [vp, vp, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
@@ -126,7 +131,8 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_check_text_device", "bk_release_cached", "bk_bedmap_host", "bk_chop", "bk_find_start", "bk_plan_cuts",
            "bk_cut_offset", "bk_bed_reach_start", "bk_bed_chrom_max_end", "bk_bed_concat", "bk_shard_plan_make",
            "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in", "bk_sort_bed",
-           "bk_sort_bed_device", "bk_bed_pad"]
+           "bk_sort_bed_device", "bk_bed_pad", "bk_is_starch", "bk_unstarch", "bk_starch_inflate_host",
+           "bk_host_free"]
 
 
 class Bed:
@@ -310,9 +316,11 @@ class BedKit:
         self.lib.bk_mapspec_default(C.byref(spec))
         spec.n_ops = len(ops)
         for k, o in enumerate(ops):
-            name, _, arg = o.partition(":")          # "kth:0.25"
+            name, _, arg = o.partition(":")          # "kth:0.25", "tmean:0.1:0.2"
             spec.ops[k] = OPS[name]
-            spec.op_arg[k] = float(arg) if arg else 0.0
+            a1, _, a2 = arg.partition(":")
+            spec.op_arg[k] = float(a1) if a1 else 0.0
+            spec.op_arg2[k] = float(a2) if a2 else 0.0
         kind, val = overlap
         spec.overlap_kind = OVERLAP[kind]
         if kind in ("bp", "range"):
@@ -339,6 +347,12 @@ class BedKit:
         t = _Text()
         self._chk(self.lib.bk_chop(self.ctx, arr, len(files), chunk, stagger, int(exclude_short), chrom, int(on_device),
                                    C.byref(t)))
+        return self._take(t, on_device)
+
+    def unstarch(self, archive: bytes, chrom: Optional[bytes] = None, on_device: bool = False):
+        """a Starch v2 archive -> the BED text `unstarch` prints"""
+        t = _Text()
+        self._chk(self.lib.bk_unstarch(self.ctx, archive, len(archive), chrom, int(on_device), C.byref(t)))
         return self._take(t, on_device)
 
     def pad(self, bed: "Bed", lpad: int, rpad: int) -> "Bed":

@@ -226,6 +226,7 @@ extern "C" const char* bk_strerror(int code) {
     case BK_ERR_STARCH: return "Starch archive input is not supported; supply plain BED text";
     case BK_ERR_UNSORTED: return "input is not sorted per sort-bed";
     case BK_ERR_CHECK: return "error-check (--ec) failure";
+    case BK_ERR_NAN_ELEMENT: return "Unable to process a 'NAN' with PrintAllScorePrecision.";
   }
   return "unknown error";
 }

@@ -353,7 +353,9 @@ struct BedmapRow {
   OverlapSpec     ov;
   int             n_ops;
   unsigned char   ops[BK_MAX_OPS];
-  double          kth_arg[BK_MAX_OPS];  // BK_OP_KTH fraction
+  double          kth_arg[BK_MAX_OPS];  // BK_OP_KTH fraction, BK_OP_MAD multiplier, BK_OP_TMEAN <low>
+  double          arg2[BK_MAX_OPS];     // BK_OP_TMEAN <hi>
+  uint64_t        stop_row;             // --max/min-element: the first unmapped row (printed up to the element column), or ~0
   int             prec;
   int             sci;
   int             skip_unmapped;
@@ -635,6 +637,140 @@ struct BedmapRow {
     }
   }
 
+  // --wmean: sum(w * score) / sum(w), w = overlap / reference length (WeightedAverageVisitor.hpp:55-70).  The reference
+  // adds in heap-address order (std::set<MapType*>); here in file order -- equal up to the rounding of the sums.
+  template <class Sink>
+  __device__ __noinline__ void wmean_op(Sink& s, uint64_t i, uint64_t row) const {
+    if (count[i] == 0) {
+      s.puts_("NAN", 3);
+      return;
+    }
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    double         value = 0.0, wsum = 0.0;
+    for (uint64_t k = lo; k < hi; k++) {
+      uint32_t       ovl;
+      const uint32_t s0 = ms[k], e0 = me[k];
+      if (!qualifies(ov, a, b, s0, e0, ovl)) continue;
+      const uint32_t x = e0 < b ? e0 : b, y = s0 > a ? s0 : a;
+      const double   w = (double)(x > y ? x - y : 0u) / (double)(b - a);
+      value += w * mscore[k];
+      wsum += w;
+    }
+    if (wsum == 0.0 && value == 0.0) {  // --range hits that do not touch the row: 0/0, printed by printf as "-nan"
+      s.puts_("-nan", 4);
+      return;
+    }
+    put_score(s, value / wsum, 1, i);
+  }
+
+  // --tmean <low> <hi> (TrimmedMeanVisitor.hpp:93-141): the mean of the sorted scores after dropping the lowest
+  // round(low*n) and the highest round(hi*n); sums in file order over the hits whose rank falls in the kept range.
+  __device__ __forceinline__ static double iround(double d) {  // :231-238 (d >= 0 here)
+    const double d1 = ceil(d);
+    return (d1 - d > 0.5) ? floor(d) : d1;
+  }
+  template <class Sink>
+  __device__ __noinline__ void tmean_op(Sink& s, uint64_t i, uint64_t row, double low, double high) const {
+    const uint32_t n = count[i];
+    if (n == 0) {
+      s.puts_("NAN", 3);
+      return;
+    }
+    const double eps = 2.220446049250313e-16;
+    const bool   do_kth = fabs(1.0 - low - high) <= eps, symmetric = fabs(low - high) <= eps;
+    uint64_t     pl = (uint64_t)iround(low * (double)n), ph = (uint64_t)n - (uint64_t)iround(high * (double)n);
+    if (symmetric) {
+      const uint64_t t = (uint64_t)n - ph;
+      pl = pl > t ? pl : t;
+      ph = (uint64_t)n - pl;
+    }
+    const bool do_low = pl > 0;
+    if (do_low) --pl;
+    if (ph > 0) --ph;
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    if (do_kth || (do_low && ph == pl)) {  // a single element
+      put_score(s, score_at_rank(lo, hi, a, b, (uint32_t)ph), 1, i);
+      return;
+    }
+    // ranks (value, then file order) of the kept range: (pl, ph] when something is trimmed below, [0, ph] otherwise
+    double sum = 0.0;
+    for (uint64_t x = lo; x < hi; x++) {
+      uint32_t ovl;
+      if (!qualifies(ov, a, b, ms[x], me[x], ovl)) continue;
+      const double vx = mscore[x];
+      uint64_t     rank = 0;
+      for (uint64_t y = lo; y < hi; y++) {
+        if (!qualifies(ov, a, b, ms[y], me[y], ovl)) continue;
+        const double vy = mscore[y];
+        rank += (vy < vx || (vy == vx && y < x)) ? 1u : 0u;
+      }
+      if (rank <= ph && (!do_low || rank > pl)) sum += vx;
+    }
+    put_score(s, do_low ? sum / (double)(ph - pl) : sum / (double)(ph + 1), 1, i);
+  }
+
+  // --max-element / --min-element (ExtremeVisitor.hpp:84-134 over ScoreThenGenomicCompare{Greater,Lesser},
+  // BedCompare.hpp:263-288): the best score; among equal scores the genomically last (max) or first (min) row; among
+  // equal rows the first in file order (the std::set keeps the first it was given).  Printed by PrintAllScorePrecision
+  // (ProcessBedVisitorRow.hpp:181-222): chrom, start, end, id, score with --prec/--sci, rest of the line.
+  template <class Sink>
+  __device__ __noinline__ void element_op(Sink& s, bool want_max, uint64_t i, uint64_t row) const {
+    const uint64_t lo = win_lo[i], hi = lo + win_n[i];
+    const uint32_t a = rs[row], b = re[row];
+    uint64_t       best = ~0ull;
+    double         bv = 0.0;
+    for (uint64_t k = lo; k < hi; k++) {
+      uint32_t       ovl;
+      const uint32_t s0 = ms[k], e0 = me[k];
+      if (!qualifies(ov, a, b, s0, e0, ovl)) continue;
+      const double v = mscore[k];
+      bool         better = best == ~0ull;
+      if (!better) {
+        if (v != bv) better = want_max ? v > bv : v < bv;
+        else if (s0 != ms[best]) better = want_max ? s0 > ms[best] : s0 < ms[best];
+        else if (e0 != me[best]) better = want_max ? e0 > me[best] : e0 < me[best];
+      }
+      if (better) {
+        best = k;
+        bv = v;
+      }
+    }
+    if (best == ~0ull) return;
+    const char* p = mtext + (mline[best] & kLineOffMask);
+    int         n = 0;
+    while (is_tok((unsigned char)p[n])) n++;
+    s.copy(p, n);
+    s.put('\t');
+    s.put_u32(ms[best]);
+    s.put('\t');
+    s.put_u32(me[best]);
+    const char* q = p + n;
+    for (int f = 0; f < 2; f++) {
+      while (is_ws((unsigned char)*q)) q++;
+      if (*q == '+') q++;
+      while (is_digit((unsigned char)*q)) q++;
+    }
+    while (is_ws((unsigned char)*q)) q++;
+    int idn = 0;
+    while (is_tok((unsigned char)q[idn])) idn++;
+    s.put('\t');
+    s.copy(q, idn);
+    q += idn;
+    while (is_ws((unsigned char)*q)) q++;
+    GlobalCursor gc{q};
+    int64_t      adv = 0;
+    double       dummy;
+    parse_decimal(gc, adv, dummy);  // only to find where strtod stopped: the rest of the line starts there
+    q += adv;
+    s.put('\t');
+    put_score(s, bv, 1, i);
+    int m = 0;
+    while (q[m] != '\n') m++;
+    s.copy(q, m);
+  }
+
   template <class Sink>
   __device__ void operator()(uint64_t i, Sink& s) const {
     const uint32_t cnt = count[i];
@@ -687,6 +823,18 @@ struct BedmapRow {
         case BK_OP_MAD:
           if (RARE & 4) mad_op(s, i, row, kth_arg[c] > 0.0 ? kth_arg[c] : 1.0);
           break;
+        case BK_OP_WMEAN:
+          if (RARE & 4) wmean_op(s, i, row);
+          break;
+        case BK_OP_TMEAN:
+          if (RARE & 4) tmean_op(s, i, row, kth_arg[c], arg2[c]);
+          break;
+        case BK_OP_MAX_ELEMENT: case BK_OP_MIN_ELEMENT:
+          if (RARE & 4) {
+            if (i == stop_row) return;  // the reference threw here: the row ends after the delimiter, without NL
+            element_op(s, ops[c] == BK_OP_MAX_ELEMENT, i, row);
+          }
+          break;
         case BK_OP_ECHO_REF_SIZE: s.put_u32(re[row] - rs[row]); break;
         case BK_OP_ECHO_REF_NAME: {
           const char* p = rtext + (rline[row] & kLineOffMask);
@@ -710,6 +858,12 @@ struct BedmapRow {
     s.put('\n');
   }
 };
+
+// first row without a mapped element: scratch[SC_COUNT_A] = ~row (atomicMax; 0 = none)
+__global__ void __launch_bounds__(256) k_first_unmapped(const uint32_t* __restrict__ count, uint64_t n, uint64_t* scratch) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n && count[i] == 0) atomicMax(reinterpret_cast<unsigned long long*>(&scratch[SC_COUNT_A]), ~(unsigned long long)i);
+}
 
 // rank[i] = number of rows j < i with count[j] > 0 (the rows --skip-unmapped prints): warp ranges of 2048 rows,
 // range totals -> k_scan_totals -> ranks
@@ -782,7 +936,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   unsigned need = 0;
   int      rowid_ops = 0;
   bool     need_echo = false, need_refline = false, need_ids = false, need_mapline = false, need_mapscore = false;
-  bool     window_ops = false;
+  bool     window_ops = false, element_ops = false;
   for (int c = 0; c < spec->n_ops; c++) {
     switch (spec->ops[c]) {
       case BK_OP_ECHO: need_echo = true; need_refline = true; break;
@@ -809,6 +963,16 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
         if (spec->op_arg[c] < 0.0) return fail(ctx, BK_ERR_ARG, "--mad Expect 0 < val");
         need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
       case BK_OP_VARIANCE: case BK_OP_STDEV: case BK_OP_CV: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      case BK_OP_WMEAN: need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      case BK_OP_TMEAN: {  // TrimmedMean's constructor, TrimmedMeanVisitor.hpp:60-73
+        const double lo = spec->op_arg[c], hi = spec->op_arg2[c];
+        if (!(lo >= 0 && lo <= 1)) return fail(ctx, BK_ERR_ARG, "Expect 0 <= lowerKth <= 1");
+        if (!(hi >= 0 && hi <= 1)) return fail(ctx, BK_ERR_ARG, "Expect 0 <= upperKth <= 1");
+        if (!(lo + hi <= 1 + 2.220446049250313e-16)) return fail(ctx, BK_ERR_ARG, "Expect lowerKth + upperKth <= 1");
+        need |= NEED_IDS; need_mapscore = true; window_ops = true; break;
+      }
+      case BK_OP_MAX_ELEMENT: case BK_OP_MIN_ELEMENT:
+        need |= NEED_IDS; need_mapscore = true; need_mapline = true; window_ops = true; element_ops = true; break;
       default: return fail(ctx, BK_ERR_UNSUPPORTED, "bedmap operation %d is outside the device hot path", spec->ops[c]);
     }
   }
@@ -946,6 +1110,20 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     dfree(ctx, d_base);
   }
 
+  // --max-element / --min-element throw on a row without mapped elements (unless --skip-unmapped drops it first): the
+  // reference has by then printed the earlier rows and this row up to the element's column.  Find that row.
+  uint64_t stop_row = ~0ull, n_emit = n;
+  if (element_ops && !spec->skip_unmapped) {
+    BK_TRY(reset_scratch(ctx));
+    k_first_unmapped<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(sp.count, n, ctx->d_scratch);
+    BK_LAUNCHED(ctx);
+    BK_TRY(read_scratch(ctx));
+    if (ctx->h_scratch[SC_COUNT_A]) {
+      stop_row = ~ctx->h_scratch[SC_COUNT_A];
+      n_emit = stop_row + 1;
+    }
+  }
+
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
   int      rc = BK_OK;
@@ -963,12 +1141,14 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     for (int c = 0; c < spec->n_ops; c++) {
       fn.ops[c] = (unsigned char)spec->ops[c];
       fn.kth_arg[c] = spec->op_arg[c];
+      fn.arg2[c] = spec->op_arg2[c];
     }
+    fn.stop_row = stop_row;
     fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
     fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
     fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
     fn.scratch = ctx->d_scratch;
-    rc = run_emit(ctx, fn, n, cap, &d_out, &bytes, &rows);
+    rc = run_emit(ctx, fn, n_emit, cap, &d_out, &bytes, &rows);
   };
   const bool rare_fields = need_echo && ref->min_fields > 3;
   if (window_ops) emit(BedmapRow<7>{});  // the list operations are not the hot path: one instantiation carries everything
@@ -982,5 +1162,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     dfree(ctx, d_out);
     return rc;
   }
-  return finish_text(ctx, d_out, bytes, rows, spec->out_on_device, out);
+  rc = finish_text(ctx, d_out, bytes, rows, spec->out_on_device, out);
+  if (rc == BK_OK && stop_row != ~0ull) return fail(ctx, BK_ERR_NAN_ELEMENT, "Unable to process a 'NAN' with PrintAllScorePrecision.");
+  return rc;
 }

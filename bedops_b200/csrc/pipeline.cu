@@ -61,8 +61,11 @@ extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len,
   if (!ctx || !spec || !out || (!ref_text && ref_len) || (!map_text && map_len)) return BK_ERR_ARG;
   memset(out, 0, sizeof(*out));
   const bool one_chrom = spec->chrom && strcmp(spec->chrom, "all") != 0;
+  bool       element_ops = false;  // --max/min-element may abort the run in the middle of the output: one unsplit call
+  for (int c = 0; c < spec->n_ops && c < BK_MAX_OPS; c++)
+    element_ops |= spec->ops[c] == BK_OP_MAX_ELEMENT || spec->ops[c] == BK_OP_MIN_ELEMENT;
   std::vector<bk_chrom_span> rix, mix;
-  if (one_chrom || spec->out_on_device || index_of(ref_text, ref_len, &rix) != BK_OK ||
+  if (one_chrom || element_ops || spec->out_on_device || index_of(ref_text, ref_len, &rix) != BK_OK ||
       index_of(map_text, map_len, &mix) != BK_OK || !strictly_sorted(rix) || !strictly_sorted(mix) || rix.size() < 2)
     return plain(ctx, ref_text, ref_len, map_text, map_len, ref_fields, ref_cols, map_fields, map_cols, spec, out);
 

@@ -23,17 +23,18 @@ const OpInfo kOps[] = {
     {"echo-map-id-uniq", BK_OP_ECHO_MAP_ID_UNIQ, 4, 0},         {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, 0},        {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, 0},
     {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, 0},           {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
     {"indicator", BK_OP_INDICATOR, 3, 0},  {"max", BK_OP_MAX, 5, 0},          {"max-element-rand", 0, 5, 0},
-    {"max-element", 0, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
-    {"min-element", 0, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
+    {"max-element", BK_OP_MAX_ELEMENT, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
+    {"min-element", BK_OP_MIN_ELEMENT, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
     {"stdev", BK_OP_STDEV, 5, 0},                    {"cv", BK_OP_CV, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
-    {"wmean", 0, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", BK_OP_MAD, 5, -1},
-    {"kth", BK_OP_KTH, 5, 1},                      {"tmean", 0, 5, 2},
+    {"wmean", BK_OP_WMEAN, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", BK_OP_MAD, 5, -1},
+    {"kth", BK_OP_KTH, 5, 1},                      {"tmean", BK_OP_TMEAN, 5, 2},
 };
 
 struct Options {
   std::string ref, map;
   std::vector<int> ops;
-  std::vector<double> op_args;  // parallel to ops (--kth <val>)
+  std::vector<double> op_args;  // parallel to ops (--kth <val>, --mad <mult>, --tmean <low>)
+  std::vector<double> op_args2; // --tmean <hi>
   std::string unsupported_op;
   int         overlap_kind = -1;
   long        range_bp = 0, overlap_bp = 0;
@@ -149,8 +150,23 @@ Options parse_args(int argc, char** argv) {
       for (const OpInfo& k : kOps)
         if (next == k.name) info = &k;
       if (!info) throw UserError("Unknown option: --" + next);
-      double op_arg = 0;
-      if (info->nargs > 0) {
+      double op_arg = 0, op_arg2 = 0;
+      int    op = info->op;
+      if (op == BK_OP_TMEAN) {  // Input.hpp:303-326
+        require(i < argc, "No <low> arg given for --" + next);
+        const std::string lo = argv[i++];
+        require(cli::only_chars(lo, reals), "Non-numeric argument: " + lo + " for --" + next);
+        require(i < argc, "No <hi> arg given for --" + next);
+        const std::string hi = argv[i++];
+        require(cli::only_chars(hi, reals), "Non-numeric argument: " + hi + " for --" + next);
+        op_arg = op_arg2 = 100;
+        std::stringstream cl(lo), ch(hi);
+        cl >> op_arg;
+        ch >> op_arg2;
+        require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= low < hi <= 1");
+        require(op_arg2 >= 0 && op_arg2 <= 1, "--" + next + " Expect 0 <= low < hi <= 1");
+        require(op_arg + op_arg2 <= 1, "--" + next + " Expect (low + hi) <= 1.");
+      } else if (info->nargs > 0) {
         require(i + info->nargs <= argc, "No arg for --" + next);
         if (info->op == BK_OP_KTH) {  // Input.hpp:290-302
           const std::string sval = argv[i];
@@ -159,6 +175,8 @@ Options parse_args(int argc, char** argv) {
           std::stringstream conv(sval);
           conv >> op_arg;
           require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= val <= 1");
+          if (op_arg == 0) op = BK_OP_MIN;       // "min faster" / "max faster", Bedmap.cpp:495-498
+          else if (op_arg == 1) op = BK_OP_MAX;
         }
         i += info->nargs;
       } else if (info->nargs < 0 && i < argc && cli::only_chars(argv[i], reals)) {  // optional multiplier of --mad
@@ -168,9 +186,10 @@ Options parse_args(int argc, char** argv) {
         require(op_arg > 0, "--" + next + " Expect 0 < val");  // Input.hpp:275-288
         i++;
       }
-      if (!info->op && o.unsupported_op.empty()) o.unsupported_op = next;
-      o.ops.push_back(info->op);
+      if (!op && o.unsupported_op.empty()) o.unsupported_op = next;
+      o.ops.push_back(op);
       o.op_args.push_back(op_arg);
+      o.op_args2.push_back(op_arg2);
       o.min_map_fields = std::max(o.min_map_fields, info->map_fields);
       o.min_ref_fields = std::max(o.min_ref_fields, 3);
       has_op = true;
@@ -220,15 +239,24 @@ int main(int argc, char** argv) {
     cli::Input rtext, mtext;
     if (!rtext.open(o.ref)) throw UserError("Unable to find file: " + o.ref);
     if (o.num_files == 2 && !mtext.open(o.map)) throw UserError("Unable to find file: " + o.map);
+    if (cli::any_archive({&rtext, &mtext})) {
+      cli::Engine eng;
+      cli::unstarch_if_archive(eng, rtext);
+      cli::unstarch_if_archive(eng, mtext);
+    }
 
     bk_mapspec spec;
     bk_mapspec_default(&spec);
-    bool need_line = false, need_score = false, need_id = false, need_mapline = false;
+    bool need_line = false, need_score = false, need_id = false, need_mapline = false, element_ops = false;
     if (o.ops.size() > (size_t)BK_MAX_OPS)  // bk_mapspec carries a fixed table (the reference chains any number of visitors)
       throw UserError("More than " + std::to_string(BK_MAX_OPS) + " operations given; this build prints at most that many columns.");
     for (size_t k = 0; k < o.ops.size(); k++) {
       const int op = o.ops[k];
       spec.op_arg[spec.n_ops] = o.op_args[k];
+      spec.op_arg2[spec.n_ops] = o.op_args2[k];
+      element_ops |= op == BK_OP_MAX_ELEMENT || op == BK_OP_MIN_ELEMENT;
+      need_mapline |= op == BK_OP_MAX_ELEMENT || op == BK_OP_MIN_ELEMENT;
+      need_score |= op == BK_OP_WMEAN || op == BK_OP_TMEAN || op == BK_OP_MAX_ELEMENT || op == BK_OP_MIN_ELEMENT;
       spec.ops[spec.n_ops++] = op;
       need_line |= op == BK_OP_ECHO || op == BK_OP_ECHO_REF_NAME || op == BK_OP_ECHO_MAP_RANGE;
       need_score |= op == BK_OP_SUM || op == BK_OP_MEAN || op == BK_OP_MAX || op == BK_OP_MIN || op == BK_OP_ECHO_MAP_SCORE ||
@@ -268,7 +296,7 @@ int main(int argc, char** argv) {
     const int gpus = cli::gpus_requested();
     // N GPUs: ONE dataset cut into genomic ranges with boundary halos (include/bedkit.h); the printed-row counter of
     // --echo-ref-row-id runs across shards, so that operation stays on one GPU
-    if (gpus > 1 && o.num_files == 2 && o.chrom == "all" && !row_ids &&
+    if (gpus > 1 && o.num_files == 2 && o.chrom == "all" && !row_ids && !element_ops &&
         cli::run_range_sharded_bedmap(rtext, mtext, 3, ref_cols, o.min_map_fields, map_cols, spec, gpus))
       return EXIT_SUCCESS;
     cli::Engine eng;
@@ -281,6 +309,11 @@ int main(int argc, char** argv) {
       bk_bed* ref = eng.load(rtext, o.min_ref_fields, map_cols | (need_line ? BK_COL_LINE : 0));
       rc = bk_bedmap(eng.ctx, ref, nullptr, &spec, &out);
       bk_free_bed(eng.ctx, ref);
+    }
+    if (rc == BK_ERR_NAN_ELEMENT) {  // the rows the reference had printed before it threw, then its message
+      cli::write_all(out.ptr, out.len);
+      bk_free_text(eng.ctx, &out);
+      eng.raise(rc);
     }
     if (rc != BK_OK) eng.raise(rc);
     cli::write_all(out.ptr, out.len);  // pinned result buffer -> stdout, no intermediate copy

@@ -270,6 +270,14 @@ int main(int argc, char** argv) {
     std::vector<cli::Input> texts(o.files.size());
     for (size_t f = 0; f < o.files.size(); f++)
       if (!texts[f].open(o.files[f])) throw UserError("Cannot find " + o.files[f]);
+    {
+      bool archive = false;
+      for (auto& t : texts) archive |= bk_is_starch(t.data, t.size) != 0;
+      if (archive) {
+        cli::Engine eng;
+        for (auto& t : texts) cli::unstarch_if_archive(eng, t);
+      }
+    }
     const bool has_ref = op == BK_SETOP_ELEMENT_OF || op == BK_SETOP_NOT_ELEMENT_OF;
     const bool all_lines = op == BK_SETOP_EVERYTHING;  // every row of every file is echoed
     const unsigned hdr = o.ec ? BK_LOAD_HEADERS : 0;

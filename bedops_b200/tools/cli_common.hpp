@@ -131,6 +131,27 @@ struct Engine {
   }
 };
 
+// Starch archives are accepted wherever BED is (AllocateIterator_BED_starch.hpp:100-112): the library inflates and
+// un-transforms the archive (bk_unstarch), the tool goes on with the BED text
+inline void unstarch_if_archive(const Engine& eng, Input& in) {
+  if (!bk_is_starch(in.data, in.size)) return;
+  bk_text out{};
+  int     rc = bk_unstarch(eng.ctx, in.data, in.size, nullptr, 0, &out);
+  if (rc != BK_OK) eng.raise(rc);
+  std::vector<char> text(out.ptr, out.ptr + out.len);
+  bk_free_text(eng.ctx, &out);
+  if (in.map) ::munmap(in.map, in.map_len);
+  in.map = nullptr;
+  in.owned.swap(text);
+  in.data = in.owned.data();
+  in.size = in.owned.size();
+}
+inline bool any_archive(std::initializer_list<const Input*> ins) {
+  for (const Input* i : ins)
+    if (bk_is_starch(i->data, i->size)) return true;
+  return false;
+}
+
 // --ec / --header: run the device validation (bk_check_text) on a text that ends with NL (Input::ensure_final_newline);
 // failures are reported the way BedCheckIterator.hpp:589-593 words them.
 inline void ec_prepare(Input& text) { text.ensure_final_newline(); }

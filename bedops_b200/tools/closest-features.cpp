@@ -65,6 +65,11 @@ int main(int argc, char** argv) {
     cli::Input rtext, qtext;
     if (!rtext.open(o.ref)) throw UserError("Unable to find file: " + o.ref);
     if (!qtext.open(o.query)) throw UserError("Unable to find file: " + o.query);
+    if (cli::any_archive({&rtext, &qtext})) {
+      cli::Engine eng;
+      cli::unstarch_if_archive(eng, rtext);
+      cli::unstarch_if_archive(eng, qtext);
+    }
     bk_cfspec spec;
     bk_cfspec_default(&spec);
     spec.dist = o.dist;

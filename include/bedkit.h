@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BEDKIT_ABI_VERSION 2
+#define BEDKIT_ABI_VERSION 3
 
 typedef struct bk_ctx bk_ctx; /* one per GPU: stream, cached device blocks, pinned staging, last error text */
 typedef struct bk_bed bk_bed; /* a parsed, device-resident sorted BED file: SoA columns + chromosome runs */
@@ -53,7 +53,9 @@ enum {
   BK_ERR_UNSUPPORTED = 6, /* option combination outside the hot path (named in the message) */
   BK_ERR_STARCH = 7,      /* input is a Starch archive; only plain BED text is accepted */
   BK_ERR_UNSORTED = 8,    /* chromosome runs not in strcmp order / repeated chromosome run */
-  BK_ERR_CHECK = 9        /* --ec validation failed (message mirrors BedCheckIterator.hpp:589-593) */
+  BK_ERR_CHECK = 9,       /* --ec validation failed (message mirrors BedCheckIterator.hpp:589-593) */
+  BK_ERR_NAN_ELEMENT = 10 /* bedmap --max-element/--min-element reached a reference row with no mapped element: the result text
+                             holds what the reference had printed when it threw (ProcessBedVisitorRow.hpp:206-208); print it, then fail */
 };
 
 /* ---- context --------------------------------------------------------------------------------------------- */
@@ -145,7 +147,13 @@ enum { /* operations, printed left to right in the order given (MultiVisitor.hpp
   /* generalised median of the scores (RollingKthAverageVisitor.hpp:37-68 over RollingKthVisitor.hpp:75-95) */
   BK_OP_MEDIAN = 24,            /* --median             = --kth 0.5 */
   BK_OP_KTH = 25,               /* --kth <val>          0 < val < 1 in bk_mapspec.op_arg[] of the same slot */
-  BK_OP_MAD = 26                /* --mad [mult]         median absolute deviation * mult (op_arg[], 0 = default 1); MedianAbsoluteDeviationVisitor.hpp:57-93 */
+  BK_OP_MAD = 26,               /* --mad [mult]         median absolute deviation * mult (op_arg[], 0 = default 1); MedianAbsoluteDeviationVisitor.hpp:57-93 */
+  BK_OP_WMEAN = 27,             /* --wmean              scores weighted by overlap / reference length (WeightedAverageVisitor.hpp:55-70) */
+  BK_OP_TMEAN = 28,             /* --tmean <low> <hi>   mean after trimming the fractions op_arg[] / op_arg2[] of the sorted scores (TrimmedMeanVisitor.hpp:93-141) */
+  BK_OP_MAX_ELEMENT = 29,       /* --max-element        the highest-scoring map row, ties to the genomically last (ExtremeVisitor.hpp:84-134,
+                                                        BedCompare.hpp:263-288), printed chrom start end id score rest (ProcessBedVisitorRow.hpp:181-222) */
+  BK_OP_MIN_ELEMENT = 30        /* --min-element        the lowest-scoring map row, ties to the genomically first.  Both abort the run at the
+                                                        first reference row without a mapped element (BK_ERR_NAN_ELEMENT), as the reference does */
 };
 enum { /* overlap criterion (Bedmap.cpp:107-156; BedDistances.hpp:41-317) */
   BK_OVR_BP = 0,          /* --bp-ovr N (default N = 1) */
@@ -173,6 +181,7 @@ typedef struct bk_mapspec {
   double      op_arg[BK_MAX_OPS]; /* per-operation argument (BK_OP_KTH: the fraction, BK_OP_MAD: the multiplier); 0 otherwise */
   uint64_t    row_id_base;   /* --echo-ref-row-id: rows already printed by earlier calls of the same command (the reference
                                 counts printed rows, ProcessBedVisitorRow.hpp:347-354); 0 for a whole-file call */
+  double      op_arg2[BK_MAX_OPS]; /* second per-operation argument (BK_OP_TMEAN: <hi>); 0 otherwise */
 } bk_mapspec;
 void bk_mapspec_default(bk_mapspec* spec);
 /* map == NULL: single-file mode, ref is mapped onto itself (Input.hpp:359-364) */
@@ -231,6 +240,20 @@ typedef struct bk_cfspec {
 } bk_cfspec;
 void bk_cfspec_default(bk_cfspec* spec);
 int  bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, const bk_cfspec* spec, bk_text* out);
+
+/* ---- Starch v2 archives as input ---------------------------------------------------------------- */
+/* Replaces the reading side of interfaces/src/data/starch/unstarchHelpers.c (UNSTARCH_extractDataWithBzip2 :265-355,
+ * UNSTARCH_extractDataWithGzip :57-263, UNSTARCH_reverseTransformHeaderlessInput :1161-1238) behind the archive
+ * detection of allocate_iterator_starch_bed (AllocateIterator_BED_starch.hpp:100-112).  The host inflates the
+ * per-chromosome bzip2 / gzip streams (libbz2.so.1.0 at run time, zlib), the device undoes the delta coding (two scans)
+ * and writes plain BED text: what `unstarch archive` prints, byte for byte.  chrom: NULL / "all" or one chromosome
+ * (`unstarch chrN archive`).  Not read (BK_ERR_STARCH with a message): v1 archives, archives made with --header. */
+int bk_is_starch(const char* bytes, size_t nbytes); /* magic ca 5c ad e5 */
+int bk_unstarch(bk_ctx* ctx, const char* archive, size_t nbytes, const char* chrom, int out_on_device, bk_text* out);
+/* host stage alone (no device needed; tests): the inflated, still delta-coded streams as ">chrom\n<stream>" blocks in
+ * archive order, in a malloc'ed buffer the caller releases with bk_host_free */
+int  bk_starch_inflate_host(const char* archive, size_t nbytes, const char* chrom, char** text, size_t* len);
+void bk_host_free(void* p);
 
 /* ---- sort-bed ------------------------------------------------------------------------------ */
 /* Replaces processData / lexSortBedData / printBed (applications/bed/sort-bed/src/SortDetails.cpp:530-1208): BED rows in

@@ -183,6 +183,15 @@ def echo_b3rest(r: Row) -> bytes:
     return r.chrom + b"\t" + str(r.start).encode() + b"\t" + str(r.end).encode() + r.rest3
 
 
+class NanElement(Exception):
+    """--max-element / --min-element on a reference row without mapped elements: the reference throws "Unable to process
+    a 'NAN' with PrintAllScorePrecision." (ProcessBedVisitorRow.hpp:206-208); .stdout is what it had printed by then."""
+
+    def __init__(self, stdout: bytes):
+        super().__init__("Unable to process a 'NAN' with PrintAllScorePrecision.")
+        self.stdout = stdout
+
+
 def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overlap: Tuple[str, object] = ("bp", 1),
            prec: int = 6, sci: bool = False, delim: bytes = b"|", multidelim: bytes = b";",
            skip_unmapped: bool = False, chrom: Optional[bytes] = None) -> bytes:
@@ -193,7 +202,8 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
     identical for exactly representable partial sums, see DESIGN.md parity notes)."""
     need_fields = 3
     for o in ops:
-        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:") or o.startswith("mad"):
+        if o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median", "wmean", "max-element",
+                 "min-element") or o.startswith("kth:") or o.startswith("mad") or o.startswith("tmean:"):
             need_fields = max(need_fields, 5)   # Input.hpp:404-420: the map record type is the widest any visitor needs
         elif o in ("echo-map-id", "echo-map-id-uniq"):
             need_fields = max(need_fields, 4)
@@ -316,6 +326,68 @@ def bedmap(ref_text: bytes, map_text: Optional[bytes], ops: Sequence[str], overl
                         cols.append(b"NAN")
                     else:
                         cols.append(_fmt_score(math.sqrt(var) / (sm / n), prec, sci))
+            elif o == "wmean":
+                # WeightedAverageVisitor.hpp:55-70: sum(w*score)/sum(w), w = overlap/length of the reference row.  The
+                # reference adds in heap-address order; file order here (equal up to the rounding of the two sums)
+                if cnt == 0:
+                    cols.append(b"NAN")
+                else:
+                    value = wsum = 0.0
+                    for m in hits:
+                        w = max(0, min(r.end, m.end) - max(r.start, m.start)) / float(r.end - r.start)
+                        value += w * m.score
+                        wsum += w
+                    cols.append(b"-nan" if wsum == 0.0 and value == 0.0 else _fmt_score(value / wsum, prec, sci))
+            elif o.startswith("tmean:"):
+                # TrimmedMeanVisitor.hpp:93-141 with both markers freshly positioned (the reference leaves the lower
+                # marker where earlier rows put it when round(low*n) == 0: see DESIGN.md parity notes)
+                low, high = (float(x) for x in o[6:].split(":"))
+                v = sorted(m.score for m in hits)
+                n = len(v)
+                if n == 0:
+                    cols.append(b"NAN")
+                else:
+                    def iround(d):
+                        d1 = math.ceil(d)
+                        return math.floor(d) if d1 - d > 0.5 else d1
+                    do_kth = abs(1.0 - low - high) <= DBL_EPS
+                    pl, ph = int(iround(low * n)), n - int(iround(high * n))
+                    if abs(low - high) <= DBL_EPS:
+                        pl = max(pl, n - ph)
+                        ph = n - pl
+                    do_low = pl > 0
+                    if do_low:
+                        pl -= 1
+                    if ph > 0:
+                        ph -= 1
+                    if do_kth or (do_low and ph == pl):
+                        cols.append(_fmt_score(v[ph], prec, sci))
+                    else:
+                        # file order, like the device (the reference's rolling sums are exact for integer scores)
+                        ranked = sorted(range(n), key=lambda k: (hits[k].score, k))
+                        keep = set(ranked[pl + 1:ph + 1] if do_low else ranked[:ph + 1])
+                        sm = 0.0
+                        for k in range(n):
+                            if k in keep:
+                                sm += hits[k].score
+                        cols.append(_fmt_score(sm / (ph - pl) if do_low else sm / (ph + 1), prec, sci))
+            elif o in ("max-element", "min-element"):
+                # ExtremeVisitor.hpp:84-134 ordered by ScoreThenGenomicCompare{Greater,Lesser} (BedCompare.hpp:263-288): best
+                # score, then the genomically last (max) / first (min) row, then the first in file order; printed by
+                # PrintAllScorePrecision (ProcessBedVisitorRow.hpp:181-222), which throws on an empty set
+                if cnt == 0:
+                    out.append(delim.join(cols) + (delim if cols else b""))
+                    raise NanElement(b"".join(out))
+                best = hits[0]
+                for m in hits[1:]:
+                    if o == "max-element":
+                        better = (m.score, m.start, m.end) > (best.score, best.start, best.end)
+                    else:
+                        better = (m.score, m.start, m.end) < (best.score, best.start, best.end)
+                    if better:
+                        best = m
+                cols.append(best.chrom + b"\t%d\t%d\t" % (best.start, best.end) + best.id + b"\t" +
+                            _fmt_score(best.score, prec, sci) + best.rest)
             elif o == "echo-map":        # EchoMapBed<PrintRangeDelim<PrintAll>>: the map rows as their record type prints them
                 cols.append(multidelim.join(echo_row(m, need_fields) for m in hits))
             elif o == "echo-map-score":  # PrintRangeDelim<PrintScorePrecision> (ProcessBedVisitorRow.hpp:152-176)
@@ -976,4 +1048,48 @@ def bedops_partition(texts: Sequence[bytes], chrom: Optional[bytes] = None) -> b
                 heapq.heappop(ends)
             if ends:
                 out.append(c + b"\t%d\t%d\n" % (a, b))
+    return b"".join(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Starch v2 archives (interfaces/src/data/starch/unstarchHelpers.c)
+# ---------------------------------------------------------------------------------------------------------
+def starch_streams(archive: bytes):
+    """[(chromosome, delta-coded text)] of a Starch v2 archive: magic ca5cade5, the per-chromosome bzip2/gzip streams, the
+    JSON metadata and the 127-byte footer holding its offset (starchHelpers.c STARCH2_writeStarchFooter)."""
+    import bz2
+    import json
+    import zlib
+    assert archive[:4] == b"\xca\x5c\xad\xe5", "not a Starch v2 archive"
+    md_off = int(archive[-127:-107])                     # the footer on disk is STARCH2_MD_FOOTER_LENGTH - 1 = 127 bytes
+    md = json.loads(archive[md_off:-127])                # (starchMetadataHelpers.c:1113-1119, :1178)
+    comp = md["archive"]["compressionFormat"]            # 0 bzip2, 1 gzip (starchMetadataHelpers.h CompressionType)
+    out, at = [], 4
+    for st in md["streams"]:
+        n = int(st["size"])
+        blob = archive[at:at + n]
+        at += n
+        text = bz2.decompress(blob) if comp == 0 else zlib.decompress(blob, 15 + 32)
+        out.append((st["chromosome"].encode(), text))
+    return out
+
+
+def unstarch(archive: bytes, chrom: Optional[bytes] = None) -> bytes:
+    """UNSTARCH_reverseTransformHeaderlessInput (unstarchHelpers.c:1161-1238): "p<len>" sets the length of the rows that
+    follow; "<d>[\\t<rest>]" is a row with start = end of the previous row + d, end = start + len."""
+    out = []
+    for c, text in starch_streams(archive):
+        if chrom is not None and chrom != b"all" and c != chrom:
+            continue
+        last_end = plen = 0
+        for line in text.split(b"\n"):
+            if not line:
+                continue
+            if line[:1] == b"p":
+                plen = int(line[1:])
+                continue
+            d, _, rest = line.partition(b"\t")
+            start = last_end + int(d)
+            last_end = start + plen
+            out.append(c + b"\t%d\t%d" % (start, last_end) + (b"\t" + rest if rest else b"") + b"\n")
     return b"".join(out)

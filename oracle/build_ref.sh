@@ -10,7 +10,7 @@
 #     directly with gcc (they are linked only for Starch archive I/O, which is off the hot path);
 #   * the eight starch support objects and the three tools use the reference's own flags
 #     (-O3 -std=c++11 -static; applications/bed/bedmap/src/Makefile:26-31).
-# Output: oracle/_ref/bin/{bedops,bedmap,closest-features,sort-bed,bedextract}  (static binaries, so they
+# Output: oracle/_ref/bin/{bedops,bedmap,closest-features,sort-bed,bedextract,starch,unstarch}  (static binaries, so they
 # run unchanged on the GPU box, where /root/reference does not exist).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -77,5 +77,16 @@ build_tool closest-features "$A/closestfeats/src" ClosestFeature.cpp &
 build_tool bedextract       "$A/bedextract/src"   ExtractRows.cpp &
 build_tool sort-bed         "$A/sort-bed/src"     Sort.cpp SortDetails.cpp CheckSort.cpp &
 build_tool bedmap           "$A/bedmap/src"       Bedmap.cpp &
+# starch / unstarch: C sources the reference compiles with its C++ compiler (applications/bed/starch/src/Makefile:67);
+# they make and read the archives the Starch-input tests use
+build_c_tool() { # name, source
+  if [ ! -x "$BIN/$1" ]; then
+    g++ -static -s $CXXFLAGS -D__STDC_CONSTANT_MACROS -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE=1 -DUSE_ZLIB -DUSE_BZLIB \
+        -x c++ $INC -o "$BIN/$1" "$2" -x none "${deps[@]}" "$TP/libthird.a"
+    echo "built $BIN/$1"
+  fi
+}
+build_c_tool starch   "$A/starch/src/starch.c" &
+build_c_tool unstarch "$A/starch/src/unstarch.c" &
 wait
 ls -la "$BIN"

@@ -4,7 +4,8 @@ import bed_oracle as O
 
 BEDMAP_OPS = {"echo", "count", "indicator", "bases", "sum", "mean", "max", "min", "echo-map-id", "echo-ref-size",
               "echo-ref-name", "echo-ref-row-id", "echo-map", "echo-map-score", "echo-map-size", "echo-overlap-size",
-              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv", "echo-map-id-uniq", "median"}
+              "echo-map-range", "bases-uniq", "bases-uniq-f", "variance", "stdev", "cv", "echo-map-id-uniq", "median", "wmean",
+              "max-element", "min-element"}
 
 
 def parse_argv(tool, argv, known_files):
@@ -78,7 +79,11 @@ def parse_argv(tool, argv, known_files):
                 d["ops"].append(a[2:])
             elif a == "--kth":
                 i += 1
-                d["ops"].append("kth:" + argv[i])
+                k = float(argv[i])                                # 0 -> min, 1 -> max (Bedmap.cpp:495-498)
+                d["ops"].append("min" if k == 0 else "max" if k == 1 else "kth:" + argv[i])
+            elif a == "--tmean":
+                d["ops"].append("tmean:%s:%s" % (argv[i + 1], argv[i + 2]))
+                i += 2
             elif a == "--mad":   # optional multiplier (Input.hpp:275-288): a following all-numeric argument
                 if i + 1 < len(argv) and argv[i + 1] and all(c in ".-0123456789" for c in argv[i + 1]):
                     i += 1
@@ -199,12 +204,13 @@ def run_kit(kit, tool, argv, files, stdin=None):
         return out
     if tool == "bedmap":
         ops = d["ops"]
-        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median") or o.startswith("kth:") or o.startswith("mad")
-                    for o in ops)
+        score = any(o in ("sum", "mean", "max", "min", "echo-map-score", "variance", "stdev", "cv", "median", "wmean", "max-element",
+                          "min-element") or o.startswith("kth:") or o.startswith("mad") or o.startswith("tmean:") for o in ops)
+        element = any(o in ("max-element", "min-element") for o in ops)
         ids = "echo-map-id" in ops or "echo-map-id-uniq" in ops
         line = any(o in ("echo", "echo-ref-name", "echo-map-range") for o in ops)
         mf = 5 if score else (4 if ids else 3)
-        mcols = (COL_SCORE if score else 0) | ((COL_ID | COL_LINE) if ids else 0) | (COL_LINE if "echo-map" in ops else 0)
+        mcols = (COL_SCORE if score else 0) | ((COL_ID | COL_LINE) if ids else 0) | (COL_LINE if "echo-map" in ops or element else 0)
         if len(texts) > 1:
             ref = kit.load(texts[0], 3, COL_LINE if line else 0)
             mp = kit.load(texts[1], mf, mcols)

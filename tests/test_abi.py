@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "libbedkit.so does not export %s" % s
     from bedops_b200._lib import EXPORTS
     assert sorted(EXPORTS) == syms
-    assert lib.bk_abi_version() == 2
+    assert lib.bk_abi_version() == 3
 
 
 def test_abi_is_plain_c():
