@@ -47,7 +47,8 @@ class _CfSpec(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "libbedkit.so")
+    # BEDKIT_LIB: an alternative build of the same library (kernel tuning experiments: profiles/tools/build_variants.sh)
+    return os.environ.get("BEDKIT_LIB") or os.path.join(_HERE, "lib", "libbedkit.so")
 
 
 def tool_path(name: str) -> str:

@@ -356,6 +356,7 @@ struct BedmapRow {
   double          kth_arg[BK_MAX_OPS];  // BK_OP_KTH fraction, BK_OP_MAD multiplier, BK_OP_TMEAN <low>
   double          arg2[BK_MAX_OPS];     // BK_OP_TMEAN <hi>
   uint64_t        stop_row;             // --max/min-element: the first unmapped row (printed up to the element column), or ~0
+  uint64_t*       idfill_off;           // --echo-map-id filled by k_fill_ids: where the column of row i lands in the result (else null)
   int             prec;
   int             sci;
   int             skip_unmapped;
@@ -796,6 +797,11 @@ struct BedmapRow {
             s.copy(nullptr, idbytes[i]);
             break;
           }
+          if (idfill_off) {  // the ids are written by a warp per row afterwards (k_fill_ids): leave the room, note the place
+            idfill_off[i] = s.gpos();
+            s.skip(idbytes[i]);
+            break;
+          }
           const uint64_t lo = win_lo[i], hi = lo + win_n[i];
           const uint32_t a = rs[row], b = re[row];
           bool           first = true;
@@ -858,6 +864,67 @@ struct BedmapRow {
     s.put('\n');
   }
 };
+
+// --echo-map-id, cooperative form (EchoMapBedVisitor.hpp:39-66): one warp per reference row.  The lanes test 32 window
+// rows at a time, a warp scan over (id length + delimiter) gives every hit its place in the column, and each lane copies
+// its own id: neighbouring lanes write neighbouring bytes, instead of one thread walking ~70 ids of ~10 bytes (the
+// per-row emitter leaves the column's room empty and records where it starts).
+struct FillIdsParams {
+  const uint32_t* rs;
+  const uint32_t* re;
+  uint64_t        row0, n;
+  const uint32_t* ms;
+  const uint32_t* me;
+  const uint32_t* midspan;
+  const uint64_t* mline;
+  const char*     mtext;
+  const uint64_t* win_lo;
+  const uint32_t* win_n;
+  const uint32_t* idbytes;
+  const uint64_t* col_off;
+  OverlapSpec     ov;
+  char            mdelim[24];
+  uint32_t        mdelim_len;
+  char*           out;
+};
+__global__ void __launch_bounds__(256) k_fill_ids(FillIdsParams p) {
+  const int      lane = threadIdx.x & 31;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((uint64_t)gridDim.x * 256) >> 5;
+  for (uint64_t i = w0; i < p.n; i += nw) {
+    if (p.idbytes[i] == 0) continue;
+    const uint64_t row = p.row0 + i;
+    const uint32_t a = p.rs[row], b = p.re[row];
+    const uint64_t lo = p.win_lo[i], hi = lo + p.win_n[i];
+    char*          dst = p.out + p.col_off[i];
+    uint32_t       run = 0;
+    bool           none_yet = true;
+    for (uint64_t k0 = lo; k0 < hi; k0 += 32) {
+      const uint64_t k = k0 + lane;
+      uint32_t       ovl, len = 0;
+      bool           q = false;
+      uint32_t       sp = 0;
+      if (k < hi && qualifies(p.ov, a, b, p.ms[k], p.me[k], ovl)) {
+        q = true;
+        sp = p.midspan[k];
+        len = sp & 0xFFFFu;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, q);
+      if (m == 0) continue;
+      const bool     lead = none_yet && q && (m & ((1u << lane) - 1u)) == 0;  // the very first id has no delimiter in front
+      const uint32_t contrib = q ? len + (lead ? 0u : p.mdelim_len) : 0u;
+      const uint32_t incl = warp_incl_scan(contrib);
+      if (q) {
+        char* d = dst + run + (incl - contrib);
+        if (!lead)
+          for (uint32_t t = 0; t < p.mdelim_len; t++) *d++ = p.mdelim[t];
+        const char* src = p.mtext + (p.mline[k] & kLineOffMask) + (sp >> 16);
+        for (uint32_t t = 0; t < len; t++) d[t] = src[t];
+      }
+      run += __shfl_sync(0xffffffffu, incl, 31);
+      none_yet = false;
+    }
+  }
+}
 
 // first row without a mapped element: scratch[SC_COUNT_A] = ~row (atomicMax; 0 = none)
 __global__ void __launch_bounds__(256) k_first_unmapped(const uint32_t* __restrict__ count, uint64_t n, uint64_t* scratch) {
@@ -1124,6 +1191,17 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     }
   }
 
+  // one --echo-map-id column: the per-row emitter leaves its room empty, a warp per row fills it afterwards
+  uint64_t* d_idfill = nullptr;
+  {
+    int id_cols = 0;
+    for (int c = 0; c < spec->n_ops; c++) id_cols += spec->ops[c] == BK_OP_ECHO_MAP_ID;
+    if (id_cols == 1 && stop_row == ~0ull) {
+      d_idfill = dalloc<uint64_t>(ctx, n);
+      if (!d_idfill) return BK_ERR_NOMEM;
+    }
+  }
+
   char*    d_out = nullptr;
   uint64_t bytes = 0, rows = 0;
   int      rc = BK_OK;
@@ -1144,6 +1222,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       fn.arg2[c] = spec->op_arg2[c];
     }
     fn.stop_row = stop_row;
+    fn.idfill_off = d_idfill;
     fn.prec = spec->precision; fn.sci = spec->sci; fn.skip_unmapped = spec->skip_unmapped;
     fn.delim_len = (int)dl; memcpy(fn.delim, delim, dl);
     fn.mdelim_len = (int)strlen(mdelim); memcpy(fn.mdelim, mdelim, fn.mdelim_len);
@@ -1156,6 +1235,21 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   else if (spec->sci && !rare_fields) emit(BedmapRow<1>{});
   else if (!spec->sci) emit(BedmapRow<2>{});
   else emit(BedmapRow<3>{});
+  if (rc == BK_OK && d_idfill && bytes) {
+    FillIdsParams fp{};
+    fp.rs = ref->start; fp.re = ref->end; fp.row0 = row0; fp.n = n;
+    fp.ms = map->start; fp.me = map->end; fp.midspan = map->idspan; fp.mline = map->line_off; fp.mtext = map->d_text;
+    fp.win_lo = sp.win_lo; fp.win_n = sp.win_n; fp.idbytes = sp.idbytes; fp.col_off = d_idfill; fp.ov = ov;
+    fp.mdelim_len = (uint32_t)strlen(mdelim); memcpy(fp.mdelim, mdelim, fp.mdelim_len);
+    fp.out = d_out;
+    const uint64_t want = (n + 7) / 8, cap_blocks = (uint64_t)kSMs * 64;
+    prof_begin(ctx, "k_fill_ids");
+    k_fill_ids<<<(unsigned)(want < cap_blocks ? want : cap_blocks), 256, 0, ctx->stream>>>(fp);
+    prof_end(ctx);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = BK_ERR_CUDA;
+  }
+  dfree(ctx, d_idfill);
   dfree(ctx, sp.count); dfree(ctx, sp.bases); dfree(ctx, sp.sum); dfree(ctx, sp.vmax); dfree(ctx, sp.vmin);
   dfree(ctx, sp.win_lo); dfree(ctx, sp.win_n); dfree(ctx, sp.idbytes); dfree(ctx, d_rank);
   if (rc != BK_OK) {

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(E_THREADS, 4) k_emit(RowFn fn, uint64_t n, cha
     const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15);
     if (total + shift <= E_STAGE) {
       if (len) {
-        MemSink ms{stage + shift + off};
+        MemSink ms{stage + shift + off, stage + shift + off, base + off};
         fn(i, ms);
       }
       __syncthreads();
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(E_THREADS, 4) k_emit(RowFn fn, uint64_t n, cha
       }
       __syncthreads();  // the stage is rewritten by the next tile
     } else if (len) {
-      MemSink ms{out + base + off};
+      MemSink ms{out + base + off, out + base + off, base + off};
       fn(i, ms);
     }
   }

@@ -32,11 +32,17 @@ struct CountSink {
   __device__ __forceinline__ void put_padded(uint64_t, int width) { n += width; }
   __device__ __forceinline__ void copy(const char*, uint64_t len) { n += len; }
   __device__ __forceinline__ void puts_(const char* s, int len) { n += len; }
+  __device__ __forceinline__ uint64_t gpos() const { return n; }
+  __device__ __forceinline__ void     skip(uint64_t len) { n += len; }
   static constexpr bool counting = true;
 };
 
 struct MemSink {  // generic-address writer (shared or global)
-  char* p;
+  char*    p;
+  char*    p0 = nullptr;  // where the row began, and the byte offset of that place in the result text: a column can
+  uint64_t g0 = 0;        // ask where it lands (gpos) and leave its bytes to a later cooperative pass (skip)
+  __device__ __forceinline__ uint64_t gpos() const { return g0 + (uint64_t)(p - p0); }
+  __device__ __forceinline__ void     skip(uint64_t n) { p += n; }
   __device__ __forceinline__ void put(char c) { *p++ = c; }
   __device__ __forceinline__ void put_u32(uint32_t v) {
     const int n = ndigits_u32(v);

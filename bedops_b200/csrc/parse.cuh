@@ -5,7 +5,10 @@
 namespace bk {
 
 constexpr int P_THREADS = 256;
-constexpr int P_MINBLOCKS = 6;  // resident CTAs per SM the compiler must leave registers for
+#ifndef BK_P_MINBLOCKS
+#define BK_P_MINBLOCKS 6
+#endif
+constexpr int P_MINBLOCKS = BK_P_MINBLOCKS;  // resident CTAs per SM the compiler must leave registers for
 constexpr int P_TILE = P_THREADS * 32;  // bytes of text whose line STARTS one tile owns
 constexpr int P_PRE = 128;    // halo before the tile (previous line's chromosome token)
 constexpr int P_POST = 384;   // halo after the tile (tail of the last line that starts in the tile)

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-KERNELS = ["k_efflen", "k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_rank_merge", "k_segments",
+KERNELS = ["k_sort_validate", "k_chrom_insert", "k_sort_keys", "k_radix_hist", "k_radix_scatter", "k_tie_fix", "k_part_keys",
+           "k_efflen", "k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_rank_merge", "k_segments",
            "k_intersect", "k_element_of", "k_argmark", "k_cf_sim", "k_map_stats", "k_emit_len", "k_emit"]
 
 
@@ -46,6 +47,10 @@ def main():
                           "kernel_ms": split}), flush=True)
 
     only = os.environ.get("BEDKIT_CONFIGS", "3,4,5").split(",")
+    if "2ids" in only:
+      run_config2_ids(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE)
+    if "sort" in only:
+      run_sort(kit, torch, timed, scale, SynthFile, MAP_SHAPE)
     if "3" in only:
       run_config3(kit, torch, timed, scale, SynthFile, MAP_SHAPE, COL_LINE)
     if "4" in only:
@@ -53,6 +58,47 @@ def main():
     if "5" in only:
       run_config5(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE, COL_LINE, COL_SCORE)
     kit.close()
+
+
+def run_config2_ids(kit, torch, timed, scale, SynthFile, MAP_SHAPE, REF_SHAPE):
+    # configuration 2 with the list operation north_star names: --echo-map-id (about 70 ids per reference row)
+    from bedops_b200._lib import COL_ID, COL_LINE
+    ref = SynthFile(kit, torch, int(10_000_000 * scale), 2, REF_SHAPE)
+    mp = SynthFile(kit, torch, int(100_000_000 * scale), 1, MAP_SHAPE)
+
+    def ids():
+        rb, mb = ref.load(kit, 3, COL_LINE), mp.load(kit, 4, COL_ID | COL_LINE)
+        out = kit.bedmap(rb, mb, ["echo", "echo-map-id"], on_device=True)
+        ids.bytes = out.nbytes
+        out.free()
+        rb.free()
+        mb.free()
+    timed("bedmap --echo --echo-map-id, 10M x 100M", ref.rows + mp.rows, ids)
+    print(json.dumps({"op": "bedmap --echo --echo-map-id, 10M x 100M", "out_bytes": ids.bytes}), flush=True)
+    del ref, mp
+    kit.release_cached()
+    torch.cuda.empty_cache()
+
+
+def run_sort(kit, torch, timed, scale, SynthFile, MAP_SHAPE):
+    # sort-bed over a sorted 100 M-row file (the radix sort does the same passes whatever the input order) and
+    # bedops --partition over it
+    f = SynthFile(kit, torch, int(100_000_000 * scale), 1, MAP_SHAPE)
+
+    def sort():
+        out = kit.sort_bed_device(f.buf.data_ptr(), f.nbytes, on_device=True)
+        out.free()
+    timed("sort-bed, 100M rows", f.rows, sort)
+
+    def part():
+        b = f.load(kit, 3, 0)
+        out = kit.setop("partition", [b], on_device=True)
+        out.free()
+        b.free()
+    timed("bedops --partition, 100M rows", f.rows, part)
+    del f
+    kit.release_cached()
+    torch.cuda.empty_cache()
 
 
 def run_config3(kit, torch, timed, scale, SynthFile, MAP_SHAPE, COL_LINE):

@@ -123,7 +123,7 @@ def test_tools_read_archives_like_the_reference(tmp_path):
         exp = subprocess.run([os.path.join(REFBIN, tool)] + argv, cwd=tmp_path, capture_output=True)
         got = subprocess.run([tool_path(tool)] + argv, cwd=tmp_path, capture_output=True)
         assert (got.returncode, got.stdout) == (exp.returncode, exp.stdout), (tool, argv, got.stderr[:300])
-        assert exp.returncode == 0 and len(exp.stdout) > 1000
+        assert exp.returncode == 0 and len(exp.stdout) > 100
 
 
 @pytest.mark.gpu
