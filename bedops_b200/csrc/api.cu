@@ -231,8 +231,10 @@ extern "C" const char* bk_strerror(int code) {
   return "unknown error";
 }
 
-extern "C" const char* bk_last_error(const bk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
-extern "C" uint64_t    bk_launch_count(const bk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" const char* bk_last_error(const bk_ctx* ctx) {
+  bk::DeviceGuard device_guard(ctx); return ctx ? ctx->last_error.c_str() : ""; }
+extern "C" uint64_t    bk_launch_count(const bk_ctx* ctx) {
+  bk::DeviceGuard device_guard(ctx); return ctx ? ctx->launches : 0; }
 
 extern "C" int bk_init(bk_ctx** out, int device) {
   if (!out) return BK_ERR_ARG;
@@ -288,6 +290,7 @@ extern "C" void bk_destroy(bk_ctx* ctx) {
 }
 
 extern "C" int bk_set_stream(bk_ctx* ctx, void* cuda_stream) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx) return BK_ERR_ARG;
   cudaStreamSynchronize(ctx->stream);
   ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
@@ -295,12 +298,14 @@ extern "C" int bk_set_stream(bk_ctx* ctx, void* cuda_stream) {
 }
 
 extern "C" int bk_release_cached(bk_ctx* ctx) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx) return BK_ERR_ARG;
   release_cached(ctx);
   return BK_OK;
 }
 
 extern "C" int bk_profile(bk_ctx* ctx, int enable) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx) return BK_ERR_ARG;
   cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->prof) {
@@ -313,6 +318,7 @@ extern "C" int bk_profile(bk_ctx* ctx, int enable) {
 }
 
 extern "C" int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !kernel) return BK_ERR_ARG;
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double   ms = 0;
@@ -331,6 +337,7 @@ extern "C" int bk_profile_query(bk_ctx* ctx, const char* kernel, double* total_m
 }
 
 extern "C" int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx) return BK_ERR_ARG;
   if (nbytes) BK_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, ctx->stream));
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -338,6 +345,7 @@ extern "C" int bk_copy(bk_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 }
 
 extern "C" int bk_sync(bk_ctx* ctx) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx) return BK_ERR_ARG;
   BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BK_OK;
@@ -376,6 +384,7 @@ static bool looks_like_starch(const unsigned char* h, size_t n) {
 }
 
 extern "C" int bk_load_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, int min_fields, unsigned cols, bk_bed** out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !out || (!host_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   *out = nullptr;
@@ -400,6 +409,7 @@ extern "C" int bk_load_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, in
 }
 
 extern "C" int bk_load_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int min_fields, unsigned cols, bk_bed** out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !out || (!dev_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   *out = nullptr;
@@ -411,6 +421,7 @@ extern "C" int bk_load_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbyt
 }
 
 extern "C" void bk_free_bed(bk_ctx* ctx, bk_bed* bed) {
+  bk::DeviceGuard device_guard(ctx);
   if (!bed || !ctx) return;
   if (bed->owns_text) dfree(ctx, const_cast<char*>(bed->d_text));
   dfree(ctx, bed->start);
@@ -434,6 +445,7 @@ extern "C" uint64_t bk_bed_chrom_rows(const bk_bed* bed, int i) {
 
 extern "C" int bk_bed_copy_columns(bk_ctx* ctx, const bk_bed* bed, uint32_t* start, uint32_t* end, double* score,
                                    uint64_t* line_off) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !bed) return BK_ERR_ARG;
   const uint64_t n = bed->nrows;
   if (n == 0) return BK_OK;
@@ -454,6 +466,7 @@ extern "C" int bk_bed_copy_columns(bk_ctx* ctx, const bk_bed* bed, uint32_t* sta
 }
 
 extern "C" void bk_free_text(bk_ctx* ctx, bk_text* text) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !text || !text->ptr) return;
   if (text->on_device) dfree(ctx, text->ptr); else pinned_put(ctx, text->ptr);
   text->ptr = nullptr;
@@ -489,6 +502,7 @@ struct FormatBedRow {
 
 extern "C" int bk_format_bed_device(bk_ctx* ctx, const char* chrom, const uint32_t* d_start, const uint32_t* d_end,
                                     const uint32_t* d_score, uint64_t n, int64_t id_base, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !chrom || !out || strlen(chrom) > 127) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

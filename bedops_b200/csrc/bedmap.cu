@@ -989,6 +989,7 @@ extern "C" void bk_mapspec_default(bk_mapspec* spec) {
 }
 
 extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, const bk_mapspec* spec, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !ref || !spec || !out) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

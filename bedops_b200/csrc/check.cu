@@ -281,6 +281,7 @@ using namespace bk;
 // Validate device-resident text.  On failure returns BK_ERR_CHECK and bk_last_error() holds
 // "<message>\nSee row: <line>" (the tool prefixes "in <file>\n" exactly like BedCheckIterator.hpp:589-593).
 extern "C" int bk_check_text_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int n_fields, int has_rest, int nest_check) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || (!dev_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   if (nbytes == 0) return BK_OK;
@@ -311,6 +312,7 @@ extern "C" int bk_check_text_device(bk_ctx* ctx, const char* dev_text, size_t nb
 }
 
 extern "C" int bk_check_text(bk_ctx* ctx, const char* host_text, size_t nbytes, int n_fields, int has_rest, int nest_check) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || (!host_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   if (nbytes == 0) return BK_OK;

@@ -383,6 +383,7 @@ extern "C" void bk_cfspec_default(bk_cfspec* spec) {
 }
 
 extern "C" int bk_closest(bk_ctx* ctx, const bk_bed* ref, const bk_bed* query, const bk_cfspec* spec, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !ref || !query || !spec || !out) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

@@ -82,6 +82,22 @@ struct bk_bed {
 
 namespace bk {
 
+// Every entry point that takes a ctx runs on the ctx's device whatever the calling thread's current device is (a host
+// with one ctx per GPU may call them from one thread), and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int  prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const bk_ctx* c) {
+    if (!c) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int  fail(bk_ctx* ctx, int code, const char* fmt, ...);
 int  cuda_fail(bk_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
 void  release_cached(bk_ctx* ctx);         // give every cached device block back to the driver

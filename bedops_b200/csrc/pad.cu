@@ -225,6 +225,7 @@ static int flag_ranks(bk_ctx* ctx, const uint8_t* flags, uint64_t n, uint8_t bit
 using namespace bk;
 
 extern "C" int bk_bed_pad(bk_ctx* ctx, const bk_bed* src, long long lpad, long long rpad, bk_bed** out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !src || !out) return BK_ERR_ARG;
   *out = nullptr;
   ctx->last_error.clear();

@@ -58,6 +58,7 @@ int plain(bk_ctx* ctx, const char* ref_text, size_t ref_len, const char* map_tex
 extern "C" int bk_bedmap_host(bk_ctx* ctx, const char* ref_text, size_t ref_len, int ref_fields, unsigned ref_cols,
                               const char* map_text, size_t map_len, int map_fields, unsigned map_cols,
                               const bk_mapspec* spec, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !spec || !out || (!ref_text && ref_len) || (!map_text && map_len)) return BK_ERR_ARG;
   memset(out, 0, sizeof(*out));
   const bool one_chrom = spec->chrom && strcmp(spec->chrom, "all") != 0;
@@ -340,6 +341,7 @@ extern "C" int bk_shard_plan_make(const char* ref_text, size_t ref_len, const ch
 }
 
 extern "C" void bk_shard_free(bk_ctx* ctx, bk_shard* sh) {
+  bk::DeviceGuard device_guard(ctx);
   if (!sh) return;
   bk_free_bed(ctx, sh->ref);
   bk_free_bed(ctx, sh->map);
@@ -352,6 +354,7 @@ extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int
                                      int ref_fields, unsigned ref_cols, const char* map_text, size_t map_len, int map_fields,
                                      unsigned map_cols, const char* ref_src, const char* map_src, const bk_mapspec* spec,
                                      bk_shard** out, uint64_t* reach) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !plan || !spec || !out || !reach || rank < 0 || rank >= plan->n_shards) return BK_ERR_ARG;
   (void)ref_len;
   (void)map_len;
@@ -410,6 +413,7 @@ extern "C" int bk_bedmap_shard_begin(bk_ctx* ctx, const bk_shard_plan* plan, int
 }
 
 extern "C" int bk_bedmap_shard_finish(bk_ctx* ctx, bk_shard* sh, const uint64_t* all_reach, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !sh || !out || (!all_reach && sh->rank > 0)) return BK_ERR_ARG;
   memset(out, 0, sizeof(*out));
   const int n = sh->plan.n_shards, rank = sh->rank;

@@ -1205,6 +1205,7 @@ using namespace bk;
 
 extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_files, double thr, int thr_is_pct,
                         const char* chrom, int out_on_device, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !files || !out || n_files < 1) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));
@@ -1365,6 +1366,7 @@ extern "C" int bk_setop(bk_ctx* ctx, int op, const bk_bed* const* files, int n_f
 
 extern "C" int bk_chop(bk_ctx* ctx, const bk_bed* const* files, int n_files, uint64_t chunk, uint64_t stagger,
                        int exclude_short, const char* chrom, int out_on_device, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !files || !out || n_files < 1) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

@@ -33,6 +33,7 @@ static const ChromRun* run_named(const bk_bed* b, const char* name) {
 using namespace bk;
 
 extern "C" int bk_bed_reach_start(bk_ctx* ctx, const bk_bed* bed, const char* chrom, uint64_t pos, uint64_t* start_out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !bed || !chrom || !start_out) return BK_ERR_ARG;
   *start_out = ~0ull;
   const ChromRun* r = run_named(bed, chrom);
@@ -47,6 +48,7 @@ extern "C" int bk_bed_reach_start(bk_ctx* ctx, const bk_bed* bed, const char* ch
 }
 
 extern "C" int bk_bed_chrom_max_end(bk_ctx* ctx, const bk_bed* bed, const char* chrom, uint64_t* end_out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !bed || !chrom || !end_out) return BK_ERR_ARG;
   *end_out = 0;
   const ChromRun* r = run_named(bed, chrom);
@@ -60,6 +62,7 @@ extern "C" int bk_bed_chrom_max_end(bk_ctx* ctx, const bk_bed* bed, const char* 
 }
 
 extern "C" int bk_bed_concat(bk_ctx* ctx, const bk_bed* head, const bk_bed* tail, bk_bed** out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !head || !tail || !out) return BK_ERR_ARG;
   *out = nullptr;
   ctx->last_error.clear();

@@ -582,6 +582,7 @@ using namespace bk;
 
 extern "C" int bk_sort_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int out_on_device, bk_text* out,
                                   uint64_t* bad_offset) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !out || (!dev_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));
@@ -589,6 +590,7 @@ extern "C" int bk_sort_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbyt
 }
 
 extern "C" int bk_sort_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, int out_on_device, bk_text* out, uint64_t* bad_offset) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !out || (!host_text && nbytes)) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

@@ -545,6 +545,7 @@ extern "C" int bk_starch_inflate_host(const char* archive, size_t nbytes, const 
 extern "C" void bk_host_free(void* p) { free(p); }
 
 extern "C" int bk_unstarch(bk_ctx* ctx, const char* archive, size_t nbytes, const char* chrom, int out_on_device, bk_text* out) {
+  bk::DeviceGuard device_guard(ctx);
   if (!ctx || !out || !archive) return BK_ERR_ARG;
   ctx->last_error.clear();
   memset(out, 0, sizeof(*out));

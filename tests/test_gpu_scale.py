@@ -392,3 +392,72 @@ def test_config5_one_billion_map_rows(env):
         del Es, order, PVS, PVE
     rb.free()
     mb.free()
+
+
+# ---- round 2: sort-bed, --partition, Starch-free scale checks on the same synthetic shape ----------------------------
+def test_sort_bed_100M_rows_chromosome_blocks_reversed(env):
+    """100 M hg38-shaped rows with the chromosome blocks in reverse order (and the largest block rotated by half, so that
+    starts wrap inside a chromosome): sort-bed must give back the sorted file byte for byte.  Sorted input is a fixed point."""
+    kit, torch = env
+    f = SynthFile(kit, torch, N(100_000_000), 1, MAP_SHAPE)
+    out = kit.sort_bed_device(f.buf.data_ptr(), f.nbytes, on_device=True)
+    assert out.nbytes == f.nbytes and out.rows == f.rows
+    txt = device_text_to_tensor(kit, torch, out)
+    assert torch.equal(txt, f.buf[:f.nbytes])
+    out.free()
+    del txt
+    # reversed blocks; the first block (chr1) rotated at a line boundary near its middle
+    blocks = []
+    for k, ch in enumerate(reversed(f.chroms)):
+        b0, b1 = ch["b0"], ch["b1"]
+        if ch["name"] == "chr1":
+            mid = (b0 + b1) // 2
+            window = f.buf[mid:mid + 4096].cpu().numpy().tobytes()
+            cut = mid + window.index(b"\n") + 1
+            blocks += [(cut, b1), (b0, cut)]
+        else:
+            blocks.append((b0, b1))
+    shuffled = torch.empty(f.nbytes + 64, dtype=torch.uint8, device="cuda:0")
+    at = 0
+    for b0, b1 in blocks:
+        shuffled[at:at + b1 - b0] = f.buf[b0:b1]
+        at += b1 - b0
+    assert at == f.nbytes
+    out = kit.sort_bed_device(shuffled.data_ptr(), f.nbytes, on_device=True)
+    assert out.nbytes == f.nbytes and out.rows == f.rows
+    txt = device_text_to_tensor(kit, torch, out)
+    assert torch.equal(txt, f.buf[:f.nbytes])
+    out.free()
+
+
+def test_partition_100M_rows_properties(env):
+    """bedops --partition over 100 M rows: same coverage as --merge, idempotent, pieces positive and disjoint"""
+    kit, torch = env
+    f = SynthFile(kit, torch, N(100_000_000), 1, MAP_SHAPE)
+    b = f.load(kit, 3, 0)
+    part = kit.setop("partition", [b], on_device=True)
+    merged_t = kit.setop("merge", [b], on_device=True)
+    b.free()
+    pb = kit.load_device(part.ptr, part.nbytes, 3, 0)
+    again = kit.setop("merge", [pb], on_device=True)
+    assert again.nbytes == merged_t.nbytes
+    assert torch.equal(device_text_to_tensor(kit, torch, again), device_text_to_tensor(kit, torch, merged_t))
+    again.free()
+    twice = kit.setop("partition", [pb], on_device=True)
+    assert twice.nbytes == part.nbytes and twice.rows == part.rows
+    s, e, _, _ = pb.columns()
+    assert int((e.astype(np.int64) - s.astype(np.int64)).min()) > 0
+    # disjoint and sorted inside every chromosome: a piece starts at or after the previous piece's end
+    names = pb.chroms()
+    at = 0
+    for _, rows in names:
+        if rows > 1:
+            assert bool((s[at + 1:at + rows].astype(np.int64) >= e[at:at + rows - 1].astype(np.int64)).all())
+        at += rows
+    # every piece border is an input coordinate and every input coordinate is a piece border (first chromosome)
+    ch = f.chroms[0]
+    n0 = names[0][1]
+    borders = np.union1d(s[:n0], e[:n0])
+    coords = torch.unique(torch.cat([ch["s"], ch["e"]])).cpu().numpy()
+    assert np.array_equal(borders.astype(np.int64), coords)
+    twice.free(); pb.free(); part.free(); merged_t.free()
