@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
                                                            const uint64_t* __restrict__ scratch,
                                                            uint32_t* __restrict__ local_prefix, uint64_t* __restrict__ warp_total,
                                                            uint32_t ntiles, uint32_t tiles_per_warp, uint32_t nwarps,
-                                                           int skip_headers, int strict_blank) {
+                                                           int skip_headers, int strict_blank, uint32_t* __restrict__ cm_arr,
+                                                           uint32_t* __restrict__ ls_arr) {
   const int      lane = threadIdx.x & 31;
   const uint32_t wid = (blockIdx.x * CR_THREADS + threadIdx.x) >> 5;
   if (wid >= nwarps) return;
@@ -306,6 +307,12 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
         }
       }
       cnt += __popc(smask);
+      // the packed control-byte mask and the final line-start mask of these 32 bytes, for pass 2 (one bit per text byte
+      // each: 1/4 of the text size written here and read there, instead of building both masks twice)
+      if (p0 < nbytes_raw) {
+        cm_arr[p0 >> 5] = cm;
+        ls_arr[p0 >> 5] = smask;
+      }
     }
     run += __reduce_add_sync(0xffffffffu, cnt);
   }
@@ -343,7 +350,7 @@ template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p) {
   __shared__ __align__(128) unsigned char smbuf[2][P_BUF + 16];  // double-buffered text window
   __shared__ uint32_t                     ctlp2[2][P_NW + 4];
-  __shared__ uint32_t                     nlw2[2][P_PRE / 32 + P_TILE / 32];  // packed NL mask of window bytes [0, PRE+TILE)
+  __shared__ uint32_t                     lsw2[2][P_PRE / 32 + P_TILE / 32];  // line-start mask of window bytes [0, PRE+TILE)
   __shared__ uint32_t                     wsum2[2][P_THREADS / 32];
   __shared__ uint64_t                     base2[2];
   __shared__ uint16_t                     lstart[P_MAXROWS];
@@ -394,7 +401,29 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     const int64_t        g0 = ts - P_PRE;
     unsigned char* const sm = smbuf[buf];
     uint32_t* const      ctlp = ctlp2[buf];
-    uint32_t* const      nlw = nlw2[buf];
+    uint32_t* const      lsw = lsw2[buf];
+    // ---- [B] masks of the window from pass 1 (issued before the wait on the text: the loads overlap it) -------------
+    // word j of the window covers window bytes [32j, 32j+32); global word index = tile * (P_TILE/32) - P_PRE/32 + j
+    const int      off = P_PRE + tid * 32;
+    uint32_t       smask, cm;
+    {
+      const int64_t w0g = (int64_t)tile * (P_TILE / 32) - P_PRE / 32;
+      const int64_t gw = w0g + P_PRE / 32 + tid;  // this thread's own 32 bytes
+      const bool    in = (uint64_t)gw < p.nwords;
+      cm = in ? __ldg(&p.cm_arr[gw]) : 0xFFFFFFFFu;  // beyond the text: zero bytes, i.e. control bytes
+      smask = in ? __ldg(&p.ls_arr[gw]) : 0u;
+      ctlp[tid] = cm;
+      lsw[P_PRE / 32 + tid] = smask;
+      if (tid < P_PRE / 32) {  // head halo: line starts only (the row in front of the tile's first row)
+        const int64_t g = w0g + tid;
+        lsw[tid] = (g >= 0 && (uint64_t)g < p.nwords) ? __ldg(&p.ls_arr[g]) : 0u;
+      } else if (tid >= 32 && tid < 32 + P_POST / 32) {  // tail halo: control bytes only
+        const int64_t g = w0g + P_PRE / 32 + P_TILE / 32 + (tid - 32);
+        ctlp[P_TILE / 32 + tid - 32] = (uint64_t)g < p.nwords ? __ldg(&p.cm_arr[g]) : 0xFFFFFFFFu;
+      } else if (tid >= 64 && tid < 68) {
+        ctlp[P_TILE / 32 + P_POST / 32 + tid - 64] = 0;  // padding words read by the 64-bit line windows
+      }
+    }
     // ---- [A] this tile's text -----------------------------------------------------------------------------------
     if (bulkable(tile)) {
       mbar_wait(&mbar[buf], (phase >> buf) & 1u);
@@ -403,59 +432,7 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
       stage_edge(tile, sm);  // the buffer is free: every thread passed [S2] of the previous tile after leaving tile-2
       __syncthreads();
     }
-
-    // ---- [B] control-byte masks; line starts: position q starts a line iff q == 0 or byte q-1 is '\n' ---------
-    Cursor        cur{sm, g0, text, eff};
-    const int     off = P_PRE + tid * 32;
-    const int64_t p0 = ts + tid * 32;  // global offset of this thread's first byte
-    uint32_t      smask = 0;           // packed line-start mask of this thread's 32 bytes
-    uint32_t      cm = 0;              // packed control-byte mask of this thread's 32 bytes
-    {
-      const uint4* v4 = reinterpret_cast<const uint4*>(sm + off);
-      const uint4  a = v4[0], c = v4[1];
-      const uint32_t w8[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-      uint32_t nlp;
-      pack_masks32(w8, cm, nlp);
-      smask = (nlp << 1) | ((p0 == 0 || sm[off - 1] == '\n') ? 1u : 0u);  // a line starts after every NL
-      ctlp[tid] = cm;
-      nlw[P_PRE / 32 + tid] = nlp;
-      if (tid >= 32 && tid < 32 + P_PRE / 32) {  // head halo: NL mask only (previous line of the tile's first row)
-        const uint4* h4 = reinterpret_cast<const uint4*>(sm + (tid - 32) * 32);
-        const uint4  ha = h4[0], hc = h4[1];
-        const uint32_t h8[8] = {ha.x, ha.y, ha.z, ha.w, hc.x, hc.y, hc.z, hc.w};
-        uint32_t     hm = 0;
-#pragma unroll
-        for (int i = 7; i >= 0; i--) hm = push_flags4(hm, nl_mask4(h8[i], ctl_mask4(h8[i])));
-        nlw[tid - 32] = hm;
-      }
-      if (tid >= 64 && tid < 64 + P_POST / 32) {  // tail halo
-        const uint4* t4 = reinterpret_cast<const uint4*>(sm + P_PRE + P_TILE + (tid - 64) * 32);
-        const uint4  ta = t4[0], tc = t4[1];
-        const uint32_t t8[8] = {ta.x, ta.y, ta.z, ta.w, tc.x, tc.y, tc.z, tc.w};
-        uint32_t     tm = 0;
-#pragma unroll
-        for (int i = 7; i >= 0; i--) tm = push_flags4(tm, ctl_mask4(t8[i]));
-        ctlp[P_TILE / 32 + tid - 64] = tm;
-      } else if (tid >= 96 && tid < 100) {
-        ctlp[P_TILE / 32 + P_POST / 32 + tid - 96] = 0;  // padding words read by the 64-bit line windows
-      }
-    }
-    if ((uint64_t)ts + P_TILE > eff && (uint64_t)p0 + 32 > eff)  // clip to the effective text length (last tile only)
-      smask = (uint64_t)p0 >= eff ? 0u : (smask & ((1u << (int)(eff - (uint64_t)p0)) - 1u));
-    // drop blank lines (fscanf's %s skips them: whitespace, including '\n', is not a record); only a line that
-    // begins with a control byte can be blank
-    for (uint32_t m = smask & cm; m; m &= m - 1) {
-      const int j = __ffs(m) - 1;
-      int64_t   q = off + j;
-      if (!(p.cols & BK_LOAD_SORTBED))
-        while (is_ws(cur.at(q))) q++;
-      if (cur.at(q) == '\n') smask &= ~(1u << j);
-    }
-    if (p.cols & BK_LOAD_HEADERS)
-      for (uint32_t m = smask; m; m &= m - 1) {
-        const int j = __ffs(m) - 1;
-        if (is_header_line(cur, off + j)) smask &= ~(1u << j);
-      }
+    Cursor cur{sm, g0, text, eff};
     const uint32_t cnt = __popc(smask);
     const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31) wsum2[buf][warp] = incl;
@@ -584,13 +561,12 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
         if (toklen <= 8 && tok0 == q0) {
           int ps = -1;
           if (i > 0) ps = lstart[i - 1];
-          else if (q0 >= 2 && g0 + q0 >= 2) {
-            const int x = q0 - 2;
+          else if (q0 >= 1) {  // the last line start in front of q0 (rows only: blank and header lines are not in the mask)
+            const int x = q0 - 1;
             int       w = x >> 5;
-            uint32_t  pm = nlw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
-            while (!pm && w > 0) pm = nlw[--w];
-            if (pm) ps = 32 * w + 32 - __clz(pm);   // first byte after that NL
-            else if (g0 <= 0) ps = (int)(-g0);      // the previous line is the first line of the file
+            uint32_t  pm = lsw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
+            while (!pm && w > 0) pm = lsw[--w];
+            if (pm) ps = 32 * w + 31 - __clz(pm);
           }
           if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
             const uint2 t8 = token8(sm, q0, toklen), c = token8(sm, ps, toklen);
@@ -745,7 +721,10 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   uint32_t*      d_lpre = dalloc<uint32_t>(ctx, ntiles);
   uint64_t*      d_wtot = dalloc<uint64_t>(ctx, nwarps);
   uint64_t*      d_wbase = dalloc<uint64_t>(ctx, (size_t)nwarps + 1);
-  if (!d_heads || !d_lpre || !d_wtot || !d_wbase) return BK_ERR_NOMEM;
+  const uint64_t nwords = (nbytes_raw + 31) / 32;
+  uint32_t*      d_cm = dalloc<uint32_t>(ctx, nwords);
+  uint32_t*      d_ls = dalloc<uint32_t>(ctx, nwords);
+  if (!d_heads || !d_lpre || !d_wtot || !d_wbase || !d_cm || !d_ls) return BK_ERR_NOMEM;
   // pass 1: effective length, rows per tile, exclusive scan -> exact row count
   prof_begin(ctx, "k_efflen");
   k_efflen<<<1, 32, 0, ctx->stream>>>(text, nbytes_raw, ctx->d_scratch);
@@ -754,7 +733,7 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
   prof_begin(ctx, "k_count_rows");
   k_count_rows<<<(nwarps * 32 + CR_THREADS - 1) / CR_THREADS, CR_THREADS, 0, ctx->stream>>>(
       text, nbytes_raw, ctx->d_scratch, d_lpre, d_wtot, ntiles, tiles_per_warp, nwarps, (bed->cols & BK_LOAD_HEADERS) ? 1 : 0,
-      (bed->cols & BK_LOAD_SORTBED) ? 1 : 0);
+      (bed->cols & BK_LOAD_SORTBED) ? 1 : 0, d_cm, d_ls);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
   prof_begin(ctx, "k_scan_warps");
@@ -799,6 +778,9 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     p.heads = d_heads;
     p.heads_cap = heads_cap;
     p.tile_base = d_tbase;
+    p.cm_arr = d_cm;
+    p.ls_arr = d_ls;
+    p.nwords = nwords;
     // tiles whose whole window [tile*P_TILE - P_PRE, +P_BUF) lies inside the text travel by bulk copy: tiles 1 .. bulk_tiles
     p.bulk_tiles = nbytes_raw >= (uint64_t)(P_TILE + P_POST) ? (uint32_t)((nbytes_raw - P_TILE - P_POST) / P_TILE) : 0u;
     prof_begin(ctx, "k_parse");
@@ -819,6 +801,8 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     BK_CUDA(ctx, cudaMemcpyAsync(heads_pre, d_heads, kHeadsInline * sizeof(HeadRec), cudaMemcpyDeviceToHost, ctx->stream));
     BK_TRY(read_scratch(ctx));
     dfree(ctx, d_tbase);
+    dfree(ctx, d_cm);
+    dfree(ctx, d_ls);
     const uint64_t* h = ctx->h_scratch;
     if (h[SC_ERR_CODE]) {
       int code = (int)h[SC_ERR_CODE];

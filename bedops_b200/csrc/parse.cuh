@@ -35,6 +35,9 @@ struct ParseParams {
   const uint64_t* tile_base;     // [ntiles] first row of every tile (pass 1: warp-range base + prefix inside the range)
   uint32_t    ntiles;
   uint32_t    bulk_tiles;        // tiles 1..bulk_tiles have their whole window inside the text (staged by cp.async.bulk)
+  const uint32_t* cm_arr;        // pass 1: packed control-byte mask, one word per 32 text bytes
+  const uint32_t* ls_arr;        // pass 1: packed line-start mask (rows only: blank and header lines already dropped)
+  uint64_t    nwords;            // words in each of the two arrays
   uint64_t*   scratch;
   HeadRec*    heads;
   uint32_t    heads_cap;
