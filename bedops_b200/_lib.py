@@ -113,6 +113,7 @@ def load_library() -> C.CDLL:
         "bk_unstarch": (i, [vp, C.c_char_p, C.c_size_t, C.c_char_p, i, C.POINTER(_Text)]),
         "bk_starch_inflate_host": (i, [C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         "bk_host_free": (None, [vp]),
+        "bk_radix_sort_pairs": (i, [vp, vp, vp, u64, i]),
         "bk_bed_pad": (i, [vp, vp, C.c_longlong, C.c_longlong, C.POINTER(vp)]),
         "bk_sort_bed": (i, [vp, C.c_char_p, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
         "bk_sort_bed_device": (i, [vp, vp, C.c_size_t, i, C.POINTER(_Text), C.POINTER(u64)]),
@@ -133,7 +134,7 @@ EXPORTS = ["bk_init", "bk_destroy", "bk_set_stream", "bk_sync", "bk_strerror", "
            "bk_cut_offset", "bk_bed_reach_start", "bk_bed_chrom_max_end", "bk_bed_concat", "bk_shard_plan_make",
            "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_shard_free", "bk_shard_bytes_in", "bk_sort_bed",
            "bk_sort_bed_device", "bk_bed_pad", "bk_is_starch", "bk_unstarch", "bk_starch_inflate_host",
-           "bk_host_free"]
+           "bk_host_free", "bk_radix_sort_pairs"]
 
 
 class Bed:
@@ -349,6 +350,10 @@ class BedKit:
         self._chk(self.lib.bk_chop(self.ctx, arr, len(files), chunk, stagger, int(exclude_short), chrom, int(on_device),
                                    C.byref(t)))
         return self._take(t, on_device)
+
+    def radix_sort_pairs(self, d_keys: int, d_vals: Optional[int], n: int, nbits: int):
+        """stable radix sort of device arrays (u64 keys, optional u32 values) by key bits [0, nbits)"""
+        self._chk(self.lib.bk_radix_sort_pairs(self.ctx, d_keys, d_vals, n, nbits))
 
     def unstarch(self, archive: bytes, chrom: Optional[bytes] = None, on_device: bool = False):
         """a Starch v2 archive -> the BED text `unstarch` prints"""

@@ -580,6 +580,28 @@ int sort_bed_device(bk_ctx* ctx, const char* d_text, uint64_t nbytes, int on_dev
 
 using namespace bk;
 
+// the radix sort by itself on caller-owned device arrays (tests; hosts that need an order the input does not have)
+extern "C" int bk_radix_sort_pairs(bk_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, int nbits) {
+  bk::DeviceGuard device_guard(ctx);
+  if (!ctx || !d_keys || nbits < 1 || nbits > 64) return BK_ERR_ARG;
+  ctx->last_error.clear();
+  if (n < 2) return BK_OK;
+  uint64_t* k2 = dalloc<uint64_t>(ctx, n);
+  uint32_t* v2 = d_vals ? dalloc<uint32_t>(ctx, n) : nullptr;
+  if (!k2 || (d_vals && !v2)) return BK_ERR_NOMEM;
+  uint64_t *ka = d_keys, *kb = k2;
+  uint32_t *va = d_vals, *vb = v2;
+  int       rc = radix_sort_pairs(ctx, &ka, d_vals ? &va : nullptr, &kb, d_vals ? &vb : nullptr, n, nbits);
+  if (rc == BK_OK && ka != d_keys) {  // an odd number of passes left the result in the scratch pair
+    if (cudaMemcpyAsync(d_keys, ka, n * 8, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = BK_ERR_CUDA;
+    if (d_vals && cudaMemcpyAsync(d_vals, va, n * 4, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = BK_ERR_CUDA;
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = BK_ERR_CUDA;
+  dfree(ctx, k2);
+  dfree(ctx, v2);
+  return rc;
+}
+
 extern "C" int bk_sort_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int out_on_device, bk_text* out,
                                   uint64_t* bad_offset) {
   bk::DeviceGuard device_guard(ctx);

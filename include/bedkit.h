@@ -266,6 +266,9 @@ void bk_host_free(void* p);
 int bk_sort_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, int out_on_device, bk_text* out, uint64_t* bad_offset);
 int bk_sort_bed_device(bk_ctx* ctx, const char* dev_text, size_t nbytes, int out_on_device, bk_text* out,
                        uint64_t* bad_offset);
+/* the sorter's engine by itself: stable least-significant-digit radix sort of n (u64 key, u32 value) pairs in device
+ * memory by key bits [0, 8 * ceil(nbits / 8)) -- whole 8-bit passes --, in place from the caller's point of view (d_vals may be NULL) */
+int bk_radix_sort_pairs(bk_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, uint64_t n, int nbits);
 
 /* ---- BED writer used by the synthetic-input generator and tests -------------------------------------------- */
 /* format n rows "chrom\tstart\tend[\tid<k>\tscore]\n" from device SoA arrays (one chromosome name per call);

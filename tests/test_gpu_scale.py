@@ -423,6 +423,7 @@ def test_sort_bed_100M_rows_chromosome_blocks_reversed(env):
         shuffled[at:at + b1 - b0] = f.buf[b0:b1]
         at += b1 - b0
     assert at == f.nbytes
+    torch.cuda.synchronize()   # torch filled the buffer on its own stream; the library works on the context's stream
     out = kit.sort_bed_device(shuffled.data_ptr(), f.nbytes, on_device=True)
     assert out.nbytes == f.nbytes and out.rows == f.rows
     txt = device_text_to_tensor(kit, torch, out)

@@ -224,3 +224,35 @@ def test_million_shuffled_rows_against_reference_binary(tmp_path):
     ref = subprocess.run([os.path.join(REFBIN, "sort-bed"), "s.bed"], cwd=tmp_path, capture_output=True)
     assert ours.returncode == 0 and ours.stderr == b""
     assert ours.stdout == ref.stdout
+
+
+@pytest.mark.gpu
+def test_radix_sort_against_torch(kit):
+    """the sorter's engine by itself: random keys of every width against torch's stable sort, keys only and with payload;
+    sizes that leave partial tiles and sub-tiles, skewed digits (all equal, two values), 30 M keys for many tiles per CTA"""
+    import torch
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(5)
+    for n, nbits in [(2, 1), (33, 8), (2048, 16), (2049, 9), (16384, 64), (16385, 40), (100_003, 50), (1_000_000, 53), (30_000_000, 50)]:
+        hi = (1 << min(nbits, 62)) - 1
+        keys = torch.randint(0, hi + 1, (n,), device="cuda:0", dtype=torch.int64, generator=g)
+        width = 8 * ((nbits + 7) // 8)          # whole 8-bit passes: the sort orders by key bits [0, width)
+        if width <= 52:
+            junk = torch.randint(0, 1 << 10, (n,), device="cuda:0", dtype=torch.int64, generator=g) << width   # bits the sort must ignore
+            keys = keys | junk
+        for skew in (0, 1, 2):
+            k = keys.clone()
+            if skew == 1:
+                k[:] = k[0]
+            elif skew == 2:
+                k = torch.where(torch.arange(n, device="cuda:0") % 3 == 0, k[0], k[n // 2])
+            vals = torch.arange(n, device="cuda:0", dtype=torch.int32)
+            order = torch.sort(k & ((1 << width) - 1) if width < 63 else k, stable=True).indices
+            torch.cuda.synchronize()
+            kk, vv = k.clone(), vals.clone()
+            kit.radix_sort_pairs(kk.data_ptr(), vv.data_ptr(), n, nbits)
+            assert torch.equal(vv.long(), order), (n, nbits, skew)
+            assert torch.equal(kk, k[order]), (n, nbits, skew)
+            k2 = k.clone()
+            kit.radix_sort_pairs(k2.data_ptr(), None, n, nbits)
+            assert torch.equal(k2, k[order]), (n, nbits, skew)
