@@ -233,6 +233,7 @@ void usage(FILE* f) { std::fputs(kUsageBedmap, f); }  // byte for byte the refer
 
 int main(int argc, char** argv) {
   try {
+    cli::trace_lap("start");
     Options o = parse_args(argc, argv);
     if (!o.unsupported_op.empty())
       throw UserError("--" + o.unsupported_op + " is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
@@ -299,7 +300,9 @@ int main(int argc, char** argv) {
     if (gpus > 1 && o.num_files == 2 && o.chrom == "all" && !row_ids && !element_ops &&
         cli::run_range_sharded_bedmap(rtext, mtext, 3, ref_cols, o.min_map_fields, map_cols, spec, gpus))
       return EXIT_SUCCESS;
+    cli::trace_lap("inputs mapped");
     cli::Engine eng;
+    cli::trace_lap("bk_init done");
     bk_text     out;
     int         rc;
     if (o.num_files == 2) {
@@ -316,9 +319,12 @@ int main(int argc, char** argv) {
       eng.raise(rc);
     }
     if (rc != BK_OK) eng.raise(rc);
+    cli::trace_lap("result on the host");
     cli::write_all(out.ptr, out.len);  // pinned result buffer -> stdout, no intermediate copy
-    bk_free_text(eng.ctx, &out);
-    return EXIT_SUCCESS;
+    cli::trace_lap("written");
+    rtext.settle();
+    mtext.settle();
+    cli::finish_now(EXIT_SUCCESS);
   } catch (const Help&) {
     cli::banner(stdout, "bedmap");
     usage(stdout);

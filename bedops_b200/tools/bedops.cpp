@@ -330,6 +330,8 @@ int main(int argc, char** argv) {
       for (auto& t : texts) sl.push_back(cli::Slice{t.data, t.size});
       std::string text = run_one(eng, sl);
       cli::write_all(text.data(), text.size());
+      for (auto& t : texts) t.settle();
+      cli::finish_now(EXIT_SUCCESS);
     }
     return EXIT_SUCCESS;
   } catch (const Help& h) {

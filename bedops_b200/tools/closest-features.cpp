@@ -109,6 +109,9 @@ int main(int argc, char** argv) {
       cli::Engine eng;
       std::string text = run_one(eng, {cli::Slice{rtext.data, rtext.size}, cli::Slice{qtext.data, qtext.size}});
       cli::write_all(text.data(), text.size());
+      rtext.settle();
+      qtext.settle();
+      cli::finish_now(EXIT_SUCCESS);
     }
     return EXIT_SUCCESS;
   } catch (const Help&) {

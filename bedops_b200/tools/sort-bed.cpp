@@ -293,8 +293,8 @@ int main(int argc, char** argv) {
       return EXIT_FAILURE;
     }
     cli::write_all(out.ptr ? out.ptr : "", out.len);
-    bk_free_text(eng.ctx, &out);
-    return EXIT_SUCCESS;
+    for (auto& in : inputs) in->settle();
+    cli::finish_now(EXIT_SUCCESS);
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());
   }
