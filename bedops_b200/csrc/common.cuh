@@ -189,6 +189,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                "r"(bytes), "r"(b)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // release.cta: the arriving thread's earlier writes are visible to waiters
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
   asm volatile(

@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(CR_THREADS) k_count_rows(const unsigned char* 
       // the packed control-byte mask and the final line-start mask of these 32 bytes, for pass 2 (one bit per text byte
       // each: 1/4 of the text size written here and read there, instead of building both masks twice)
       if (p0 < nbytes_raw) {
-        cm_arr[p0 >> 5] = cm;
-        ls_arr[p0 >> 5] = smask;
+        __stcs(&cm_arr[p0 >> 5], cm);  // streaming stores: written once here, read once by pass 2
+        __stcs(&ls_arr[p0 >> 5], smask);
       }
     }
     run += __reduce_add_sync(0xffffffffu, cnt);
@@ -332,6 +332,167 @@ __device__ __forceinline__ uint32_t parse_digits_short(const unsigned char* sm, 
   const uint32_t m0 = len >= 4 ? 0u : (0xFFFFFFFFu >> (8 * len));  // the bytes in front of the field become '0'
   g0 = (g0 & ~m0) | (0x30303030u & m0);
   return digits4(g0, bad);
+}
+
+// ---- one line of a staged tile -----------------------------------------------------------------------------------
+// What a tile offers the thread that parses line i: the staged text window, the control-byte mask of [PRE, PRE+TILE+POST),
+// the line-start mask of [0, PRE+TILE) (rows only), the window index of line i (q0) and of line i-1 (prev_q0, -1 for the
+// tile's first line), the tile's first row.
+struct TileView {
+  const unsigned char* sm;
+  const uint32_t*      ctlp;
+  const uint32_t*      lsw;
+  int64_t              g0;
+  uint64_t             base;
+};
+template <int NSEP, bool WANT_SCORE>
+__device__ __forceinline__ void parse_tile_line(const ParseParams& p, const TileView& tv, const Cursor& cur, uint32_t i, int q0, int prev_q0) {
+  const unsigned char* const sm = tv.sm;
+  const uint32_t* const      ctlp = tv.ctlp;
+  const uint32_t* const      lsw = tv.lsw;
+  const int64_t              g0 = tv.g0;
+  const uint64_t             base = tv.base;
+  uint32_t  v_start = 0, v_end = 0, v_id = 0;
+  double    v_score = 0.0;
+  int       tok0 = q0, toklen = 0, err = 0;
+  uint32_t  linelen = 0xFFFFu;  // bytes up to the NL when the line is canonical (echo = verbatim copy), else 0xFFFF
+  bool      head = false;
+  // 64 line bytes of control-byte mask, starting at the line start
+  const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
+  const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
+  uint32_t Wlo = __funnelshift_r(c0, c1, sh), Whi = __funnelshift_r(c1, c2, sh);  // bytes 0..31 / 32..63 of the line
+  int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
+  bool fast = true;
+#pragma unroll
+  for (int f = 0; f < NSEP; f++) {
+    if (Wlo) {
+      sp[f] = __ffs(Wlo) - 1;
+      Wlo &= Wlo - 1;
+    } else {
+      fast = fast && Whi != 0;
+      sp[f] = 31 + __ffs(Whi);
+      Whi &= Whi - 1;
+    }
+  }
+  uint32_t bad = 0;
+  if (fast) {
+    // every separator but the last must be a TAB, the last a TAB or the NL
+#pragma unroll
+    for (int f = 0; f < NSEP; f++) {
+      const unsigned char c = sm[q0 + sp[f]];
+      bad |= (c == '\t' || (f + 1 == NSEP && c == '\n')) ? 0u : 1u;
+    }
+    toklen = sp[0];
+    const int l1 = sp[1] - sp[0] - 1, l2 = sp[2] - sp[1] - 1;
+    bad |= (toklen < 1 || toklen > 127 || l1 < 1 || l1 > 9 || l2 < 1 || l2 > 9) ? 1u : 0u;
+    if (!bad) {
+      v_start = parse_digits_swar(sm, q0 + sp[1], l1, bad);
+      v_end = parse_digits_swar(sm, q0 + sp[2], l2, bad);
+    }
+    if (NSEP >= 4) {
+      const int idlen = sp[NSEP >= 4 ? 3 : 0] - sp[2] - 1;
+      bad |= (idlen < 1 || idlen > 16383) ? 1u : 0u;
+      v_id = ((uint32_t)(sp[2] + 1) << 16) | (uint32_t)idlen;
+    }
+    if (NSEP >= 5) {
+      const int s3 = sp[NSEP >= 5 ? 3 : 0], s4 = sp[NSEP >= 5 ? 4 : 0];
+      const int l4 = s4 - s3 - 1;
+      bad |= l4 < 1 ? 1u : 0u;
+      if (WANT_SCORE && !bad) {
+        uint32_t sbad = l4 > 9 ? 1u : 0u;
+        if (l4 <= 4) v_score = (double)parse_digits_short(sm, q0 + s4, l4, sbad);
+        else if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
+        if (sbad) bad |= parse_score_slow(sm, q0 + s3 + 1, v_score) ? 1u : 0u;  // exact strtod on the field
+      }
+    }
+    fast = bad == 0;
+    if (fast && p.line_off) {
+      // canonical for echo: single TABs (checked above), no leading zeros -> re-printing the numbers reproduces the
+      // input bytes, so the whole line can be copied.  Find the NL among the remaining control bytes.
+      int nlpos = -1;
+      if (sm[q0 + sp[NSEP - 1]] == '\n') nlpos = sp[NSEP - 1];
+      else {
+        unsigned long long W = ((unsigned long long)Whi << 32) | Wlo;  // the remaining control bytes
+        for (int it = 0; nlpos < 0 && W != 0 && it < 8; it++) {
+          const int r = __ffsll((long long)W) - 1;
+          if (sm[q0 + r] == '\n') nlpos = r;
+          W &= W - 1;
+        }
+      }
+      const bool lz = (sm[q0 + sp[0] + 1] == '0' && l1 > 1) || (sm[q0 + sp[1] + 1] == '0' && l2 > 1);
+      if (nlpos >= 0 && !lz) linelen = (uint32_t)nlpos;
+    }
+  }
+  if (!fast) {  // general path: fscanf-equivalent tokeniser (out of line: keeps the fast path's registers low)
+    RowOut r;
+    parse_line_slow(cur, q0, p.min_fields, p.cols, r);
+    err = r.err;
+    v_start = (uint32_t)r.start;
+    v_end = (uint32_t)r.end;
+    v_score = r.score;
+    v_id = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
+    tok0 = (int)r.tok0;
+    toklen = r.toklen;
+  }
+  const uint64_t row = base + i;
+  if (p.cols & BK_LOAD_SORTBED) {
+    // sort-bed reading: any chromosome order (no run heads), and a row this tokeniser does not take is left to the
+    // sorter's own validation (k_sort_validate re-reads every non-canonical row by sort-bed's grammar)
+    if (row < p.cap) {
+      const bool plain = fast && err == 0;
+      p.start[row] = plain ? v_start : 0u;
+      p.end[row] = plain ? v_end : 0u;
+      p.line_off[row] = ((uint64_t)(plain ? linelen : 0xFFFFu) << 48) | (uint64_t)(g0 + q0);
+      if (p.idspan) p.idspan[row] = plain ? (uint32_t)sp[2] : 0u;  // offset of the separator after the end coordinate
+    }
+    return;
+  }
+  if (err) {
+    dev_set_error(p.scratch, err, row);
+    return;
+  }
+  // chromosome run head?  Compare the token with the previous row's: row i-1 of this tile starts at lstart[i-1];
+  // the row before the tile's first one starts after the last NL but one before q0 (NL mask of the head halo).
+  {
+    bool done = false;
+    if (toklen <= 8 && tok0 == q0) {
+      int ps = -1;
+      if (i > 0) ps = prev_q0;
+      else if (q0 >= 1) {  // the last line start in front of q0 (rows only: blank and header lines are not in the mask)
+        const int x = q0 - 1;
+        int       w = x >> 5;
+        uint32_t  pm = lsw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
+        while (!pm && w > 0) pm = lsw[--w];
+        if (pm) ps = 32 * w + 31 - __clz(pm);
+      }
+      if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
+        const uint2 t8 = token8(sm, q0, toklen), c = token8(sm, ps, toklen);
+        head = t8.x != c.x || t8.y != c.y || sm[ps + toklen] > 0x20;
+        done = true;
+      }
+    }
+    if (!done) {
+      int64_t pt = prev_line_token(cur, q0);
+      head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
+    }
+  }
+  if (head) {
+    uint32_t h = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_NHEADS]), 1ull);
+    if (h < p.heads_cap) {
+      HeadRec* hr = &p.heads[h];
+      hr->row = row;
+      hr->len = toklen;
+      for (int k = 0; k < toklen; k++) hr->name[k] = cur.at(tok0 + k);
+      hr->name[toklen] = 0;
+    }
+  }
+  if (row < p.cap) {
+    p.start[row] = v_start;
+    p.end[row] = v_end;
+    if (WANT_SCORE) p.score[row] = v_score;
+    if (p.line_off) p.line_off[row] = ((uint64_t)linelen << 48) | (uint64_t)(g0 + tok0);
+    if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
+  }
 }
 
 // NSEP = min_fields (3|4|5): separators a canonical line must have, one after each of the first min_fields fields.
@@ -454,150 +615,159 @@ __global__ void __launch_bounds__(P_THREADS, P_MINBLOCKS) k_parse(ParseParams p)
     // ---- [D] thread i parses line i ---------------------------------------------------------------------------
 #pragma unroll 1
     for (uint32_t i = tid; i < nl; i += P_THREADS) {
-      const int q0 = lstart[i];
-      uint32_t  v_start = 0, v_end = 0, v_id = 0;
-      double    v_score = 0.0;
-      int       tok0 = q0, toklen = 0, err = 0;
-      uint32_t  linelen = 0xFFFFu;  // bytes up to the NL when the line is canonical (echo = verbatim copy), else 0xFFFF
-      bool      head = false;
-      // 64 line bytes of control-byte mask, starting at the line start
-      const int      b0 = q0 - P_PRE, w0 = b0 >> 5, sh = b0 & 31;
-      const uint32_t c0 = ctlp[w0], c1 = ctlp[w0 + 1], c2 = ctlp[w0 + 2];
-      uint32_t Wlo = __funnelshift_r(c0, c1, sh), Whi = __funnelshift_r(c1, c2, sh);  // bytes 0..31 / 32..63 of the line
-      int  sp[NSEP];  // offsets (from q0) of the control bytes that end the first NSEP fields
-      bool fast = true;
-#pragma unroll
-      for (int f = 0; f < NSEP; f++) {
-        if (Wlo) {
-          sp[f] = __ffs(Wlo) - 1;
-          Wlo &= Wlo - 1;
-        } else {
-          fast = fast && Whi != 0;
-          sp[f] = 31 + __ffs(Whi);
-          Whi &= Whi - 1;
-        }
-      }
-      uint32_t bad = 0;
-      if (fast) {
-        // every separator but the last must be a TAB, the last a TAB or the NL
-#pragma unroll
-        for (int f = 0; f < NSEP; f++) {
-          const unsigned char c = sm[q0 + sp[f]];
-          bad |= (c == '\t' || (f + 1 == NSEP && c == '\n')) ? 0u : 1u;
-        }
-        toklen = sp[0];
-        const int l1 = sp[1] - sp[0] - 1, l2 = sp[2] - sp[1] - 1;
-        bad |= (toklen < 1 || toklen > 127 || l1 < 1 || l1 > 9 || l2 < 1 || l2 > 9) ? 1u : 0u;
-        if (!bad) {
-          v_start = parse_digits_swar(sm, q0 + sp[1], l1, bad);
-          v_end = parse_digits_swar(sm, q0 + sp[2], l2, bad);
-        }
-        if (NSEP >= 4) {
-          const int idlen = sp[NSEP >= 4 ? 3 : 0] - sp[2] - 1;
-          bad |= (idlen < 1 || idlen > 16383) ? 1u : 0u;
-          v_id = ((uint32_t)(sp[2] + 1) << 16) | (uint32_t)idlen;
-        }
-        if (NSEP >= 5) {
-          const int s3 = sp[NSEP >= 5 ? 3 : 0], s4 = sp[NSEP >= 5 ? 4 : 0];
-          const int l4 = s4 - s3 - 1;
-          bad |= l4 < 1 ? 1u : 0u;
-          if (WANT_SCORE && !bad) {
-            uint32_t sbad = l4 > 9 ? 1u : 0u;
-            if (l4 <= 4) v_score = (double)parse_digits_short(sm, q0 + s4, l4, sbad);
-            else if (!sbad) v_score = (double)parse_digits_swar(sm, q0 + s4, l4, sbad);
-            if (sbad) bad |= parse_score_slow(sm, q0 + s3 + 1, v_score) ? 1u : 0u;  // exact strtod on the field
-          }
-        }
-        fast = bad == 0;
-        if (fast && p.line_off) {
-          // canonical for echo: single TABs (checked above), no leading zeros -> re-printing the numbers reproduces the
-          // input bytes, so the whole line can be copied.  Find the NL among the remaining control bytes.
-          int nlpos = -1;
-          if (sm[q0 + sp[NSEP - 1]] == '\n') nlpos = sp[NSEP - 1];
-          else {
-            unsigned long long W = ((unsigned long long)Whi << 32) | Wlo;  // the remaining control bytes
-            for (int it = 0; nlpos < 0 && W != 0 && it < 8; it++) {
-              const int r = __ffsll((long long)W) - 1;
-              if (sm[q0 + r] == '\n') nlpos = r;
-              W &= W - 1;
-            }
-          }
-          const bool lz = (sm[q0 + sp[0] + 1] == '0' && l1 > 1) || (sm[q0 + sp[1] + 1] == '0' && l2 > 1);
-          if (nlpos >= 0 && !lz) linelen = (uint32_t)nlpos;
-        }
-      }
-      if (!fast) {  // general path: fscanf-equivalent tokeniser (out of line: keeps the fast path's registers low)
-        RowOut r;
-        parse_line_slow(cur, q0, p.min_fields, p.cols, r);
-        err = r.err;
-        v_start = (uint32_t)r.start;
-        v_end = (uint32_t)r.end;
-        v_score = r.score;
-        v_id = ((uint32_t)(r.id0 - r.tok0) << 16) | (uint32_t)r.idlen;
-        tok0 = (int)r.tok0;
-        toklen = r.toklen;
-      }
-      const uint64_t row = base + i;
-      if (p.cols & BK_LOAD_SORTBED) {
-        // sort-bed reading: any chromosome order (no run heads), and a row this tokeniser does not take is left to the
-        // sorter's own validation (k_sort_validate re-reads every non-canonical row by sort-bed's grammar)
-        if (row < p.cap) {
-          const bool plain = fast && err == 0;
-          p.start[row] = plain ? v_start : 0u;
-          p.end[row] = plain ? v_end : 0u;
-          p.line_off[row] = ((uint64_t)(plain ? linelen : 0xFFFFu) << 48) | (uint64_t)(g0 + q0);
-          if (p.idspan) p.idspan[row] = plain ? (uint32_t)sp[2] : 0u;  // offset of the separator after the end coordinate
-        }
-        continue;
-      }
-      if (err) {
-        dev_set_error(p.scratch, err, row);
-        continue;
-      }
-      // chromosome run head?  Compare the token with the previous row's: row i-1 of this tile starts at lstart[i-1];
-      // the row before the tile's first one starts after the last NL but one before q0 (NL mask of the head halo).
-      {
-        bool done = false;
-        if (toklen <= 8 && tok0 == q0) {
-          int ps = -1;
-          if (i > 0) ps = lstart[i - 1];
-          else if (q0 >= 1) {  // the last line start in front of q0 (rows only: blank and header lines are not in the mask)
-            const int x = q0 - 1;
-            int       w = x >> 5;
-            uint32_t  pm = lsw[w] & (0xFFFFFFFFu >> (31 - (x & 31)));
-            while (!pm && w > 0) pm = lsw[--w];
-            if (pm) ps = 32 * w + 31 - __clz(pm);
-          }
-          if (ps >= 0 && ps + toklen < q0 && sm[ps] > 0x20) {
-            const uint2 t8 = token8(sm, q0, toklen), c = token8(sm, ps, toklen);
-            head = t8.x != c.x || t8.y != c.y || sm[ps + toklen] > 0x20;
-            done = true;
-          }
-        }
-        if (!done) {
-          int64_t pt = prev_line_token(cur, q0);
-          head = (pt == INT64_MIN) || !same_token(cur, tok0, toklen, pt);
-        }
-      }
-      if (head) {
-        uint32_t h = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(&p.scratch[SC_NHEADS]), 1ull);
-        if (h < p.heads_cap) {
-          HeadRec* hr = &p.heads[h];
-          hr->row = row;
-          hr->len = toklen;
-          for (int k = 0; k < toklen; k++) hr->name[k] = cur.at(tok0 + k);
-          hr->name[toklen] = 0;
-        }
-      }
-      if (row < p.cap) {
-        p.start[row] = v_start;
-        p.end[row] = v_end;
-        if (WANT_SCORE) p.score[row] = v_score;
-        if (p.line_off) p.line_off[row] = ((uint64_t)linelen << 48) | (uint64_t)(g0 + tok0);
-        if (NSEP >= 4 && p.idspan) p.idspan[row] = v_id;
-      }
+      const TileView tv{sm, ctlp, lsw, g0, base};
+      parse_tile_line<NSEP, WANT_SCORE>(p, tv, cur, i, lstart[i], i ? (int)lstart[i - 1] : -1);
     }
     // no barrier here: [S2] of the next tile is the point where every thread has left this tile's [D]
+  }
+}
+
+// ---- pass 2, warp-specialised form ---------------------------------------------------------------------------------
+// The same tiles and the same per-line work as k_parse, without block barriers: warp 0 PRODUCES a tile (issues the bulk
+// copy of its text, loads the two masks of pass 1, turns the line-start mask into the list of line starts), warps 1..7
+// CONSUME it (thread c of 224 parses lines c, c+224, ...).  Two buffers; full[b] (producer -> consumers: masks and line
+// list ready), txt[b] (copy engine -> consumers: text landed), empty[b] (consumers -> producer: buffer free).  The producer
+// runs up to two tiles ahead, so the consumers find their next tile ready and never wait for one another.
+constexpr int WS_CONSUMERS = P_THREADS - 32;
+constexpr int WS_LSCAP = 1024;  // line starts listed per tile; a tile with more (lines of < 8 bytes) selects bits from the mask
+#ifndef BK_WS_MINBLOCKS
+#define BK_WS_MINBLOCKS 5  // 48 registers: no spills; measured 2.81 ms against 2.91 ms with 6 CTAs of 40 registers
+#endif
+template <int NSEP, bool WANT_SCORE>
+__global__ void __launch_bounds__(P_THREADS, BK_WS_MINBLOCKS) k_parse_ws(ParseParams p) {
+  __shared__ __align__(128) unsigned char smbuf[2][P_BUF + 16];
+  __shared__ uint32_t                     ctlp2[2][P_NW + 4];
+  __shared__ uint32_t                     lsw2[2][P_PRE / 32 + P_TILE / 32];
+  __shared__ uint16_t                     lstart2[2][WS_LSCAP];
+  __shared__ uint16_t                     wpre2[2][P_TILE / 32 + 1];  // line starts in front of every word of the tile
+  __shared__ uint32_t                     nl2[2];
+  __shared__ uint64_t                     base2[2];
+  __shared__ __align__(8) uint64_t        txt[2], full[2], empty[2];
+  const int            tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t       eff = p.scratch[SC_EFFLEN];
+  const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
+  auto bulkable = [&](uint32_t tile) { return tile - 1u < p.bulk_tiles; };
+  if (tid == 0) {
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&txt[b], 1);
+      mbar_init(&full[b], 1);
+      mbar_init(&empty[b], WS_CONSUMERS / 32);
+    }
+    mbar_init_fence();
+    if (p.line_off && blockIdx.x == 0) p.line_off[p.cap] = eff;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ---- producer ---------------------------------------------------------------------------------------------
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+      const int      b = it & 1;
+      const uint32_t use = it >> 1;
+      mbar_wait(&empty[b], (use & 1u) ^ 1u);  // the consumers have left the tile that used this buffer two tiles ago
+      unsigned char* const sm = smbuf[b];
+      if (bulkable(tile)) {
+        if (lane == 0) {
+          fence_proxy_async();
+          bulk_g2s(sm, text + ((int64_t)tile * P_TILE - P_PRE), P_BUF, &txt[b]);
+        }
+      } else {  // first / last tiles of the file: staged by this warp, zero-filled outside the text
+        const int64_t g0 = (int64_t)tile * P_TILE - P_PRE;
+        for (int v = lane; v < P_BUF / 16; v += 32) {
+          const int64_t g = g0 + (int64_t)v * 16;
+          uint32_t      w[4] = {0, 0, 0, 0};
+          if (g >= 0 && (uint64_t)g + 16 <= p.nbytes_raw) {
+            const uint4 q = *reinterpret_cast<const uint4*>(text + g);
+            w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+          } else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < p.nbytes_raw) {
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) {
+              const int64_t gi = g + i;
+              if (gi >= 0 && (uint64_t)gi < p.nbytes_raw) w[i >> 2] |= (uint32_t)text[gi] << (8 * (i & 3));
+            }
+          }
+          reinterpret_cast<uint4*>(sm)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      // masks of pass 1: lane L owns words 8L .. 8L+7 of the tile (word j covers window bytes [PRE+32j, PRE+32j+32))
+      uint32_t* const ctlp = ctlp2[b];
+      uint32_t* const lsw = lsw2[b];
+      const int64_t   w0g = (int64_t)tile * (P_TILE / 32) - P_PRE / 32;
+      uint32_t        ls[8];
+      uint32_t        cnt = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const int     j = lane * 8 + t;
+        const int64_t gw = w0g + P_PRE / 32 + j;
+        const bool    in = (uint64_t)gw < p.nwords;
+        ctlp[j] = in ? __ldg(&p.cm_arr[gw]) : 0xFFFFFFFFu;
+        ls[t] = in ? __ldg(&p.ls_arr[gw]) : 0u;
+        lsw[P_PRE / 32 + j] = ls[t];
+        cnt += __popc(ls[t]);
+      }
+      if (lane < P_PRE / 32) {
+        const int64_t g = w0g + lane;
+        lsw[lane] = (g >= 0 && (uint64_t)g < p.nwords) ? __ldg(&p.ls_arr[g]) : 0u;
+      } else if (lane < P_PRE / 32 + P_POST / 32) {
+        const int64_t g = w0g + P_PRE / 32 + P_TILE / 32 + (lane - P_PRE / 32);
+        ctlp[P_TILE / 32 + lane - P_PRE / 32] = (uint64_t)g < p.nwords ? __ldg(&p.cm_arr[g]) : 0xFFFFFFFFu;
+      } else if (lane < P_PRE / 32 + P_POST / 32 + 4) {
+        ctlp[P_TILE / 32 + P_POST / 32 + lane - (P_PRE / 32 + P_POST / 32)] = 0;
+      }
+      const uint32_t incl = warp_incl_scan(cnt);
+      uint32_t       ex = incl - cnt;
+      const uint32_t nl = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const int j = lane * 8 + t;
+        wpre2[b][j] = (uint16_t)ex;
+        for (uint32_t m = ls[t]; m; m &= m - 1) {
+          if (ex < (uint32_t)WS_LSCAP) lstart2[b][ex] = (uint16_t)(P_PRE + 32 * j + __ffs(m) - 1);
+          ex++;
+        }
+      }
+      if (lane == 31) wpre2[b][P_TILE / 32] = (uint16_t)ex;
+      if (lane == 0) {
+        nl2[b] = nl;
+        base2[b] = p.tile_base[tile];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[b]);
+    }
+    return;
+  }
+
+  // ---- consumers ------------------------------------------------------------------------------------------------
+  const uint32_t ctid = (uint32_t)tid - 32u;
+  uint32_t       it = 0, tphase = 0;  // tphase bit b: parity of the next completion of txt[b]
+  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+    const int      b = it & 1;
+    const uint32_t use = it >> 1;
+    mbar_wait(&full[b], use & 1u);
+    if (bulkable(tile)) {
+      mbar_wait(&txt[b], (tphase >> b) & 1u);
+      tphase ^= 1u << b;
+    }
+    const int64_t   g0 = (int64_t)tile * P_TILE - P_PRE;
+    const TileView  tv{smbuf[b], ctlp2[b], lsw2[b], g0, base2[b]};
+    const Cursor    cur{smbuf[b], g0, text, eff};
+    const uint32_t  nl = nl2[b];
+    const uint16_t* lst = lstart2[b];
+    auto start_of = [&](uint32_t i) -> int {  // window index of line i of the tile
+      if (nl <= (uint32_t)WS_LSCAP) return lst[i];
+      int lo = 0, hi = P_TILE / 32;  // last word with wpre <= i
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (wpre2[b][mid] <= i) lo = mid; else hi = mid;
+      }
+      uint32_t m = lsw2[b][P_PRE / 32 + lo];
+      for (uint32_t k = i - wpre2[b][lo]; k; k--) m &= m - 1;
+      return P_PRE + 32 * lo + __ffs(m) - 1;
+    };
+#pragma unroll 1
+    for (uint32_t i = ctid; i < nl; i += WS_CONSUMERS) parse_tile_line<NSEP, WANT_SCORE>(p, tv, cur, i, start_of(i), i ? start_of(i - 1) : -1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[b]);
   }
 }
 
@@ -786,8 +956,12 @@ int parse_bed(bk_ctx* ctx, bk_bed* bed, uint64_t nbytes_raw) {
     prof_begin(ctx, "k_parse");
     {
       const bool sc = (p.cols & BK_COL_SCORE) != 0;
-#define BK_PARSE(N, S) \
-  k_parse<N, S><<<grid_for(ctx, (const void*)k_parse<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p)
+      static const bool ws = getenv("BEDKIT_PARSE_BLOCK") == nullptr;  // BEDKIT_PARSE_BLOCK=1: the block-barrier form (A/B measurements)
+#define BK_PARSE(N, S)                                                                                                        \
+  do {                                                                                                                        \
+    if (ws) k_parse_ws<N, S><<<grid_for(ctx, (const void*)k_parse_ws<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p); \
+    else k_parse<N, S><<<grid_for(ctx, (const void*)k_parse<N, S>, P_THREADS, p.ntiles), P_THREADS, 0, ctx->stream>>>(p);          \
+  } while (0)
       if (p.min_fields == 3) BK_PARSE(3, false);
       else if (p.min_fields == 4) BK_PARSE(4, false);
       else if (sc) BK_PARSE(5, true);
