@@ -170,6 +170,25 @@ int upload(bk_ctx* ctx, char* d_dst, const char* src, size_t n, cudaStream_t st)
   return BK_OK;
 }
 
+int upload_params(bk_ctx* ctx, void* d_dst, const void* src, size_t n) {
+  if (n == 0) return BK_OK;
+  const size_t need = (n + 63) & ~(size_t)63;
+  if (!ctx->h_params || need > kParamRing) {  // no ring (allocation failed) or a table larger than it: the plain way
+    BK_CUDA(ctx, cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BK_OK;
+  }
+  if (ctx->h_params_used + need > kParamRing) {  // earlier tables may still be in flight: drain, then start over
+    BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->h_params_used = 0;
+  }
+  char* h = ctx->h_params + ctx->h_params_used;
+  memcpy(h, src, n);
+  ctx->h_params_used += need;
+  BK_CUDA(ctx, cudaMemcpyAsync(d_dst, h, n, cudaMemcpyHostToDevice, ctx->stream));
+  return BK_OK;
+}
+
 static cudaEvent_t prof_event(bk_ctx* ctx) {
   if (!ctx->prof_free.empty()) {
     cudaEvent_t e = ctx->prof_free.back();
@@ -266,6 +285,10 @@ extern "C" int bk_init(bk_ctx** out, int device) {
     bk_destroy(ctx);
     return BK_ERR_NOMEM;
   }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_params), kParamRing, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    ctx->h_params = nullptr;  // upload_params falls back to synchronous copies
+  }
   *out = ctx;
   return BK_OK;
 }
@@ -288,6 +311,7 @@ extern "C" void bk_destroy(bk_ctx* ctx) {
   }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+  if (ctx->h_params) cudaFreeHost(ctx->h_params);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

@@ -1112,7 +1112,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   tab.insert(tab.end(), rrb.begin(), rrb.end());
   tab.insert(tab.end(), rmb.begin(), rmb.end());
   tab.insert(tab.end(), rme.begin(), rme.end());
-  BK_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  BK_TRY(upload_params(ctx, d_tab, tab.data(), tab.size() * 8));
 
   MapStatsParams sp{};
   sp.rs = ref->start; sp.re = ref->end; sp.row0 = row0; sp.n = n;
@@ -1154,8 +1154,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     prof_end(ctx);
     BK_LAUNCHED(ctx);
   }
-  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host table `tab` must outlive its copy
-  dfree(ctx, d_tab);
+  dfree(ctx, d_tab);  // stream-ordered reuse; the table went through the pinned ring
 
 
   const uint64_t dl = strlen(delim);

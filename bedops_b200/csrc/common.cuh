@@ -36,6 +36,10 @@ struct bk_ctx {
   // small device scratch reused by every call: error record, counters
   uint64_t* d_scratch = nullptr;  // 64 x u64
   uint64_t* h_scratch = nullptr;  // pinned mirror
+  // pinned ring for the small host tables a call hands to its kernels (chromosome run tables ...): a copy out of it is truly
+  // asynchronous (a copy from pageable memory first waits for the stream) and the table need not outlive the call
+  char*  h_params = nullptr;
+  size_t h_params_used = 0;
   // pinned host staging pool (result text / input upload)
   struct Pinned {
     char*  ptr;
@@ -108,6 +112,10 @@ void  dfree(bk_ctx* ctx, void* p);
 // threads, so that the copy runs at PCIe speed rather than at one core's page-fault-and-memcpy speed.  Returns after
 // the last chunk has been QUEUED (the source may be reused once the stream reaches that point -- callers sync).
 int   upload(bk_ctx* ctx, char* d_dst, const char* src, size_t n, cudaStream_t st);
+constexpr size_t kParamRing = 256 << 10;
+// device copy of a small host table, queued on the ctx stream without any synchronisation (through the pinned ring; tables
+// that do not fit wait for the stream and restart the ring)
+int   upload_params(bk_ctx* ctx, void* d_dst, const void* src, size_t n);
 char* pinned_get(bk_ctx* ctx, size_t bytes);
 void  pinned_put(bk_ctx* ctx, char* p);
 

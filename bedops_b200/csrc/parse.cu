@@ -1033,7 +1033,7 @@ int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, c
   PmRun*    d_runs = dalloc<PmRun>(ctx, pr.size());
   uint32_t* d_rmax = dalloc<uint32_t>(ctx, nranges);
   if (!d_runs || !d_rmax) return BK_ERR_NOMEM;
-  BK_CUDA(ctx, cudaMemcpyAsync(d_runs, pr.data(), pr.size() * sizeof(PmRun), cudaMemcpyHostToDevice, ctx->stream));
+  BK_TRY(upload_params(ctx, d_runs, pr.data(), pr.size() * sizeof(PmRun)));
   const uint64_t want = (nranges + PM_THREADS / 32 - 1) / (PM_THREADS / 32);
   const uint32_t ga = (uint32_t)std::min<uint64_t>(want, (uint64_t)grid_for(ctx, (const void*)k_pmax_reduce, PM_THREADS, 0xFFFFFFFFu));
   const uint32_t gb = (uint32_t)std::min<uint64_t>(want, (uint64_t)grid_for(ctx, (const void*)k_pmax, PM_THREADS, 0xFFFFFFFFu));
@@ -1045,8 +1045,7 @@ int seg_prefix_max(bk_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, c
   k_pmax<<<gb, PM_THREADS, 0, ctx->stream>>>(in, out, d_runs, (int)pr.size(), nranges, d_rmax);
   prof_end(ctx);
   BK_LAUNCHED(ctx);
-  BK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pr (host vector) must outlive the copy
-  dfree(ctx, d_runs);
+  dfree(ctx, d_runs);  // stream-ordered reuse; the table went through the pinned ring
   dfree(ctx, d_rmax);
   return BK_OK;
 }
