@@ -61,6 +61,7 @@ struct MapStatsParams {
   const uint32_t* bmax;  // max end per 32-row block of the map file (global row index / 32)
   const double*   score;
   const uint32_t* idspan;
+  uint64_t        map_rows;  // rows of the whole map file (k_map_group clamps its column loads to it)
   OverlapSpec     ov;
   unsigned        need;
   uint32_t        mdelim_len;
@@ -300,6 +301,289 @@ __global__ void __launch_bounds__(MS_THREADS) k_map_stats(MapStatsParams p) {
         p.idbytes[i] = out_idb;
       }
     }
+  }
+}
+
+// ---- lane-per-row form ---------------------------------------------------------------------------------------------
+// The same windows reduced without any cross-lane reduction: a lane OWNS one reference row, and the eight lanes of a group
+// (eight consecutive reference rows, whose windows overlap almost completely: rows are sorted) walk the union of their
+// windows together.  The group stages 64 map rows at a time in its own 1 KB of shared memory (coalesced column loads, start
+// and end interleaved), then every lane tests the same staged row against its own reference row: the shared-memory reads
+// are broadcasts (four distinct 16-byte addresses per warp instruction, the groups' buffers are skewed by 16 banks), a hit
+// costs a predicated add, and each lane sums its hits in file order.  Per map row and lane ~12 instructions and no
+// shuffle; the warp-per-row kernel above spends ~270 warp instructions per reference row at configuration 2, this form
+// ~110 (a lane also tests the rows that only its neighbours' windows hold: 196 instead of 126 rows).
+// Rows in front of a lane's own lo never qualify (their end does not reach the reference row) but may belong to the
+// previous chromosome, so a lane looks at rows [glo, gend) only: a 64-bit mask per chunk.
+constexpr int MG_THREADS = 256;
+constexpr int MG_G = 8;    // lanes = reference rows per group
+constexpr int MG_CH = 64;  // map rows per staged chunk
+struct alignas(16) MgBuf {
+  uint2    se[MG_CH];  // (start, end)
+  double   sc[MG_CH];
+  uint32_t skew[16];   // group stride = 1088 bytes = 16 banks: the two groups of a half-warp touch disjoint banks (STS.64 and LDS.128)
+};
+
+__device__ __forceinline__ uint32_t group_min_u32(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < MG_G; d <<= 1) {
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, d);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+
+#ifndef BK_MG_COOP
+#define BK_MG_COOP 6  // at most this many unfinished lanes: their rows go to the whole warp (break-even ~14, see below)
+#endif
+
+// The phase in which every lane walks its group's chunks pays for the longest union among the four groups of the warp,
+// and window lengths are heavy-tailed (log-normal reference and map lengths: one 20 kb reference row keeps its group
+// busy for ten chunks while 31 lanes idle).  A chunk step costs ~1000 warp instructions whatever the number of lanes
+// that still need it, the warp-cooperative step of k_map_stats ~75 per reference row and 64 map rows: once no more than
+// BK_MG_COOP lanes are unfinished, the rest of each one's window is scanned by all 32 lanes (coalesced column loads, one
+// warp reduction per row) and added to the lane's sums.  Map row indices are 32-bit here (the caller checks the file).
+template <int KIND, unsigned FLAGS>
+__global__ void __launch_bounds__(MG_THREADS) k_map_group(MapStatsParams p) {
+  __shared__ MgBuf bufs[MG_THREADS / MG_G];
+  const int      lane = threadIdx.x & 31;
+  const int      l8 = lane & (MG_G - 1);
+  const unsigned gmask = ((1u << MG_G) - 1u) << (lane & ~(MG_G - 1));
+  MgBuf&         B = bufs[threadIdx.x / MG_G];
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * MG_THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * MG_THREADS) >> 5;
+  const uint64_t nbatch = (p.n + 31) >> 5;
+  OverlapSpec    ov = p.ov;
+  if (KIND >= 0) ov.kind = KIND;
+  const uint32_t pad = ov.kind == BK_OVR_RANGE ? ov.bp : 0;
+  const uint32_t bp1 = ov.bp > 1 ? ov.bp : 1;
+  constexpr bool kScore = (FLAGS & (NEED_SUM | NEED_MAX | NEED_MIN)) != 0;
+  constexpr bool kMinMax = (FLAGS & (NEED_MAX | NEED_MIN)) != 0;
+  const uint32_t last_row = (uint32_t)p.map_rows - 1u;
+  for (uint64_t batch = warp0; batch < nbatch; batch += nwarps) {
+    const uint64_t i = (batch << 5) + lane;
+    const bool     valid = i < p.n;
+    const uint64_t row = p.row0 + (valid ? i : p.n - 1);
+    const uint32_t rs = p.rs[row], re = p.re[row];
+    int my_run = 0;
+    {
+      int hi_r = p.nruns;
+      while (hi_r - my_run > 1) {
+        int mid = (my_run + hi_r) >> 1;
+        if (p.run_ref_begin[mid] <= row) my_run = mid; else hi_r = mid;
+      }
+    }
+    // window starts of the batch: as in k_map_stats
+    const int      nj = (int)((p.n - (batch << 5)) < 32 ? (p.n - (batch << 5)) : 32);
+    const uint32_t my_key = rs >= pad ? rs - pad + 1 : 0;
+    const uint32_t mbl = (uint32_t)p.run_map_begin[my_run];
+    const uint32_t gend = (uint32_t)p.run_map_end[my_run];
+    uint32_t       my_lo;
+    {
+      const int run_a = __shfl_sync(0xffffffffu, my_run, 0);
+      if (__all_sync(0xffffffffu, my_run == run_a)) {
+        const uint32_t  nr0 = gend - mbl;
+        const uint32_t* pm0 = p.pm + mbl;
+        const uint32_t  key_a = __shfl_sync(0xffffffffu, my_key, 0), key_b = __shfl_sync(0xffffffffu, my_key, nj - 1);
+        uint32_t        a = warp_search32(pm0, nr0, key_a, lane);
+        uint32_t        b = warp_gallop(pm0, a, nr0, key_b, lane, true);
+        while (a < b) {
+          const uint32_t mid = a + ((b - a) >> 1);
+          if (__ldg(&pm0[mid]) < my_key) a = mid + 1; else b = mid;
+        }
+        my_lo = a;
+      } else {
+        my_lo = (uint32_t)lower_bound_u32(p.pm + mbl, 0, gend - mbl, my_key);
+      }
+    }
+    const uint32_t glo = mbl + my_lo;
+    const uint64_t re_pad64 = (uint64_t)re + pad;
+    const uint32_t re_pad = re_pad64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)re_pad64;
+
+    uint32_t cnt = 0, idb = 0, nwin = 0;
+    uint64_t bases = 0;
+    double   sum = 0.0, vmax = 0.0, vmin = 0.0;
+    bool     have = false;
+    bool     fin = !valid || glo >= gend;
+    uint32_t c0 = group_min_u32(fin ? 0xFFFFFFFFu : glo) & ~7u;  // next chunk of my group (sector-aligned column loads)
+    unsigned live;
+    while (__popc(live = __ballot_sync(0xffffffffu, !fin)) > BK_MG_COOP) {
+      if (live & gmask) {  // stage map rows [c0, c0+64) of the columns; rows past the file repeat its last row (masked below)
+#pragma unroll
+        for (int r = 0; r < MG_CH / MG_G; r++) {
+          const uint32_t k = c0 + (uint32_t)(r * MG_G + l8);
+          const uint32_t idx = k < last_row ? k : last_row;
+          B.se[r * MG_G + l8] = make_uint2(__ldg(&p.ms[idx]), __ldg(&p.me[idx]));
+          if (kScore) B.sc[r * MG_G + l8] = __ldg(&p.score[idx]);
+        }
+      }
+      __syncwarp();
+      uint64_t wmask = 0;  // bit r: staged row c0+r is one of my rows [glo, gend)
+      if (!fin) {
+        const uint32_t a = glo > c0 ? (glo - c0 < 64u ? glo - c0 : 64u) : 0u;
+        const uint32_t b = gend - c0 < 64u ? gend - c0 : 64u;  // gend > c0: the lane is not finished
+        const uint64_t upto_b = b >= 64u ? ~0ull : ((1ull << b) - 1ull);
+        const uint64_t upto_a = a >= 64u ? ~0ull : ((1ull << a) - 1ull);
+        wmask = upto_b & ~upto_a;
+      }
+#pragma unroll 1
+      for (int j = 0; j < MG_CH / 8; j++) {
+        const uint32_t m8 = (uint32_t)(wmask >> (8 * j)) & 0xFFu;
+        if (!__any_sync(0xffffffffu, m8 != 0u)) continue;
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const uint4 se2 = *reinterpret_cast<const uint4*>(&B.se[8 * j + u]);
+          double2     v2 = make_double2(0.0, 0.0);
+          if (kScore) v2 = *reinterpret_cast<const double2*>(&B.sc[8 * j + u]);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const uint32_t s = h ? se2.z : se2.x, e = h ? se2.w : se2.y;
+            const double   v = h ? v2.y : v2.x;
+            const bool     mine = (m8 >> (u + h)) & 1u;
+            uint32_t       ovl;
+            bool           q;
+            if (KIND == BK_OVR_BP) {
+              const uint32_t mn = rs > s ? rs : s, mx = re < e ? re : e;
+              ovl = mx - (mn < mx ? mn : mx);
+              q = mine && ovl >= bp1;
+            } else {
+              q = mine && s < re_pad && qualifies(ov, rs, re, s, e, ovl);
+            }
+            if (q) {
+              cnt++;
+              if (FLAGS & NEED_BASES) bases += ovl;
+              if (kScore) {
+                sum += v;
+                if (kMinMax) {
+                  vmax = have ? (v > vmax ? v : vmax) : v;
+                  vmin = have ? (v < vmin ? v : vmin) : v;
+                  have = true;
+                }
+              }
+              if ((FLAGS & NEED_IDS) && p.idspan) idb += __ldg(&p.idspan[c0 + (uint32_t)(8 * j + u + h)]) & 0xFFFFu;
+            }
+            if (FLAGS & NEED_IDS) nwin += (mine && s < re_pad) ? 1u : 0u;
+          }
+        }
+      }
+      // a lane is finished when its chromosome is used up or the last staged row (one of its rows) starts at/after its end
+      const uint32_t s_last = B.se[MG_CH - 1].x;
+      const uint32_t c1 = c0 + MG_CH;
+      if (!fin && (c1 >= gend || (c1 > glo && s_last >= re_pad))) fin = true;
+      __syncwarp();  // everyone has read the chunk before the next one is staged
+      c0 = group_min_u32(fin ? 0xFFFFFFFFu : (glo > c1 ? glo & ~7u : c1));  // skips gaps (chromosome change, sparse windows)
+    }
+    // the stragglers, one after the other: rows [max(c0, glo), gend) of lane j's window by the whole warp, 64 rows per step
+    while (live) {
+      const int j = __ffs(live) - 1;
+      live &= live - 1;
+      const uint32_t rs_j = __shfl_sync(0xffffffffu, rs, j), re_j = __shfl_sync(0xffffffffu, re, j);
+      const uint32_t rp_j = __shfl_sync(0xffffffffu, re_pad, j), end_j = __shfl_sync(0xffffffffu, gend, j);
+      const uint32_t from_j = __shfl_sync(0xffffffffu, c0 > glo ? c0 : glo, j);
+      uint32_t       cnt2 = 0, idb2 = 0, nwin2 = 0;
+      uint64_t       bases2 = 0;
+      double         sum2 = 0.0, vmax2 = 0.0, vmin2 = 0.0;
+      bool           have2 = false;
+#pragma unroll 1
+      for (uint32_t k0 = from_j; k0 < end_j; k0 += 64) {
+        const uint32_t ka = k0 + lane, kb = ka + 32;
+        const bool     va = ka < end_j, vb = kb < end_j;
+        const uint32_t sa = va ? __ldg(&p.ms[ka]) : 0xFFFFFFFFu, sb = vb ? __ldg(&p.ms[kb]) : 0xFFFFFFFFu;
+        const uint32_t ea = va ? __ldg(&p.me[ka]) : 0u, eb = vb ? __ldg(&p.me[kb]) : 0u;
+        const bool     ina = sa < rp_j, inb = sb < rp_j;  // rp_j <= 0xFFFFFFFF: the sentinel is never in range
+        uint32_t       ova = 0, ovb = 0;
+        const bool     qa = ina && qualifies(ov, rs_j, re_j, sa, ea, ova);
+        const bool     qb = inb && qualifies(ov, rs_j, re_j, sb, eb, ovb);
+        if (qa) {
+          cnt2++;
+          if (FLAGS & NEED_BASES) bases2 += ova;
+          if (kScore) {
+            const double v = __ldg(&p.score[ka]);
+            sum2 += v;
+            if (kMinMax) {
+              vmax2 = have2 ? (v > vmax2 ? v : vmax2) : v;
+              vmin2 = have2 ? (v < vmin2 ? v : vmin2) : v;
+              have2 = true;
+            }
+          }
+          if ((FLAGS & NEED_IDS) && p.idspan) idb2 += __ldg(&p.idspan[ka]) & 0xFFFFu;
+        }
+        if (qb) {
+          cnt2++;
+          if (FLAGS & NEED_BASES) bases2 += ovb;
+          if (kScore) {
+            const double v = __ldg(&p.score[kb]);
+            sum2 += v;
+            if (kMinMax) {
+              vmax2 = have2 ? (v > vmax2 ? v : vmax2) : v;
+              vmin2 = have2 ? (v < vmin2 ? v : vmin2) : v;
+              have2 = true;
+            }
+          }
+          if ((FLAGS & NEED_IDS) && p.idspan) idb2 += __ldg(&p.idspan[kb]) & 0xFFFFu;
+        }
+        const unsigned mb_ = __ballot_sync(0xffffffffu, inb);
+        if (FLAGS & NEED_IDS) nwin2 += __popc(__ballot_sync(0xffffffffu, ina)) + __popc(mb_);
+        if (mb_ != 0xffffffffu) break;
+      }
+      cnt2 = __reduce_add_sync(0xffffffffu, cnt2);
+      if (FLAGS & NEED_BASES) bases2 = warp_sum_u64(bases2);
+      if (kScore) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          sum2 += __shfl_xor_sync(0xffffffffu, sum2, d);
+          if (kMinMax) {
+            const double omx = __shfl_xor_sync(0xffffffffu, vmax2, d);
+            const double omn = __shfl_xor_sync(0xffffffffu, vmin2, d);
+            const bool   oh = __shfl_xor_sync(0xffffffffu, (int)have2, d);
+            if (oh) {
+              vmax2 = have2 ? (omx > vmax2 ? omx : vmax2) : omx;
+              vmin2 = have2 ? (omn < vmin2 ? omn : vmin2) : omn;
+              have2 = true;
+            }
+          }
+        }
+      }
+      if (FLAGS & NEED_IDS) idb2 = __reduce_add_sync(0xffffffffu, idb2);
+      if (lane == j) {
+        cnt += cnt2;
+        bases += bases2;
+        sum += sum2;
+        if (kMinMax && have2) {
+          vmax = have ? (vmax2 > vmax ? vmax2 : vmax) : vmax2;
+          vmin = have ? (vmin2 < vmin ? vmin2 : vmin) : vmin2;
+          have = true;
+        }
+        idb += idb2;
+        nwin += nwin2;
+      }
+    }
+    if (valid) {
+      p.count[i] = cnt;
+      if (FLAGS & NEED_BASES) p.bases[i] = bases;
+      if ((FLAGS & NEED_SUM) && p.sum) p.sum[i] = sum;
+      if ((FLAGS & NEED_MAX) && p.vmax) p.vmax[i] = vmax;
+      if ((FLAGS & NEED_MIN) && p.vmin) p.vmin[i] = vmin;
+      if (FLAGS & NEED_IDS) {
+        if (cnt) idb += (cnt - 1) * p.mdelim_len;
+        p.win_lo[i] = glo;
+        p.win_n[i] = nwin;
+        p.idbytes[i] = idb;
+      }
+    }
+  }
+}
+
+// MAX and MIN share an instantiation (both are kept; a null output pointer drops the store), SUM rides along with them
+template <int KIND>
+static void launch_map_group(unsigned need, unsigned blocks, cudaStream_t st, const MapStatsParams& sp) {
+  unsigned f = need & 31u;
+  if (f & (NEED_MAX | NEED_MIN)) f |= NEED_MAX | NEED_MIN;
+  switch (f) {
+#define BK_F(F) case F: k_map_group<KIND, F><<<blocks, MG_THREADS, 0, st>>>(sp); break;
+    BK_F(0) BK_F(1) BK_F(2) BK_F(3) BK_F(12) BK_F(13) BK_F(14) BK_F(15)
+    BK_F(16) BK_F(17) BK_F(18) BK_F(19) BK_F(28) BK_F(29) BK_F(30) BK_F(31)
+#undef BK_F
   }
 }
 
@@ -1118,7 +1402,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
   sp.rs = ref->start; sp.re = ref->end; sp.row0 = row0; sp.n = n;
   sp.run_ref_begin = d_tab; sp.run_map_begin = d_tab + nruns + 1; sp.run_map_end = d_tab + 2 * nruns + 1; sp.nruns = nruns;
   sp.ms = map->start; sp.me = map->end; sp.pm = map->pmax_end; sp.score = map->score;
-  sp.idspan = map->idspan;
+  sp.idspan = map->idspan; sp.map_rows = map->nrows;
   sp.ov = ov; sp.need = need; sp.mdelim_len = (uint32_t)strlen(mdelim);
   sp.count = dalloc<uint32_t>(ctx, n);
   if (need & NEED_BASES) sp.bases = dalloc<uint64_t>(ctx, n);
@@ -1139,16 +1423,23 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     uint64_t       blocks = (batches + per_block - 1) / per_block;
     const uint64_t cap = (uint64_t)kSMs * 8 * 8;  // several resident waves; warps stride over the batches
     if (blocks > cap) blocks = cap;
+    // the lane-per-row form (k_map_group) is the default: 2.07 ms against 3.04 ms at configuration 2, 26.9 against 43.3 ms
+    // (block-skipping scan) at configuration 5; the warp-per-row forms serve map files of 2^32 rows and more and
+    // BEDKIT_MAP_KERNEL=row (A/B measurements, tests)
+    const char* const mk_env = getenv("BEDKIT_MAP_KERNEL");
+    const bool group = !(mk_env && mk_env[0] == 'r') && map->nrows > 0 && map->nrows < 0xFFFFFF00ull;
     // the default criterion (--bp-ovr) gets its own instantiation; the other six share the generic predicate
-    // dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows) take the variant
-    // that skips dead 32-row blocks; it costs ~20 % on short windows, so it is not the default
-    const bool dense = ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
+    // warp-per-row: dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows) take the
+    // variant that skips dead 32-row blocks; it costs ~20 % on short windows
+    const bool dense = !group && ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
     if (dense) {
       BK_TRY(ensure_bmax(ctx, map));
       sp.bmax = map->bmax_end;
     }
     prof_begin(ctx, "k_map_stats");
-    if (dense) launch_map_stats<BK_OVR_BP, true>(need, (unsigned)blocks, ctx->stream, sp);
+    if (group && ov.kind == BK_OVR_BP) launch_map_group<BK_OVR_BP>(need, (unsigned)blocks, ctx->stream, sp);
+    else if (group) launch_map_group<-1>(need, (unsigned)blocks, ctx->stream, sp);
+    else if (dense) launch_map_stats<BK_OVR_BP, true>(need, (unsigned)blocks, ctx->stream, sp);
     else if (ov.kind == BK_OVR_BP) launch_map_stats<BK_OVR_BP, false>(need, (unsigned)blocks, ctx->stream, sp);
     else launch_map_stats<-1, false>(need, (unsigned)blocks, ctx->stream, sp);
     prof_end(ctx);

@@ -633,22 +633,26 @@ constexpr int WS_LSCAP = 1024;  // line starts listed per tile; a tile with more
 #ifndef BK_WS_MINBLOCKS
 #define BK_WS_MINBLOCKS 5  // 48 registers: no spills; measured 2.81 ms against 2.91 ms with 6 CTAs of 40 registers
 #endif
+#ifndef BK_WS_STAGES
+#define BK_WS_STAGES 2  // tile buffers per CTA (13.4 KB each): the producer runs up to this many tiles ahead
+#endif
+constexpr int WS_ST = BK_WS_STAGES;
 template <int NSEP, bool WANT_SCORE>
 __global__ void __launch_bounds__(P_THREADS, BK_WS_MINBLOCKS) k_parse_ws(ParseParams p) {
-  __shared__ __align__(128) unsigned char smbuf[2][P_BUF + 16];
-  __shared__ uint32_t                     ctlp2[2][P_NW + 4];
-  __shared__ uint32_t                     lsw2[2][P_PRE / 32 + P_TILE / 32];
-  __shared__ uint16_t                     lstart2[2][WS_LSCAP];
-  __shared__ uint16_t                     wpre2[2][P_TILE / 32 + 1];  // line starts in front of every word of the tile
-  __shared__ uint32_t                     nl2[2];
-  __shared__ uint64_t                     base2[2];
-  __shared__ __align__(8) uint64_t        txt[2], full[2], empty[2];
+  __shared__ __align__(128) unsigned char smbuf[WS_ST][P_BUF + 16];
+  __shared__ uint32_t                     ctlp2[WS_ST][P_NW + 4];
+  __shared__ uint32_t                     lsw2[WS_ST][P_PRE / 32 + P_TILE / 32];
+  __shared__ uint16_t                     lstart2[WS_ST][WS_LSCAP];
+  __shared__ uint16_t                     wpre2[WS_ST][P_TILE / 32 + 1];  // line starts in front of every word of the tile
+  __shared__ uint32_t                     nl2[WS_ST];
+  __shared__ uint64_t                     base2[WS_ST];
+  __shared__ __align__(8) uint64_t        txt[WS_ST], full[WS_ST], empty[WS_ST];
   const int            tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t       eff = p.scratch[SC_EFFLEN];
   const unsigned char* text = reinterpret_cast<const unsigned char*>(p.text);
   auto bulkable = [&](uint32_t tile) { return tile - 1u < p.bulk_tiles; };
   if (tid == 0) {
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < WS_ST; b++) {
       mbar_init(&txt[b], 1);
       mbar_init(&full[b], 1);
       mbar_init(&empty[b], WS_CONSUMERS / 32);
@@ -660,11 +664,10 @@ __global__ void __launch_bounds__(P_THREADS, BK_WS_MINBLOCKS) k_parse_ws(ParsePa
 
   if (warp == 0) {
     // ---- producer ---------------------------------------------------------------------------------------------
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
-      const int      b = it & 1;
-      const uint32_t use = it >> 1;
-      mbar_wait(&empty[b], (use & 1u) ^ 1u);  // the consumers have left the tile that used this buffer two tiles ago
+    int      b = 0;
+    uint32_t use = 0;  // tile number it of this CTA uses buffer it % WS_ST for the (it / WS_ST)-th time
+    for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, b = b + 1 == WS_ST ? 0 : b + 1, use += b == 0) {
+      mbar_wait(&empty[b], (use & 1u) ^ 1u);  // the consumers have left the tile that used this buffer WS_ST tiles ago
       unsigned char* const sm = smbuf[b];
       if (bulkable(tile)) {
         if (lane == 0) {
@@ -739,10 +742,10 @@ __global__ void __launch_bounds__(P_THREADS, BK_WS_MINBLOCKS) k_parse_ws(ParsePa
 
   // ---- consumers ------------------------------------------------------------------------------------------------
   const uint32_t ctid = (uint32_t)tid - 32u;
-  uint32_t       it = 0, tphase = 0;  // tphase bit b: parity of the next completion of txt[b]
-  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
-    const int      b = it & 1;
-    const uint32_t use = it >> 1;
+  uint32_t       tphase = 0;  // tphase bit b: parity of the next completion of txt[b]
+  int            b = 0;
+  uint32_t       use = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, b = b + 1 == WS_ST ? 0 : b + 1, use += b == 0) {
     mbar_wait(&full[b], use & 1u);
     if (bulkable(tile)) {
       mbar_wait(&txt[b], (tphase >> b) & 1u);
