@@ -8,6 +8,7 @@
 // Every row in [lo,hi) is tested with the exact overlap predicate (Bed::Overlapping / RangedDist / PercentOverlap* /
 // Exact, BedDistances.hpp:41-317) and reduced; the prefix-max index makes the range tight under nesting.
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 #include "emit.cuh"
 #include "fmt.cuh"
@@ -400,11 +401,46 @@ __global__ void __launch_bounds__(MG_THREADS) k_map_group(MapStatsParams p) {
     const uint64_t re_pad64 = (uint64_t)re + pad;
     const uint32_t re_pad = re_pad64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)re_pad64;
 
-    uint32_t cnt = 0, idb = 0, nwin = 0;
+    uint32_t idb = 0, nwin = 0;
     uint64_t bases = 0;
-    double   sum = 0.0, vmax = 0.0, vmin = 0.0;
+    double   cntd = 0.0, sum = 0.0, vmax = 0.0, vmin = 0.0;  // hits are counted on the FP64 pipe (exact; the ALU pipe is the busy one)
     bool     have = false;
     bool     fin = !valid || glo >= gend;
+    // the reference row the tests use: a finished lane carries a null row that no map row overlaps
+    uint32_t rs_e = fin ? 0xFFFFFFFFu : rs, re_e = fin ? 0u : re, rp_e = fin ? 0u : re_pad;
+    // one staged map row against my reference row; `mine`: the row is one of [glo, gend) (constant true on the fast path).
+    // NARROW: overlaps are summed in 32 bits and folded into the 64-bit sum once per chunk (one add per row instead of
+    // two; the ALU pipe, two cycles per warp instruction, is the busy one); the caller guarantees 64 * (re - rs) < 2^32.
+    uint32_t bases32 = 0;
+    auto test_row = [&](auto narrow, uint32_t s, uint32_t e, double v, bool mine, uint32_t k) {
+      uint32_t ovl;
+      bool     q;
+      if (KIND == BK_OVR_BP) {
+        const uint32_t mn = rs_e > s ? rs_e : s, mx = re_e < e ? re_e : e;
+        ovl = mx - (mn < mx ? mn : mx);
+        q = mine && ovl >= bp1;
+      } else {
+        q = mine && s < rp_e && qualifies(ov, rs_e, re_e, s, e, ovl);
+      }
+      if (q) {  // the adds as volatile asm: a predicated DADD each, not an unconditional add followed by two selects
+        asm volatile("add.f64 %0, %0, 0d3FF0000000000000;" : "+d"(cntd));
+        if (FLAGS & NEED_BASES) {
+          if (decltype(narrow)::value) bases32 += ovl;
+          else bases += ovl;
+        }
+        if (kScore) {
+          asm volatile("add.f64 %0, %0, %1;" : "+d"(sum) : "d"(v));
+          if (kMinMax) {
+            vmax = have ? (v > vmax ? v : vmax) : v;
+            vmin = have ? (v < vmin ? v : vmin) : v;
+            have = true;
+          }
+        }
+        if ((FLAGS & NEED_IDS) && p.idspan) idb += __ldg(&p.idspan[k]) & 0xFFFFu;
+      }
+      if (FLAGS & NEED_IDS) nwin += (mine && s < rp_e) ? 1u : 0u;
+    };
+    const bool huge = re - rs >= (1u << 26);  // 64 overlaps of this reference row may not fit 32 bits: masked path
     uint32_t c0 = group_min_u32(fin ? 0xFFFFFFFFu : glo) & ~7u;  // next chunk of my group (sector-aligned column loads)
     unsigned live;
     while (__popc(live = __ballot_sync(0xffffffffu, !fin)) > BK_MG_COOP) {
@@ -418,61 +454,60 @@ __global__ void __launch_bounds__(MG_THREADS) k_map_group(MapStatsParams p) {
         }
       }
       __syncwarp();
-      uint64_t wmask = 0;  // bit r: staged row c0+r is one of my rows [glo, gend)
-      if (!fin) {
-        const uint32_t a = glo > c0 ? (glo - c0 < 64u ? glo - c0 : 64u) : 0u;
-        const uint32_t b = gend - c0 < 64u ? gend - c0 : 64u;  // gend > c0: the lane is not finished
-        const uint64_t upto_b = b >= 64u ? ~0ull : ((1ull << b) - 1ull);
-        const uint64_t upto_a = a >= 64u ? ~0ull : ((1ull << a) - 1ull);
-        wmask = upto_b & ~upto_a;
-      }
+      // Fast path: the chunk lies inside the chromosome of every unfinished lane.  Rows in front of a lane's lo cannot
+      // qualify (their end does not reach the reference row), so no per-row mask is needed: 64 rows, ~9 instructions each.
+      // (Reference rows longer than 2^26 bases also send the warp to the masked path: see test_row.)
+      const bool edge = !fin && (c0 < mbl || c0 + MG_CH > gend || huge);
+      if (!(FLAGS & NEED_IDS) && !__any_sync(0xffffffffu, edge)) {
 #pragma unroll 1
-      for (int j = 0; j < MG_CH / 8; j++) {
-        const uint32_t m8 = (uint32_t)(wmask >> (8 * j)) & 0xFFu;
-        if (!__any_sync(0xffffffffu, m8 != 0u)) continue;
+        for (int j = 0; j < MG_CH / 8; j++) {
 #pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const uint4 se2 = *reinterpret_cast<const uint4*>(&B.se[8 * j + u]);
-          double2     v2 = make_double2(0.0, 0.0);
-          if (kScore) v2 = *reinterpret_cast<const double2*>(&B.sc[8 * j + u]);
+          for (int u = 0; u < 8; u += 2) {
+            const uint4 se2 = *reinterpret_cast<const uint4*>(&B.se[8 * j + u]);
+            double2     v2 = make_double2(0.0, 0.0);
+            if (kScore) v2 = *reinterpret_cast<const double2*>(&B.sc[8 * j + u]);
+            test_row(std::true_type{}, se2.x, se2.y, v2.x, true, 0u);
+            test_row(std::true_type{}, se2.z, se2.w, v2.y, true, 0u);
+          }
+        }
+        if (FLAGS & NEED_BASES) {
+          bases += bases32;
+          bases32 = 0;
+        }
+      } else {  // chromosome edges and the list operations (which need the exact window): per-row mask of my rows [glo, gend)
+        uint64_t wmask = 0;
+        if (!fin) {
+          const uint32_t a = glo > c0 ? (glo - c0 < 64u ? glo - c0 : 64u) : 0u;
+          const uint32_t b = gend - c0 < 64u ? gend - c0 : 64u;  // gend > c0: the lane is not finished
+          const uint64_t upto_b = b >= 64u ? ~0ull : ((1ull << b) - 1ull);
+          const uint64_t upto_a = a >= 64u ? ~0ull : ((1ull << a) - 1ull);
+          wmask = upto_b & ~upto_a;
+        }
+#pragma unroll 1
+        for (int j = 0; j < MG_CH / 8; j++) {
+          const uint32_t m8 = (uint32_t)(wmask >> (8 * j)) & 0xFFu;
+          if (!__any_sync(0xffffffffu, m8 != 0u)) continue;
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const uint32_t s = h ? se2.z : se2.x, e = h ? se2.w : se2.y;
-            const double   v = h ? v2.y : v2.x;
-            const bool     mine = (m8 >> (u + h)) & 1u;
-            uint32_t       ovl;
-            bool           q;
-            if (KIND == BK_OVR_BP) {
-              const uint32_t mn = rs > s ? rs : s, mx = re < e ? re : e;
-              ovl = mx - (mn < mx ? mn : mx);
-              q = mine && ovl >= bp1;
-            } else {
-              q = mine && s < re_pad && qualifies(ov, rs, re, s, e, ovl);
-            }
-            if (q) {
-              cnt++;
-              if (FLAGS & NEED_BASES) bases += ovl;
-              if (kScore) {
-                sum += v;
-                if (kMinMax) {
-                  vmax = have ? (v > vmax ? v : vmax) : v;
-                  vmin = have ? (v < vmin ? v : vmin) : v;
-                  have = true;
-                }
-              }
-              if ((FLAGS & NEED_IDS) && p.idspan) idb += __ldg(&p.idspan[c0 + (uint32_t)(8 * j + u + h)]) & 0xFFFFu;
-            }
-            if (FLAGS & NEED_IDS) nwin += (mine && s < re_pad) ? 1u : 0u;
+          for (int u = 0; u < 8; u += 2) {
+            const uint4 se2 = *reinterpret_cast<const uint4*>(&B.se[8 * j + u]);
+            double2     v2 = make_double2(0.0, 0.0);
+            if (kScore) v2 = *reinterpret_cast<const double2*>(&B.sc[8 * j + u]);
+            test_row(std::false_type{}, se2.x, se2.y, v2.x, (m8 >> u) & 1u, c0 + (uint32_t)(8 * j + u));
+            test_row(std::false_type{}, se2.z, se2.w, v2.y, (m8 >> (u + 1)) & 1u, c0 + (uint32_t)(8 * j + u + 1));
           }
         }
       }
       // a lane is finished when its chromosome is used up or the last staged row (one of its rows) starts at/after its end
       const uint32_t s_last = B.se[MG_CH - 1].x;
       const uint32_t c1 = c0 + MG_CH;
-      if (!fin && (c1 >= gend || (c1 > glo && s_last >= re_pad))) fin = true;
+      if (!fin && (c1 >= gend || (c1 > glo && s_last >= re_pad))) {
+        fin = true;
+        rs_e = 0xFFFFFFFFu; re_e = 0u; rp_e = 0u;
+      }
       __syncwarp();  // everyone has read the chunk before the next one is staged
       c0 = group_min_u32(fin ? 0xFFFFFFFFu : (glo > c1 ? glo & ~7u : c1));  // skips gaps (chromosome change, sparse windows)
     }
+    uint32_t cnt = (uint32_t)cntd;
     // the stragglers, one after the other: rows [max(c0, glo), gend) of lane j's window by the whole warp, 64 rows per step
     while (live) {
       const int j = __ffs(live) - 1;

@@ -19,3 +19,8 @@ for i, n in enumerate(h):
         if "pct" in n or n.endswith(".sum") or "ratio" in n:
             print(n, r[i])
 PY
+# per-source-line instruction profile when a mangled-name key is given as 4th argument
+if [ -n "${4:-}" ]; then
+  python profiles/tools/sass_by_line.py /tmp/$TAG.ncu-rep 0 bedops_b200/lib/libbedkit.so "$4" 400 > gpurun_out/${TAG}_by_line.txt 2>&1
+  head -45 gpurun_out/${TAG}_by_line.txt
+fi

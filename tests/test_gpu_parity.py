@@ -520,3 +520,58 @@ def test_windows_far_longer_than_a_warp_step(kit):
             assert_same(kit.bedmap(rb, mb, ops), O.bedmap(ref, mp_, ops))
         rb.free()
         mb.free()
+
+
+def test_both_window_kernels_on_chromosome_edges_gaps_and_giant_rows(kit, monkeypatch):
+    """The lane-per-row window kernel (k_map_group, the default) and the warp-per-row one (BEDKIT_MAP_KERNEL=row) against
+    the oracle where their bookkeeping differs from the common case: many short chromosomes (a batch of 32 reference
+    rows and even a group of 8 straddles several), chromosomes missing on either side, windows separated by empty
+    stretches (the chunk stream jumps), a reference row longer than 2^26 bases (64 overlaps do not fit 32 bits), a
+    reference row covering a whole dense chromosome (finished by the whole warp), every overlap criterion and the list
+    operations (which need the exact window)."""
+    from bedops_b200._lib import COL_ID, COL_LINE, COL_SCORE
+    rng = np.random.default_rng(11)
+    ref_rows, map_rows = [], []
+    names = ["c%02d" % k for k in range(40)]
+    for k, nm in enumerate(names):
+        if k % 7 != 3:   # map rows: clusters with gaps of 1e6 between them
+            n = int(rng.integers(1, 400))
+            base = rng.choice([0, 1_000_000, 5_000_000], n) + rng.integers(0, 3000, n)
+            ln = np.maximum(1, rng.lognormal(3.5, 1.2, n).astype(np.int64))
+            for a, b in sorted(zip(base.tolist(), (base + ln).tolist())):
+                map_rows.append((nm, a, b))
+        if k % 5 != 4:   # reference rows: 1..12 per chromosome, some far from any map row
+            n = int(rng.integers(1, 13))
+            st = np.sort(rng.choice([0, 500_000, 1_000_000, 5_000_000, 9_000_000], n) + rng.integers(0, 3500, n))
+            ln = np.maximum(1, rng.lognormal(5.0, 1.5, n).astype(np.int64))
+            rr = sorted(zip(st.tolist(), (st + ln).tolist()))
+            for a, b in rr:
+                ref_rows.append((nm, a, b))
+    # a dense chromosome with a reference row over all of it and a giant reference row (> 2^26 bases) among short ones
+    dn = 5000
+    ds = np.sort(rng.integers(0, 100_000_000, dn))
+    de = ds + np.maximum(1, rng.lognormal(8.0, 2.0, dn).astype(np.int64))
+    for a, b in sorted(zip(ds.tolist(), de.tolist())):
+        map_rows.append(("d00", a, b))
+    dref = [(0, 99_000_000), (10, 70_000_000)] + [(int(a), int(a) + 5000) for a in np.sort(rng.integers(0, 100_000_000, 300))]
+    for a, b in sorted(dref):
+        ref_rows.append(("d00", a, b))
+    ref = "".join("%s\t%d\t%d\n" % r for r in ref_rows).encode()
+    mp_ = "".join("%s\t%d\t%d\tid%d\t%d\n" % (c, a, b, k, (k * 7919) % 1000 - 300) for k, (c, a, b) in enumerate(map_rows)).encode()
+    cases = [(["echo", "count", "sum", "bases"], ("bp", 1)), (["count", "max", "min", "mean"], ("bp", 1)),
+             (["count", "bases", "mean"], ("bp", 40)), (["count", "bases", "sum"], ("range", 2000)),
+             (["count", "sum"], ("fraction-map", 0.5)), (["count", "min"], ("fraction-ref", 0.1)),
+             (["count", "bases"], ("fraction-either", 0.3)), (["count"], ("fraction-both", 0.2)), (["count", "sum"], ("exact", 0)),
+             (["echo-map-id", "count"], ("bp", 1)), (["echo-map-id-uniq", "bases"], ("range", 100)),
+             (["echo-map-range", "sum"], ("bp", 1))]
+    exp = [O.bedmap(ref, mp_, ops, overlap=ov) for ops, ov in cases]
+    for env in (None, "row"):
+        if env:
+            monkeypatch.setenv("BEDKIT_MAP_KERNEL", env)
+        else:
+            monkeypatch.delenv("BEDKIT_MAP_KERNEL", raising=False)
+        rb, mb = kit.load(ref, 3, COL_LINE), kit.load(mp_, 5, COL_SCORE | COL_ID | COL_LINE)
+        for (ops, ov), e in zip(cases, exp):
+            assert_same(kit.bedmap(rb, mb, ops, overlap=ov), e)
+        rb.free()
+        mb.free()
