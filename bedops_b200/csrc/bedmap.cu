@@ -1471,7 +1471,7 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
       BK_TRY(ensure_bmax(ctx, map));
       sp.bmax = map->bmax_end;
     }
-    prof_begin(ctx, "k_map_stats");
+    prof_begin(ctx, group ? "k_map_group" : "k_map_stats");
     if (group && ov.kind == BK_OVR_BP) launch_map_group<BK_OVR_BP>(need, (unsigned)blocks, ctx->stream, sp);
     else if (group) launch_map_group<-1>(need, (unsigned)blocks, ctx->stream, sp);
     else if (dense) launch_map_stats<BK_OVR_BP, true>(need, (unsigned)blocks, ctx->stream, sp);

@@ -385,7 +385,7 @@ def main():
 
 
 def kernel_split(kit, steps):
-    names = ["k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_block_max", "k_map_stats", "k_emit_len", "k_emit"]
+    names = ["k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_block_max", "k_map_group", "k_map_stats", "k_emit_len", "k_emit"]
     out = {}
     for k in names:
         ms, n = kit.profile_query(k)

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 KERNELS = ["k_fill_ids", "k_sort_validate", "k_chrom_insert", "k_sort_keys", "k_radix_hist", "k_radix_scatter", "k_tie_fix", "k_part_keys",
            "k_efflen", "k_count_rows", "k_scan_warps", "k_parse", "k_pmax_reduce", "k_pmax", "k_rank_merge", "k_segments",
-           "k_intersect", "k_element_of", "k_argmark", "k_cf_sim", "k_map_stats", "k_emit_len", "k_emit"]
+           "k_intersect", "k_element_of", "k_argmark", "k_cf_sim", "k_map_group", "k_map_stats", "k_emit_len", "k_emit"]
 
 
 def main():

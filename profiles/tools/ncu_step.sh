@@ -40,14 +40,14 @@ di = h.index("gpu__time_duration.sum")
 best = {}
 for idx, r in enumerate(rows[2:]):
     name = r[ki]
-    for want in ("k_parse", "k_map_stats", "k_emit<", "k_count_rows", "k_emit_len"):
+    for want in ("k_parse", "k_map_group", "k_emit<", "k_count_rows", "k_emit_len"):
         if want in name or (want == "k_emit<" and name.startswith("k_emit") and "len" not in name):
             d = float(r[di].replace(",", ""))
             if want not in best or d > best[want][1]:
                 best[want] = (idx, d, name)
 for want, (idx, d, name) in best.items():
     print(want, idx, d, name[:60])
-    key = {"k_parse": "k_parse_wsILi5ELb1", "k_map_stats": "k_map_statsILi0ELj3ELb0", "k_emit<": "k_emitINS_9BedmapRowILi0E", "k_count_rows": "k_count_rows",
+    key = {"k_parse": "k_parse_wsILi5ELb1", "k_map_group": "k_map_groupILi0ELj3E", "k_emit<": "k_emitINS_9BedmapRowILi0E", "k_count_rows": "k_count_rows",
            "k_emit_len": "k_emit_lenINS_9BedmapRowILi0E"}[want]
     out = open("gpurun_out/%s_%s_by_line.txt" % (sys.argv[2], want.strip("<")), "w")
     subprocess.run([sys.executable, "profiles/tools/sass_by_line.py", "/tmp/%s.ncu-rep" % sys.argv[2], str(idx), "bedops_b200/lib/libbedkit.so", key, "400"], stdout=out, stderr=subprocess.STDOUT)
