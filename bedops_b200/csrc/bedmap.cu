@@ -441,9 +441,33 @@ __global__ void __launch_bounds__(MG_THREADS) k_map_group(MapStatsParams p) {
       if (FLAGS & NEED_IDS) nwin += (mine && s < rp_e) ? 1u : 0u;
     };
     const bool huge = re - rs >= (1u << 26);  // 64 overlaps of this reference row may not fit 32 bits: masked path
-    uint32_t c0 = group_min_u32(fin ? 0xFFFFFFFFu : glo) & ~7u;  // next chunk of my group (sector-aligned column loads)
+    // chunk starts are multiples of 8 rows (sector-aligned column loads); with the block-max index (dense map files) of 32
+    const uint32_t calign = p.bmax ? ~31u : ~7u;
+    uint32_t c0 = group_min_u32(fin ? 0xFFFFFFFFu : glo) & calign;  // next chunk of my group
     unsigned live;
     while (__popc(live = __ballot_sync(0xffffffffu, !fin)) > BK_MG_COOP) {
+      if (p.bmax) {
+        // Dense map files: most rows between lo and the first hit are short rows that end in front of the reference rows.
+        // A chunk (two 32-row blocks of the block-max-end index) in which no end reaches the smallest key of the group's
+        // unfinished lanes holds no hit for them and not the row that ends a window either (start >= ref.end implies
+        // that its end reaches): when that is so for all four groups, the chunk is neither staged nor scanned.
+        const uint32_t gk = group_min_u32(fin ? 0xFFFFFFFFu : my_key);
+        bool           dead = true;
+        if (live & gmask) {
+          const uint32_t b0 = c0 >> 5;
+          const uint32_t m0 = __ldg(&p.bmax[b0]), m1 = c0 + 32u <= last_row ? __ldg(&p.bmax[b0 + 1]) : 0u;
+          dead = m0 < gk && m1 < gk;
+        }
+        if (__all_sync(0xffffffffu, dead)) {
+          const uint32_t c1 = c0 + MG_CH;
+          if (!fin && c1 >= gend) {
+            fin = true;
+            rs_e = 0xFFFFFFFFu; re_e = 0u; rp_e = 0u;
+          }
+          c0 = group_min_u32(fin ? 0xFFFFFFFFu : (glo > c1 ? glo & calign : c1));
+          continue;
+        }
+      }
       if (live & gmask) {  // stage map rows [c0, c0+64) of the columns; rows past the file repeat its last row (masked below)
 #pragma unroll
         for (int r = 0; r < MG_CH / MG_G; r++) {
@@ -505,7 +529,7 @@ __global__ void __launch_bounds__(MG_THREADS) k_map_group(MapStatsParams p) {
         rs_e = 0xFFFFFFFFu; re_e = 0u; rp_e = 0u;
       }
       __syncwarp();  // everyone has read the chunk before the next one is staged
-      c0 = group_min_u32(fin ? 0xFFFFFFFFu : (glo > c1 ? glo & ~7u : c1));  // skips gaps (chromosome change, sparse windows)
+      c0 = group_min_u32(fin ? 0xFFFFFFFFu : (glo > c1 ? glo & calign : c1));  // skips gaps (chromosome change, sparse windows)
     }
     uint32_t cnt = (uint32_t)cntd;
     // the stragglers, one after the other: rows [max(c0, glo), gend) of lane j's window by the whole warp, 64 rows per step
@@ -1464,9 +1488,9 @@ extern "C" int bk_bedmap(bk_ctx* ctx, const bk_bed* ref, const bk_bed* map, cons
     const char* const mk_env = getenv("BEDKIT_MAP_KERNEL");
     const bool group = !(mk_env && mk_env[0] == 'r') && map->nrows > 0 && map->nrows < 0xFFFFFF00ull;
     // the default criterion (--bp-ovr) gets its own instantiation; the other six share the generic predicate
-    // warp-per-row: dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows) take the
-    // variant that skips dead 32-row blocks; it costs ~20 % on short windows
-    const bool dense = !group && ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
+    // dense map files (>= 32 map rows per reference row: candidate windows of several hundred rows): both forms skip
+    // dead 32-row blocks with the block-max-end index (warp-per-row: its own instantiation, ~20 % slower on short windows)
+    const bool dense = ov.kind == BK_OVR_BP && !(need & NEED_IDS) && map->nrows / 32 >= n;
     if (dense) {
       BK_TRY(ensure_bmax(ctx, map));
       sp.bmax = map->bmax_end;

@@ -200,8 +200,24 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // release.cta: the arriving thread's earlier writes are visible to waiters
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
+#ifndef BK_MBAR_HINT_NS
+#define BK_MBAR_HINT_NS 0  // > 0: suspend-time hint of try_wait (the thread sleeps in hardware until the phase completes or the time is up)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+#if BK_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(b),
+      "r"(parity), "r"((uint32_t)BK_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -213,6 +229,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(b),
       "r"(parity)
       : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {  // streaming 16-byte load, no L1 allocation

@@ -165,15 +165,21 @@ def test_synthetic_vs_oracle_bytes(kit, synth_files):
         assert_same(oracle_cli.run_kit(kit, tool, argv, synth_files), oracle_cli.run(tool, argv, synth_files))
 
 
-def test_dense_map_file_takes_the_block_skipping_scan(kit, synth_files):
-    """>= 32 map rows per reference row selects the k_map_stats variant that skips 32-row blocks with no reaching end."""
+def test_dense_map_file_takes_the_block_skipping_scan(kit, synth_files, monkeypatch):
+    """>= 32 map rows per reference row: both window kernels skip 32-row blocks in which no end reaches the reference rows
+    (k_map_group: whole chunks, when all four groups of the warp agree; k_map_stats<SKIP> under BEDKIT_MAP_KERNEL=row)."""
     files = dict(synth_files)
     files["few.bed"] = b"".join(l + b"\n" for l in synth_files["dr.bed"].split(b"\n")[:-1][::12])
     assert files["dm.bed"].count(b"\n") >= 32 * files["few.bed"].count(b"\n")
-    for argv in (["--echo", "--count", "--mean", "--bases", "few.bed", "dm.bed"],
-                 ["--count", "--sum", "--max", "--min", "--indicator", "few.bed", "dm.bed"],
-                 ["--bp-ovr", "50", "--count", "--bases", "few.bed", "dm.bed"]):
-        assert_same(oracle_cli.run_kit(kit, "bedmap", argv, files), oracle_cli.run("bedmap", argv, files))
+    for env in (None, "row"):
+        if env:
+            monkeypatch.setenv("BEDKIT_MAP_KERNEL", env)
+        else:
+            monkeypatch.delenv("BEDKIT_MAP_KERNEL", raising=False)
+        for argv in (["--echo", "--count", "--mean", "--bases", "few.bed", "dm.bed"],
+                     ["--count", "--sum", "--max", "--min", "--indicator", "few.bed", "dm.bed"],
+                     ["--bp-ovr", "50", "--count", "--bases", "few.bed", "dm.bed"]):
+            assert_same(oracle_cli.run_kit(kit, "bedmap", argv, files), oracle_cli.run("bedmap", argv, files))
 
 
 def test_everything_orders_ties_by_the_rest_of_the_line_then_by_file(kit):
