@@ -482,8 +482,8 @@ static int starch_inflate(const char* archive, size_t nbytes, const char* chrom,
     if (!json_string_after(js, pos, "size", &v, true)) return bad_archive("Starch metadata: stream without size");
     st.size = strtoull(v.c_str(), nullptr, 10);
     st.offset = at;
+    if (st.size > md_off - at) return bad_archive("Starch metadata: streams overrun the archive");  // (no wrap: at <= md_off)
     at += st.size;
-    if (at > md_off) return bad_archive("Starch metadata: streams overrun the archive");
     streams.push_back(st);
   }
   const bool all = !chrom || !*chrom || strcmp(chrom, "all") == 0;

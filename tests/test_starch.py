@@ -56,6 +56,32 @@ def test_golden_archives():
     assert host_inflate(blob[:4] + b"\0" * 300)[0] == 7             # magic without a footer
 
 
+def test_damaged_archives_are_refused_not_followed():
+    """The host stage walks offsets and sizes it reads from the archive: truncated files, a footer that points outside,
+    stream sizes that overrun (or would wrap a 64-bit sum) and flipped bytes all end in BK_ERR_STARCH or in a clean
+    inflate, never in a read outside the buffer."""
+    import random
+    import re
+    rng = random.Random(11)
+    for name in ("starch_bz2.starch", "starch_gz.starch"):
+        blob = open(os.path.join(GOLDEN, name), "rb").read()
+        for cut in (4, 5, 130, 131, len(blob) // 2, len(blob) - 127, len(blob) - 1):
+            assert host_inflate(blob[:cut])[0] == 7, cut
+        for off in (0, 3, len(blob) - 126, len(blob), 2 ** 63, 10 ** 19):
+            b = bytearray(blob)
+            b[len(b) - 127:len(b) - 107] = (b"%020d" % off)[:20]
+            assert host_inflate(bytes(b))[0] == 7, off
+        m = re.search(rb'"size"\s*:\s*"?(\d+)', blob)
+        for size in (b"18446744073709551615", b"18446744073709551000", b"99999999999999999999999", b"%d" % len(blob)):
+            b = blob[:m.start(1)] + size + blob[m.end(1):]   # the metadata follows the streams: its offset in the footer still holds
+            assert host_inflate(b)[0] == 7, size
+        for _ in range(150):
+            b = bytearray(blob)
+            for _ in range(rng.randrange(1, 6)):
+                b[rng.randrange(4, len(b))] = rng.randrange(256)
+            assert host_inflate(bytes(b))[0] in (0, 7)
+
+
 @pytest.mark.skipif(not have_starch(), reason="reference starch/unstarch not built")
 def test_oracle_matches_reference_unstarch(tmp_path):
     for seed in range(60):
