@@ -245,7 +245,7 @@ extern "C" const char* bk_strerror(int code) {
     case BK_ERR_PARSE: return "BED parse error";
     case BK_ERR_COORD_RANGE: return "coordinate outside the 32-bit device layout";
     case BK_ERR_UNSUPPORTED: return "option outside the device hot path";
-    case BK_ERR_STARCH: return "Starch archive input is not supported; supply plain BED text";
+    case BK_ERR_STARCH: return "Starch archive where plain BED text is expected (see bk_unstarch), or an archive that is not read (v1, --header, damaged)";
     case BK_ERR_UNSORTED: return "input is not sorted per sort-bed";
     case BK_ERR_CHECK: return "error-check (--ec) failure";
     case BK_ERR_NAN_ELEMENT: return "Unable to process a 'NAN' with PrintAllScorePrecision.";
@@ -416,7 +416,7 @@ extern "C" int bk_load_bed(bk_ctx* ctx, const char* host_text, size_t nbytes, in
   ctx->last_error.clear();
   *out = nullptr;
   if (looks_like_starch(reinterpret_cast<const unsigned char*>(host_text), nbytes))
-    return fail(ctx, BK_ERR_STARCH, "input is a Starch/compressed archive");
+    return fail(ctx, BK_ERR_STARCH, "input is a Starch/compressed archive: expand it with bk_unstarch first");
   bk_bed* bed = new bk_bed();
   char*   d = reinterpret_cast<char*>(dmalloc(ctx, nbytes + 64));
   if (!d) {

@@ -51,7 +51,7 @@ enum {
   BK_ERR_PARSE = 4,       /* a BED line the device parser does not accept (message names the row) */
   BK_ERR_COORD_RANGE = 5, /* coordinate >= 2^32 - 1: outside this build's 32-bit device layout */
   BK_ERR_UNSUPPORTED = 6, /* option combination outside the hot path (named in the message) */
-  BK_ERR_STARCH = 7,      /* input is a Starch archive; only plain BED text is accepted */
+  BK_ERR_STARCH = 7,      /* a Starch archive where plain text is required (bk_load_bed), or one that is not read: v1, --header, damaged */
   BK_ERR_UNSORTED = 8,    /* chromosome runs not in strcmp order / repeated chromosome run */
   BK_ERR_CHECK = 9,       /* --ec validation failed (message mirrors BedCheckIterator.hpp:589-593) */
   BK_ERR_NAN_ELEMENT = 10 /* bedmap --max-element/--min-element reached a reference row with no mapped element: the result text
