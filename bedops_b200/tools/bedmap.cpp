@@ -9,25 +9,48 @@ namespace {
 
 using cli::UserError;
 
+// What follows an operation's name on the command line (Input.hpp:275-326)
+enum class OpArg { None, Multiplier /* --mad [mult] */, Quantile /* --kth <val> */, TrimPair /* --tmean <low> <hi> */ };
+
 struct OpInfo {
   const char* name;
   int         op;          // BK_OP_* or 0 if the operation is outside the device hot path
   int         map_fields;  // Input.hpp:401-418 (MapFields::num)
-  int         nargs;       // fixed extra arguments (only the out-of-scope ops take any)
+  OpArg       arg;
 };
 const OpInfo kOps[] = {
-    {"bases", BK_OP_BASES, 3, 0},          {"bases-uniq", BK_OP_BASES_UNIQ, 3, 0},           {"bases-uniq-f", BK_OP_BASES_UNIQ_F, 3, 0},
-    {"echo", BK_OP_ECHO, 3, 0},            {"echo-ref-size", BK_OP_ECHO_REF_SIZE, 3, 0},
-    {"echo-ref-name", BK_OP_ECHO_REF_NAME, 3, 0},                             {"echo-ref-row-id", BK_OP_ECHO_REF_ROW_ID, 3, 0},
-    {"echo-map", BK_OP_ECHO_MAP, 3, 0},                 {"echo-map-id", BK_OP_ECHO_MAP_ID, 4, 0},
-    {"echo-map-id-uniq", BK_OP_ECHO_MAP_ID_UNIQ, 4, 0},         {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, 0},        {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, 0},
-    {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, 0},           {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, 0},       {"count", BK_OP_COUNT, 3, 0},
-    {"indicator", BK_OP_INDICATOR, 3, 0},  {"max", BK_OP_MAX, 5, 0},          {"max-element-rand", 0, 5, 0},
-    {"max-element", BK_OP_MAX_ELEMENT, 5, 0},              {"min", BK_OP_MIN, 5, 0},          {"min-element-rand", 0, 5, 0},
-    {"min-element", BK_OP_MIN_ELEMENT, 5, 0},              {"mean", BK_OP_MEAN, 5, 0},        {"variance", BK_OP_VARIANCE, 5, 0},
-    {"stdev", BK_OP_STDEV, 5, 0},                    {"cv", BK_OP_CV, 5, 0},                   {"sum", BK_OP_SUM, 5, 0},
-    {"wmean", BK_OP_WMEAN, 5, 0},                    {"median", BK_OP_MEDIAN, 5, 0},               {"mad", BK_OP_MAD, 5, -1},
-    {"kth", BK_OP_KTH, 5, 1},                      {"tmean", BK_OP_TMEAN, 5, 2},
+    {"bases", BK_OP_BASES, 3, OpArg::None},
+    {"bases-uniq", BK_OP_BASES_UNIQ, 3, OpArg::None},
+    {"bases-uniq-f", BK_OP_BASES_UNIQ_F, 3, OpArg::None},
+    {"echo", BK_OP_ECHO, 3, OpArg::None},
+    {"echo-ref-size", BK_OP_ECHO_REF_SIZE, 3, OpArg::None},
+    {"echo-ref-name", BK_OP_ECHO_REF_NAME, 3, OpArg::None},
+    {"echo-ref-row-id", BK_OP_ECHO_REF_ROW_ID, 3, OpArg::None},
+    {"echo-map", BK_OP_ECHO_MAP, 3, OpArg::None},
+    {"echo-map-id", BK_OP_ECHO_MAP_ID, 4, OpArg::None},
+    {"echo-map-id-uniq", BK_OP_ECHO_MAP_ID_UNIQ, 4, OpArg::None},
+    {"echo-map-size", BK_OP_ECHO_MAP_SIZE, 3, OpArg::None},
+    {"echo-overlap-size", BK_OP_ECHO_OVERLAP_SIZE, 3, OpArg::None},
+    {"echo-map-range", BK_OP_ECHO_MAP_RANGE, 3, OpArg::None},
+    {"echo-map-score", BK_OP_ECHO_MAP_SCORE, 5, OpArg::None},
+    {"count", BK_OP_COUNT, 3, OpArg::None},
+    {"indicator", BK_OP_INDICATOR, 3, OpArg::None},
+    {"max", BK_OP_MAX, 5, OpArg::None},
+    {"max-element-rand", 0, 5, OpArg::None},
+    {"max-element", BK_OP_MAX_ELEMENT, 5, OpArg::None},
+    {"min", BK_OP_MIN, 5, OpArg::None},
+    {"min-element-rand", 0, 5, OpArg::None},
+    {"min-element", BK_OP_MIN_ELEMENT, 5, OpArg::None},
+    {"mean", BK_OP_MEAN, 5, OpArg::None},
+    {"variance", BK_OP_VARIANCE, 5, OpArg::None},
+    {"stdev", BK_OP_STDEV, 5, OpArg::None},
+    {"cv", BK_OP_CV, 5, OpArg::None},
+    {"sum", BK_OP_SUM, 5, OpArg::None},
+    {"wmean", BK_OP_WMEAN, 5, OpArg::None},
+    {"median", BK_OP_MEDIAN, 5, OpArg::None},
+    {"mad", BK_OP_MAD, 5, OpArg::Multiplier},
+    {"kth", BK_OP_KTH, 5, OpArg::Quantile},
+    {"tmean", BK_OP_TMEAN, 5, OpArg::TrimPair},
 };
 
 struct Options {
@@ -52,149 +75,211 @@ void require(bool ok, const std::string& msg) {
   if (!ok) throw UserError(msg);
 }
 
-double parse_frac(const std::string& sval) {
-  std::stringstream conv(sval);
-  double            v = 0;
-  conv >> v;
-  return v;
-}
-
 struct Help {};
 struct Version {};
 struct NoInput {};
 
+// ---- the settings (everything that is not an operation) as data ---------------------------------------------------
+// The reference's Input constructor (Input.hpp:92-330) is one long if-chain; what it accepts and what it says when it
+// does not is kept here as a table that one interpreter walks.  A row names where the value goes, the complaints in the
+// reference's words, and -- because the chain does not always complain in the same order -- whether the missing value
+// or the repetition is noticed first.
+enum class Takes { Nothing, Text, Count, Fraction };
+constexpr const char* kDigits = "0123456789";
+constexpr const char* kReal = ".-0123456789";
+
+struct Setting {
+  const char* name;
+  Takes       takes;
+  bool Options::*        seen;        // Nothing: the switch itself; Count / Fraction: "was given" (repetition test)
+  std::string Options::* text;        // Text: destination; "given before" = differs from its default
+  const char* text_default;
+  const char* role;                   // Text: "Apparent option: X where <role> expected."
+  const char* repeated;               // complaint on repetition (nullptr: repeating is harmless)
+  const char* missing;                // complaint when argv ends here
+  bool        missing_first;          // --prec looks for its value before it notices the repetition
+  void (*store)(Options&, const std::string& value);  // Count / Fraction: convert, range-check, store
+  void (*before)(Options&);           // conflicts the reference tests before anything else
+};
+
+// The reference converts with `stringstream >> member`: an empty word leaves the member as it was (a failed sentry does not
+// touch the target), an overflowing one saturates it.  Extract into the very field, as it does.
+template <class T>
+void extract(const std::string& word, T& into) {
+  std::stringstream conv(word);
+  conv >> into;
+}
+// argv[argc]: the reference builds a std::string from it in two places without looking (Input.hpp:116, :124, :132, :275)
+[[noreturn]] void null_word() { throw UserError("basic_string: construction from null is not valid"); }
+
+const Setting kSettings[] = {
+    {"ec", Takes::Nothing, &Options::ec},
+    {"header", Takes::Nothing, &Options::ec},
+    {"faster", Takes::Nothing, &Options::fast},
+    {"sweep-all", Takes::Nothing, &Options::sweep_all},
+    {"skip-unmapped", Takes::Nothing, &Options::skip_unmapped},
+    {"sci", Takes::Nothing, &Options::sci},
+    {"exact", Takes::Nothing, &Options::exact, nullptr, nullptr, nullptr, "multiple --exact's detected - use one"},
+    {"delim", Takes::Text, nullptr, &Options::delim, "|", "output delimiter", "--delim specified multiple times", "No output delimiter given"},
+    {"multidelim", Takes::Text, nullptr, &Options::multidelim, ";", "output delimiter", "--multidelim specified multiple times",
+     "No multi-value column delimmiter given"},
+    {"chrom", Takes::Text, nullptr, &Options::chrom, "all", "chromosome", "--chrom specified multiple times", "No chromosome name given"},
+    {"prec", Takes::Count, &Options::set_prec, nullptr, nullptr, nullptr, "--prec specified multiple times.", "No precision value given", true,
+     [](Options& o, const std::string& v) {
+       extract(v, o.precision);
+       require(o.precision >= 0, "--prec value must be >= 0");
+     }},
+    {"bp-ovr", Takes::Count, &Options::is_bp, nullptr, nullptr, nullptr, "multiple --bp-ovr's detected", "No arg for --bp-ovr", false,
+     [](Options& o, const std::string& v) {
+       extract(v, o.overlap_bp);
+       require(o.overlap_bp > 0, "--bp-ovr value must be > 0");
+     },
+     [](Options& o) { require(!o.range_alias, "--range and --bp-ovr detected.  Choose one."); }},
+    {"range", Takes::Count, &Options::is_range, nullptr, nullptr, nullptr, "multiple --range's detected", "No arg for --range", false,
+     [](Options& o, const std::string& v) {
+       extract(v, o.range_bp);
+       require(o.range_bp >= 0, "--range value must be >= 0");
+     },
+     [](Options& o) { require(!o.range_alias, "multiple --range's detected"); }},
+    {"fraction-ref", Takes::Fraction, &Options::pr},
+    {"fraction-map", Takes::Fraction, &Options::pm},
+    {"fraction-either", Takes::Fraction, &Options::pe},
+    {"fraction-both", Takes::Fraction, &Options::pb},
+};
+
+// argv cursor: the interpreter and the operation arguments pull their values from it
+struct Args {
+  int    argc;
+  char** argv;
+  int    i = 1;
+  bool        more() const { return i < argc; }
+  int         left() const { return argc - i; }
+  std::string take() { return argv[i++]; }
+  const char* peek() const { return argv[i]; }
+};
+
+void apply_setting(const Setting& st, Options& o, Args& a) {
+  const std::string dashed = std::string("--") + st.name;
+  if (st.before) st.before(o);
+  const bool again = st.takes == Takes::Text ? o.*st.text != st.text_default : (st.takes != Takes::Nothing || st.repeated) && o.*st.seen;
+  const std::string repeated = st.repeated ? st.repeated : "multiple " + dashed + "'s detected";
+  const std::string missing = st.missing ? st.missing : "No arg for " + dashed;
+  if (st.takes == Takes::Nothing) {
+    require(!again, repeated);
+    o.*st.seen = true;
+    return;
+  }
+  if (st.missing_first) require(a.more(), missing);
+  require(!again, repeated);
+  require(a.more(), missing);
+  const std::string value = a.take();
+  switch (st.takes) {
+    case Takes::Text:
+      o.*st.text = value;
+      // the complaint is put together before the test, and from the word AFTER the value: with nothing behind the value
+      // that alone fails, and a value that looks like an option is reported under its successor's name
+      if (!a.more()) null_word();
+      require(value.find("--") != 0, std::string("Apparent option: ") + a.peek() + " where " + st.role + " expected.");
+      return;
+    case Takes::Count:
+      require(cli::only_chars(value, kDigits), "Non-positive-integer argument: " + value + " for " + dashed);
+      st.store(o, value);
+      break;
+    case Takes::Fraction:
+      require(cli::only_chars(value, kReal), "Non-numeric argument: " + value + " for " + dashed);
+      extract(value, o.frac);
+      require(o.frac > 0 && o.frac <= 1, dashed + " value must be: >0-1.0");
+      break;
+    default: break;
+  }
+  o.*st.seen = true;
+}
+
+// the numbers that may follow an operation's name; returns the operation actually run (--kth 0 / 1 are --min / --max)
+int read_op_args(const OpInfo& info, const std::string& dashed, Args& a, double* arg1, double* arg2) {
+  auto number = [&](const std::string& text, double otherwise) {
+    require(cli::only_chars(text, kReal), "Non-numeric argument: " + text + " for " + dashed);
+    double            v = otherwise;
+    std::stringstream conv(text);
+    conv >> v;
+    return v;
+  };
+  switch (info.arg) {
+    case OpArg::None: break;
+    case OpArg::Multiplier:  // optional: only a numeric-looking word is taken (Input.hpp:275-288); the word is read unseen
+      if (!a.more()) null_word();
+      if (cli::only_chars(a.peek(), kReal)) {
+        *arg1 = number(a.take(), -1);
+        require(*arg1 > 0, dashed + " Expect 0 < val");
+      }
+      break;
+    case OpArg::Quantile:  // Input.hpp:290-302
+      require(a.more(), "No arg for " + dashed);
+      *arg1 = number(a.take(), -1);
+      require(*arg1 >= 0 && *arg1 <= 1, dashed + " Expect 0 <= val <= 1");
+      if (*arg1 == 0) return BK_OP_MIN;  // "min faster" / "max faster", Bedmap.cpp:495-498
+      if (*arg1 == 1) return BK_OP_MAX;
+      break;
+    case OpArg::TrimPair: {  // Input.hpp:303-326: both words are looked at before either number is judged
+      require(a.more(), "No <low> arg given for " + dashed);
+      const std::string lo = a.take();
+      require(cli::only_chars(lo, kReal), "Non-numeric argument: " + lo + " for " + dashed);
+      require(a.more(), "No <hi> arg given for " + dashed);
+      const std::string hi = a.take();
+      *arg1 = number(lo, 100);
+      *arg2 = number(hi, 100);
+      require(*arg1 >= 0 && *arg1 <= 1, dashed + " Expect 0 <= low < hi <= 1");
+      require(*arg2 >= 0 && *arg2 <= 1, dashed + " Expect 0 <= low < hi <= 1");
+      require(*arg1 + *arg2 <= 1, dashed + " Expect (low + hi) <= 1.");
+      break;
+    }
+  }
+  return info.op;
+}
+
+template <class Row, size_t N>
+const Row* lookup(const Row (&table)[N], const std::string& name) {
+  const Row* hit = nullptr;
+  for (const Row& r : table)
+    if (name == r.name) hit = &r;
+  return hit;
+}
+
 Options parse_args(int argc, char** argv) {
   Options o;
   if (argc <= 1) throw NoInput();
-  const char* pos_ints = "0123456789";
-  const char* reals = ".-0123456789";
-  int         i = 1;
-  bool        has_op = false;
-  while (i < argc) {
-    std::string next = argv[i++];
-    if (next.find("--") == std::string::npos && argc - i < 2) break;  // file inputs
-    require(next.find("--") == 0, "Option " + next + " does not start with '--'");
-    next = next.substr(2);
-    auto frac_opt = [&](bool& flag, const char* nm) {
-      require(!flag, std::string("multiple --") + nm + "'s detected");
-      require(i < argc, std::string("No arg for --") + nm);
-      std::string sval = argv[i++];
-      require(cli::only_chars(sval, reals), "Non-numeric argument: " + sval + " for --" + nm);
-      o.frac = parse_frac(sval);
-      require(o.frac > 0 && o.frac <= 1, std::string("--") + nm + " value must be: >0-1.0");
-      flag = true;
-    };
-    if (next == "help") throw Help();
-    else if (next == "version") throw Version();
-    else if (next == "ec" || next == "header") o.ec = true;
-    else if (next == "faster") o.fast = true;
-    else if (next == "sweep-all") o.sweep_all = true;
-    else if (next == "delim") {
-      require(o.delim == "|", "--delim specified multiple times");
-      require(i < argc, "No output delimiter given");
-      o.delim = argv[i++];
-      require(o.delim.find("--") != 0, "Apparent option: " + o.delim + " where output delimiter expected.");
-    } else if (next == "chrom") {
-      require(o.chrom == "all", "--chrom specified multiple times");
-      require(i < argc, "No chromosome name given");
-      o.chrom = argv[i++];
-      require(o.chrom.find("--") != 0, "Apparent option: " + o.chrom + " where chromosome expected.");
-    } else if (next == "multidelim") {
-      require(o.multidelim == ";", "--multidelim specified multiple times");
-      require(i < argc, "No multi-value column delimmiter given");
-      o.multidelim = argv[i++];
-      require(o.multidelim.find("--") != 0, "Apparent option: " + o.multidelim + " where output delimiter expected.");
-    } else if (next == "skip-unmapped") o.skip_unmapped = true;
-    else if (next == "sci") o.sci = true;
-    else if (next == "prec") {
-      require(i < argc, "No precision value given");
-      require(!o.set_prec, "--prec specified multiple times.");
-      std::string sval = argv[i++];
-      require(cli::only_chars(sval, pos_ints), "Non-positive-integer argument: " + sval + " for --prec");
-      o.precision = std::atoi(sval.c_str());
-      require(o.precision >= 0, "--prec value must be >= 0");
-      o.set_prec = true;
-    } else if (next == "bp-ovr") {
-      require(!o.range_alias, "--range and --bp-ovr detected.  Choose one.");
-      require(!o.is_bp, "multiple --bp-ovr's detected");
-      require(i < argc, "No arg for --bp-ovr");
-      std::string sval = argv[i++];
-      require(cli::only_chars(sval, pos_ints), "Non-positive-integer argument: " + sval + " for --bp-ovr");
-      o.overlap_bp = std::atol(sval.c_str());
-      require(o.overlap_bp > 0, "--bp-ovr value must be > 0");
-      o.is_bp = true;
-    } else if (next == "range") {
-      require(!o.is_range && !o.range_alias, "multiple --range's detected");
-      require(i < argc, "No arg for --range");
-      std::string sval = argv[i++];
-      require(cli::only_chars(sval, pos_ints), "Non-positive-integer argument: " + sval + " for --range");
-      o.range_bp = std::atol(sval.c_str());
-      require(o.range_bp >= 0, "--range value must be >= 0");
-      o.is_range = true;
-      if (o.range_bp == 0) {  // alias for --bp-ovr 1
+  Args a{argc, argv};
+  bool has_op = false;
+  while (a.more()) {
+    const std::string word = a.take();
+    if (word.find("--") == std::string::npos && a.left() < 2) break;  // file inputs
+    require(word.find("--") == 0, "Option " + word + " does not start with '--'");
+    const std::string name = word.substr(2);
+    if (name == "help") throw Help();
+    if (name == "version") throw Version();
+    if (const Setting* st = lookup(kSettings, name)) {
+      apply_setting(*st, o, a);
+      if (st->store && o.is_range && o.range_bp == 0 && name == "range") {  // --range 0 is an alias for --bp-ovr 1
         require(!o.is_bp, "--bp-ovr and --range detected.  Choose one.");
         o.is_range = false;
-        o.is_bp = true;
-        o.range_alias = true;
+        o.is_bp = o.range_alias = true;
         o.overlap_bp = 1;
       }
-    } else if (next == "fraction-ref") frac_opt(o.pr, "fraction-ref");
-    else if (next == "fraction-map") frac_opt(o.pm, "fraction-map");
-    else if (next == "fraction-either") frac_opt(o.pe, "fraction-either");
-    else if (next == "fraction-both") frac_opt(o.pb, "fraction-both");
-    else if (next == "exact") {
-      require(!o.exact, "multiple --exact's detected - use one");
-      o.exact = true;
-    } else {
-      const OpInfo* info = nullptr;
-      for (const OpInfo& k : kOps)
-        if (next == k.name) info = &k;
-      if (!info) throw UserError("Unknown option: --" + next);
-      double op_arg = 0, op_arg2 = 0;
-      int    op = info->op;
-      if (op == BK_OP_TMEAN) {  // Input.hpp:303-326
-        require(i < argc, "No <low> arg given for --" + next);
-        const std::string lo = argv[i++];
-        require(cli::only_chars(lo, reals), "Non-numeric argument: " + lo + " for --" + next);
-        require(i < argc, "No <hi> arg given for --" + next);
-        const std::string hi = argv[i++];
-        require(cli::only_chars(hi, reals), "Non-numeric argument: " + hi + " for --" + next);
-        op_arg = op_arg2 = 100;
-        std::stringstream cl(lo), ch(hi);
-        cl >> op_arg;
-        ch >> op_arg2;
-        require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= low < hi <= 1");
-        require(op_arg2 >= 0 && op_arg2 <= 1, "--" + next + " Expect 0 <= low < hi <= 1");
-        require(op_arg + op_arg2 <= 1, "--" + next + " Expect (low + hi) <= 1.");
-      } else if (info->nargs > 0) {
-        require(i + info->nargs <= argc, "No arg for --" + next);
-        if (info->op == BK_OP_KTH) {  // Input.hpp:290-302
-          const std::string sval = argv[i];
-          require(cli::only_chars(sval, reals), "Non-numeric argument: " + sval + " for --" + next);
-          op_arg = -1;
-          std::stringstream conv(sval);
-          conv >> op_arg;
-          require(op_arg >= 0 && op_arg <= 1, "--" + next + " Expect 0 <= val <= 1");
-          if (op_arg == 0) op = BK_OP_MIN;       // "min faster" / "max faster", Bedmap.cpp:495-498
-          else if (op_arg == 1) op = BK_OP_MAX;
-        }
-        i += info->nargs;
-      } else if (info->nargs < 0 && i < argc && cli::only_chars(argv[i], reals)) {  // optional multiplier of --mad
-        op_arg = -1;
-        std::stringstream conv(std::string(argv[i]));
-        conv >> op_arg;
-        require(op_arg > 0, "--" + next + " Expect 0 < val");  // Input.hpp:275-288
-        i++;
-      }
-      if (!op && o.unsupported_op.empty()) o.unsupported_op = next;
-      o.ops.push_back(op);
-      o.op_args.push_back(op_arg);
-      o.op_args2.push_back(op_arg2);
-      o.min_map_fields = std::max(o.min_map_fields, info->map_fields);
-      o.min_ref_fields = std::max(o.min_ref_fields, 3);
-      has_op = true;
+      continue;
     }
+    const OpInfo* info = lookup(kOps, name);
+    if (!info) throw UserError("Unknown option: --" + name);
+    double    arg1 = 0, arg2 = 0;
+    const int op = read_op_args(*info, "--" + name, a, &arg1, &arg2);
+    if (!op && o.unsupported_op.empty()) o.unsupported_op = name;
+    o.ops.push_back(op);
+    o.op_args.push_back(arg1);
+    o.op_args2.push_back(arg2);
+    o.min_map_fields = std::max(o.min_map_fields, info->map_fields);
+    o.min_ref_fields = std::max(o.min_ref_fields, 3);
+    has_op = true;
   }
+  const int i = a.i;
   if (!(o.pm || o.pr || o.pe || o.pb || o.is_range || o.is_bp || o.exact)) {
     o.is_bp = true;
     o.overlap_bp = 1;
@@ -227,6 +312,16 @@ std::string unescape_delim(const std::string& d) {  // PrintDelim, ProcessVisito
   return d;
 }
 
+void dump_options(const Options& o) {
+  std::printf("ref=%s map=%s files=%d overlap=%d range_bp=%ld overlap_bp=%ld frac=%.17g prec=%d sci=%d ec=%d sweep_all=%d fast=%d "
+              "skip_unmapped=%d delim=[%s] multidelim=[%s] chrom=[%s] ref_fields=%d map_fields=%d unsupported=[%s] ops=",
+              o.ref.c_str(), o.map.c_str(), o.num_files, o.overlap_kind, o.range_bp, o.overlap_bp, o.frac, o.precision, (int)o.sci, (int)o.ec,
+              (int)o.sweep_all, (int)o.fast, (int)o.skip_unmapped, o.delim.c_str(), o.multidelim.c_str(), o.chrom.c_str(), o.min_ref_fields,
+              o.min_map_fields, o.unsupported_op.c_str());
+  for (size_t k = 0; k < o.ops.size(); k++) std::printf("%s%d(%.17g,%.17g)", k ? "," : "", o.ops[k], o.op_args[k], o.op_args2[k]);
+  std::printf("\n");
+}
+
 void usage(FILE* f) { std::fputs(kUsageBedmap, f); }  // byte for byte the reference's text (help_text.hpp)
 
 }  // namespace
@@ -235,11 +330,17 @@ int main(int argc, char** argv) {
   try {
     cli::trace_lap("start");
     Options o = parse_args(argc, argv);
+    if (std::getenv("BEDKIT_DUMP_OPTIONS")) {  // what the command line was understood as, then stop (host-logic tests, no GPU)
+      dump_options(o);
+      return EXIT_SUCCESS;
+    }
     if (!o.unsupported_op.empty())
       throw UserError("--" + o.unsupported_op + " is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
     cli::Input rtext, mtext;
-    if (!rtext.open(o.ref)) throw UserError("Unable to find file: " + o.ref);
-    if (o.num_files == 2 && !mtext.open(o.map)) throw UserError("Unable to find file: " + o.map);
+    // FPWrap.hpp:42 says "Unable to find file: X"; the --ec branch opens ifstreams itself and says "Unable to find: X" (Bedmap.cpp:231, :300-302)
+    const std::string not_found = o.ec ? "Unable to find: " : "Unable to find file: ";
+    if (!rtext.open(o.ref)) throw UserError(not_found + o.ref);
+    if (o.num_files == 2 && !mtext.open(o.map)) throw UserError(not_found + o.map);
     if (cli::any_archive({&rtext, &mtext})) {
       cli::Engine eng;
       cli::unstarch_if_archive(eng, rtext);

@@ -12,6 +12,14 @@ namespace {
 
 using cli::UserError;
 
+// `stringstream >> int` as Input.hpp:237, :248 use it: an empty word leaves the previous value, an overflowing one saturates
+int as_the_reference_reads_an_int(const std::string& word, int previous) {
+  std::stringstream s;
+  s << word;
+  s >> previous;
+  return previous;
+}
+
 enum Mode { MERGE, INTERSECTION, ELEMENTOF, NOTELEMENTOF, COMPLEMENT, DIFFERENCE, SYMMDIFF, UNIONALL, PARTITION, CHOP };
 
 struct Options {
@@ -191,7 +199,7 @@ Options parse_args(int argc, char** argv) {
               require(i + 2 < argc, "No #nt value found for --stagger suboption in --chop");
               std::string v = argv[i + 2];
               require(cli::only_chars(v, ints), "Invalid --stagger suboption #nt value in --chop.  Expect a +integer.");
-              o.chop_stagger = std::atol(v.c_str());
+              o.chop_stagger = as_the_reference_reads_an_int(v, (int)o.chop_stagger);
               require(o.chop_stagger > 0, "nt setting for chop's --stagger suboption must be > 0");
               stagger_set = aux_set = true;
               i += 2;
@@ -199,10 +207,10 @@ Options parse_args(int argc, char** argv) {
               require(!o.chop_cut_short, "chop's -x suboption specified multiple times.");
               o.chop_cut_short = aux_set = true;
               i += 1;
-            } else if (!a.empty() && cli::only_chars(a, ints)) {
+            } else if (cli::only_chars(a, ints)) {  // an empty word passes this test too, and leaves the default in place
               require(!value_set, "Stray integer found (invalid argument for --chop?)");
               require(!aux_set, "Stray integer value found: not valid for --chop");
-              o.chop_bp = std::atol(a.c_str());
+              o.chop_bp = as_the_reference_reads_an_int(a, (int)o.chop_bp);
               require(o.chop_bp > 0, "bp setting for chop must be > 0");
               value_set = true;
               i += 1;
