@@ -3,6 +3,7 @@ has no torch types in its ABI, and the product fails loudly (no CPU fallback) wh
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -117,3 +118,70 @@ def test_more_operations_than_the_spec_table_holds_is_a_clean_error(tmp_path):
     (tmp_path / "a.bed").write_bytes(b"chr1\t1\t2\n")
     p = subprocess.run([bedops_b200.tool_path("bedmap")] + ["--count"] * 200 + ["a.bed", "a.bed"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode == 1 and "operations given" in p.stderr and "stack smashing" not in p.stderr
+
+
+def test_entry_points_answer_null_handles_with_an_error_code_not_a_crash():
+    """No GPU needed: every entry point that takes a ctx / bed / shard / text looks at its pointers before it touches the
+    device (the two *_default functions fill a caller-provided struct and are the exception, as in any C API)."""
+    import bedops_b200
+    bedops_b200.load_library()
+    calls = {
+      "bk_destroy": "lib.bk_destroy(None)",
+      "bk_set_stream": "lib.bk_set_stream(None,None)",
+      "bk_sync": "lib.bk_sync(None)",
+      "bk_last_error": "lib.bk_last_error(None)",
+      "bk_launch_count": "lib.bk_launch_count(None)",
+      "bk_profile": "lib.bk_profile(None,1)",
+      "bk_profile_query": "lib.bk_profile_query(None,b'k',None,None)",
+      "bk_copy": "lib.bk_copy(None,None,None,C.c_size_t(0))",
+      "bk_release_cached": "lib.bk_release_cached(None)",
+      "bk_load_bed": "lib.bk_load_bed(None,b'x',C.c_size_t(1),3,0,None)",
+      "bk_load_bed_device": "lib.bk_load_bed_device(None,None,C.c_size_t(0),3,0,None)",
+      "bk_free_bed": "lib.bk_free_bed(None,None)",
+      "bk_bed_rows": "lib.bk_bed_rows(None)",
+      "bk_bed_nchrom": "lib.bk_bed_nchrom(None)",
+      "bk_bed_chrom_name": "lib.bk_bed_chrom_name(None,0)",
+      "bk_bed_chrom_rows": "lib.bk_bed_chrom_rows(None,0)",
+      "bk_bed_copy_columns": "lib.bk_bed_copy_columns(None,None,None,None,None,None)",
+      "bk_check_text": "lib.bk_check_text(None,b'x',C.c_size_t(1),3,1,0)",
+      "bk_check_text_device": "lib.bk_check_text_device(None,None,C.c_size_t(0),3,1,0)",
+      "bk_bedmap": "lib.bk_bedmap(None,None,None,None,None)",
+      "bk_bedmap_host": "lib.bk_bedmap_host(None,None,C.c_size_t(0),3,0,None,C.c_size_t(0),3,0,None,None)",
+      "bk_setop": "lib.bk_setop(None,0,None,0,C.c_double(1.0),0,None,0,None)",
+      "bk_chop": "lib.bk_chop(None,None,0,C.c_uint64(1),C.c_uint64(0),0,None,0,None)",
+      "bk_bed_pad": "lib.bk_bed_pad(None,None,C.c_longlong(0),C.c_longlong(0),None)",
+      "bk_closest": "lib.bk_closest(None,None,None,None,None)",
+      "bk_is_starch": "lib.bk_is_starch(None,C.c_size_t(0))",
+      "bk_unstarch": "lib.bk_unstarch(None,None,C.c_size_t(0),None,0,None)",
+      "bk_starch_inflate_host": "lib.bk_starch_inflate_host(None,C.c_size_t(0),None,None,None)",
+      "bk_host_free": "lib.bk_host_free(None)",
+      "bk_sort_bed": "lib.bk_sort_bed(None,None,C.c_size_t(0),0,None,None)",
+      "bk_sort_bed_device": "lib.bk_sort_bed_device(None,None,C.c_size_t(0),0,None,None)",
+      "bk_radix_sort_pairs": "lib.bk_radix_sort_pairs(None,None,None,C.c_uint64(0),64)",
+      "bk_format_bed_device": "lib.bk_format_bed_device(None,None,None,None,None,None,C.c_uint64(0),None)",
+      "bk_free_text": "lib.bk_free_text(None,None)",
+      "bk_chrom_index": "lib.bk_chrom_index(None,C.c_size_t(0),None,0,None)",
+      "bk_plan_shards": "lib.bk_plan_shards(None,0,0,None)",
+      "bk_find_start": "lib.bk_find_start(None,C.c_uint64(0),C.c_uint64(10),C.c_uint64(1))",
+      "bk_plan_cuts": "lib.bk_plan_cuts(None,C.c_size_t(0),None,0,0,None)",
+      "bk_cut_offset": "lib.bk_cut_offset(None,C.c_size_t(0),None,0,None)",
+      "bk_bed_reach_start": "lib.bk_bed_reach_start(None,None,None,C.c_uint64(0),None)",
+      "bk_bed_chrom_max_end": "lib.bk_bed_chrom_max_end(None,None,None,None)",
+      "bk_bed_concat": "lib.bk_bed_concat(None,None,None,None)",
+      "bk_shard_plan_make": "lib.bk_shard_plan_make(None,C.c_size_t(0),None,C.c_size_t(0),0,None)",
+      "bk_bedmap_shard_begin": "lib.bk_bedmap_shard_begin(None,None,0,None,C.c_size_t(0),3,0,None,C.c_size_t(0),3,0,None,None,None)",
+      "bk_bedmap_shard_finish": "lib.bk_bedmap_shard_finish(None,None,None,None)",
+      "bk_shard_free": "lib.bk_shard_free(None,None)",
+      "bk_shard_bytes_in": "lib.bk_shard_bytes_in(None)",
+    }
+    prog = ("import ctypes as C\nlib = C.CDLL(%r)\nlib.bk_last_error.restype = C.c_char_p\nlib.bk_bed_chrom_name.restype = C.c_char_p\n"
+            "lib.bk_find_start.restype = C.c_uint64\nlib.bk_cut_offset.restype = C.c_uint64\n" % bedops_b200.lib_path())
+    for name, expr in calls.items():
+        prog += "r = %s\nprint(%r, r)\n" % (expr, name)
+    p = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, (p.stdout[-300:], p.stderr[-300:])
+    seen = dict(line.split(" ", 1) for line in p.stdout.strip().split("\n"))
+    assert len(seen) == len(calls)
+    for name in ("bk_load_bed", "bk_bedmap", "bk_bedmap_host", "bk_setop", "bk_closest", "bk_sort_bed", "bk_unstarch", "bk_bed_pad",
+                 "bk_bedmap_shard_begin", "bk_bedmap_shard_finish", "bk_check_text", "bk_chop", "bk_bed_concat"):
+        assert seen[name] == "3", (name, seen[name])   # BK_ERR_ARG
