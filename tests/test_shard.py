@@ -244,3 +244,35 @@ def test_gloo_range_shards_with_halos_concatenate_to_the_unsharded_result(synth_
     for p in procs:
         p.join(timeout=60)
     assert bad == []
+
+
+@pytest.mark.parametrize("world", [8, 13])
+def test_many_range_shards_in_one_process_concatenate_to_the_unsharded_result(synth_files, world):
+    """The same protocol at the shard counts `bench.py --gpus 8` uses (and one that divides nothing), ranks as threads
+    and the allgather as a barrier over a shared table: halos that begin more than one shard back, shards without reference
+    rows, cuts in a single chromosome."""
+    import threading
+    barrier = threading.Barrier(world)
+    for ref, mp_, ops, overlap in halo_cases(synth_files):
+        table, parts, errors = [None] * world, [None] * world, []
+
+        def rank_main(rank):
+            def gather(v):
+                table[rank] = v
+                barrier.wait(timeout=300)
+                snapshot = list(table)
+                barrier.wait(timeout=300)
+                return snapshot
+            try:
+                parts[rank] = range_shard_with_oracle(rank, world, ref, mp_, ops, overlap, gather)
+            except Exception as e:   # a dead rank must not leave the others at the barrier
+                errors.append((rank, repr(e)))
+                barrier.abort()
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=600)
+        assert not errors, errors
+        assert b"".join(parts) == O.bedmap(ref, mp_, ops, overlap=overlap), (world, ops, overlap)
