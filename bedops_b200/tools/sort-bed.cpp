@@ -175,12 +175,13 @@ int main(int argc, char** argv) {
   try {
     if (o.check) {  // CheckSort.cpp:35-56
       try {
-        cli::Engine eng;
+        std::unique_ptr<cli::Engine> eng;  // made when the first file is there: a missing file is reported without touching the GPU
         for (const std::string& name : o.files) {
           cli::Input in;
           if (!in.open(name)) throw std::runtime_error("Unable to find: " + name);
+          if (!eng) eng.reset(new cli::Engine());
           cli::ec_prepare(in);
-          cli::ec_check(eng, in, name, 3, true, false);
+          cli::ec_check(*eng, in, name, 3, true, false);
         }
         return EXIT_SUCCESS;
       } catch (const std::exception& e) {
@@ -188,7 +189,24 @@ int main(int argc, char** argv) {
         return EXIT_FAILURE;
       }
     }
-    // checkfiles, SortDetails.cpp:359-387
+    // checkfiles, SortDetails.cpp:359-387: a pass of its own over all the names before anything is read -- whatever fopen
+    // opens passes (a directory does), stdin may be named once
+    {
+      int stdin_count = 0;
+      for (const std::string& name : o.files) {
+        if (name != "-") {
+          const int fd = ::open(name.c_str(), O_RDONLY);
+          if (fd < 0) {
+            std::fprintf(stderr, "Unable to access %s\n", name.c_str());
+            return EXIT_FAILURE;
+          }
+          ::close(fd);
+        } else if (++stdin_count > 1) {
+          std::fprintf(stderr, "stdin specified multiple times\n");
+          return EXIT_FAILURE;
+        }
+      }
+    }
     std::vector<std::unique_ptr<cli::Input>> inputs;
     for (const std::string& name : o.files) {
       inputs.emplace_back(new cli::Input());
