@@ -105,7 +105,11 @@ def test_refused_command_lines_are_refused_in_the_reference_s_words(tmp_path, to
         argv = gen(rng)
         got = run(ours, argv, tmp_path)
         if b"CUDA failure" in got[2] or b"no usable sm_100" in got[2]:
-            continue   # a complete command line over readable input: the device's business
+            # a complete command line over readable input (here: stdin alone) is the device's business -- but then the
+            # reference must not have refused it either (sort-bed --check-sort reads stdin before it misses a later file)
+            if not (tool == "sort-bed" and "--check-sort" in argv):
+                assert run(ref, argv, tmp_path)[0] == 0, (tool, argv)
+            continue
         if tool == "bedmap" and any("-element" in w for w in argv) and got[0] == 0:
             continue
         exp = run(ref, argv, tmp_path)
